@@ -1,0 +1,159 @@
+"""Oracle (test infrastructure): functional NCSNv2 / NCSNv2Deepest forward on a reference-layout state dict.
+
+Restates `ncsn/models/ncsnv2.py`, `layers.py` and `normalization.py` of the reference as pure
+functions over a `dict[str, Tensor]` whose keys are the reference's state-dict names
+(`res1.0.conv1.weight`, `refine5.msf.convs.0.bias`, ...), using torch CPU ops.
+"""
+import torch
+import torch.nn.functional as F
+
+
+def _conv(P, key, x, dilation=1, kernel=3):
+    """3x3 (pad = dilation) or 1x1 convolution, bias iff present in the state dict.
+    Reference: conv3x3 / dilated_conv3x3 / conv1x1, layers.py:28-60."""
+    w = P[key + ".weight"]
+    b = P.get(key + ".bias")
+    pad = dilation if kernel == 3 else 0
+    return F.conv2d(x, w, b, stride=1, padding=pad, dilation=dilation)
+
+
+def instance_norm_plus(P, key, x, eps=1e-5):
+    """InstanceNorm++: gamma*(IN(x) + alpha*m_hat) + beta, m_hat = channel-standardised spatial
+    means (unbiased variance over C). Reference: InstanceNorm2dPlus.forward, normalization.py:163-176."""
+    mu = x.mean(dim=(2, 3))
+    m_hat = (mu - mu.mean(dim=-1, keepdim=True)) / torch.sqrt(mu.var(dim=-1, keepdim=True) + eps)
+    var = x.var(dim=(2, 3), unbiased=False, keepdim=True)
+    h = (x - mu[..., None, None]) / torch.sqrt(var + eps)
+    h = h + (m_hat * P[key + ".alpha"])[..., None, None]
+    out = P[key + ".gamma"].view(1, -1, 1, 1) * h
+    if key + ".beta" in P:
+        out = out + P[key + ".beta"].view(1, -1, 1, 1)
+    return out
+
+
+def mean_pool2(x):
+    """Average of the four stride-2 phases. Reference: ConvMeanPool.forward, layers.py:309-313."""
+    return (x[:, :, ::2, ::2] + x[:, :, 1::2, ::2] + x[:, :, ::2, 1::2] + x[:, :, 1::2, 1::2]) / 4.0
+
+
+def residual_block(P, key, x, resample, dilation):
+    """IN++ -> ELU -> conv1 -> IN++ -> ELU -> conv2(+pool) + shortcut. Reference: ResidualBlock,
+    layers.py:401-456 (down & no dilation: conv2 and shortcut are ConvMeanPool 3x3 / 1x1;
+    dilation: all three convs dilated, no pooling)."""
+    d = 1 if dilation is None else dilation
+    h = F.elu(instance_norm_plus(P, key + ".normalize1", x))
+    h = _conv(P, key + ".conv1", h, d)
+    h = F.elu(instance_norm_plus(P, key + ".normalize2", h))
+    pooled = resample == "down" and dilation is None
+    if pooled:
+        h = mean_pool2(_conv(P, key + ".conv2.conv", h, 1))
+    else:
+        h = _conv(P, key + ".conv2", h, d)
+    if key + ".shortcut.conv.weight" in P:
+        sc = mean_pool2(_conv(P, key + ".shortcut.conv", x, 1, kernel=1))
+    elif key + ".shortcut.weight" in P:
+        k = P[key + ".shortcut.weight"].shape[-1]
+        sc = _conv(P, key + ".shortcut", x, d if k == 3 else 1, kernel=k)
+    else:
+        sc = x
+    return sc + h
+
+
+def rcu(P, key, x, n_blocks, n_stages=2):
+    """Residual conv unit: per block r=x; (ELU, conv)*n_stages; x+=r. Reference: RCUBlock, layers.py:112-134."""
+    for i in range(n_blocks):
+        r = x
+        for j in range(n_stages):
+            x = _conv(P, f"{key}.{i + 1}_{j + 1}_conv", F.elu(x))
+        x = x + r
+    return x
+
+
+def crp(P, key, x, n_stages=2):
+    """Chained residual pooling with 5x5/s1 max-pool. Reference: CRPBlock, layers.py:62-83."""
+    x = F.elu(x)
+    path = x
+    for i in range(n_stages):
+        path = F.max_pool2d(path, kernel_size=5, stride=1, padding=2)
+        path = _conv(P, f"{key}.convs.{i}", path)
+        x = path + x
+    return x
+
+
+def msf(P, key, xs, shape):
+    """sum_i bilinear_{align_corners}(conv_i(x_i)). Reference: MSFBlock, layers.py:165-184."""
+    total = None
+    for i, xi in enumerate(xs):
+        h = F.interpolate(_conv(P, f"{key}.convs.{i}", xi), size=shape, mode="bilinear", align_corners=True)
+        total = h if total is None else total + h
+    return total
+
+
+def refine(P, key, xs, shape, end=False):
+    """adapt RCUs -> MSF (if >1 input) -> CRP -> output RCU (3 blocks when `end`).
+    Reference: RefineBlock, layers.py:214-249."""
+    hs = [rcu(P, f"{key}.adapt_convs.{i}", xi, 2) for i, xi in enumerate(xs)]
+    h = msf(P, key + ".msf", hs, shape) if len(hs) > 1 else hs[0]
+    h = crp(P, key + ".crp", h)
+    return rcu(P, key + ".output_convs", h, 3 if end else 1)
+
+
+# (stage name, [(resample, dilation) for the two blocks])
+ENCODERS = {
+    # Reference: NCSNv2.__init__, ncsnv2.py:29-63
+    "NCSNv2": [("res1", [(None, None), (None, None)]), ("res2", [("down", None), (None, None)]),
+               ("res3", [("down", 2), (None, 2)]), ("res4", [("down", 4), (None, 4)])],
+    # Reference: NCSNv2Deepest.__init__, ncsnv2.py:215-255
+    "NCSNv2Deepest": [("res1", [(None, None), (None, None)]), ("res2", [("down", None), (None, None)]),
+                      ("res3", [("down", None), (None, None)]), ("res31", [("down", None), (None, None)]),
+                      ("res4", [("down", 2), (None, 2)]), ("res5", [("down", 4), (None, 4)])],
+}
+# decoder: (refine name, skip stage index into the encoder list); deepest stage first
+DECODERS = {
+    "NCSNv2": ["refine1", "refine2", "refine3", "refine4"],                                   # ncsnv2.py:65-68,86-89
+    "NCSNv2Deepest": ["refine1", "refine2", "refine31", "refine3", "refine4", "refine5"],      # ncsnv2.py:257-262,284-289
+}
+
+
+def score_forward(arch, P, x, labels, logit_transform=False, rescaled=False):
+    """Reference: NCSNv2.forward (ncsnv2.py:70-101) / NCSNv2Deepest.forward (:269-299)."""
+    h = 2 * x - 1.0 if (not logit_transform and not rescaled) else x
+    h = _conv(P, "begin_conv", h)
+    feats = []
+    for stage, blocks in ENCODERS[arch]:
+        for i, (resample, dil) in enumerate(blocks):
+            h = residual_block(P, f"{stage}.{i}", h, resample, dil)
+        feats.append(h)
+    names = DECODERS[arch]
+    out = refine(P, names[0], [feats[-1]], feats[-1].shape[2:])
+    for j, name in enumerate(names[1:], start=2):
+        skip = feats[-j]
+        out = refine(P, name, [skip, out], skip.shape[2:], end=(j == len(names)))
+    out = F.elu(instance_norm_plus(P, "normalizer", out))
+    out = _conv(P, "end_conv", out)
+    sig = P["sigmas"][labels].view(x.shape[0], 1, 1, 1)
+    return out / sig
+
+
+def synth_state_dict(spec, seed, sigmas):
+    """Deterministic random weights for a list of (key, shape): every tensor comes from its own
+    torch.Generator seeded by (seed, position), so the reference model (via load_state_dict), this
+    oracle and the CUDA path all see identical parameters without shipping them as fixtures.
+    Conv weights ~ N(0, 1/fan_in) * 1.4, biases ~ N(0, 0.05), alpha/gamma ~ N(1, 0.02) (the
+    reference's own init, normalization.py:157-160), beta ~ N(0, 0.05)."""
+    P = {}
+    for idx, (key, shape) in enumerate(spec):
+        if key == "sigmas":
+            P[key] = sigmas.clone().float()
+            continue
+        g = torch.Generator().manual_seed(seed * 100003 + idx)
+        t = torch.randn(*shape, generator=g)
+        if key.endswith(".weight"):
+            fan_in = shape[1] * shape[2] * shape[3]
+            t = t * (1.4 / fan_in ** 0.5)
+        elif key.endswith(".alpha") or key.endswith(".gamma"):
+            t = 1.0 + 0.02 * t
+        else:
+            t = 0.05 * t
+        P[key] = t
+    return P
