@@ -1,0 +1,202 @@
+/* ipdm_b200 -- C ABI of the B200 (sm_100a) kernels behind the ALD MRI-reconstruction hot path of
+ * 10258392511/InverseProblemWithDiffusionModel.
+ *
+ * The reference has no FFI layer of its own (it is pure Python/PyTorch on this path, SURVEY.md
+ * section 8b); each entry point below names the reference call it replaces (file:line relative to
+ * the reference root).  The Python host code in `inverseproblemwithdiffusionmodel_b200/` binds these
+ * with ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *  - plain pointers, sizes and scalars only; every pointer is a DEVICE pointer unless it says host;
+ *  - complex64 tensors are interleaved (re,im) float pairs ("c64"); `planar` state tensors are two
+ *    float planes [2][...] (plane 0 = real part, plane 1 = imaginary part);
+ *  - activations of the score network are NHWC; "f16" = IEEE half; accumulation is always fp32;
+ *  - all calls are asynchronous on `stream` (a cudaStream_t passed as void*), never allocate, never
+ *    synchronise, and are capturable in a CUDA graph;
+ *  - return value 0 = ok, >0 = cudaError_t, <0 = IPDM_E_*; `ipdm_last_error()` gives the text.
+ */
+#ifndef IPDM_B200_H
+#define IPDM_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IPDM_E_BADARG (-1)      /* unsupported shape / null pointer / bad flag          */
+#define IPDM_E_UNSUPPORTED (-2) /* transform length not a power of two in [8,512], ... */
+#define IPDM_E_DRIVER (-3)      /* driver entry point (tensor-map encode) unavailable  */
+
+int ipdm_abi_version(void);
+const char* ipdm_last_error(void);
+/* number of kernels launched by this library in this process so far (bench.py's gpu_launches) */
+unsigned long long ipdm_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Centred orthonormal 2-D DFT, SENSE forward / adjoint
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Bytes of scratch the FFT/SENSE calls need for (ncoils, batch, H, W): one c64 image per coil image. */
+size_t ipdm_sense_workspace_bytes(int ncoils, int batch, int H, int W);
+
+/* out[c,b] = mask[b % mask_frames] * i2k(maps[c] * x[b]).
+ *   x     c64 [batch][H][W]
+ *   maps_re / maps_im  f32 [ncoils][H][W]; maps_im may be NULL (real maps); maps_re NULL => ncoils
+ *         must be 1 and no coil multiply is done (plain `i2k_complex`)
+ *   mask  u8 [mask_frames][W] (column mask, broadcast over H), NULL => no mask; mask_frames is 1 or
+ *         any value with image b using row b % mask_frames (the reference's (24,1,1,W) mask)
+ *   out   c64 [ncoils][batch][H][W]
+ * Replaces: SENSE.__call__ (ncsn/linear_transforms/undersampling_fourier.py:140-150),
+ *   RandomUndersamplingFourier.__call__ (:77-82), i2k_complex (ncsn/linear_transforms/__init__.py:36-45). */
+int ipdm_sense_forward(const void* x, const float* maps_re, const float* maps_im, const uint8_t* mask,
+                       int mask_frames, void* out, int ncoils, int batch, int H, int W, void* workspace,
+                       void* stream);
+
+/* out[b] = sum_c conj(maps[c]) * k2i(S[c,b]).  `mask` (may be NULL) is only a promise that S is zero
+ * on unmasked columns so they can be skipped; the public conj_op passes NULL (quirk Q3: no mask).
+ *   ssos != 0: out is f32 [batch][H][W] = sqrt(sum_c |k2i(S[c,b])|^2) instead (maps unused).
+ * Replaces: SENSE.conj_op (:152-160), SENSE.SSOS (:162-170), RandomUndersamplingFourier.conj_op
+ *   (:84-87), k2i_complex (ncsn/linear_transforms/__init__.py:48-57). */
+int ipdm_sense_adjoint(const void* S, const float* maps_re, const float* maps_im, const uint8_t* mask,
+                       int mask_frames, void* out, int ncoils, int batch, int H, int W, int ssos,
+                       void* workspace, void* stream);
+
+/* k-space elementwise helpers for SingleCoil / projection (proximal_op.py:72-94,
+ * undersampling_fourier.py:89-97):  mode 0: S *= 1/(1 + a*mask);
+ * mode 1: S = a*Y + (1-a)*mask*S + (1-mask)*S   (Y = measured k-space, a = lamda);  mode 2: S *= mask.
+ * S is c64 [batch][H][W]; image i uses mask row i % mask_frames. */
+int ipdm_kspace_combine(void* S, const void* Y, const uint8_t* mask, int mask_frames, float a, int mode,
+                        int batch, int H, int W, void* stream);
+
+/* out = a + s * b  on c64 (n complex elements); used for z + alpha*k2i(y) and log_lh_grad. */
+int ipdm_caxpy(void* out, const void* a, const void* b, float s, size_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Annealed Langevin update (+ fused SENSE L2-penalty proximal step)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Per-step scalars, either passed by value (sched == NULL) or read on the device from
+ * sched[*cursor] so that one captured CUDA graph serves every noise level. */
+typedef struct {
+  float step;        /* step_lr * (sigma/sigma_L)^2                 (ALD_optimizers.py:101,217,438) */
+  float noise_scale; /* sqrt(2*step)                                (:117,239,241)                  */
+  float kappa;       /* 0.05 * step_lr*lr_scaled / (Nc*W)           (proximal_op.py:26-49) */
+  float sigma;       /* sigma of this level (informational)                                          */
+} ipdm_ald_scalars;
+
+/* x <- x + step*grad + noise_scale*noise, n floats.  noise == NULL => in-kernel Philox4x32-10 N(0,1)
+ * keyed by (seed, element index, *cursor or rng_step).  step_per_sample (f32 [batch], may be NULL)
+ * overrides `step`/`noise_scale` per sample (sde corrector, sde/sampling.py:320-322); per_sample_elems
+ * = elements per sample.  x_mean (may be NULL) receives x + step*grad.
+ * Replaces: ALDOptimizer.__call__ update (ncsn/models/ALD_optimizers.py:114-117),
+ *   anneal_Langevin_dynamics (ncsn/models/__init__.py:58-61), AnnealedLangevinDynamics.update_fn. */
+int ipdm_langevin_update(float* x, const float* grad, const float* noise, float* x_mean, size_t n,
+                         const ipdm_ald_scalars* scalars_host, const ipdm_ald_scalars* sched, const int* cursor,
+                         const float* step_per_sample, size_t per_sample_elems, uint64_t seed, uint32_t rng_step,
+                         void* stream);
+
+/* One fused data-consistency ALD step on the planar state x f32 [2][batch][H][W]:
+ *     z = x + step*grad + noise_scale*noise          (real and imaginary planes, independent noises)
+ *     x <- z - kappa * (A^H A z - b)                 b = A^H y, planar f32 [2][batch][H][W]
+ * with A the SENSE operator (maps, column mask).  Because the mask acts on W only, the H-axis
+ * transform cancels in A^H A and the kernel needs only length-W row FFTs.
+ * grad planar f32 [2][batch][H][W] (score of the real plane, score of the imaginary plane);
+ * noise planar or NULL (Philox).  tv_lamda is reserved (0).
+ * Replaces: the loop body of ALDInvSegProximalRealImag.__call__ + post_processing
+ *   (ALD_optimizers.py:238-241,288-327), ALD2DTime.spatial_step update + proximal_step (:442-449,
+ *   543-554) with L2Penalty.__call__ (proximal_op.py:19-51). */
+int ipdm_ald_sense_step(float* x, const float* grad, const float* noise, const float* b, const float* maps_re,
+                        const float* maps_im, const uint8_t* mask, int mask_frames, int ncoils, int batch, int H,
+                        int W, const ipdm_ald_scalars* scalars_host, const ipdm_ald_scalars* sched,
+                        const int* cursor, uint64_t seed, uint32_t rng_step, void* stream);
+
+/* labels[i] = *cursor / n_steps_each for i < batch, then (*cursor)++  (one tiny launch per step). */
+int ipdm_ald_advance(int* cursor, int64_t* labels, int batch, int n_steps_each, void* stream);
+
+/* Temporal total-variation step of ALD2DTime: x += -lamda * D^T sign(D x) along T (circular), on
+ * each plane of planar x f32 [2][B][T][HW].  Replaces FiniteDiff.log_lh_grad
+ *   (ncsn/linear_transforms/finite_diff.py:29-35) as used at ALD_optimizers.py:455-462. */
+int ipdm_temporal_tv_step(float* x, int B, int T, size_t hw, float lamda, void* stream);
+
+/* planar f32 [2][n]  <->  interleaved c64 [n] */
+int ipdm_planar_to_c64(const float* planar, void* c64, size_t n, void* stream);
+int ipdm_c64_to_planar(const void* c64, float* planar, size_t n, void* stream);
+
+/* acc f64 [4][hw] += per-pixel (|x|, |x|^2, angle x, angle^2 x) summed over `chains` images of x c64
+ * [chains][hw].  The cross-GPU sum is a plain all-reduce of acc.  Replaces the numpy mean/std of
+ * helpers/visualizations.py:93-95,117-142. */
+int ipdm_chain_stats_accumulate(const void* x, double* acc, int chains, size_t hw, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * NCSNv2 score network building blocks (NHWC)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Epilogue / operand description of one implicit-GEMM convolution. */
+typedef struct {
+  const void* in_f16;     /* A operand, f16 NHWC [N][H][W][Cin]                                         */
+  const void* w_f16;      /* weights, f16 [Cout][taps][Cin] (taps = 9 row-major ky,kx, or 1)            */
+  const float* bias;      /* f32 [Cout] or NULL                                                         */
+  const float* residual;  /* f32 NHWC [N][H][W][Cout] or NULL: added before the stores                 */
+  float* out_f32;         /* f32 NHWC or NULL: acc + bias + residual                                    */
+  void* out_f16;          /* f16 NHWC or NULL: see flags                                                */
+  float* stats;           /* f32 [N][Cout][2] or NULL: (zeroed, then) sum / sum-of-squares of the f32 result
+                             per (n, channel), un-pivoted -- feeds InstanceNorm++ without a second pass  */
+  int N, H, W, Cin, Cout;
+  int taps;               /* 9 (3x3, zero padding = dilation) or 1 (1x1)                                */
+  int dilation;
+  int flags;              /* IPDM_CONV_* below                                                          */
+} ipdm_conv_desc;
+
+#define IPDM_CONV_F16_ELU 1       /* out_f16 = f16(ELU(v)) instead of f16(v)                               */
+#define IPDM_CONV_F16_PRE_RES 2   /* out_f16 is taken from acc+bias (before the residual add)            */
+#define IPDM_CONV_RES_ELU 4       /* residual is ELU(residual[...]) (CRP entry, layers.py:77)            */
+#define IPDM_CONV_POOL2 8         /* 2x2 mean-pool the result: residual/out tensors are [N][H/2][W/2][Cout]
+                                     (ConvMeanPool, layers.py:309-313)                                    */
+
+/* 3x3 (dilated) / 1x1 stride-1 convolution as a tcgen05 implicit GEMM: M = N*H*W pixels (8x16-pixel
+ * tiles), N = Cout, K = taps*Cin; TMA-fed, fp32 accumulators in TMEM.  Cin % 64 == 0, Cout % 64 == 0.
+ * Replaces nn.Conv2d inside ResidualBlock / RCUBlock / CRPBlock / MSFBlock / ConvMeanPool
+ *   (ncsn/models/layers.py:28-60,62-83,112-134,165-184,291-313,401-456). */
+int ipdm_conv_igemm(const ipdm_conv_desc* desc_host, void* stream);
+
+/* Same contract on CUDA cores, any Cin/Cout (used for narrow test nets and as the on-device
+ * cross-check of the tensor-core kernel; not used by the product path when the igemm applies). */
+int ipdm_conv_direct(const ipdm_conv_desc* desc_host, void* stream);
+
+/* begin_conv: out f32 NHWC [N][H][W][Cout] = conv3x3(affine ? 2x-1 : x) + bias, x f32 [N][H][W]
+ * (Cin == 1), w f32 [Cout][9].  Also fills `stats` like ipdm_conv_desc.stats when non-NULL.
+ * Replaces ncsnv2.py:270-275. */
+int ipdm_conv_first(const float* x, const float* w, const float* bias, float* out, float* stats, int N, int H,
+                    int W, int Cout, int affine, void* stream);
+
+/* end_conv: out f32 [N][H][W] = (conv3x3(in f16 NHWC [N][H][W][Cin], w f32 [9][Cin]) + bias) / sigmas[labels[n]].
+ * Replaces ncsnv2.py:293-297. */
+int ipdm_conv_last(const void* in_f16, const float* w, const float* bias, const float* sigmas,
+                   const int64_t* labels, float* out, int N, int H, int W, int Cin, void* stream);
+
+/* InstanceNorm++ (normalization.py:163-176).  stats f32 [N][C][2] = per-(n,c) sum and sum of squares of
+ * (x - pivot), pivot = x[n,0,0,c] if `pivoted` else 0 (the conv epilogues produce the un-pivoted form);
+ * apply: out_f16 = f16(ELU(gamma*(IN(x) + alpha*m_hat) + beta)), `stats_pivoted` as given to stats. */
+int ipdm_instnorm_stats(const float* x, float* stats, int N, int HW, int C, int pivoted, void* stream);
+int ipdm_instnorm_apply_elu(const float* x, const float* stats, int stats_pivoted, const float* alpha,
+                            const float* gamma, const float* beta, void* out_f16, int N, int HW, int C,
+                            void* stream);
+
+/* out_f16 = f16(elu ? ELU(x) : x), n elements (layers.py:12-13). */
+int ipdm_act_to_f16(const float* x, void* out_f16, size_t n, int elu, void* stream);
+/* 5x5 stride-1 max pool with -inf padding on f16 NHWC (CRPBlock, layers.py:69-70,80). */
+int ipdm_maxpool5_f16(const void* in_f16, void* out_f16, int N, int H, int W, int C, void* stream);
+/* dst f32 [N][H][W][C] (+)= bilinear_align_corners(src f32 [N][h][w][C]) (MSFBlock, layers.py:182-183);
+ * out_elu_f16 (may be NULL) also receives f16(ELU(dst)) -- the CRP block that follows wants it. */
+int ipdm_bilinear_add(const float* src, float* dst, void* out_elu_f16, int N, int h, int w, int H, int W, int C,
+                      int accumulate, void* stream);
+/* out f32 [N][H/2][W/2][C] = mean of the four stride-2 phases of in (+ add if non-NULL). */
+int ipdm_meanpool2(const float* in, const float* add, float* out, int N, int H, int W, int C, void* stream);
+/* f32 [Cout][Cin][kh][kw] (PyTorch OIHW) -> f16 [Cout][kh*kw][Cin] weight repack for the igemm. */
+int ipdm_pack_weights_f16(const float* w_oihw, void* w_f16, int Cout, int Cin, int taps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPDM_B200_H */

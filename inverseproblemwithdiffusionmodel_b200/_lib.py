@@ -1,0 +1,103 @@
+"""ctypes binding of libipdm_b200.so (the C ABI declared in include/ipdm_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails, this raises.
+Build the library with `python -c "import __graft_entry__ as g; g.build()"` or
+`inverseproblemwithdiffusionmodel_b200/csrc/build.sh`.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint32, c_uint64, c_ulonglong, c_void_p, POINTER
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libipdm_b200.so")
+
+
+class AldScalars(ctypes.Structure):
+    """mirror of `ipdm_ald_scalars`"""
+    _fields_ = [("step", c_float), ("noise_scale", c_float), ("kappa", c_float), ("sigma", c_float)]
+
+
+class ConvDesc(ctypes.Structure):
+    """mirror of `ipdm_conv_desc`"""
+    _fields_ = [("in_f16", c_void_p), ("w_f16", c_void_p), ("bias", c_void_p), ("residual", c_void_p),
+                ("out_f32", c_void_p), ("out_f16", c_void_p), ("stats", c_void_p),
+                ("N", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int), ("Cout", c_int),
+                ("taps", c_int), ("dilation", c_int), ("flags", c_int)]
+
+
+CONV_F16_ELU, CONV_F16_PRE_RES, CONV_RES_ELU, CONV_POOL2 = 1, 2, 4, 8
+
+# name -> (restype, argtypes); every symbol of include/ipdm_b200.h
+SIGNATURES = {
+    "ipdm_abi_version": (c_int, []),
+    "ipdm_last_error": (c_char_p, []),
+    "ipdm_launch_count": (c_ulonglong, []),
+    "ipdm_sense_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "ipdm_sense_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ipdm_sense_adjoint": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ipdm_kspace_combine": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_int, c_int, c_int, c_void_p]),
+    "ipdm_caxpy": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_size_t, c_void_p]),
+    "ipdm_langevin_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, POINTER(AldScalars), c_void_p, c_void_p,
+                                     c_void_p, c_size_t, c_uint64, c_uint32, c_void_p]),
+    "ipdm_ald_sense_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                    c_int, c_int, POINTER(AldScalars), c_void_p, c_void_p, c_uint64, c_uint32, c_void_p]),
+    "ipdm_ald_advance": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "ipdm_temporal_tv_step": (c_int, [c_void_p, c_int, c_int, c_size_t, c_float, c_void_p]),
+    "ipdm_planar_to_c64": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ipdm_c64_to_planar": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ipdm_chain_stats_accumulate": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p]),
+    "ipdm_conv_igemm": (c_int, [POINTER(ConvDesc), c_void_p]),
+    "ipdm_conv_direct": (c_int, [POINTER(ConvDesc), c_void_p]),
+    "ipdm_conv_first": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ipdm_conv_last": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "ipdm_instnorm_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "ipdm_instnorm_apply_elu": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "ipdm_act_to_f16": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "ipdm_maxpool5_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "ipdm_bilinear_add": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ipdm_meanpool2": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "ipdm_pack_weights_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+}
+
+_lib = None
+
+
+class IpdmError(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded library (loads on first use; raises if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise IpdmError(f"{LIB_PATH} not found: build the CUDA extension first (there is no CPU fallback)")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().ipdm_last_error().decode()
+        raise IpdmError(f"{what or 'ipdm call'} failed (rc={rc}): {msg}")
+
+
+def ptr(t):
+    """device pointer of a torch tensor (None -> NULL)"""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise IpdmError("ipdm_b200 runs on CUDA tensors only (no CPU fallback): got a tensor on " + str(t.device))

@@ -1,0 +1,76 @@
+// Shared host/device helpers for the ipdm_b200 kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include "../../include/ipdm_b200.h"
+
+namespace ipdm {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<unsigned long long> g_launches;
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Call after every kernel launch: counts it and surfaces launch-configuration errors.
+inline int launched(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return static_cast<int>(e);
+  }
+  return 0;
+}
+
+#define IPDM_REQUIRE(cond, code, ...)     \
+  do {                                    \
+    if (!(cond)) {                        \
+      ::ipdm::set_error(__VA_ARGS__);     \
+      return (code);                      \
+    }                                     \
+  } while (0)
+
+#define IPDM_CUDA(call)                                                        \
+  do {                                                                         \
+    cudaError_t e__ = (call);                                                  \
+    if (e__ != cudaSuccess) {                                                  \
+      ::ipdm::set_error("%s: %s", #call, cudaGetErrorString(e__));             \
+      return static_cast<int>(e__);                                            \
+    }                                                                          \
+  } while (0)
+
+__device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v); }
+
+// ---- Philox4x32-10 (Salmon et al.) + Box-Muller: two N(0,1) per call -------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// (n0, n1) ~ N(0,1) for element `idx` of step `step` under `seed`.
+__device__ __forceinline__ float2 philox_normal2(uint64_t seed, uint64_t idx, uint32_t step) {
+  uint32_t r[4];
+  philox4x32_10(static_cast<uint32_t>(idx), static_cast<uint32_t>(idx >> 32), step, 0x1BD11BDAu,
+                static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
+  const float u0 = (static_cast<float>(r[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
+  const float u1 = (static_cast<float>(r[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float rad = sqrtf(-2.0f * logf(u0));
+  float s, c;
+  sincospif(2.0f * u1, &s, &c);
+  return make_float2(rad * c, rad * s);
+}
+
+}  // namespace ipdm

@@ -1,0 +1,687 @@
+// SENSE operator, centred FFTs and the fused Langevin + data-consistency step for sm_100a.
+//
+// Data flow: i2k(x) = sigma * P * FFT2(P * x) / sqrt(HW) with P = (-1)^(h+w) and
+// sigma = (-1)^(H/2+W/2), so the four fftshift copies of the reference become sign flips folded
+// into loads and stores.  A 2-D transform is a row pass (along W, contiguous) and a column pass
+// (along H) that meet in a TRANSPOSED scratch T[c][b][k][h]: the row kernel transforms 16 rows of
+// one image for every coil and writes 128-byte h-chunks per k-space column, the column kernel reads
+// whole columns contiguously and writes 16-column output tiles -- every global access is a full
+// 128-byte segment.  Columns the sampling mask removes are never written, read or transformed; the
+// coil multiply lives in the first pass of the forward row kernel and the conj-coil reduction in the
+// last pass of the adjoint row kernel, so coil images never exist in HBM.
+// For the per-step data-consistency term A^H A z the H-axis transforms cancel and one row-only
+// kernel does update + prox (k_ald_sense).
+#include "common.cuh"
+#include "fft_core.cuh"
+
+namespace ipdm {
+
+__device__ __forceinline__ int spad(int i) { return i + (i >> 3); }
+template <int L> struct Tile {
+  static constexpr int TPF = FftPlan<L>::TPF;
+  static constexpr int E = FftRegs<L>::E;
+  static constexpr int ROWS = (TPF * 16 > 512) ? 8 : 16;   // transforms per CTA
+  static constexpr int NT = TPF * ROWS;
+  static constexpr int PITCH = (L + L / 8) | 1;
+  static constexpr size_t SMEM = (size_t)(ROWS * PITCH + L) * sizeof(cf32);
+};
+
+template <int L>
+__device__ __forceinline__ void fill_twiddles(cf32* tw, int tid, int nt) {
+  for (int m = tid; m < L; m += nt) {
+    float s, c;
+    sincospif(-2.0f * (float)m / (float)L, &s, &c);
+    tw[m] = cf32{c, s};
+  }
+}
+
+// register permutations between "q order" (u[q] <-> position t + q*TPF) and the leg order of pass P
+template <int L, int P>
+__device__ __forceinline__ void q_to_regs(const cf32* u, cf32* v) {
+  constexpr int R = PassRadix<L, P>::value, NB = (L / R) / FftPlan<L>::TPF;
+#pragma unroll
+  for (int i = 0; i < NB; ++i)
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[i * R + r] = u[i + r * NB];
+}
+template <int L, int P>
+__device__ __forceinline__ void regs_to_q(const cf32* v, cf32* u) {
+  constexpr int R = PassRadix<L, P>::value, NB = (L / R) / FftPlan<L>::TPF;
+#pragma unroll
+  for (int i = 0; i < NB; ++i)
+#pragma unroll
+    for (int r = 0; r < R; ++r) u[i + r * NB] = v[i * R + r];
+}
+
+// Length-L transform of the values held in q order by the TPF threads of one row; `row` is that
+// row's smem line.  In: u[q] = input at position t+q*TPF.  Out: u[q] = output at position t+q*TPF.
+// All threads of the CTA must call it together (block-wide barriers between passes).
+template <int L, int DIR>
+__device__ __forceinline__ void fft_regs(cf32* u, cf32* row, const cf32* tw, int t) {
+  using PL = FftPlan<L>;
+  constexpr int E = FftRegs<L>::E;
+  cf32 v[E];
+  auto ld = [&](int i) { return row[spad(i)]; };
+  auto st = [&](int i, cf32 val) { row[spad(i)] = val; };
+  q_to_regs<L, 0>(u, v);
+  pass_compute<L, 0, DIR>(t, v, tw);
+  if constexpr (PL::NP == 1) {
+    regs_to_q<L, 0>(v, u);
+  } else {
+    __syncthreads();  // earlier readers of the tile are done
+    pass_store<L, 0>(t, v, st);
+    __syncthreads();
+    pass_load<L, 1>(t, v, ld);
+    pass_compute<L, 1, DIR>(t, v, tw);
+    if constexpr (PL::NP == 2) {
+      regs_to_q<L, 1>(v, u);
+    } else {
+      __syncthreads();
+      pass_store<L, 1>(t, v, st);
+      __syncthreads();
+      pass_load<L, 2>(t, v, ld);
+      pass_compute<L, 2, DIR>(t, v, tw);
+      if constexpr (PL::NP == 3) {
+        regs_to_q<L, 2>(v, u);
+      } else {
+        __syncthreads();
+        pass_store<L, 2>(t, v, st);
+        __syncthreads();
+        pass_load<L, 3>(t, v, ld);
+        pass_compute<L, 3, DIR>(t, v, tw);
+        regs_to_q<L, 3>(v, u);
+      }
+    }
+  }
+}
+
+struct SenseArgs {
+  const cf32* in;
+  cf32* out;
+  cf32* ws;
+  const float* mre;
+  const float* mim;
+  const uint8_t* mask;
+  int mask_frames, ncoils, batch, H, W, ssos;
+  float scale;  // 1/sqrt(HW) * sigma
+};
+
+__device__ __forceinline__ float sgn(int i) { return (i & 1) ? -1.f : 1.f; }
+__device__ __forceinline__ bool col_on(const SenseArgs& a, int b, int k) {
+  return a.mask == nullptr || a.mask[(size_t)(b % a.mask_frames) * a.W + k] != 0;
+}
+
+// ---- forward, pass 1: rows.  grid (ceil(H/ROWS), batch) ---------------------------------------
+template <int L>
+__global__ void __launch_bounds__(Tile<L>::NT) k_fwd_rows(SenseArgs a) {
+  using TL = Tile<L>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cf32* tile = reinterpret_cast<cf32*>(smem_raw);
+  cf32* tw = tile + TL::ROWS * TL::PITCH;
+  const int tid = threadIdx.x, r = tid / TL::TPF, t = tid % TL::TPF;
+  const int b = blockIdx.y, h0 = blockIdx.x * TL::ROWS, h = h0 + r;
+  const bool valid = h < a.H;
+  fill_twiddles<L>(tw, tid, TL::NT);
+  cf32 xq[TL::E];
+#pragma unroll
+  for (int q = 0; q < TL::E; ++q) {
+    const int w = t + q * TL::TPF;
+    xq[q] = valid ? cscale(a.in[((size_t)b * a.H + h) * L + w], sgn(h + w)) : cf32{0.f, 0.f};
+  }
+  __syncthreads();
+  for (int c = 0; c < a.ncoils; ++c) {
+    cf32 u[TL::E];
+#pragma unroll
+    for (int q = 0; q < TL::E; ++q) {
+      const int w = t + q * TL::TPF;
+      u[q] = xq[q];
+      if (a.mre != nullptr && valid) {
+        const size_t mi = ((size_t)c * a.H + h) * L + w;
+        const cf32 m{a.mre[mi], a.mim ? a.mim[mi] : 0.f};
+        u[q] = cmul(u[q], m);
+      }
+    }
+    fft_regs<L, -1>(u, tile + r * TL::PITCH, tw, t);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < TL::E; ++q) tile[r * TL::PITCH + spad(t + q * TL::TPF)] = u[q];
+    __syncthreads();
+    const size_t img = (size_t)c * a.batch + b;
+    for (int idx = tid; idx < TL::ROWS * L; idx += TL::NT) {
+      const int rr = idx % TL::ROWS, k = idx / TL::ROWS;
+      if (h0 + rr < a.H && col_on(a, b, k)) a.ws[(img * L + k) * a.H + h0 + rr] = tile[rr * TL::PITCH + spad(k)];
+    }
+  }
+}
+
+// ---- forward, pass 2: columns.  grid (ceil(W/ROWS), ncoils*batch) -------------------------------
+template <int L>
+__global__ void __launch_bounds__(Tile<L>::NT) k_fwd_cols(SenseArgs a) {
+  using TL = Tile<L>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cf32* tile = reinterpret_cast<cf32*>(smem_raw);
+  cf32* tw = tile + TL::ROWS * TL::PITCH;
+  const int tid = threadIdx.x, cc = tid / TL::TPF, t = tid % TL::TPF;
+  const size_t img = blockIdx.y;
+  const int b = (int)(img % a.batch), k0 = blockIdx.x * TL::ROWS, k = k0 + cc;
+  const bool active = k < a.W && col_on(a, b, k);
+  const int any = __syncthreads_or(active ? 1 : 0);
+  if (!any) {
+    for (int idx = tid; idx < TL::ROWS * L; idx += TL::NT) {
+      const int kk = idx % TL::ROWS, h = idx / TL::ROWS;
+      if (k0 + kk < a.W) a.out[(img * L + h) * a.W + k0 + kk] = cf32{0.f, 0.f};
+    }
+    return;
+  }
+  fill_twiddles<L>(tw, tid, TL::NT);
+  cf32 u[TL::E];
+#pragma unroll
+  for (int q = 0; q < TL::E; ++q)
+    u[q] = active ? a.ws[(img * a.W + k) * L + t + q * TL::TPF] : cf32{0.f, 0.f};
+  __syncthreads();
+  fft_regs<L, -1>(u, tile + cc * TL::PITCH, tw, t);
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < TL::E; ++q) tile[cc * TL::PITCH + spad(t + q * TL::TPF)] = u[q];
+  __syncthreads();
+  for (int idx = tid; idx < TL::ROWS * L; idx += TL::NT) {
+    const int kk = idx % TL::ROWS, h = idx / TL::ROWS;
+    if (k0 + kk < a.W)
+      a.out[(img * L + h) * a.W + k0 + kk] = cscale(tile[kk * TL::PITCH + spad(h)], a.scale * sgn(h + k0 + kk));
+  }
+}
+
+// ---- adjoint, pass 1: columns (inverse along H).  grid (ceil(W/ROWS), ncoils*batch) -------------
+template <int L>
+__global__ void __launch_bounds__(Tile<L>::NT) k_adj_cols(SenseArgs a) {
+  using TL = Tile<L>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cf32* tile = reinterpret_cast<cf32*>(smem_raw);
+  cf32* tw = tile + TL::ROWS * TL::PITCH;
+  const int tid = threadIdx.x, cc = tid / TL::TPF, t = tid % TL::TPF;
+  const size_t img = blockIdx.y;
+  const int b = (int)(img % a.batch), k0 = blockIdx.x * TL::ROWS, k = k0 + cc;
+  const bool active = k < a.W && col_on(a, b, k);
+  const int any = __syncthreads_or(active ? 1 : 0);
+  if (!any) return;
+  fill_twiddles<L>(tw, tid, TL::NT);
+  for (int idx = tid; idx < TL::ROWS * L; idx += TL::NT) {
+    const int kk = idx % TL::ROWS, h = idx / TL::ROWS;
+    cf32 v{0.f, 0.f};
+    if (k0 + kk < a.W && col_on(a, b, k0 + kk)) v = cscale(a.in[(img * L + h) * a.W + k0 + kk], sgn(h + k0 + kk));
+    tile[kk * TL::PITCH + spad(h)] = v;
+  }
+  __syncthreads();
+  cf32 u[TL::E];
+#pragma unroll
+  for (int q = 0; q < TL::E; ++q) u[q] = tile[cc * TL::PITCH + spad(t + q * TL::TPF)];
+  fft_regs<L, +1>(u, tile + cc * TL::PITCH, tw, t);
+  if (active) {
+#pragma unroll
+    for (int q = 0; q < TL::E; ++q) a.ws[(img * a.W + k) * L + t + q * TL::TPF] = u[q];
+  }
+}
+
+// ---- adjoint, pass 2: rows (inverse along W) + conj-coil sum.  grid (ceil(H/ROWS), batch) ------
+template <int L>
+__global__ void __launch_bounds__(Tile<L>::NT) k_adj_rows(SenseArgs a) {
+  using TL = Tile<L>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cf32* tile = reinterpret_cast<cf32*>(smem_raw);
+  cf32* tw = tile + TL::ROWS * TL::PITCH;
+  const int tid = threadIdx.x, r = tid / TL::TPF, t = tid % TL::TPF;
+  const int b = blockIdx.y, h0 = blockIdx.x * TL::ROWS, h = h0 + r;
+  const bool valid = h < a.H;
+  fill_twiddles<L>(tw, tid, TL::NT);
+  cf32 acc[TL::E];
+#pragma unroll
+  for (int q = 0; q < TL::E; ++q) acc[q] = cf32{0.f, 0.f};
+  for (int c = 0; c < a.ncoils; ++c) {
+    const size_t img = (size_t)c * a.batch + b;
+    __syncthreads();
+    for (int idx = tid; idx < TL::ROWS * L; idx += TL::NT) {
+      const int rr = idx % TL::ROWS, k = idx / TL::ROWS;
+      cf32 v{0.f, 0.f};
+      if (h0 + rr < a.H && col_on(a, b, k)) v = a.ws[(img * L + k) * a.H + h0 + rr];
+      tile[rr * TL::PITCH + spad(k)] = v;
+    }
+    __syncthreads();
+    cf32 u[TL::E];
+#pragma unroll
+    for (int q = 0; q < TL::E; ++q) u[q] = tile[r * TL::PITCH + spad(t + q * TL::TPF)];
+    fft_regs<L, +1>(u, tile + r * TL::PITCH, tw, t);
+#pragma unroll
+    for (int q = 0; q < TL::E; ++q) {
+      const int w = t + q * TL::TPF;
+      const cf32 v = cscale(u[q], a.scale * sgn(h + w));
+      if (a.ssos) {
+        acc[q].x += v.x * v.x + v.y * v.y;
+      } else if (a.mre != nullptr && valid) {
+        const size_t mi = ((size_t)c * a.H + h) * L + w;
+        acc[q] = cadd(acc[q], cmulc(v, cf32{a.mre[mi], a.mim ? a.mim[mi] : 0.f}));
+      } else {
+        acc[q] = cadd(acc[q], v);
+      }
+    }
+  }
+  if (!valid) return;
+#pragma unroll
+  for (int q = 0; q < TL::E; ++q) {
+    const size_t o = ((size_t)b * a.H + h) * L + t + q * TL::TPF;
+    if (a.ssos) reinterpret_cast<float*>(a.out)[o] = sqrtf(acc[q].x);
+    else a.out[o] = acc[q];
+  }
+}
+
+// ---- fused Langevin update + SENSE L2-penalty step (row-only).  grid (ceil(H/ROWS), batch) -----
+struct AldArgs {
+  float* x;
+  const float* grad;
+  const float* noise;
+  const float* bvec;
+  const float* mre;
+  const float* mim;
+  const uint8_t* mask;
+  int mask_frames, ncoils, batch, H, W;
+  ipdm_ald_scalars sc;
+  const ipdm_ald_scalars* sched;
+  const int* cursor;
+  uint64_t seed;
+  uint32_t rng_step;
+};
+
+template <int L>
+__global__ void __launch_bounds__(Tile<L>::NT) k_ald_sense(AldArgs a) {
+  using TL = Tile<L>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cf32* tile = reinterpret_cast<cf32*>(smem_raw);
+  cf32* tw = tile + TL::ROWS * TL::PITCH;
+  const int tid = threadIdx.x, r = tid / TL::TPF, t = tid % TL::TPF;
+  const int b = blockIdx.y, h = blockIdx.x * TL::ROWS + r;
+  const bool valid = h < a.H;
+  ipdm_ald_scalars sc = a.sc;
+  uint32_t rstep = a.rng_step;
+  if (a.sched != nullptr) {
+    const int cur = *a.cursor;
+    sc = a.sched[cur];
+    rstep += (uint32_t)cur;
+  }
+  fill_twiddles<L>(tw, tid, TL::NT);
+  const size_t plane = (size_t)a.batch * a.H * L;
+  const size_t rowoff = ((size_t)b * a.H + (valid ? h : 0)) * L;
+  const uint8_t* mrow = a.mask ? a.mask + (size_t)(b % a.mask_frames) * L : nullptr;
+  cf32 z[TL::E], acc[TL::E];
+#pragma unroll
+  for (int q = 0; q < TL::E; ++q) {
+    const size_t o = rowoff + t + q * TL::TPF;
+    float2 n;
+    if (a.noise != nullptr) n = make_float2(a.noise[o], a.noise[plane + o]);
+    else n = philox_normal2(a.seed, o, rstep);
+    z[q].x = a.x[o] + sc.step * a.grad[o] + sc.noise_scale * n.x;
+    z[q].y = a.x[plane + o] + sc.step * a.grad[plane + o] + sc.noise_scale * n.y;
+    acc[q] = cf32{0.f, 0.f};
+  }
+  __syncthreads();
+  for (int c = 0; c < a.ncoils; ++c) {
+    cf32 u[TL::E], m[TL::E];
+#pragma unroll
+    for (int q = 0; q < TL::E; ++q) {
+      const int w = t + q * TL::TPF;
+      const size_t mi = ((size_t)c * a.H + (valid ? h : 0)) * L + w;
+      m[q] = cf32{a.mre[mi], a.mim ? a.mim[mi] : 0.f};
+      u[q] = cscale(cmul(z[q], m[q]), sgn(w));
+    }
+    fft_regs<L, -1>(u, tile + r * TL::PITCH, tw, t);
+    if (mrow != nullptr) {
+#pragma unroll
+      for (int q = 0; q < TL::E; ++q)
+        if (mrow[t + q * TL::TPF] == 0) u[q] = cf32{0.f, 0.f};
+    }
+    fft_regs<L, +1>(u, tile + r * TL::PITCH, tw, t);
+#pragma unroll
+    for (int q = 0; q < TL::E; ++q) acc[q] = cadd(acc[q], cscale(cmulc(u[q], m[q]), sgn(t + q * TL::TPF)));
+  }
+  if (!valid) return;
+  const float invW = 1.0f / (float)L;
+#pragma unroll
+  for (int q = 0; q < TL::E; ++q) {
+    const size_t o = rowoff + t + q * TL::TPF;
+    a.x[o] = z[q].x - sc.kappa * (acc[q].x * invW - a.bvec[o]);
+    a.x[plane + o] = z[q].y - sc.kappa * (acc[q].y * invW - a.bvec[plane + o]);
+  }
+}
+
+// ---- launch helpers ---------------------------------------------------------------------------
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) IPDM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+#define IPDM_FOR_LEN(LEN, MACRO)                                       \
+  switch (LEN) {                                                       \
+    case 8: MACRO(8); break;                                           \
+    case 16: MACRO(16); break;                                         \
+    case 32: MACRO(32); break;                                         \
+    case 64: MACRO(64); break;                                         \
+    case 128: MACRO(128); break;                                       \
+    case 256: MACRO(256); break;                                       \
+    case 512: MACRO(512); break;                                       \
+    default:                                                           \
+      set_error("transform length %d unsupported (power of two in [8,512])", LEN); \
+      return IPDM_E_UNSUPPORTED;                                       \
+  }
+
+static int launch_rows(bool fwd, const SenseArgs& a, cudaStream_t s) {
+#define ROWS_CASE(LL)                                                                              \
+  {                                                                                                \
+    using TL = Tile<LL>;                                                                           \
+    dim3 grid((a.H + TL::ROWS - 1) / TL::ROWS, a.batch);                                           \
+    if (fwd) {                                                                                     \
+      if (int e = set_smem(k_fwd_rows<LL>, TL::SMEM)) return e;                                    \
+      k_fwd_rows<LL><<<grid, TL::NT, TL::SMEM, s>>>(a);                                            \
+    } else {                                                                                       \
+      if (int e = set_smem(k_adj_rows<LL>, TL::SMEM)) return e;                                    \
+      k_adj_rows<LL><<<grid, TL::NT, TL::SMEM, s>>>(a);                                            \
+    }                                                                                              \
+  }
+  IPDM_FOR_LEN(a.W, ROWS_CASE)
+#undef ROWS_CASE
+  return launched(fwd ? "k_fwd_rows" : "k_adj_rows");
+}
+
+static int launch_cols(bool fwd, const SenseArgs& a, cudaStream_t s) {
+#define COLS_CASE(LL)                                                                              \
+  {                                                                                                \
+    using TL = Tile<LL>;                                                                           \
+    dim3 grid((a.W + TL::ROWS - 1) / TL::ROWS, a.ncoils * a.batch);                                \
+    if (fwd) {                                                                                     \
+      if (int e = set_smem(k_fwd_cols<LL>, TL::SMEM)) return e;                                    \
+      k_fwd_cols<LL><<<grid, TL::NT, TL::SMEM, s>>>(a);                                            \
+    } else {                                                                                       \
+      if (int e = set_smem(k_adj_cols<LL>, TL::SMEM)) return e;                                    \
+      k_adj_cols<LL><<<grid, TL::NT, TL::SMEM, s>>>(a);                                            \
+    }                                                                                              \
+  }
+  IPDM_FOR_LEN(a.H, COLS_CASE)
+#undef COLS_CASE
+  return launched(fwd ? "k_fwd_cols" : "k_adj_cols");
+}
+
+static bool pow2_ok(int n) { return n >= 8 && n <= 512 && (n & (n - 1)) == 0; }
+
+// ---- small elementwise kernels ------------------------------------------------------------------
+__global__ void k_kspace_combine(cf32* S, const cf32* Y, const uint8_t* mask, int mask_frames, float a, int mode,
+                                 int H, int W, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % W);
+    const int b = (int)(i / ((size_t)H * W));
+    const float m = mask[(size_t)(b % mask_frames) * W + k] ? 1.f : 0.f;
+    cf32 s = S[i];
+    if (mode == 0) {
+      const float f = 1.0f / (1.0f + m * a);
+      s = cscale(s, f);
+    } else if (mode == 2) {
+      s = cscale(s, m);
+    } else {
+      const cf32 y = Y[i];
+      const float keep = (1.f - a) * m + (1.f - m);
+      s = cf32{a * y.x + keep * s.x, a * y.y + keep * s.y};
+    }
+    S[i] = s;
+  }
+}
+
+__global__ void k_caxpy(cf32* out, const cf32* a, const cf32* b, float s, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const cf32 x = a[i], y = b[i];
+    out[i] = cf32{x.x + s * y.x, x.y + s * y.y};
+  }
+}
+
+__global__ void k_planar_to_c64(const float* p, cf32* c, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    c[i] = cf32{p[i], p[n + i]};
+}
+__global__ void k_c64_to_planar(const cf32* c, float* p, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const cf32 v = c[i];
+    p[i] = v.x;
+    p[n + i] = v.y;
+  }
+}
+
+struct LangevinArgs {
+  float* x;
+  const float* grad;
+  const float* noise;
+  float* x_mean;
+  size_t n;
+  ipdm_ald_scalars sc;
+  const ipdm_ald_scalars* sched;
+  const int* cursor;
+  const float* step_per_sample;
+  size_t per_sample;
+  uint64_t seed;
+  uint32_t rng_step;
+};
+
+__global__ void k_langevin(LangevinArgs a) {
+  ipdm_ald_scalars sc = a.sc;
+  uint32_t rstep = a.rng_step;
+  if (a.sched != nullptr) {
+    const int cur = *a.cursor;
+    sc = a.sched[cur];
+    rstep += (uint32_t)cur;
+  }
+  // two elements per thread so one Philox call feeds both
+  const size_t pairs = (a.n + 1) / 2;
+  for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < pairs; p += (size_t)gridDim.x * blockDim.x) {
+    const size_t i0 = 2 * p, i1 = 2 * p + 1;
+    float2 nz;
+    if (a.noise != nullptr) nz = make_float2(a.noise[i0], i1 < a.n ? a.noise[i1] : 0.f);
+    else nz = philox_normal2(a.seed, p, rstep);
+    float st0 = sc.step, ns0 = sc.noise_scale, st1 = sc.step, ns1 = sc.noise_scale;
+    if (a.step_per_sample != nullptr) {
+      st0 = a.step_per_sample[i0 / a.per_sample];
+      ns0 = sqrtf(2.f * st0);
+      if (i1 < a.n) {
+        st1 = a.step_per_sample[i1 / a.per_sample];
+        ns1 = sqrtf(2.f * st1);
+      }
+    }
+    const float m0 = a.x[i0] + st0 * a.grad[i0];
+    if (a.x_mean) a.x_mean[i0] = m0;
+    a.x[i0] = m0 + ns0 * nz.x;
+    if (i1 < a.n) {
+      const float m1 = a.x[i1] + st1 * a.grad[i1];
+      if (a.x_mean) a.x_mean[i1] = m1;
+      a.x[i1] = m1 + ns1 * nz.y;
+    }
+  }
+}
+
+__global__ void k_advance(int* cursor, int64_t* labels, int batch, int n_steps_each) {
+  const int cur = *cursor;
+  if (labels != nullptr) {
+    const int64_t lvl = (cur + 1) / n_steps_each;
+    for (int i = threadIdx.x; i < batch; i += blockDim.x) labels[i] = lvl;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *cursor = cur + 1;
+}
+
+// x[p][b][t][i] += -lamda * (s[t-1] - s[t]),  s[t] = sign(x[t+1] - x[t]) (circular in t)
+__global__ void k_temporal_tv(float* x, int T, size_t hw, float lamda, size_t nvol) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvol * hw; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t vol = i / hw, pix = i % hw;
+    float* base = x + vol * T * hw + pix;
+    auto sg = [](float d) { return d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); };
+    const float first = base[0];
+    float prev_x = first;
+    float s_prev = sg(first - base[(size_t)(T - 1) * hw]);  // s[T-1] = sign(x[0] - x[T-1])
+    for (int t = 0; t < T; ++t) {
+      const float nxt = (t + 1 < T) ? base[(size_t)(t + 1) * hw] : first;
+      const float s_t = sg(nxt - prev_x);
+      base[(size_t)t * hw] = prev_x - lamda * (s_prev - s_t);
+      s_prev = s_t;
+      prev_x = nxt;
+    }
+  }
+}
+
+__global__ void k_chain_stats(const cf32* x, double* acc, int chains, size_t hw) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < hw; i += (size_t)gridDim.x * blockDim.x) {
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    for (int c = 0; c < chains; ++c) {
+      const cf32 v = x[(size_t)c * hw + i];
+      const float mag = sqrtf(v.x * v.x + v.y * v.y);
+      const float ang = atan2f(v.y, v.x);
+      s0 += mag;
+      s1 += (double)mag * mag;
+      s2 += ang;
+      s3 += (double)ang * ang;
+    }
+    acc[i] += s0;
+    acc[hw + i] += s1;
+    acc[2 * hw + i] += s2;
+    acc[3 * hw + i] += s3;
+  }
+}
+
+static int grid_for(size_t n, int block) {
+  size_t g = (n + block - 1) / block;
+  const size_t cap = 148 * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace ipdm
+
+using namespace ipdm;
+
+extern "C" size_t ipdm_sense_workspace_bytes(int ncoils, int batch, int H, int W) {
+  return (size_t)ncoils * batch * H * W * sizeof(cf32);
+}
+
+extern "C" int ipdm_sense_forward(const void* x, const float* maps_re, const float* maps_im, const uint8_t* mask,
+                                  int mask_frames, void* out, int ncoils, int batch, int H, int W, void* workspace,
+                                  void* stream) {
+  IPDM_REQUIRE(x && out && workspace, IPDM_E_BADARG, "sense_forward: null pointer");
+  IPDM_REQUIRE(ncoils >= 1 && batch >= 1, IPDM_E_BADARG, "sense_forward: bad ncoils/batch");
+  IPDM_REQUIRE(maps_re != nullptr || ncoils == 1, IPDM_E_BADARG, "sense_forward: maps NULL needs ncoils == 1");
+  IPDM_REQUIRE(pow2_ok(H) && pow2_ok(W), IPDM_E_UNSUPPORTED, "sense_forward: H=%d W=%d must be powers of two in [8,512]", H, W);
+  IPDM_REQUIRE(mask == nullptr || mask_frames >= 1, IPDM_E_BADARG, "sense_forward: mask_frames");
+  SenseArgs a{};
+  a.in = (const cf32*)x; a.out = (cf32*)out; a.ws = (cf32*)workspace;
+  a.mre = maps_re; a.mim = maps_im; a.mask = mask; a.mask_frames = mask ? mask_frames : 1;
+  a.ncoils = ncoils; a.batch = batch; a.H = H; a.W = W; a.ssos = 0;
+  a.scale = (((H / 2 + W / 2) & 1) ? -1.f : 1.f) / sqrtf((float)H * (float)W);
+  if (int e = launch_rows(true, a, as_stream(stream))) return e;
+  return launch_cols(true, a, as_stream(stream));
+}
+
+extern "C" int ipdm_sense_adjoint(const void* S, const float* maps_re, const float* maps_im, const uint8_t* mask,
+                                  int mask_frames, void* out, int ncoils, int batch, int H, int W, int ssos,
+                                  void* workspace, void* stream) {
+  IPDM_REQUIRE(S && out && workspace, IPDM_E_BADARG, "sense_adjoint: null pointer");
+  IPDM_REQUIRE(ncoils >= 1 && batch >= 1, IPDM_E_BADARG, "sense_adjoint: bad ncoils/batch");
+  IPDM_REQUIRE(pow2_ok(H) && pow2_ok(W), IPDM_E_UNSUPPORTED, "sense_adjoint: H=%d W=%d must be powers of two in [8,512]", H, W);
+  SenseArgs a{};
+  a.in = (const cf32*)S; a.out = (cf32*)out; a.ws = (cf32*)workspace;
+  a.mre = ssos ? nullptr : maps_re; a.mim = ssos ? nullptr : maps_im;
+  a.mask = mask; a.mask_frames = mask ? mask_frames : 1;
+  a.ncoils = ncoils; a.batch = batch; a.H = H; a.W = W; a.ssos = ssos ? 1 : 0;
+  a.scale = (((H / 2 + W / 2) & 1) ? -1.f : 1.f) / sqrtf((float)H * (float)W);
+  if (int e = launch_cols(false, a, as_stream(stream))) return e;
+  return launch_rows(false, a, as_stream(stream));
+}
+
+extern "C" int ipdm_kspace_combine(void* S, const void* Y, const uint8_t* mask, int mask_frames, float a, int mode,
+                                   int batch, int H, int W, void* stream) {
+  IPDM_REQUIRE(S && mask && mask_frames >= 1, IPDM_E_BADARG, "kspace_combine: null pointer");
+  IPDM_REQUIRE(mode == 0 || mode == 2 || (mode == 1 && Y), IPDM_E_BADARG, "kspace_combine: mode");
+  const size_t n = (size_t)batch * H * W;
+  k_kspace_combine<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>((cf32*)S, (const cf32*)Y, mask, mask_frames, a, mode, H, W, n);
+  return launched("k_kspace_combine");
+}
+
+extern "C" int ipdm_caxpy(void* out, const void* a, const void* b, float s, size_t n, void* stream) {
+  IPDM_REQUIRE(out && a && b, IPDM_E_BADARG, "caxpy: null pointer");
+  k_caxpy<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>((cf32*)out, (const cf32*)a, (const cf32*)b, s, n);
+  return launched("k_caxpy");
+}
+
+extern "C" int ipdm_planar_to_c64(const float* planar, void* c64, size_t n, void* stream) {
+  IPDM_REQUIRE(planar && c64, IPDM_E_BADARG, "planar_to_c64: null pointer");
+  k_planar_to_c64<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(planar, (cf32*)c64, n);
+  return launched("k_planar_to_c64");
+}
+
+extern "C" int ipdm_c64_to_planar(const void* c64, float* planar, size_t n, void* stream) {
+  IPDM_REQUIRE(planar && c64, IPDM_E_BADARG, "c64_to_planar: null pointer");
+  k_c64_to_planar<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>((const cf32*)c64, planar, n);
+  return launched("k_c64_to_planar");
+}
+
+extern "C" int ipdm_langevin_update(float* x, const float* grad, const float* noise, float* x_mean, size_t n,
+                                    const ipdm_ald_scalars* scalars_host, const ipdm_ald_scalars* sched,
+                                    const int* cursor, const float* step_per_sample, size_t per_sample_elems,
+                                    uint64_t seed, uint32_t rng_step, void* stream) {
+  IPDM_REQUIRE(x && grad, IPDM_E_BADARG, "langevin_update: null pointer");
+  IPDM_REQUIRE(scalars_host || (sched && cursor) || step_per_sample, IPDM_E_BADARG, "langevin_update: no step size given");
+  IPDM_REQUIRE(!step_per_sample || per_sample_elems > 0, IPDM_E_BADARG, "langevin_update: per_sample_elems");
+  LangevinArgs a{};
+  a.x = x; a.grad = grad; a.noise = noise; a.x_mean = x_mean; a.n = n;
+  if (scalars_host) a.sc = *scalars_host;
+  a.sched = sched; a.cursor = cursor; a.step_per_sample = step_per_sample; a.per_sample = per_sample_elems;
+  a.seed = seed; a.rng_step = rng_step;
+  k_langevin<<<grid_for((n + 1) / 2, 256), 256, 0, as_stream(stream)>>>(a);
+  return launched("k_langevin");
+}
+
+extern "C" int ipdm_ald_sense_step(float* x, const float* grad, const float* noise, const float* b,
+                                   const float* maps_re, const float* maps_im, const uint8_t* mask, int mask_frames,
+                                   int ncoils, int batch, int H, int W, const ipdm_ald_scalars* scalars_host,
+                                   const ipdm_ald_scalars* sched, const int* cursor, uint64_t seed, uint32_t rng_step,
+                                   void* stream) {
+  IPDM_REQUIRE(x && grad && b && maps_re, IPDM_E_BADARG, "ald_sense_step: null pointer");
+  IPDM_REQUIRE(scalars_host || (sched && cursor), IPDM_E_BADARG, "ald_sense_step: no scalars given");
+  IPDM_REQUIRE(pow2_ok(W), IPDM_E_UNSUPPORTED, "ald_sense_step: W=%d must be a power of two in [8,512]", W);
+  IPDM_REQUIRE(ncoils >= 1 && batch >= 1 && H >= 1, IPDM_E_BADARG, "ald_sense_step: bad shape");
+  AldArgs a{};
+  a.x = x; a.grad = grad; a.noise = noise; a.bvec = b; a.mre = maps_re; a.mim = maps_im;
+  a.mask = mask; a.mask_frames = mask ? mask_frames : 1;
+  a.ncoils = ncoils; a.batch = batch; a.H = H; a.W = W;
+  if (scalars_host) a.sc = *scalars_host;
+  a.sched = sched; a.cursor = cursor; a.seed = seed; a.rng_step = rng_step;
+  cudaStream_t s = as_stream(stream);
+#define ALD_CASE(LL)                                                         \
+  {                                                                          \
+    using TL = Tile<LL>;                                                     \
+    dim3 grid((H + TL::ROWS - 1) / TL::ROWS, batch);                         \
+    if (int e = set_smem(k_ald_sense<LL>, TL::SMEM)) return e;               \
+    k_ald_sense<LL><<<grid, TL::NT, TL::SMEM, s>>>(a);                       \
+  }
+  IPDM_FOR_LEN(W, ALD_CASE)
+#undef ALD_CASE
+  return launched("k_ald_sense");
+}
+
+extern "C" int ipdm_ald_advance(int* cursor, int64_t* labels, int batch, int n_steps_each, void* stream) {
+  IPDM_REQUIRE(cursor && n_steps_each >= 1, IPDM_E_BADARG, "ald_advance: bad argument");
+  k_advance<<<1, 128, 0, as_stream(stream)>>>(cursor, labels, batch, n_steps_each);
+  return launched("k_advance");
+}
+
+extern "C" int ipdm_temporal_tv_step(float* x, int B, int T, size_t hw, float lamda, void* stream) {
+  IPDM_REQUIRE(x && B >= 1 && T >= 2, IPDM_E_BADARG, "temporal_tv_step: bad argument");
+  const size_t nvol = (size_t)2 * B;
+  k_temporal_tv<<<grid_for(nvol * hw, 256), 256, 0, as_stream(stream)>>>(x, T, hw, lamda, nvol);
+  return launched("k_temporal_tv");
+}
+
+extern "C" int ipdm_chain_stats_accumulate(const void* x, double* acc, int chains, size_t hw, void* stream) {
+  IPDM_REQUIRE(x && acc && chains >= 1, IPDM_E_BADARG, "chain_stats_accumulate: bad argument");
+  k_chain_stats<<<grid_for(hw, 256), 256, 0, as_stream(stream)>>>((const cf32*)x, acc, chains, hw);
+  return launched("k_chain_stats");
+}

@@ -1,0 +1,459 @@
+"""Mirror of `ncsn/models/ALD_optimizers.py`: the annealed-Langevin samplers.
+
+Same constructors, hooks and return convention (`[x.to('cpu')]`) as the reference; what changed is the
+loop body.  The chain state lives on the GPU as one planar float32 tensor [2][B][H][W] (real plane,
+imaginary plane), so that
+
+  * the two score evaluations of a step (real part, imaginary part -- ALD_optimizers.py:227-228,
+    440-441) are ONE batched forward of 2B images,
+  * the Langevin update of both parts and the `L2Penalty` data-consistency step are ONE kernel
+    (`ipdm_ald_sense_step`: z = x + step*g + sqrt(2 step)*n ;  x = z - kappa*(A^H A z - A^H y)),
+  * a whole step (forward + update + schedule advance) is captured once in a CUDA graph and replayed
+    for all L*n_steps_each steps; per-level scalars are read on the device from a schedule table.
+
+Noise is drawn in-kernel (Philox4x32-10 keyed by seed / element / step, so a chain does not depend
+on how chains are spread over GPUs) unless `noise_fn(shape)` is given, which injects host-chosen
+tensors in the reference's draw order -- that is how the parity tests feed identical noise.
+The reference's per-step prints (host syncs) and PNG snapshots are side effects, not results, and
+are not reproduced.  Extra keyword arguments accepted by every `__call__`: `noise_fn`, `seed`,
+`cuda_graph` (default True), `x_init` (override the initial state).
+"""
+import abc
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import ald_schedule
+from .proximal_op import Proximal, L2Penalty, l2_kappa, _mask_kspace
+from ..linear_transforms.undersampling_fourier import SENSE
+from ... import _lib
+
+
+def get_lh_weights(sigmas, start_time, curve_type="linear"):
+    """Guidance-weight ramp (reference :23-38)."""
+    assert 0 <= start_time <= 1
+    lh_weights = torch.zeros_like(sigmas)
+    if start_time == 1:
+        return lh_weights
+    start_idx = int(len(sigmas) * start_time)
+    if curve_type == "linear":
+        lh_weights[start_idx:] = torch.linspace(0, 1, len(sigmas) - start_idx, device=sigmas.device)
+        return lh_weights
+    raise NotImplementedError
+
+
+def _default_device():
+    return torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
+
+
+def _scalars(step, kappa=0.0, sigma=0.0, noise_on=True):
+    step32 = torch.tensor(float(step), dtype=torch.float32)
+    return _lib.AldScalars(float(step32), float(torch.sqrt(step32 * 2)) if noise_on else 0.0, float(kappa), float(sigma))
+
+
+def _to_planar(xc):
+    """complex64 (B,1,H,W) -> planar float32 [2][B][H][W]"""
+    xc = xc.to(torch.complex64).contiguous()
+    B, C, H, W = xc.shape
+    out = torch.empty((2, B * C, H, W), dtype=torch.float32, device=xc.device)
+    _lib.check(_lib.lib().ipdm_c64_to_planar(xc.data_ptr(), out.data_ptr(), xc.numel(), _lib.stream()), "c64_to_planar")
+    return out
+
+
+def _to_complex(planar, shape):
+    out = torch.empty(shape, dtype=torch.complex64, device=planar.device)
+    _lib.check(_lib.lib().ipdm_planar_to_c64(planar.data_ptr(), out.data_ptr(), out.numel(), _lib.stream()), "planar_to_c64")
+    return out
+
+
+class _StepGraph:
+    """Captures `body()` once on a side stream and replays it; falls back to eager calls when
+    `enabled` is False (injected noise, user hooks)."""
+
+    def __init__(self, body, enabled):
+        self.body, self.enabled, self.graph = body, enabled, None
+
+    def __call__(self):
+        if not self.enabled:
+            self.body()
+            return
+        if self.graph is None:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.body()  # warm-up outside capture: allocates plan buffers, builds tensor maps
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.body()
+            self.warm = True
+            return  # the warm-up call was this step; the capture itself does not execute
+        self.graph.replay()
+
+
+class ALDOptimizer(abc.ABC):
+    def __init__(self, x_mod_shape, scorenet, sigmas, params, config,
+                 measurement=None, linear_tfm=None, clf=None, seg=None, device=None):
+        """params: n_steps_each, step_lr, denoise, final_only   (reference :50-64)"""
+        self.x_mod_shape = x_mod_shape
+        self.scorenet = scorenet
+        self.sigmas = sigmas
+        self.params = params
+        self.config = config
+        self.measurement = measurement
+        self.linear_tfm = linear_tfm
+        self.clf = clf
+        self.seg = seg
+        self.device = device if device is not None else _default_device()
+        self.launches_per_step = None
+
+    # ---- hooks (same names as the reference) ----------------------------------------------------
+    def preprocessing_steps(self, **kwargs):
+        pass
+
+    def init_x_mod(self):
+        return torch.rand(*self.x_mod_shape).to(self.device)
+
+    def init_estimation(self, x_mod, **kwargs):
+        return x_mod
+
+    def adjust_grad(self, grad, x_mod, **kwargs):
+        return grad
+
+    def _hooks_overridden(self):
+        cls = type(self)
+        return (cls.adjust_grad is not ALDOptimizer.adjust_grad or cls.init_estimation is not ALDOptimizer.init_estimation)
+
+    def _score_into(self, x, labels, out):
+        if hasattr(self.scorenet, "forward_into"):
+            return self.scorenet.forward_into(x, labels, out)
+        out.copy_(self.scorenet(x, labels))
+        return out
+
+    # ---- generic loop (reference :66-137) ----------------------------------------------------------
+    def __call__(self, **kwargs):
+        torch.set_grad_enabled(False)
+        noise_fn = kwargs.pop("noise_fn", None)
+        seed = int(kwargs.pop("seed", 0))
+        use_graph = bool(kwargs.pop("cuda_graph", True))
+        x_init = kwargs.pop("x_init", None)
+        sigmas = self.sigmas
+        n_steps_each = self.params["n_steps_each"]
+        step_lr = self.params["step_lr"]
+        L = _lib.lib()
+
+        x_mod = self.init_x_mod() if x_init is None else x_init
+        x_mod = x_mod.to(self.device, torch.float32).contiguous().clone()
+        _lib.require_cuda(x_mod)
+        self.preprocessing_steps(**kwargs)
+        B = x_mod.shape[0]
+        grad = torch.empty_like(x_mod)
+        labels = torch.zeros(B, dtype=torch.long, device=x_mod.device)
+        images = []
+        hooks = self._hooks_overridden()
+        fast = use_graph and noise_fn is None and not hooks and self.params["final_only"]
+        if fast:
+            sched = ald_schedule(sigmas, n_steps_each, step_lr).to(x_mod.device)
+            cursor = torch.zeros(1, dtype=torch.int32, device=x_mod.device)
+            n_total = sched.shape[0]
+
+            def body():
+                self._score_into(x_mod, labels, grad)
+                _lib.check(L.ipdm_langevin_update(x_mod.data_ptr(), grad.data_ptr(), None, None, x_mod.numel(), None,
+                                                  sched.data_ptr(), cursor.data_ptr(), None, 0, seed, 0, _lib.stream()), "langevin_update")
+                _lib.check(L.ipdm_ald_advance(cursor.data_ptr(), labels.data_ptr(), B, n_steps_each, _lib.stream()), "ald_advance")
+
+            before = L.ipdm_launch_count()
+            step = _StepGraph(body, True)
+            step()
+            self.launches_per_step = (L.ipdm_launch_count() - before) // 2  # warm-up + capture both count
+            for _ in range(1, n_total):
+                step()
+        else:
+            k = 0
+            for c, sigma in enumerate(sigmas):
+                labels.fill_(c)
+                step_size = step_lr * (sigma / sigmas[-1]) ** 2
+                x_mod = self.init_estimation(x_mod, alpha=step_size, **kwargs)
+                for s in range(n_steps_each):
+                    self._score_into(x_mod, labels, grad)
+                    g = self.adjust_grad(grad, x_mod, sigma=sigma, **kwargs)
+                    noise = None if noise_fn is None else noise_fn(x_mod.shape).to(x_mod.device, torch.float32).contiguous()
+                    _lib.check(L.ipdm_langevin_update(x_mod.data_ptr(), g.contiguous().data_ptr(), _lib.ptr(noise), None,
+                                                      x_mod.numel(), _scalars(step_size), None, None, None, 0, seed, k,
+                                                      _lib.stream()), "langevin_update")
+                    k += 1
+                    if not self.params["final_only"]:
+                        images.append(x_mod.to('cpu'))
+        if self.params["denoise"]:
+            labels.fill_(len(sigmas) - 1)
+            self._score_into(x_mod, labels, grad)
+            _lib.check(L.ipdm_langevin_update(x_mod.data_ptr(), grad.data_ptr(), None, None, x_mod.numel(),
+                                              _scalars(sigmas[-1] ** 2, noise_on=False), None, None, None, 0, seed, 0,
+                                              _lib.stream()), "denoise")
+            images.append(x_mod.to('cpu'))
+        if self.params["final_only"]:
+            return [x_mod.to('cpu')]
+        return images
+
+
+class ALDUnconditionalSampler(ALDOptimizer):
+    pass
+
+
+class _SenseChainMixin:
+    """State + kernels shared by the two SENSE samplers."""
+
+    def _fused_ok(self):
+        return (isinstance(self.proximal, L2Penalty) and isinstance(self.linear_tfm, SENSE)
+                and self.proximal.lin_tfm is self.linear_tfm)
+
+    def _setup_sense(self, measurement5, device):
+        """measurement5: (Nc, B', 1, H, W) complex64 on device.  Returns planar x0 = A^H y and b = A^H(mask*y)."""
+        A = self.linear_tfm
+        x0 = A.conj_op(measurement5)
+        if self._fused_ok():
+            b = A.conj_op_masked(_mask_kspace(A, measurement5.clone()))
+        else:
+            b = x0
+        return _to_planar(x0), _to_planar(b)
+
+    def _sense_step(self, state, grad, noise, bvec, scalars=None, sched=None, cursor=None, seed=0, rng_step=0):
+        A = self.linear_tfm
+        mre, mim = A.device_maps(state.device)
+        m, frames = A.device_mask(state.device)
+        _, Bp, H, W = state.shape
+        if frames not in (1, Bp):
+            raise RuntimeError(f"mask has {frames} frames but the batch holds {Bp} images")
+        _lib.check(_lib.lib().ipdm_ald_sense_step(state.data_ptr(), grad.data_ptr(), _lib.ptr(noise), bvec.data_ptr(),
+                                                  mre.data_ptr(), _lib.ptr(mim), m.data_ptr(), frames, mre.shape[0], Bp, H, W,
+                                                  scalars, _lib.ptr(sched), _lib.ptr(cursor), seed, rng_step, _lib.stream()),
+                   "ald_sense_step")
+
+
+class ALDInvSegProximalRealImag(_SenseChainMixin, ALDOptimizer):
+    def __init__(self, proximal: Proximal, seg_start_time, seg_step_type, *args, **kwargs):
+        super(ALDInvSegProximalRealImag, self).__init__(*args, **kwargs)
+        self.proximal = proximal
+        self.seg_start_time = seg_start_time
+        self.seg_step_type = seg_step_type
+        self.lh_weights = get_lh_weights(self.sigmas, self.seg_start_time, self.seg_step_type)
+        self.if_print = False
+        self.print_args = {}
+
+    def adjust_grad(self, grad, m_mod, **kwargs):
+        """grad + d/dx log p_seg(label | x) / sigma * seg_lamda   (reference :272-286); skipped when the
+        weight is zero or no segmentation net is attached."""
+        lamda = kwargs.get("seg_lamda", 0.)
+        if self.seg is None or float(lamda) == 0.:
+            return grad
+        label, sigma, seg_mode = kwargs["label"], kwargs["sigma"], kwargs["seg_mode"]
+        with torch.enable_grad():
+            X = m_mod.detach().clone().requires_grad_(True)
+            prob = torch.softmax(self.seg(X), dim=1)
+            sel = torch.gather(prob, dim=1, index=label)
+            torch.log(sel).sum().backward()
+            g = X.grad
+        if seg_mode == "FG":
+            g = g * label
+        return grad + g / sigma * lamda
+
+    def post_processing(self, x_mod_real, x_mod_imag, **kwargs):
+        """Generic (non-fused) data-consistency step on separate real / imaginary tensors (reference :288-327)."""
+        x_mod = torch.complex(x_mod_real, x_mod_imag)
+        coeff = kwargs["alpha"] * kwargs["lr_scaled"]
+        x_mod = self.proximal(x_mod, self.measurement, coeff, 1.)
+        return torch.real(x_mod), torch.imag(x_mod)
+
+    def __call__(self, **kwargs):
+        """kwargs: label, lamda, save_dir, lr_scaled, seg_mode  (+ noise_fn, seed, cuda_graph)"""
+        torch.set_grad_enabled(False)
+        noise_fn = kwargs.pop("noise_fn", None)
+        seed = int(kwargs.pop("seed", 0))
+        use_graph = bool(kwargs.pop("cuda_graph", True))
+        sigmas = self.sigmas
+        n_steps_each = self.params["n_steps_each"]
+        step_lr = self.params["step_lr"]
+        lr_scaled = kwargs.get("lr_scaled", 1.)
+        L = _lib.lib()
+        y = self.measurement.to(self.device)
+        _lib.require_cuda(y)
+        Nc, B, C, H, W = y.shape
+        if C != 1:
+            raise _lib.IpdmError("ALDInvSegProximalRealImag: C must be 1")
+        state, bvec = self._setup_sense(y.to(torch.complex64).contiguous(), y.device)   # [2][B][H][W]
+        self.preprocessing_steps(**kwargs)
+        grad = torch.empty_like(state)
+        labels = torch.zeros(2 * B, dtype=torch.long, device=state.device)
+        x_flat = state.view(2 * B, 1, H, W)
+        g_flat = grad.view(2 * B, 1, H, W)
+        guided = self.seg is not None and bool((self.lh_weights != 0).any())
+        hooked = type(self).adjust_grad is not ALDInvSegProximalRealImag.adjust_grad or \
+            type(self).post_processing is not ALDInvSegProximalRealImag.post_processing
+        fused = self._fused_ok() and not hooked
+        fast = fused and use_graph and noise_fn is None and not guided
+        if fast:
+            kappa = l2_kappa(self.linear_tfm, state, step_lr * lr_scaled, 1.)
+            sched = ald_schedule(sigmas, n_steps_each, step_lr, kappa).to(state.device)
+            cursor = torch.zeros(1, dtype=torch.int32, device=state.device)
+
+            def body():
+                self._score_into(x_flat, labels, g_flat)
+                self._sense_step(state, grad, None, bvec, None, sched, cursor, seed, 0)
+                _lib.check(L.ipdm_ald_advance(cursor.data_ptr(), labels.data_ptr(), 2 * B, n_steps_each, _lib.stream()), "ald_advance")
+
+            before = L.ipdm_launch_count()
+            step = _StepGraph(body, True)
+            step()
+            self.launches_per_step = (L.ipdm_launch_count() - before) // 2
+            for _ in range(1, sched.shape[0]):
+                step()
+        else:
+            k = 0
+            for c, sigma in enumerate(sigmas):
+                labels.fill_(c)
+                step_size = step_lr * (sigma / sigmas[-1]) ** 2
+                w_seg = self.lh_weights[c]
+                for s in range(n_steps_each):
+                    self._score_into(x_flat, labels, g_flat)
+                    if guided or hooked:
+                        hk = dict(kwargs, sigma=sigma, seg_lamda=w_seg)
+                        grad[0].copy_(self.adjust_grad(grad[0].unsqueeze(1), state[0].unsqueeze(1), **hk).squeeze(1))
+                        grad[1].copy_(self.adjust_grad(grad[1].unsqueeze(1), state[1].unsqueeze(1), **hk).squeeze(1))
+                    noise = None
+                    if noise_fn is not None:  # reference draw order: real, then imaginary (:238-241)
+                        nr = noise_fn((B, 1, H, W))
+                        ni = noise_fn((B, 1, H, W))
+                        noise = torch.stack([nr.reshape(B, H, W), ni.reshape(B, H, W)], 0).to(state.device, torch.float32).contiguous()
+                    if fused:
+                        kappa = l2_kappa(self.linear_tfm, state, step_lr * lr_scaled, 1.)
+                        self._sense_step(state, grad, noise, bvec, _scalars(step_size, kappa, sigma), None, None, seed, k)
+                    else:
+                        _lib.check(L.ipdm_langevin_update(state.data_ptr(), grad.data_ptr(), _lib.ptr(noise), None, state.numel(),
+                                                          _scalars(step_size), None, None, None, 0, seed, k, _lib.stream()), "langevin_update")
+                        xr, xi = self.post_processing(state[0].unsqueeze(1), state[1].unsqueeze(1), alpha=step_lr, sigma=sigma, **kwargs)
+                        state[0].copy_(xr.squeeze(1))
+                        state[1].copy_(xi.squeeze(1))
+                    k += 1
+        if self.params["denoise"]:
+            labels.fill_(len(sigmas) - 1)
+            self._score_into(x_flat, labels, g_flat)
+            _lib.check(L.ipdm_langevin_update(state.data_ptr(), grad.data_ptr(), None, None, state.numel(),
+                                              _scalars(sigmas[-1] ** 2, noise_on=False), None, None, None, 0, seed, 0,
+                                              _lib.stream()), "denoise")
+        x_mod = _to_complex(state, (B, 1, H, W))
+        self.final_state = x_mod
+        return [x_mod.to('cpu')]
+
+
+class ALD2DTime(_SenseChainMixin, ALDOptimizer):
+    def __init__(self, proximal: Proximal, scorenet_T, sigmas_T, *args, **kwargs):
+        """x_mod_shape: (B, T, C, H, W); measurement: (num_sens, B, T, C, H, W)   (reference :330-349)"""
+        super(ALD2DTime, self).__init__(*args, **kwargs)
+        self.proximal = proximal
+        self.scorenet_T = scorenet_T
+        self.sigmas_T_orig = sigmas_T
+        # temporal schedule nearest-interpolated onto the tail of the spatial one, -1 = "skip" (quirk Q14)
+        n = int((self.sigmas <= sigmas_T[0]).sum())
+        self.sigmas_T = torch.ones_like(self.sigmas) * (-1)
+        if n > 0:
+            self.sigmas_T[-n:] = F.interpolate(sigmas_T.view(1, 1, -1).float(), n, mode="nearest").squeeze().to(self.sigmas.device)
+        if self.scorenet_T is not None:
+            self.scorenet_T.sigmas = self.sigmas_T
+            self.win_size = int(np.sqrt(self.scorenet_T.config.data.channels))
+        self.finite_diff = None
+
+    def __call__(self, **kwargs):
+        """kwargs: save_dir, lr_scaled, mode_T in {"none","tv","tv-only"}, lamda_T, if_random_shift
+        (+ noise_fn, seed, cuda_graph).  The learned temporal prior ("diffusion1d") is not part of this path yet."""
+        torch.set_grad_enabled(False)
+        noise_fn = kwargs.pop("noise_fn", None)
+        seed = int(kwargs.pop("seed", 0))
+        use_graph = bool(kwargs.pop("cuda_graph", True))
+        mode_T = kwargs.get("mode_T", "diffusion1d")
+        lamda_T = float(kwargs.get("lamda_T", 1.))
+        lr_scaled = kwargs["lr_scaled"]
+        if "diffusion1d" in mode_T:
+            raise NotImplementedError("mode_T='diffusion1d' needs the NCSN3D temporal prior, which is outside the implemented hot path")
+        skip_spatial = mode_T == "tv-only"
+        if skip_spatial:
+            self.sigmas_T = self.sigmas_T_orig
+            self.sigmas = self.sigmas_T_orig
+        sigmas = self.sigmas
+        n_steps_each = self.params["n_steps_each"]
+        step_lr = self.params["step_lr"]
+        L = _lib.lib()
+        self.preprocessing_steps(**kwargs)
+        y6 = self.measurement.to(self.device).to(torch.complex64)
+        _lib.require_cuda(y6)
+        Nc, B, T, C, H, W = y6.shape
+        if C != 1:
+            raise _lib.IpdmError("ALD2DTime: C must be 1")
+        if not self._fused_ok():
+            raise _lib.IpdmError("ALD2DTime: only L2Penalty over SENSE is implemented")
+        y = y6.reshape(Nc, B * T, C, H, W).contiguous()
+        state, bvec = self._setup_sense(y, y.device)                      # [2][B*T][H][W]
+        BT = B * T
+        grad = torch.zeros_like(state)
+        labels = torch.zeros(2 * BT, dtype=torch.long, device=state.device)
+        x_flat, g_flat = state.view(2 * BT, 1, H, W), grad.view(2 * BT, 1, H, W)
+        kappa = l2_kappa(self.linear_tfm, state, step_lr * lr_scaled, 1.)
+        tv = "tv" in mode_T
+        prox_only = _lib.AldScalars(0.0, 0.0, float(kappa), 0.0)
+        fast = use_graph and noise_fn is None
+
+        def one_step(c, k, noise, sched=None, cursor=None):
+            """spatial_step (:428-449) -> temporal_step (:452-462) -> proximal_step (:543-554)"""
+            if not skip_spatial:
+                self._score_into(x_flat, labels, g_flat)
+            if not tv:
+                # Langevin update and L2-penalty step in one kernel
+                if sched is not None:
+                    self._sense_step(state, grad, None, bvec, None, sched, cursor, seed, 0)
+                else:
+                    step_size = step_lr * (sigmas[c] / sigmas[-1]) ** 2
+                    self._sense_step(state, grad, noise, bvec, _scalars(step_size, kappa, sigmas[c]), None, None, seed, k)
+                return
+            if not skip_spatial:
+                if sched is not None:
+                    _lib.check(L.ipdm_langevin_update(state.data_ptr(), grad.data_ptr(), None, None, state.numel(), None,
+                                                      sched.data_ptr(), cursor.data_ptr(), None, 0, seed, 0, _lib.stream()), "langevin_update")
+                else:
+                    step_size = step_lr * (sigmas[c] / sigmas[-1]) ** 2
+                    _lib.check(L.ipdm_langevin_update(state.data_ptr(), grad.data_ptr(), _lib.ptr(noise), None, state.numel(),
+                                                      _scalars(step_size), None, None, None, 0, seed, k, _lib.stream()), "langevin_update")
+            _lib.check(L.ipdm_temporal_tv_step(state.data_ptr(), B, T, H * W, lamda_T, _lib.stream()), "temporal_tv_step")
+            # data consistency only: step = noise_scale = 0 turns the fused kernel into x - kappa*(A^H A x - b)
+            self._sense_step(state, grad, None, bvec, prox_only, None, None, seed, k)
+
+        if fast and not skip_spatial:
+            sched = ald_schedule(sigmas, n_steps_each, step_lr, kappa).to(state.device)
+            cursor = torch.zeros(1, dtype=torch.int32, device=state.device)
+
+            def body():
+                one_step(0, 0, None, sched, cursor)
+                _lib.check(L.ipdm_ald_advance(cursor.data_ptr(), labels.data_ptr(), 2 * BT, n_steps_each, _lib.stream()), "ald_advance")
+
+            before = L.ipdm_launch_count()
+            step = _StepGraph(body, True)
+            step()
+            self.launches_per_step = (L.ipdm_launch_count() - before) // 2
+            for _ in range(1, sched.shape[0]):
+                step()
+        else:
+            k = 0
+            for c in range(len(sigmas)):
+                labels.fill_(c)
+                for s in range(n_steps_each):
+                    noise = None
+                    if noise_fn is not None and not skip_spatial:  # both noises are drawn before either update (:442-443)
+                        nr = noise_fn((BT, 1, H, W))
+                        ni = noise_fn((BT, 1, H, W))
+                        noise = torch.stack([nr.reshape(BT, H, W), ni.reshape(BT, H, W)], 0).to(state.device, torch.float32).contiguous()
+                    one_step(c, k, noise)
+                    k += 1
+        x_mod = _to_complex(state, (B, T, C, H, W))
+        self.final_state = x_mod
+        return [x_mod.to("cpu")]

@@ -1,0 +1,59 @@
+"""Mirror of the annealed-Langevin part of `sde/sampling.py`: the 'ald' corrector
+(`AnnealedLangevinDynamics.update_fn`, sde/sampling.py:290-324), on the fused update kernel.
+
+Only what the north-star path names is here; predictors, the ODE sampler and the 'langevin'
+corrector (which needs two batch-mean norms per step) are out of scope.
+"""
+import torch
+
+from .. import _lib
+
+_CORRECTORS = {}
+
+
+def register_corrector(cls=None, *, name=None):
+    def _register(c):
+        key = c.__name__ if name is None else name
+        if key in _CORRECTORS:
+            raise ValueError(f'Already registered model with name: {key}')
+        _CORRECTORS[key] = c
+        return c
+    return _register if cls is None else _register(cls)
+
+
+def get_corrector(name):
+    return _CORRECTORS[name]
+
+
+class Corrector:
+    """The abstract class for a corrector algorithm (sde/sampling.py:167-190)."""
+
+    def __init__(self, sde, score_fn, snr, n_steps):
+        self.sde, self.score_fn, self.snr, self.n_steps = sde, score_fn, snr, n_steps
+
+
+@register_corrector(name='ald')
+class AnnealedLangevinDynamics(Corrector):
+    """step = (snr*std_t)^2 * 2 * alpha_t ;  x_mean = x + step*score ;  x = x_mean + sqrt(2 step)*noise.
+    `sde` needs `.marginal_prob(x, t)[1]` (and `.alphas`, `.N`, `.T` for VP-type SDEs, detected by attribute)."""
+
+    def update_fn(self, x, t, noise_fn=None, seed=0):
+        _lib.require_cuda(x, t)
+        sde = self.sde
+        if hasattr(sde, "alphas"):
+            timestep = (t * (sde.N - 1) / sde.T).long()
+            alpha = sde.alphas.to(t.device)[timestep]
+        else:
+            alpha = torch.ones_like(t)
+        std = sde.marginal_prob(x, t)[1]
+        x = x.detach().float().contiguous().clone()
+        x_mean = torch.empty_like(x)
+        per = x[0].numel()
+        L = _lib.lib()
+        for i in range(self.n_steps):
+            grad = self.score_fn(x, t).contiguous()
+            step = ((self.snr * std) ** 2 * 2 * alpha).float().contiguous()
+            noise = None if noise_fn is None else noise_fn(x.shape).to(x.device, torch.float32).contiguous()
+            _lib.check(L.ipdm_langevin_update(x.data_ptr(), grad.data_ptr(), _lib.ptr(noise), x_mean.data_ptr(), x.numel(), None,
+                                              None, None, step.data_ptr(), per, int(seed), i, _lib.stream()), "ald corrector")
+        return x, x_mean

@@ -1,0 +1,357 @@
+"""TEST INFRASTRUCTURE -- a CPU emulation of the C ABI in include/ipdm_b200.h, written with
+numpy/torch on raw host pointers.  It exists so that the HOST LOGIC of the product package (the
+kernel sequence of the score network, the samplers' bookkeeping, flags, buffer wiring) can be
+exercised by the `-m "not gpu"` suite in a container without a GPU.  It is installed by the
+`emu` fixture (monkeypatching `_lib.lib` / `_lib.require_cuda`); the product package never
+imports it and has no CPU path of its own.  Each function implements the documented contract of
+the entry point, not the kernel's algorithm.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from oracle import mri_ops as M
+
+
+def _np(ptr, shape, dtype):
+    n = int(np.prod(shape))
+    if n == 0:
+        return np.zeros(shape, dtype)
+    buf = (ctypes.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+def _t(ptr, shape, dtype):
+    return torch.from_numpy(_np(ptr, shape, dtype))
+
+
+def _deref(p):
+    if hasattr(p, "_obj"):      # ctypes.byref(...)
+        return p._obj
+    return p.contents if hasattr(p, "contents") else p
+
+
+class EmuLib:
+    def __init__(self):
+        self.launches = 0
+        self.err = b""
+
+    # ---- misc
+    def ipdm_abi_version(self):
+        return 1
+
+    def ipdm_last_error(self):
+        return self.err
+
+    def ipdm_launch_count(self):
+        return self.launches
+
+    def ipdm_sense_workspace_bytes(self, nc, b, H, W):
+        return nc * b * H * W * 8
+
+    # ---- SENSE
+    def _maps(self, mre, mim, nc, H, W):
+        if mre is None:
+            return None
+        m = _t(mre, (nc, H, W), np.float32).to(torch.complex64)
+        if mim is not None:
+            m = m + 1j * _t(mim, (nc, H, W), np.float32)
+        return m
+
+    def _mask(self, mask, frames, B, W):
+        if mask is None:
+            return None
+        m = _t(mask, (frames, W), np.uint8).float()
+        idx = torch.arange(B) % frames
+        return m[idx].view(B, 1, W)
+
+    def ipdm_sense_forward(self, x, mre, mim, mask, frames, out, nc, B, H, W, ws, stream):
+        self.launches += 2
+        X = _t(x, (B, H, W), np.complex64)
+        maps = self._maps(mre, mim, nc, H, W)
+        msk = self._mask(mask, frames, B, W)
+        O = _t(out, (nc, B, H, W), np.complex64)
+        for c in range(nc):
+            k = M.i2k(X if maps is None else maps[c] * X)
+            O[c] = k if msk is None else msk * k
+        return 0
+
+    def ipdm_sense_adjoint(self, S, mre, mim, mask, frames, out, nc, B, H, W, ssos, ws, stream):
+        self.launches += 2
+        Sx = _t(S, (nc, B, H, W), np.complex64)
+        maps = self._maps(mre, mim, nc, H, W)
+        msk = self._mask(mask, frames, B, W)
+        if msk is not None:
+            Sx = Sx * msk
+        if ssos:
+            acc = torch.zeros(B, H, W)
+            for c in range(nc):
+                acc += M.k2i(Sx[c]).abs() ** 2
+            _t(out, (B, H, W), np.float32).copy_(acc.sqrt())
+        else:
+            acc = torch.zeros(B, H, W, dtype=torch.complex64)
+            for c in range(nc):
+                v = M.k2i(Sx[c])
+                acc += v if maps is None else maps[c].conj() * v
+            _t(out, (B, H, W), np.complex64).copy_(acc)
+        return 0
+
+    def ipdm_kspace_combine(self, S, Y, mask, frames, a, mode, batch, H, W, stream):
+        self.launches += 1
+        Sx = _t(S, (batch, H, W), np.complex64)
+        m = self._mask(mask, frames, batch, W)
+        if mode == 0:
+            Sx.copy_(Sx / (1 + m * a))
+        elif mode == 2:
+            Sx.copy_(Sx * m)
+        else:
+            Yx = _t(Y, (batch, H, W), np.complex64)
+            Sx.copy_(a * Yx + (1 - a) * m * Sx + (1 - m) * Sx)
+        return 0
+
+    def ipdm_caxpy(self, out, a, b, s, n, stream):
+        self.launches += 1
+        _t(out, (n,), np.complex64).copy_(_t(a, (n,), np.complex64) + s * _t(b, (n,), np.complex64))
+        return 0
+
+    # ---- ALD
+    def _scalars(self, sc, sched, cursor):
+        if sched is not None:
+            cur = int(_np(cursor, (1,), np.int32)[0])
+            row = _np(sched + 16 * cur, (4,), np.float32)
+            return float(row[0]), float(row[1]), float(row[2])
+        sc = _deref(sc)
+        return sc.step, sc.noise_scale, sc.kappa
+
+    def ipdm_langevin_update(self, x, grad, noise, x_mean, n, sc, sched, cursor, sps, per, seed, rng_step, stream):
+        self.launches += 1
+        X, G = _t(x, (n,), np.float32), _t(grad, (n,), np.float32)
+        Nz = _t(noise, (n,), np.float32) if noise is not None else None
+        if sps is not None:
+            st = _t(sps, (n // per,), np.float32).repeat_interleave(per)
+            ns = torch.sqrt(2 * st)
+        else:
+            st, ns, _ = self._scalars(sc, sched, cursor)
+            if Nz is None and ns != 0:
+                raise RuntimeError("emulator: Philox noise is not emulated; inject noise")
+        mean = X + st * G
+        if x_mean is not None:
+            _t(x_mean, (n,), np.float32).copy_(mean)
+        X.copy_(mean if Nz is None else mean + ns * Nz)
+        return 0
+
+    def ipdm_ald_sense_step(self, x, grad, noise, b, mre, mim, mask, frames, nc, B, H, W, sc, sched, cursor, seed, rng_step, stream):
+        self.launches += 1
+        st, ns, kappa = self._scalars(sc, sched, cursor)
+        X, G, Bv = (_t(p, (2, B, H, W), np.float32) for p in (x, grad, b))
+        z = X + st * G
+        if noise is not None:
+            z = z + ns * _t(noise, (2, B, H, W), np.float32)
+        elif ns != 0:
+            raise RuntimeError("emulator: Philox noise is not emulated; inject noise")
+        zc = torch.complex(z[0], z[1])
+        maps = self._maps(mre, mim, nc, H, W)
+        msk = self._mask(mask, frames, B, W)
+        acc = torch.zeros(B, H, W, dtype=torch.complex64)
+        for c in range(nc):
+            k = M.i2k(maps[c] * zc)
+            if msk is not None:
+                k = msk * k
+            acc += maps[c].conj() * M.k2i(k)
+        bc = torch.complex(Bv[0], Bv[1])
+        new = zc - kappa * (acc - bc)
+        X[0].copy_(new.real)
+        X[1].copy_(new.imag)
+        return 0
+
+    def ipdm_ald_advance(self, cursor, labels, batch, n_each, stream):
+        self.launches += 1
+        c = _np(cursor, (1,), np.int32)
+        if labels is not None:
+            _np(labels, (batch,), np.int64)[:] = (int(c[0]) + 1) // n_each
+        c[0] += 1
+        return 0
+
+    def ipdm_temporal_tv_step(self, x, B, T, hw, lamda, stream):
+        self.launches += 1
+        X = _t(x, (2 * B, T, hw), np.float32)
+        s = torch.sign(torch.roll(X, -1, 1) - X)
+        X.copy_(X - lamda * (torch.roll(s, 1, 1) - s))
+        return 0
+
+    def ipdm_planar_to_c64(self, planar, c64, n, stream):
+        self.launches += 1
+        P = _t(planar, (2, n), np.float32)
+        _t(c64, (n,), np.complex64).copy_(torch.complex(P[0], P[1]))
+        return 0
+
+    def ipdm_c64_to_planar(self, c64, planar, n, stream):
+        self.launches += 1
+        C = _t(c64, (n,), np.complex64)
+        P = _t(planar, (2, n), np.float32)
+        P[0].copy_(C.real)
+        P[1].copy_(C.imag)
+        return 0
+
+    def ipdm_chain_stats_accumulate(self, x, acc, chains, hw, stream):
+        self.launches += 1
+        X = _t(x, (chains, hw), np.complex64)
+        A = _t(acc, (4, hw), np.float64)
+        mag, ang = X.abs().double(), torch.angle(X).double()
+        A += torch.stack([mag.sum(0), (mag * mag).sum(0), ang.sum(0), (ang * ang).sum(0)])
+        return 0
+
+    # ---- score network
+    def _conv(self, dp):
+        d = _deref(dp)
+        self.launches += 1
+        N, H, W, Cin, Cout, taps = d.N, d.H, d.W, d.Cin, d.Cout, d.taps
+        x = _t(d.in_f16, (N, H, W, Cin), np.float16).float().permute(0, 3, 1, 2)
+        k = 3 if taps == 9 else 1
+        w = _t(d.w_f16, (Cout, taps, Cin), np.float16).float().permute(0, 2, 1).reshape(Cout, Cin, k, k)
+        pad = d.dilation if k == 3 else 0
+        v = F.conv2d(x, w, None, padding=pad, dilation=d.dilation if k == 3 else 1)
+        if d.flags & 8:
+            v = (((v[:, :, ::2, ::2] + v[:, :, 1::2, ::2]) + v[:, :, ::2, 1::2]) + v[:, :, 1::2, 1::2]) * 0.25
+        Ho, Wo = v.shape[2:]
+        v = v.permute(0, 2, 3, 1)
+        if d.bias:
+            v = v + _t(d.bias, (Cout,), np.float32)
+        pre = v
+        if d.residual:
+            r = _t(d.residual, (N, Ho, Wo, Cout), np.float32).clone()
+            if d.flags & 4:
+                r = F.elu(r)
+            v = v + r
+        if d.out_f32:
+            _t(d.out_f32, (N, Ho, Wo, Cout), np.float32).copy_(v)
+        if d.out_f16:
+            s = pre if d.flags & 2 else v
+            if d.flags & 1:
+                s = F.elu(s)
+            _t(d.out_f16, (N, Ho, Wo, Cout), np.float16).copy_(s.half())
+        if d.stats:
+            st = _t(d.stats, (N, Cout, 2), np.float32)
+            flat = v.reshape(N, -1, Cout)
+            st[:, :, 0] = flat.sum(1)
+            st[:, :, 1] = (flat * flat).sum(1)
+        return 0
+
+    def ipdm_conv_igemm(self, dp, stream):
+        d = _deref(dp)
+        assert d.Cin % 64 == 0 and d.Cout % 128 == 0
+        return self._conv(dp)
+
+    def ipdm_conv_direct(self, dp, stream):
+        return self._conv(dp)
+
+    def ipdm_conv_first(self, x, w, bias, out, stats, N, H, W, Cout, affine, stream):
+        self.launches += 1
+        X = _t(x, (N, 1, H, W), np.float32)
+        if affine:
+            X = 2 * X - 1
+        Wt = _t(w, (Cout, 1, 3, 3), np.float32)
+        b = _t(bias, (Cout,), np.float32) if bias is not None else None
+        v = F.conv2d(X, Wt, b, padding=1).permute(0, 2, 3, 1)
+        _t(out, (N, H, W, Cout), np.float32).copy_(v)
+        if stats is not None:
+            st = _t(stats, (N, Cout, 2), np.float32)
+            flat = v.reshape(N, -1, Cout)
+            st[:, :, 0] = flat.sum(1)
+            st[:, :, 1] = (flat * flat).sum(1)
+        return 0
+
+    def ipdm_conv_last(self, in16, w, bias, sigmas, labels, out, N, H, W, Cin, stream):
+        self.launches += 1
+        X = _t(in16, (N, H, W, Cin), np.float16).float().permute(0, 3, 1, 2)
+        Wt = _t(w, (9, Cin), np.float32).t().reshape(1, Cin, 3, 3)
+        b = _t(bias, (1,), np.float32) if bias is not None else None
+        v = F.conv2d(X, Wt, b, padding=1)
+        lab = _np(labels, (N,), np.int64)
+        nsig = int(lab.max()) + 1
+        sg = _t(sigmas, (nsig,), np.float32)[torch.from_numpy(lab.copy())]
+        _t(out, (N, 1, H, W), np.float32).copy_(v / sg.view(N, 1, 1, 1))
+        return 0
+
+    def ipdm_instnorm_stats(self, x, stats, N, HW, C, pivoted, stream):
+        self.launches += 1
+        X = _t(x, (N, HW, C), np.float32)
+        p = X[:, 0:1, :] if pivoted else 0
+        st = _t(stats, (N, C, 2), np.float32)
+        st[:, :, 0] = (X - p).sum(1)
+        st[:, :, 1] = ((X - p) ** 2).sum(1)
+        return 0
+
+    def ipdm_instnorm_apply_elu(self, x, stats, pivoted, alpha, gamma, beta, out16, N, HW, C, stream):
+        self.launches += 1
+        X = _t(x, (N, HW, C), np.float32)
+        st = _t(stats, (N, C, 2), np.float32)
+        p = X[:, 0, :] if pivoted else 0
+        d = st[:, :, 0] / HW
+        mean = p + d
+        var = (st[:, :, 1] / HW - d * d).clamp_min(0)
+        rstd = torch.rsqrt(var + 1e-5)
+        mu = mean.mean(-1, keepdim=True)
+        mhat = (mean - mu) / torch.sqrt(mean.var(-1, keepdim=True) + 1e-5)
+        a, g = _t(alpha, (C,), np.float32), _t(gamma, (C,), np.float32)
+        h = (X - mean[:, None, :]) * rstd[:, None, :] + (mhat * a)[:, None, :]
+        o = g * h
+        if beta is not None:
+            o = o + _t(beta, (C,), np.float32)
+        _t(out16, (N, HW, C), np.float16).copy_(F.elu(o).half())
+        return 0
+
+    def ipdm_act_to_f16(self, x, out16, n, elu, stream):
+        self.launches += 1
+        X = _t(x, (n,), np.float32)
+        _t(out16, (n,), np.float16).copy_((F.elu(X) if elu else X).half())
+        return 0
+
+    def ipdm_maxpool5_f16(self, in16, out16, N, H, W, C, stream):
+        self.launches += 1
+        X = _t(in16, (N, H, W, C), np.float16).float().permute(0, 3, 1, 2)
+        o = F.max_pool2d(X, 5, 1, 2).permute(0, 2, 3, 1)
+        _t(out16, (N, H, W, C), np.float16).copy_(o.half())
+        return 0
+
+    def ipdm_bilinear_add(self, src, dst, out16, N, h, w, H, W, C, accumulate, stream):
+        self.launches += 1
+        S = _t(src, (N, h, w, C), np.float32).permute(0, 3, 1, 2)
+        up = F.interpolate(S, size=(H, W), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+        D = _t(dst, (N, H, W, C), np.float32)
+        D.copy_(D + up if accumulate else up)
+        if out16 is not None:
+            _t(out16, (N, H, W, C), np.float16).copy_(F.elu(D).half())
+        return 0
+
+    def ipdm_meanpool2(self, inp, add, out, N, H, W, C, stream):
+        self.launches += 1
+        v = _t(inp, (N, H, W, C), np.float32)
+        r = (((v[:, ::2, ::2] + v[:, 1::2, ::2]) + v[:, ::2, 1::2]) + v[:, 1::2, 1::2]) * 0.25
+        if add is not None:
+            r = r + _t(add, (N, H // 2, W // 2, C), np.float32)
+        _t(out, (N, H // 2, W // 2, C), np.float32).copy_(r)
+        return 0
+
+    def ipdm_pack_weights_f16(self, w, out16, Cout, Cin, taps, stream):
+        self.launches += 1
+        Wt = _t(w, (Cout, Cin, taps), np.float32)
+        _t(out16, (Cout, taps, Cin), np.float16).copy_(Wt.permute(0, 2, 1).half())
+        return 0
+
+
+def install(monkeypatch):
+    """Route the product package's C-ABI calls to the emulator and let it accept CPU tensors."""
+    from inverseproblemwithdiffusionmodel_b200 import _lib
+    emu = EmuLib()
+    monkeypatch.setattr(_lib, "lib", lambda: emu)
+    monkeypatch.setattr(_lib, "require_cuda", lambda *a: None)
+    monkeypatch.setattr(_lib, "stream", lambda: None)
+
+    def check(rc, what=""):
+        if rc != 0:
+            raise _lib.IpdmError(what)
+    monkeypatch.setattr(_lib, "check", check)
+    return emu

@@ -1,0 +1,264 @@
+"""Parity cases shared by the CPU host-logic suite (C ABI emulated, tests/emu_lib.py) and the GPU
+suite (real libipdm_b200.so).  Every case compares the PRODUCT package against the golden fixtures
+generated from the reference (tests/golden/) and/or the oracle on the same seeded inputs.
+
+Tolerances (relative L2): fp32 FFT/SENSE/prox work 1e-5 (north_star: SENSE fwd/adj within 1e-5);
+anything that goes through the score network uses f16 tensor-core operands with fp32 accumulation:
+score itself 5e-3, one ALD step / short chains 1e-4 on x (north_star: single ALD step within 1e-4).
+"""
+import json
+import os
+import types
+
+import numpy as np
+import torch
+
+from conftest import rel_l2, GOLDEN
+from oracle import mri_ops as M
+from oracle import ald as OALD
+from oracle import scorenet as SN
+from oracle.fixture_inputs import crandn, rrand, rrandn, phantom
+
+import inverseproblemwithdiffusionmodel_b200 as P
+from inverseproblemwithdiffusionmodel_b200.ncsn.linear_transforms import i2k_complex, k2i_complex, generate_mask
+from inverseproblemwithdiffusionmodel_b200.ncsn.linear_transforms.undersampling_fourier import (
+    SENSE, RandomUndersamplingFourier, keep_center_mask)
+from inverseproblemwithdiffusionmodel_b200.ncsn.linear_transforms.finite_diff import FiniteDiff
+from inverseproblemwithdiffusionmodel_b200.ncsn.models import get_sigmas, anneal_Langevin_dynamics
+from inverseproblemwithdiffusionmodel_b200.ncsn.models.ncsnv2 import NCSNv2, NCSNv2Deepest
+from inverseproblemwithdiffusionmodel_b200.ncsn.models.proximal_op import L2Penalty, SingleCoil, Constrained, get_proximal
+from inverseproblemwithdiffusionmodel_b200.ncsn.models import ALD_optimizers as ALD
+from inverseproblemwithdiffusionmodel_b200.sde.sampling import AnnealedLangevinDynamics
+
+TOL32 = 1e-5
+TOL_SCORE = 5e-3
+TOL_X = 1e-4
+
+
+def G(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def specs():
+    with open(os.path.join(GOLDEN, "state_dict_specs.json")) as f:
+        return json.load(f)
+
+
+def ns(**kw):
+    return types.SimpleNamespace(**kw)
+
+
+def make_config(dataset, ngf, image_size, num_classes, sigma_begin, sigma_end=0.01, device="cpu"):
+    """The nested-Namespace config the reference reads (ncsn/configs/*.yml), reduced to the used keys."""
+    model = ns(sigma_begin=sigma_begin, num_classes=num_classes, sigma_end=sigma_end, sigma_dist="geometric",
+               normalization="InstanceNorm++", nonlinearity="elu", ngf=ngf, ema=True, ema_rate=0.999, spec_norm=False)
+    data = ns(dataset=dataset, image_size=image_size, channels=1, logit_transform=False, uniform_dequantization=False,
+              gaussian_dequantization=False, random_flip=True, rescaled=False)
+    recons = ns(sigma_dist="geometric", sigma_begin=sigma_begin, num_classes=num_classes, sigma_end=sigma_end)
+    return ns(model=model, data=data, recons=recons, device=torch.device(device))
+
+
+def build_net(cls, spec_name, seed, cfg, dev):
+    net = cls(cfg)
+    spec = [(k, tuple(s)) for k, s in specs()[spec_name]]
+    assert [k for k, _ in spec] == list(net.state_dict().keys())
+    Pd = SN.synth_state_dict(spec, seed, net.sigmas.cpu())
+    net.load_state_dict(Pd)
+    return net.to(dev).eval(), Pd
+
+
+# ------------------------------------------------------------------------------------------------ FFT / SENSE
+def case_fft(dev):
+    g = G("linear_ops")
+    for n in (16, 32):
+        x = crandn(1100 + n, 2, 1, n, n).to(dev)
+        assert rel_l2(i2k_complex(x).cpu(), g[f"fft_i2k_{n}"]) < TOL32
+        assert rel_l2(k2i_complex(x).cpu(), g[f"fft_k2i_{n}"]) < TOL32
+    x = rrandn(1199, 1, 1, 8, 32).to(dev)
+    assert rel_l2(i2k_complex(x).cpu(), g["fft_i2k_rect"]) < TOL32
+    assert rel_l2(k2i_complex(x).cpu(), g["fft_k2i_rect"]) < TOL32
+
+
+def case_setup_bit_exact():
+    g = G("linear_ops")
+    assert np.array_equal(generate_mask(24, 128, sw=0.196, sm=0.5, sa=0.02, seed=3).numpy(), g["mask_R8_T24_N128_seed3"])
+    assert np.array_equal(generate_mask(1, 64, seed=5).numpy(), g["mask_T1_N64_seed5"])
+    for W in (32, 128, 256):
+        F1 = RandomUndersamplingFourier(40, 1 / 64, (1, W, W), seed=0)
+        assert F1.mask.dtype == torch.bool and tuple(F1.mask.shape) == (24, 1, 1, W)
+        assert np.array_equal(F1.mask.numpy(), g[f"mask_live_W{W}_seed0"])
+    A = SENSE("exp", 4, 40, 1 / 64, (1, 32, 32), 0)
+    assert A.sens_maps.dtype == torch.float64
+    assert np.allclose(A.sens_maps.numpy(), g["coil_maps_32_seed0"], rtol=0, atol=1e-14)
+    assert np.array_equal(keep_center_mask(32, 4, 1 / 8, 0).numpy(), G("sense_prox")["kc_mask"])
+    s = get_sigmas(make_config("ACDC", 128, 256, 2311, 348))
+    assert torch.equal(s, OALD.geometric_sigmas(348, 0.01, 2311))
+
+
+def case_sense(dev):
+    g = G("sense_prox")
+    n = 32
+    A2 = SENSE("exp", 2, 40, 1 / 64, (1, n, n), 7)
+    x24 = crandn(1201, 24, 1, n, n).to(dev)
+    S = A2(x24)
+    assert tuple(S.shape) == (2, 24, 1, n, n) and S.dtype == torch.complex64
+    assert rel_l2(S[:, [0, 5, 23]].cpu(), g["live_S_frames_0_5_23"]) < TOL32
+    assert rel_l2(A2.conj_op(S).cpu(), g["live_adj"]) < TOL32
+    assert rel_l2(A2.conj_op_masked(S).cpu(), g["live_adj"]) < TOL32
+    assert rel_l2(A2.SSOS(S).cpu(), g["live_ssos"]) < TOL32
+    # Q2: a single image against the 24-frame mask silently becomes 24 undersamplings
+    S1 = A2(x24[:1])
+    assert tuple(S1.shape) == (2, 24, 1, n, n)
+    try:
+        A2(x24[:2])
+        raise AssertionError("batch 2 against a 24-frame mask must fail like the reference broadcast")
+    except RuntimeError:
+        pass
+    A = SENSE("exp", 4, 40, 1 / 64, (1, n, n), 0)
+    assert rel_l2(A.conj_op(crandn(1202, 4, 2, 1, n, n).to(dev)).cpu(), g["dense_adj"]) < TOL32   # Q3: no mask
+    A.random_under_fourier.mask = keep_center_mask(n, 4, 1 / 8, seed=0)
+    x3 = crandn(1203, 3, 1, n, n).to(dev)
+    S3 = A(x3)
+    assert rel_l2(S3.cpu(), g["kc_S"]) < TOL32
+    assert rel_l2(A.conj_op(S3).cpu(), g["kc_adj"]) < TOL32
+    assert rel_l2(A.log_lh_grad(x3, S3 * 0.5, 0.7).cpu(), g["kc_loglh"]) < TOL32
+    return A, x3, S3
+
+
+def case_prox(dev):
+    g = G("sense_prox")
+    n = 32
+    A, x3, S3 = case_sense(dev)
+    z = crandn(1204, 3, 1, n, n).to(dev)
+    prox = get_proximal("L2Penalty")(A)
+    for tag, alpha in (("a1", 1.0), ("a1e3", 1e3)):
+        ref = torch.as_tensor(g[f"l2_{tag}"])
+        out = prox(z, S3, alpha, 1.0).cpu()
+        assert rel_l2(out, ref) < TOL32
+        assert rel_l2(out - z.cpu(), ref - z.cpu()) < 1e-4      # the data-consistency move itself
+    F1 = RandomUndersamplingFourier(4, 1 / 8, (1, n, n), seed=0)
+    F1.mask = keep_center_mask(n, 4, 1 / 8, seed=0)
+    S1 = F1(x3)
+    assert rel_l2(S1.cpu(), g["sc_S"]) < TOL32
+    xs = SingleCoil(F1)(z, S1, 0.8, 1.0)
+    assert rel_l2(xs.cpu(), g["sc_prox"]) < TOL32
+    assert rel_l2(L2Penalty(F1)(z, S1, 2.0, 1.0).cpu(), g["sc_l2"]) < TOL32
+    assert rel_l2(Constrained(F1)(z, S1, 0.3).cpu(), g["sc_proj"]) < TOL32
+    assert float(SingleCoil(F1).check_solution(xs, z, S1, 0.8, 1.0)) < 1e-7
+    # two SGD steps against the oracle's autograd implementation
+    fwd = lambda v: M.sense_forward(v, A.sens_maps, A.random_under_fourier.mask)
+    ref2 = M.l2_prox_sgd(fwd, z.cpu(), S3.cpu(), 50.0, 1.0, num_steps=2)
+    assert rel_l2(prox(z, S3, 50.0, 1.0, num_steps=2).cpu(), ref2) < TOL32
+
+
+def case_tv(dev):
+    x = rrandn(31, 2, 6, 1, 8, 8).to(dev)
+    g = FiniteDiff(dims=1).log_lh_grad(x, lamda=0.3)
+    assert rel_l2(g.cpu(), OALD.temporal_tv_grad(x.cpu(), 0.3)) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ score network
+def case_scorenet_small(dev):
+    g = G("scorenet")
+    cfg = make_config("ACDC", 8, 32, 12, 30.0)
+    net, _ = build_net(NCSNv2Deepest, "NCSNv2Deepest_ngf8", 1, cfg, dev)
+    out = net((rrand(1301, 2, 1, 32, 32) * 3 - 1).to(dev), torch.tensor([0, 7]).to(dev))
+    assert rel_l2(out.cpu(), g["deepest_out"]) < TOL_SCORE
+    cfg = make_config("MNIST", 8, 28, 12, 30.0)
+    net, _ = build_net(NCSNv2, "NCSNv2_ngf8_28", 2, cfg, dev)
+    out = net(rrand(1302, 2, 1, 28, 28).to(dev), torch.tensor([11, 3]).to(dev))
+    assert rel_l2(out.cpu(), g["v2_out"]) < TOL_SCORE
+    # a non-contiguous real view of a complex tensor is a legal input (ALD_optimizers.py:191,227)
+    xc = crandn(5, 2, 1, 28, 28).to(dev)
+    a = net(torch.real(xc), torch.tensor([1, 1]).to(dev))
+    b = net(torch.real(xc).contiguous(), torch.tensor([1, 1]).to(dev))
+    assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------ samplers
+def case_sampler_uncond(dev):
+    g = G("samplers")
+    cfg = make_config("MNIST", 8, 28, 10, 20.0, device=dev)
+    net, _ = build_net(NCSNv2, "NCSNv2_ngf8_28", 3, cfg, dev)
+    sig = get_sigmas(cfg)
+    params = {"n_steps_each": 2, "step_lr": 6.2e-6, "denoise": True, "final_only": True}
+    draw = lambda shape: torch.randn(*shape)
+    torch.manual_seed(101)
+    res = ALD.ALDUnconditionalSampler((2, 1, 28, 28), net, sig, params, cfg, device=torch.device(dev))(noise_fn=draw)
+    assert len(res) == 1 and res[0].device.type == "cpu"
+    assert rel_l2(res[0], g["uncond_final"]) < TOL_X
+    torch.manual_seed(101)
+    x0 = torch.rand(2, 1, 28, 28).to(dev)
+    res2 = anneal_Langevin_dynamics(x0, net, sig, 2, 6.2e-6, final_only=True, noise_fn=draw)
+    assert rel_l2(res2[0], g["uncond_final"]) < TOL_X
+    assert not torch.is_grad_enabled()      # Q12: the samplers leave grad mode off
+    torch.set_grad_enabled(True)
+    # sde 'ald' corrector
+    sde = ns(N=10, T=1, marginal_prob=lambda x, t: (x, 0.01 * (20.0 / 0.01) ** t))
+    score_fn = lambda x, t: net(x, torch.round((1 - t) * 9).long())
+    torch.manual_seed(404)
+    x = torch.rand(2, 1, 28, 28).to(dev)
+    t = torch.tensor([0.6, 0.2]).to(dev)
+    xo, xm = AnnealedLangevinDynamics(sde, score_fn, snr=0.176, n_steps=3).update_fn(x, t, noise_fn=draw)
+    # three corrector steps whose update is score-dominated (step ~ 0.06, |x| ~ 1): the f16-operand
+    # rounding of the score (~1e-3) shows up at ~1e-4 in x, so this case gets 5e-4
+    assert rel_l2(xo.cpu(), g["sde_x"]) < 5e-4 and rel_l2(xm.cpu(), g["sde_mean"]) < 5e-4
+
+
+def case_sampler_sense(dev):
+    g = G("samplers")
+    n = 32
+    cfg = make_config("ACDC", 8, n, 10, 30.0, device=dev)
+    net, _ = build_net(NCSNv2Deepest, "NCSNv2Deepest_ngf8", 4, cfg, dev)
+    sig = get_sigmas(cfg, mode="recons")
+    A = SENSE("exp", 4, 40, 1 / 8, (1, n, n), 0)
+    A.random_under_fourier.mask = keep_center_mask(n, 4, 1 / 8, seed=0)
+    B = 2
+    meas = A(phantom(1401, 1, 1, n, n).to(dev)).repeat(1, B, 1, 1, 1)
+    params = {"n_steps_each": 2, "step_lr": 9e-7, "denoise": True, "final_only": True}
+    draw = lambda shape: torch.randn(*shape)
+    label = torch.zeros(B, 1, n, n, dtype=torch.long)
+    for tag, lr_scaled in (("lr1e6", 1e6), ("lr1", 1.0)):
+        sampler = ALD.ALDInvSegProximalRealImag(L2Penalty(A), 1.0, "linear", (B, 1, n, n), net, sig, params, cfg,
+                                                measurement=meas, linear_tfm=A, seg=None, device=torch.device(dev))
+        torch.manual_seed(202)
+        res = sampler(label=label, lamda=1.0, save_dir="/tmp", lr_scaled=lr_scaled, seg_mode="full", noise_fn=draw)
+        assert res[0].dtype == torch.complex64 and tuple(res[0].shape) == (B, 1, n, n)
+        assert rel_l2(res[0], g[f"sense_final_{tag}"]) < TOL_X, tag
+    torch.set_grad_enabled(True)
+    # the generic (non-fused) path through post_processing / self.proximal must agree with the fused kernel
+    class Hooked(ALD.ALDInvSegProximalRealImag):
+        def post_processing(self, xr, xi, **kw):
+            return super().post_processing(xr, xi, **kw)
+    sampler = Hooked(L2Penalty(A), 1.0, "linear", (B, 1, n, n), net, sig, params, cfg,
+                     measurement=meas, linear_tfm=A, seg=None, device=torch.device(dev))
+    torch.manual_seed(202)
+    res = sampler(label=label, lamda=1.0, save_dir="/tmp", lr_scaled=1.0, seg_mode="full", noise_fn=draw)
+    assert rel_l2(res[0], g["sense_final_lr1"]) < TOL_X
+    torch.set_grad_enabled(True)
+
+
+def case_sampler_cine(dev):
+    g = G("samplers")
+    n = 32
+    cfg = make_config("CINE127", 8, n, 10, 20.0, device=dev)
+    net, _ = build_net(NCSNv2Deepest, "NCSNv2Deepest_ngf8", 5, cfg, dev)
+    sig = get_sigmas(cfg, mode="recons")
+    A = SENSE("exp", 4, 16, 1 / 8, (1, n, n), 0)
+    meas = A(phantom(1402, 24, 1, n, n).to(dev)).reshape(4, 1, 24, 1, n, n)
+    net_T = ns(sigmas=None, config=ns(data=ns(channels=64)))
+    sig_T = torch.tensor(np.exp(np.linspace(np.log(5.0), np.log(0.01), 6))).float().to(dev)
+    params = {"n_steps_each": 1, "step_lr": 1e-4}
+    draw = lambda shape: torch.randn(*shape)
+    for mode_T in ("none", "tv"):
+        sampler = ALD.ALD2DTime(L2Penalty(A), net_T, sig_T, (1, 24, 1, n, n), net, sig, params, cfg,
+                                measurement=meas, linear_tfm=A, device=torch.device(dev))
+        assert tuple(net_T.sigmas.shape) == tuple(sig.shape)      # Q14: temporal net's sigmas are overwritten
+        torch.manual_seed(303)
+        res = sampler(save_dir="/tmp", lr_scaled=1e4, mode_T=mode_T, lamda_T=0.05, if_random_shift=False, noise_fn=draw)
+        assert tuple(res[0].shape) == (1, 24, 1, n, n)
+        # script-default step_lr = 1e-4 makes the first levels score-dominated (step*|score| ~ |x|), so the
+        # ~8e-4 f16-operand error of the score (the same for an f16-operand fp32-accumulate oracle,
+        # oracle.scorenet.OPERAND_ROUND) reaches x at ~3e-4; the 1e-4 bar applies to cfg-2 steps (case above)
+        assert rel_l2(res[0], g[f"cine_final_{mode_T}"]) < 1e-3, mode_T
+    torch.set_grad_enabled(True)
