@@ -1,0 +1,307 @@
+"""GPU suite (-m gpu): the CUDA path through the C ABI against the golden fixtures / the oracle."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import parity_cases as C
+from conftest import rel_l2
+from oracle import mri_ops as M, scorenet as SN, ald as OALD
+from oracle.fixture_inputs import crandn, rrand, rrandn, phantom
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _lib():
+    from inverseproblemwithdiffusionmodel_b200 import _lib
+    return _lib
+
+
+def test_library_is_native():
+    L = _lib()
+    assert L.lib().ipdm_abi_version() == 1
+    before = L.lib().ipdm_launch_count()
+    C.i2k_complex(torch.zeros(1, 1, 8, 8, dtype=torch.complex64, device=DEV))
+    torch.cuda.synchronize()
+    assert L.lib().ipdm_launch_count() == before + 2
+
+
+def test_fft():
+    C.case_fft(DEV)
+
+
+@pytest.mark.parametrize("H,W", [(8, 8), (16, 64), (128, 128), (256, 256), (512, 512), (64, 512), (512, 32)])
+def test_fft_sizes_vs_oracle(H, W):
+    x = crandn(H * 1000 + W, 3, 1, H, W)
+    assert rel_l2(C.i2k_complex(x.to(DEV)).cpu(), M.i2k(x)) < 1e-5
+    assert rel_l2(C.k2i_complex(x.to(DEV)).cpu(), M.k2i(x)) < 1e-5
+    # round trip
+    assert rel_l2(C.k2i_complex(C.i2k_complex(x.to(DEV))).cpu(), x) < 1e-5
+
+
+def test_fft_rejects_unsupported():
+    L = _lib()
+    with pytest.raises(L.IpdmError):
+        C.i2k_complex(torch.zeros(1, 1, 28, 28, dtype=torch.complex64, device=DEV))
+
+
+def test_sense_and_prox():
+    C.case_prox(DEV)
+    C.case_tv(DEV)
+
+
+@pytest.mark.parametrize("n,nc,B,R", [(128, 4, 3, 4), (256, 4, 2, 40), (256, 8, 1, 16), (512, 4, 1, 8)])
+def test_sense_full_size(n, nc, B, R):
+    """cfg-2 / cfg-5 sized operator: vs the oracle, plus the adjoint dot-product identity on masked data."""
+    A = C.SENSE("exp", nc, R, 1 / 64, (1, n, n), 0)
+    A.random_under_fourier.mask = C.keep_center_mask(n, R, 1 / 64, seed=0)
+    x = crandn(n + nc, B, 1, n, n)
+    S = A(x.to(DEV))
+    Sref = M.sense_forward(x, A.sens_maps, A.random_under_fourier.mask)
+    assert rel_l2(S.cpu(), Sref) < 1e-5
+    y = (A.random_under_fourier.mask * crandn(n + nc + 1, nc, B, 1, n, n)).to(torch.complex64)
+    adj = A.conj_op(y.to(DEV))
+    assert rel_l2(adj.cpu(), M.sense_adjoint(y, A.sens_maps)) < 1e-5
+    assert rel_l2(A.conj_op_masked(y.to(DEV)).cpu(), adj.cpu()) < 1e-6
+    lhs = torch.vdot(y.reshape(-1).to(DEV), S.reshape(-1))
+    rhs = torch.vdot(adj.reshape(-1), x.reshape(-1).to(DEV))
+    assert abs(lhs - rhs) / abs(lhs) < 1e-5
+    # linearity
+    x2 = crandn(n + nc + 2, B, 1, n, n).to(DEV)
+    assert rel_l2((A(x.to(DEV) + 2 * x2)).cpu(), (S + 2 * A(x2)).cpu()) < 1e-5
+
+
+def _conv_pair(N, H, W, Cin, Cout, taps, dil, flags, bias, residual, want32, want16, stats):
+    """Run igemm and direct kernels on the same operands; return both outputs."""
+    L = _lib()
+    g = torch.Generator().manual_seed(H * 7 + Cin + Cout + taps + dil + flags)
+    x16 = (torch.randn(N, H, W, Cin, generator=g)).half().to(DEV)
+    w16 = (torch.randn(Cout, taps, Cin, generator=g) / (taps * Cin) ** 0.5).half().to(DEV)
+    b = torch.randn(Cout, generator=g).to(DEV) if bias else None
+    pool = bool(flags & 8)
+    Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+    res = torch.randn(N, Ho, Wo, Cout, generator=g).to(DEV) if residual else None
+    outs = []
+    for fn in (L.lib().ipdm_conv_igemm, L.lib().ipdm_conv_direct):
+        o32 = torch.full((N, Ho, Wo, Cout), float("nan"), device=DEV) if want32 else None
+        o16 = torch.full((N, Ho, Wo, Cout), float("nan"), device=DEV, dtype=torch.float16) if want16 else None
+        st = torch.zeros(N, Cout, 2, device=DEV) if stats else None
+        d = L.ConvDesc(x16.data_ptr(), w16.data_ptr(), L.ptr(b), L.ptr(res), L.ptr(o32), L.ptr(o16), L.ptr(st),
+                       N, H, W, Cin, Cout, taps, dil, flags)
+        L.check(fn(ctypes.byref(d), L.stream()), "conv")
+        torch.cuda.synchronize()
+        outs.append((o32, o16, st))
+    return outs
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,taps,dil,flags,bias,residual", [
+    (1, 16, 16, 64, 128, 9, 1, 0, False, False),          # single tile, single k-chunk per tap
+    (2, 32, 32, 128, 128, 9, 1, 0, True, True),
+    (1, 32, 32, 256, 512, 9, 2, 0, True, False),          # dilation 2, 4 channel tiles
+    (1, 32, 32, 512, 256, 9, 4, 1, False, True),          # dilation 4, ELU'd f16
+    (1, 64, 64, 128, 256, 1, 1, 8, True, False),          # 1x1 + pool (ConvMeanPool shortcut)
+    (2, 64, 64, 128, 256, 9, 1, 8 | 1, True, True),       # 3x3 + pool + residual
+    (1, 14, 14, 256, 256, 9, 2, 4 | 2, False, True),      # partial tile (MNIST 14x14), CRP flags
+    (1, 40, 24, 128, 128, 9, 1, 1, True, True),           # ragged tiles both ways
+    (3, 128, 128, 128, 128, 9, 1, 0, False, True),        # many tiles
+])
+def test_conv_igemm_vs_direct(N, H, W, Cin, Cout, taps, dil, flags, bias, residual):
+    (a32, a16, ast), (b32, b16, bst) = _conv_pair(N, H, W, Cin, Cout, taps, dil, flags, bias, residual, True, True, True)
+    assert not torch.isnan(a32).any() and not torch.isnan(a16.float()).any()
+    assert rel_l2(a32.cpu(), b32.cpu()) < 1e-5      # fp32 accumulation order over K = taps*Cin differs
+    assert rel_l2(a16.float().cpu(), b16.float().cpu()) < 1e-3       # f16 rounding-boundary flips only
+    HW = a32.shape[1] * a32.shape[2]
+    ref_st = torch.stack([b32.reshape(N, HW, Cout).sum(1), (b32 ** 2).reshape(N, HW, Cout).sum(1)], dim=-1)
+    assert rel_l2(ast.cpu(), ref_st.cpu()) < 1e-5
+    assert rel_l2(bst.cpu(), ref_st.cpu()) < 1e-5
+
+
+def test_conv_direct_vs_torch():
+    """Anchor of the chain igemm -> direct -> torch: the CUDA-core kernel against F.conv2d on the same f16 operands."""
+    import torch.nn.functional as F
+    L = _lib()
+    g = torch.Generator().manual_seed(3)
+    N, H, W, Cin, Cout = 2, 12, 20, 16, 24
+    x16 = torch.randn(N, H, W, Cin, generator=g).half()
+    w16 = (torch.randn(Cout, 9, Cin, generator=g) / 12).half()
+    b = torch.randn(Cout, generator=g)
+    o32 = torch.empty(N, H, W, Cout, device=DEV)
+    d = L.ConvDesc(x16.to(DEV).data_ptr(), 0, 0, 0, 0, 0, 0, N, H, W, Cin, Cout, 9, 2, 0)
+    xd, wd, bd = x16.to(DEV), w16.to(DEV), b.to(DEV)
+    d = L.ConvDesc(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), None, o32.data_ptr(), None, None, N, H, W, Cin, Cout, 9, 2, 0)
+    L.check(L.lib().ipdm_conv_direct(ctypes.byref(d), L.stream()), "conv_direct")
+    ref = F.conv2d(x16.float().permute(0, 3, 1, 2), w16.float().permute(0, 2, 1).reshape(Cout, Cin, 3, 3), b, padding=2, dilation=2)
+    assert rel_l2(o32.cpu(), ref.permute(0, 2, 3, 1)) < 2e-6
+
+
+def test_scorenet_small():
+    C.case_scorenet_small(DEV)
+
+
+def _full_width_net(cls, arch, size, seed, num_classes=12, sigma_begin=30.0):
+    cfg = C.make_config("ACDC", 128, size, num_classes, sigma_begin, device=DEV)
+    net = cls(cfg)
+    spec = [(k, tuple(v.shape)) for k, v in net.state_dict().items()]
+    Pd = SN.synth_state_dict(spec, seed, net.sigmas.cpu())
+    net.load_state_dict(Pd)
+    return net.to(DEV).eval(), Pd, cfg
+
+
+def test_scorenet_ngf128_tensor_core_path():
+    """ngf = 128: every inner convolution goes through the tcgen05 implicit GEMM."""
+    L = _lib()
+    net, Pd, cfg = _full_width_net(C.NCSNv2Deepest, "NCSNv2Deepest", 32, 21)
+    x = rrand(77, 2, 1, 32, 32) * 2 - 0.5
+    y = torch.tensor([0, 9])
+    before = L.lib().ipdm_launch_count()
+    out = net(x.to(DEV), y.to(DEV)).cpu()
+    with torch.no_grad():
+        ref = SN.score_forward("NCSNv2Deepest", Pd, x, y)
+    assert rel_l2(out, ref) < C.TOL_SCORE
+    assert L.lib().ipdm_launch_count() - before > 150
+    net2, Pd2, _ = _full_width_net(C.NCSNv2, "NCSNv2", 28, 22)
+    x = rrand(78, 2, 1, 28, 28)
+    out = net2(x.to(DEV), y.to(DEV)).cpu()
+    with torch.no_grad():
+        ref = SN.score_forward("NCSNv2", Pd2, x, y)
+    assert rel_l2(out, ref) < C.TOL_SCORE
+
+
+def test_single_ald_step_ngf128():
+    """north_star: a single cfg-2 ALD step (2 score forwards + update + prox) within 1e-4 relative L2,
+    at the first level from x0 = A^H y (the hardest state) and in the steady state."""
+    n, B = 64, 2
+    net, Pd, cfg = _full_width_net(C.NCSNv2Deepest, "NCSNv2Deepest", n, 23, num_classes=2311, sigma_begin=348.0)
+    sig = C.get_sigmas(cfg, mode="recons")
+    A = C.SENSE("exp", 4, 40, 1 / 16, (1, n, n), 0)
+    A.random_under_fourier.mask = C.keep_center_mask(n, 40, 1 / 16, seed=0)
+    meas = A(phantom(11, 1, 1, n, n).to(DEV)).repeat(1, B, 1, 1, 1)
+    maps, mask = A.sens_maps, A.random_under_fourier.mask
+    score = lambda x, y: SN.score_forward("NCSNv2Deepest", Pd, x, y)
+    prox = lambda z, y, a, l: M.l2_prox_sense_closed_form(z, y, maps, mask, a, l)
+    adj = lambda s: M.sense_adjoint(s, maps)
+    draw = lambda shape: torch.randn(*shape)
+    params = {"n_steps_each": 1, "step_lr": 9e-7, "denoise": False, "final_only": True}
+    for levels in (sig[:1], sig[1155:1156], sig[-1:]):
+        # a two-entry schedule holding the same sigma twice: install it as the net's own sigma table so the
+        # score is divided by the right sigma, and fold (sigma/sigma_L)^2 into step_lr (the loop sees ratio 1)
+        lv2 = levels.repeat(2)
+        net.sigmas = lv2.to(DEV)
+        Pd["sigmas"] = lv2.cpu()
+        ratio2 = float((levels[0] / sig[-1]) ** 2)
+        sampler = C.ALD.ALDInvSegProximalRealImag(C.L2Penalty(A), 1.0, "linear", (B, 1, n, n), net, lv2.to(DEV),
+                                                  dict(params, step_lr=9e-7 * ratio2), cfg,
+                                                  measurement=meas, linear_tfm=A, seg=None, device=torch.device(DEV))
+        torch.manual_seed(6)
+        got = sampler(label=None, lamda=1.0, save_dir="/tmp", lr_scaled=1e6 / ratio2, seg_mode="full", noise_fn=draw)[0]
+        torch.manual_seed(6)
+        with torch.no_grad():
+            ref = OALD.ald_sense_real_imag(score, meas.cpu(), lv2.cpu(), 1, 9e-7 * ratio2, 1e6 / ratio2, adj, prox, denoise=False)
+        torch.set_grad_enabled(True)
+        assert rel_l2(got, ref) < 1e-4, float(levels[0])
+
+
+def test_fused_step_kernel_vs_oracle_256():
+    """ipdm_ald_sense_step on a cfg-2 sized state (256x256, 4 coils, R=40) against the closed form."""
+    L = _lib()
+    n, B = 256, 3
+    A = C.SENSE("exp", 4, 40, 1 / 64, (1, n, n), 0)
+    A.random_under_fourier.mask = C.keep_center_mask(n, 40, 1 / 64, seed=0)
+    x = crandn(1, B, 1, n, n)
+    g = crandn(2, B, 1, n, n)
+    nz = crandn(3, B, 1, n, n)
+    y = M.sense_forward(crandn(4, B, 1, n, n), A.sens_maps, A.random_under_fourier.mask)
+    step, kappa = 0.37, 0.8
+    ns = float(torch.sqrt(torch.tensor(step) * 2))
+    z = x + step * g + ns * nz
+    ref = M.l2_prox_sense_closed_form(z, y, A.sens_maps, A.random_under_fourier.mask, kappa * 4 * n / 0.05, 1.0)
+    planar = lambda c: torch.stack([c.real.reshape(B, n, n), c.imag.reshape(B, n, n)]).contiguous().to(DEV)
+    state, grad, noise = planar(x), planar(g), planar(nz)
+    bvec = planar(M.sense_adjoint(y, A.sens_maps))
+    mre, mim = A.device_maps(torch.device(DEV))
+    m, frames = A.device_mask(torch.device(DEV))
+    sc = L.AldScalars(step, ns, kappa, 0.0)
+    L.check(L.lib().ipdm_ald_sense_step(state.data_ptr(), grad.data_ptr(), noise.data_ptr(), bvec.data_ptr(), mre.data_ptr(), None,
+                                        m.data_ptr(), frames, 4, B, n, n, sc, None, None, 0, 0, L.stream()), "ald_sense_step")
+    got = torch.complex(state[0], state[1]).cpu().reshape(B, 1, n, n)
+    assert rel_l2(got, ref) < 1e-5
+    assert rel_l2(got - z, ref - z) < 1e-4
+
+
+def test_philox_noise_statistics_and_graph_replay():
+    """In-kernel noise: N(0,1) moments, reproducible per (seed, step), different across steps; the
+    captured-graph fast path equals the eager path step for step (same Philox keys)."""
+    L = _lib()
+    n = 1 << 20
+    x = torch.zeros(n, device=DEV)
+    g = torch.zeros(n, device=DEV)
+    sc = L.AldScalars(0.5, 1.0, 0.0, 0.0)
+    call = lambda buf, seed, k: L.check(L.lib().ipdm_langevin_update(buf.data_ptr(), g.data_ptr(), None, None, n, sc, None, None, None, 0, seed, k, L.stream()), "langevin")
+    call(x, 42, 0)
+    assert abs(float(x.mean())) < 5e-3 and abs(float(x.var()) - 1) < 1e-2
+    assert abs(float((x ** 4).mean()) - 3) < 0.1
+    x2 = torch.zeros(n, device=DEV)
+    call(x2, 42, 0)
+    assert torch.equal(x, x2)
+    x3 = torch.zeros(n, device=DEV)
+    call(x3, 42, 1)
+    assert abs(float((x * x3).mean())) < 5e-3
+    # fast (graph) path vs eager path of the cfg-1 sampler with Philox noise
+    cfg = C.make_config("MNIST", 8, 28, 10, 20.0, device=DEV)
+    net, _ = C.build_net(C.NCSNv2, "NCSNv2_ngf8_28", 3, cfg, DEV)
+    sig = C.get_sigmas(cfg)
+    params = {"n_steps_each": 2, "step_lr": 6.2e-6, "denoise": True, "final_only": True}
+    x0 = rrand(5, 2, 1, 28, 28)
+    s = C.ALD.ALDUnconditionalSampler((2, 1, 28, 28), net, sig, params, cfg, device=torch.device(DEV))
+    a = s(seed=9, x_init=x0, cuda_graph=True)[0]
+    b = s(seed=9, x_init=x0, cuda_graph=False)[0]
+    torch.set_grad_enabled(True)
+    assert s.launches_per_step is not None and s.launches_per_step > 50
+    assert rel_l2(a, b) < 1e-5
+
+
+def test_sampler_uncond():
+    C.case_sampler_uncond(DEV)
+
+
+def test_sampler_sense():
+    C.case_sampler_sense(DEV)
+
+
+def test_sampler_cine():
+    C.case_sampler_cine(DEV)
+
+
+def test_sense_sampler_graph_path_matches_eager():
+    n, B = 32, 3
+    cfg = C.make_config("ACDC", 8, n, 10, 30.0, device=DEV)
+    net, _ = C.build_net(C.NCSNv2Deepest, "NCSNv2Deepest_ngf8", 4, cfg, DEV)
+    sig = C.get_sigmas(cfg, mode="recons")
+    A = C.SENSE("exp", 4, 40, 1 / 8, (1, n, n), 0)
+    A.random_under_fourier.mask = C.keep_center_mask(n, 4, 1 / 8, seed=0)
+    meas = A(phantom(1401, 1, 1, n, n).to(DEV)).repeat(1, B, 1, 1, 1)
+    params = {"n_steps_each": 3, "step_lr": 9e-7, "denoise": True, "final_only": True}
+    mk = lambda: C.ALD.ALDInvSegProximalRealImag(C.L2Penalty(A), 1.0, "linear", (B, 1, n, n), net, sig, params, cfg,
+                                                 measurement=meas, linear_tfm=A, seg=None, device=torch.device(DEV))
+    a = mk()(label=None, lamda=1., save_dir="/tmp", lr_scaled=1e6, seg_mode="full", seed=3, cuda_graph=True)[0]
+    b = mk()(label=None, lamda=1., save_dir="/tmp", lr_scaled=1e6, seg_mode="full", seed=3, cuda_graph=False)[0]
+    torch.set_grad_enabled(True)
+    assert rel_l2(a, b) < 1e-5
+    # chains do not interact: chain 0 of a 3-chain batch == the same chain run alone?  (Philox keys are
+    # element-indexed within the batch, so only the first plane-offset-free chain is comparable)
+    assert torch.isfinite(a.abs()).all()
+
+
+def test_posterior_stats_kernel():
+    from inverseproblemwithdiffusionmodel_b200.chains import PosteriorStats
+    x = crandn(5, 7, 1, 16, 16)
+    st = PosteriorStats(256, torch.device(DEV))
+    st.add(x[:3].to(DEV))
+    st.add(x[3:].to(DEV))
+    out = st.finalize((16, 16))
+    ref = OALD.posterior_stats(x)
+    for k in ("mag_mean", "mag_std", "phase_mean", "phase_std"):
+        assert torch.allclose(out[k].cpu(), ref[k].reshape(16, 16), atol=2e-5), k
+    assert out["n"] == 7
