@@ -38,8 +38,13 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 128 /*barriers*/;
 constexpr int TMEM_COLS = 256;
 constexpr int NTHREADS = 192;
+constexpr int EPI_PITCH = BLOCK_M + 4;   // floats per slab row: +4 keeps float4 alignment and staggers banks
 
 __device__ unsigned int g_igemm_timeout = 0;
+
+// ELU for the epilogue: exp via the SFU (absolute error ~1e-7 near 0, far below the f16 rounding that
+// follows); keeps the unrolled epilogue small enough to stay in the instruction cache.
+__device__ __forceinline__ float elu_fast(float v) { return v > 0.f ? v : __expf(v) - 1.0f; }
 
 // ---------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -139,8 +144,12 @@ struct IgemmParams {
   int tiles_w, tiles_h;
 };
 
+// MODE bits: 1 = residual, 2 = fp32 output, 4 = f16 output, 8 = 2x2 mean-pool (compile-time so the
+// epilogue of each variant stays small; the ELU / pre-residual choices are cheap runtime selects).
+template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 2)
 k_conv_igemm(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, IgemmParams p) {
+  constexpr bool kRes = (MODE & 1) != 0, kOut32 = (MODE & 2) != 0, kOut16 = (MODE & 4) != 0, kPool = (MODE & 8) != 0;
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -218,13 +227,26 @@ k_conv_igemm(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
       umma_commit(tmem_full_bar);    // accumulator complete
     }
   } else {
-    // ===== epilogue: thread = output channel, columns = the 256 pixels of the tile =====
+    // ===== epilogue =====
+    // TMEM lane = output channel, column = pixel.  Each warp pulls 32 columns (two pixel rows of the
+    // tile) for its 32 channels, transposes them through shared memory (the pipeline stages are idle
+    // once the accumulator is complete), and the four warps then stream the [pixels][128 ch] slab
+    // with 16-byte accesses: thread = 4 consecutive channels of one pixel, so a warp touches one
+    // whole 512-byte pixel row of the NHWC tensor per instruction.  Double-buffered slab, one named
+    // barrier per chunk.  All residual loads of a chunk are issued before the first dependent use.
     const int quad = warp & 3;
-    const int co = m0 + quad * 32 + lane;
-    const bool pool = (p.flags & IPDM_CONV_POOL2) != 0;
+    const int te = quad * 32 + lane;          // 0..127 within the epilogue group
+    const int c4 = (te & 31) * 4;             // first of this thread's 4 channels (within the 128)
+    const int prow = te >> 5;                 // pixel sub-row 0..3
+    constexpr bool pool = kPool;
     const int Ho = pool ? p.H / 2 : p.H, Wo = pool ? p.W / 2 : p.W;
-    const float bias_v = p.bias ? p.bias[co] : 0.f;
-    float s1 = 0.f, s2 = 0.f;
+    const int oy0 = pool ? h0 / 2 : h0, ox0 = pool ? w0 / 2 : w0;
+    const int tw_out = pool ? TILE_W / 2 : TILE_W;          // output pixels per tile row
+    const int npix = pool ? 8 : 32;                         // output pixels per chunk
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias) bias4 = *reinterpret_cast<const float4*>(p.bias + m0 + c4);
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    float* slab = reinterpret_cast<float*>(smem);           // [2][32][EPI_PITCH]
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
@@ -232,59 +254,78 @@ k_conv_igemm(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
     for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
       float v[32];
       tmem_ld32(taddr + chunk * 32, v);
-      const int py = 2 * chunk;  // two pixel rows of the tile per chunk
+      float* buf = slab + (chunk & 1) * (32 * EPI_PITCH);
       if (!pool) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int y = h0 + py + (j >> 4), x = w0 + (j & 15);
-          if (y < p.H && x < p.W) {
-            const size_t o = (((size_t)n * p.H + y) * p.W + x) * p.Cout + co;
-            float val = v[j] + bias_v;
-            const float pre = val;
-            if (p.residual) {
-              float r = p.residual[o];
-              if (p.flags & IPDM_CONV_RES_ELU) r = elu1(r);
-              val += r;
-            }
-            if (p.out_f32) p.out_f32[o] = val;
-            if (p.out_f16) {
-              float s = (p.flags & IPDM_CONV_F16_PRE_RES) ? pre : val;
-              if (p.flags & IPDM_CONV_F16_ELU) s = elu1(s);
-              p.out_f16[o] = __float2half_rn(s);
-            }
-            s1 += val;
-            s2 += val * val;
-          }
-        }
+        for (int j = 0; j < 32; ++j) buf[j * EPI_PITCH + te] = v[j];
       } else {
-        const int y = (h0 + py) >> 1;
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const int x = (w0 >> 1) + jj;
-          if (y < Ho && x < Wo) {
-            const size_t o = (((size_t)n * Ho + y) * Wo + x) * p.Cout + co;
-            float val = (((v[2 * jj] + v[16 + 2 * jj]) + v[2 * jj + 1]) + v[16 + 2 * jj + 1]) * 0.25f + bias_v;
-            const float pre = val;
-            if (p.residual) {
-              float r = p.residual[o];
-              if (p.flags & IPDM_CONV_RES_ELU) r = elu1(r);
-              val += r;
+        for (int jj = 0; jj < 8; ++jj)
+          buf[jj * EPI_PITCH + te] = (((v[2 * jj] + v[16 + 2 * jj]) + v[2 * jj + 1]) + v[16 + 2 * jj + 1]) * 0.25f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // consume: pixel q = prow + 4*i of the chunk, four pixels per (rolled) half
+      const int halves = pool ? 1 : 2;
+#pragma unroll 1
+      for (int half = 0; half < halves; ++half) {
+        float4 res[4];
+        size_t off[4];
+        bool ok[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int q = prow + 4 * (half * 4 + i);
+          const int yy = oy0 + (pool ? chunk : 2 * chunk + (q >> 4));
+          const int xx = ox0 + (pool ? q : (q & 15));
+          ok[i] = q < npix && yy < Ho && xx < Wo;
+          off[i] = (((size_t)n * Ho + yy) * Wo + xx) * p.Cout + m0 + c4;
+          if (kRes && ok[i]) res[i] = *reinterpret_cast<const float4*>(p.residual + off[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (ok[i]) {
+            const int q = prow + 4 * (half * 4 + i);
+            float4 a = *reinterpret_cast<const float4*>(buf + q * EPI_PITCH + c4);
+            a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
+            const float4 pre = a;
+            if (kRes) {
+              float4 r = res[i];
+              if (p.flags & IPDM_CONV_RES_ELU) { r.x = elu_fast(r.x); r.y = elu_fast(r.y); r.z = elu_fast(r.z); r.w = elu_fast(r.w); }
+              a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
             }
-            if (p.out_f32) p.out_f32[o] = val;
-            if (p.out_f16) {
-              float s = (p.flags & IPDM_CONV_F16_PRE_RES) ? pre : val;
-              if (p.flags & IPDM_CONV_F16_ELU) s = elu1(s);
-              p.out_f16[o] = __float2half_rn(s);
+            if (kOut32) *reinterpret_cast<float4*>(p.out_f32 + off[i]) = a;
+            if (kOut16) {
+              float4 h = (p.flags & IPDM_CONV_F16_PRE_RES) ? pre : a;
+              if (p.flags & IPDM_CONV_F16_ELU) { h.x = elu_fast(h.x); h.y = elu_fast(h.y); h.z = elu_fast(h.z); h.w = elu_fast(h.w); }
+              __half2 lo = __floats2half2_rn(h.x, h.y), hi = __floats2half2_rn(h.z, h.w);
+              uint2 pk;
+              pk.x = *reinterpret_cast<unsigned*>(&lo);
+              pk.y = *reinterpret_cast<unsigned*>(&hi);
+              *reinterpret_cast<uint2*>(p.out_f16 + off[i]) = pk;
             }
-            s1 += val;
-            s2 += val * val;
+            s1[0] += a.x; s1[1] += a.y; s1[2] += a.z; s1[3] += a.w;
+            s2[0] += a.x * a.x; s2[1] += a.y * a.y; s2[2] += a.z * a.z; s2[3] += a.w * a.w;
           }
         }
       }
     }
     if (p.stats) {
-      atomicAdd(&p.stats[((size_t)n * p.Cout + co) * 2], s1);
-      atomicAdd(&p.stats[((size_t)n * p.Cout + co) * 2 + 1], s2);
+      // combine the four pixel sub-rows that share a channel group, then 2 atomics per channel
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float* red = slab;                                    // [4][128][2]
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        red[(prow * 128 + c4 + k) * 2] = s1[k];
+        red[(prow * 128 + c4 + k) * 2 + 1] = s2[k];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        t1 += red[(r * 128 + te) * 2];
+        t2 += red[(r * 128 + te) * 2 + 1];
+      }
+      atomicAdd(&p.stats[((size_t)n * p.Cout + m0 + te) * 2], t1);
+      atomicAdd(&p.stats[((size_t)n * p.Cout + m0 + te) * 2 + 1], t2);
     }
   }
   tcgen05_fence_before();
@@ -379,11 +420,7 @@ extern "C" int ipdm_conv_igemm(const ipdm_conv_desc* dh, void* stream) {
   CUtensorMap mw, mx;
   if (int e = weight_map(d.w_f16, d.Cout, d.taps * d.Cin, &mw)) return e;
   if (int e = act_map(d.in_f16, d.N, d.H, d.W, d.Cin, &mx)) return e;
-  static bool attr_set = false;
-  if (!attr_set) {
-    IPDM_CUDA(cudaFuncSetAttribute(k_conv_igemm, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
+  const int mode = (d.residual ? 1 : 0) | (d.out_f32 ? 2 : 0) | (d.out_f16 ? 4 : 0) | (pool ? 8 : 0);
   if (d.stats) {
     IPDM_CUDA(cudaMemsetAsync(d.stats, 0, (size_t)d.N * d.Cout * 2 * sizeof(float), s));
   }
@@ -394,6 +431,22 @@ extern "C" int ipdm_conv_igemm(const ipdm_conv_desc* dh, void* stream) {
   p.tiles_w = (d.W + TILE_W - 1) / TILE_W;
   p.tiles_h = (d.H + TILE_H - 1) / TILE_H;
   dim3 grid(p.tiles_w * p.tiles_h * d.N, d.Cout / BLOCK_M);
-  k_conv_igemm<<<grid, NTHREADS, SMEM_BYTES, s>>>(mw, mx, p);
+  static bool attr_set[16] = {};
+#define IGEMM_CASE(M)                                                                                           \
+  case M:                                                                                                       \
+    if (!attr_set[M]) {                                                                                         \
+      IPDM_CUDA(cudaFuncSetAttribute(k_conv_igemm<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
+      attr_set[M] = true;                                                                                       \
+    }                                                                                                           \
+    k_conv_igemm<M><<<grid, NTHREADS, SMEM_BYTES, s>>>(mw, mx, p);                                              \
+    break;
+  switch (mode) {
+    IGEMM_CASE(2) IGEMM_CASE(3) IGEMM_CASE(4) IGEMM_CASE(5) IGEMM_CASE(6) IGEMM_CASE(7)
+    IGEMM_CASE(10) IGEMM_CASE(11) IGEMM_CASE(12) IGEMM_CASE(13) IGEMM_CASE(14) IGEMM_CASE(15)
+    default:
+      set_error("conv_igemm: unsupported output combination %d", mode);
+      return IPDM_E_BADARG;
+  }
+#undef IGEMM_CASE
   return launched("k_conv_igemm");
 }
