@@ -155,10 +155,15 @@ typedef struct {
                                      (ConvMeanPool, layers.py:309-313)                                    */
 
 /* 3x3 (dilated) / 1x1 stride-1 convolution as a tcgen05 implicit GEMM: M = N*H*W pixels (8x16-pixel
- * tiles), N = Cout, K = taps*Cin; TMA-fed, fp32 accumulators in TMEM.  Cin % 64 == 0, Cout % 64 == 0.
+ * tiles), N = Cout, K = taps*Cin; TMA-fed, fp32 accumulators in TMEM.  Cin % 64 == 0, Cout % 128 == 0.
  * Replaces nn.Conv2d inside ResidualBlock / RCUBlock / CRPBlock / MSFBlock / ConvMeanPool
  *   (ncsn/models/layers.py:28-60,62-83,112-134,165-184,291-313,401-456). */
 int ipdm_conv_igemm(const ipdm_conv_desc* desc_host, void* stream);
+
+/* Diagnostics knob (tests / profiling only): key 1 = convolution kernel variant (0 auto: persistent
+ * halo-tile kernel for 3x3 with dilation <= 2, per-tap tile kernel otherwise; 1 = always the per-tap
+ * kernel), key 2 reserved. */
+int ipdm_debug_option(int key, int value);
 
 /* Same contract on CUDA cores, any Cin/Cout (used for narrow test nets and as the on-device
  * cross-check of the tensor-core kernel; not used by the product path when the igemm applies). */

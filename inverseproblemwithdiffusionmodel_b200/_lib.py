@@ -48,6 +48,7 @@ SIGNATURES = {
     "ipdm_chain_stats_accumulate": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p]),
     "ipdm_conv_igemm": (c_int, [POINTER(ConvDesc), c_void_p]),
     "ipdm_conv_direct": (c_int, [POINTER(ConvDesc), c_void_p]),
+    "ipdm_debug_option": (c_int, [c_int, c_int]),
     "ipdm_conv_first": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ipdm_conv_last": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "ipdm_instnorm_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -1,0 +1,236 @@
+// 3x3 (dilation 1 or 2) convolution as a PERSISTENT tcgen05 implicit GEMM with halo-tile reuse.
+//
+// The per-tap kernel (conv_igemm.cu) re-fetches the 256-pixel activation tile for each of the 9 taps:
+// 864 KB of L2->SM traffic per (256 pixel x 128 channel) accumulator at Cin = 128, which made it
+// L2-bandwidth bound (~9 TB/s measured).  Here the activation tile is fetched ONCE per 64-channel chunk
+// together with its halo, and the nine taps are nine shared-memory *views* of that one buffer:
+//
+//   pixel tile = 32 rows x 8 columns (UMMA N = 256: 32 groups of 8 pixels, one group per tile row)
+//   halo buffer = (32 + 2d) rows x 16 pixel slots x 64 ch f16 -> row pitch 2048 B (a multiple of the
+//                 1024-byte SWIZZLE_128B pattern), filled by one 4-D TMA box {64, 16, 32+2d, 1}
+//   tap (ky,kx) = UMMA smem descriptor with start = halo + ky*d*2048 + kx*d*128, stride between 8-row
+//                 groups (SBO) = 2048 B (the swizzle XOR follows the absolute smem address, so a start that
+//                 is not on a 1024-byte pattern boundary needs no base-offset correction: measured)
+//
+// so L2->SM traffic per accumulator drops to 2 x 70 KB (activations) + 288 KB (weights).  Weights stream
+// through their own 3-slot ring (one 128 x 64 tile per tap).  The CTA is persistent (one per SM): TMEM
+// holds two 256-column accumulators so the epilogue of item i overlaps the MMAs of item i+1, and the TMA
+// producers run ahead across item boundaries.
+//
+// Warps (352 threads): 0 = halo TMA, 1 = MMA issuer + TMEM owner, 2 = weight TMA, 3-6 = epilogue team A
+// (columns 0-127), 7-10 = epilogue team B (columns 128-255); each team has its own slab and named barrier.
+#include "conv_common.cuh"
+
+namespace ipdm {
+
+constexpr int HT_H = 32, HT_W = 8;            // pixel tile
+constexpr int HALO_SLOTS = 16;                // pixel slots per halo row (8 + 2d used)
+constexpr int HALO_PITCH = HALO_SLOTS * 128;  // 2048 B
+constexpr int NH = 2;                         // halo ring
+constexpr int NW = 3;                         // weight ring
+constexpr int W_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr int HALO_THREADS = 352;
+
+template <int DIL> struct HaloCfg {
+  static constexpr int ROWS = HT_H + 2 * DIL;
+  static constexpr int HALO_BYTES = ROWS * HALO_PITCH;
+  static constexpr int SMEM = NH * HALO_BYTES + NW * W_BYTES + SLAB_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct HaloParams {
+  IgemmParams g;
+  int items, mtiles;
+};
+
+template <int MODE, int DIL>
+__global__ void __launch_bounds__(HALO_THREADS, 1)
+k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, HaloParams hp) {
+  using CFG = HaloCfg<DIL>;
+  const IgemmParams& p = hp.g;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* halo = smem;
+  unsigned char* wts = smem + NH * CFG::HALO_BYTES;
+  float* slab = reinterpret_cast<float*>(wts + NW * W_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(slab) + SLAB_BYTES);
+  uint64_t* halo_full = bars;             // [NH]
+  uint64_t* halo_empty = bars + NH;       // [NH]
+  uint64_t* w_full = bars + 2 * NH;       // [NW]
+  uint64_t* w_empty = w_full + NW;        // [NW]
+  uint64_t* acc_full = w_empty + NW;      // [2]
+  uint64_t* acc_empty = acc_full + 2;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kchunks = p.Cin / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+    for (int i = 0; i < NH; ++i) { mbar_init(&halo_full[i], 1); mbar_init(&halo_empty[i], 1); }
+    for (int i = 0; i < NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int item, int& n, int& h0, int& w0, int& m0) {
+    const int mt = item % hp.mtiles;
+    int tile = item / hp.mtiles;
+    const int tw = tile % p.tiles_w; tile /= p.tiles_w;
+    const int th = tile % p.tiles_h; tile /= p.tiles_h;
+    n = tile; h0 = th * HT_H; w0 = tw * HT_W; m0 = mt * BLOCK_M;
+  };
+
+  if (warp == 0) {
+    // ===== halo producer: one TMA box per (item, 64-channel chunk) =====
+    if (lane == 0) {
+      uint32_t cnt = 0;
+      for (int item = blockIdx.x; item < hp.items; item += gridDim.x) {
+        int n, h0, w0, m0;
+        decode(item, n, h0, w0, m0);
+        for (int kc = 0; kc < kchunks; ++kc, ++cnt) {
+          const int s = cnt % NH;
+          mbar_wait(&halo_empty[s], ((cnt / NH) & 1) ^ 1);
+          mbar_expect_tx(&halo_full[s], CFG::HALO_BYTES);
+          tma_load_4d(halo + s * CFG::HALO_BYTES, &tmap_x, &halo_full[s], kc * BLOCK_K, w0 - DIL, h0 - DIL, n);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===== weight producer: one 128 x 64 tile per (item, chunk, tap) =====
+    if (lane == 0) {
+      uint32_t cnt = 0;
+      for (int item = blockIdx.x; item < hp.items; item += gridDim.x) {
+        int n, h0, w0, m0;
+        decode(item, n, h0, w0, m0);
+        for (int kc = 0; kc < kchunks; ++kc) {
+          for (int tap = 0; tap < 9; ++tap, ++cnt) {
+            const int s = cnt % NW;
+            mbar_wait(&w_empty[s], ((cnt / NW) & 1) ^ 1);
+            mbar_expect_tx(&w_full[s], W_BYTES);
+            tma_load_2d(wts + s * W_BYTES, &tmap_w, &w_full[s], tap * p.Cin + kc * BLOCK_K, m0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+      uint32_t hcnt = 0, wcnt = 0, acnt = 0;
+      for (int item = blockIdx.x; item < hp.items; item += gridDim.x, ++acnt) {
+        const int as = acnt & 1;
+        mbar_wait(&acc_empty[as], ((acnt >> 1) & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tacc = tmem_base + as * BLOCK_N;
+        for (int kc = 0; kc < kchunks; ++kc, ++hcnt) {
+          const int hs = hcnt % NH;
+          mbar_wait(&halo_full[hs], (hcnt / NH) & 1);
+          const uint32_t hbase = smem_u32(halo + hs * CFG::HALO_BYTES);
+          for (int tap = 0; tap < 9; ++tap, ++wcnt) {
+            const int ws = wcnt % NW;
+            mbar_wait(&w_full[ws], (wcnt / NW) & 1);
+            tcgen05_fence_after();
+            const int dy = (tap / 3) * DIL, dx = (tap % 3) * DIL;
+            const uint64_t adesc = make_smem_desc(smem_u32(wts + ws * W_BYTES));
+            const uint64_t bdesc = make_smem_desc(hbase + dy * HALO_PITCH + dx * 128, HALO_PITCH);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_f16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | tap | k) != 0);
+            umma_commit(&w_empty[ws]);
+          }
+          umma_commit(&halo_empty[hs]);
+        }
+        umma_commit(&acc_full[as]);
+      }
+    }
+  } else {
+    // ===== epilogue teams (TMEM lane quadrant = warp % 4): A = warps 3-6, B = warps 7-10 =====
+    const int quad = warp & 3;
+    const int team = warp >= 7 ? 1 : 0;
+    float* my_slab = slab + team * (32 * EPI_PITCH);
+    uint32_t acnt = 0;
+    for (int item = blockIdx.x; item < hp.items; item += gridDim.x, ++acnt) {
+      int n, h0, w0, m0;
+      decode(item, n, h0, w0, m0);
+      const int as = acnt & 1;
+      mbar_wait(&acc_full[as], (acnt >> 1) & 1);
+      tcgen05_fence_after();
+      if (team == 0) conv_epilogue<MODE, HT_W, 1, 1, 4>(p, my_slab, tmem_base + as * BLOCK_N, quad, lane, n, h0, w0, m0, 0);
+      else conv_epilogue<MODE, HT_W, 2, 1, 4>(p, my_slab, tmem_base + as * BLOCK_N, quad, lane, n, h0, w0, m0, 4);
+      // all of this warp's TMEM reads are complete (tcgen05.wait::ld inside): hand the accumulator back
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+template <int MODE, int DIL>
+static int launch_variant(const CUtensorMap& mw, const CUtensorMap& mx, const HaloParams& hp, int grid, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    IPDM_CUDA(cudaFuncSetAttribute(k_conv_halo<MODE, DIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<DIL>::SMEM));
+    attr_set = true;
+  }
+  k_conv_halo<MODE, DIL><<<grid, HALO_THREADS, HaloCfg<DIL>::SMEM, s>>>(mw, mx, hp);
+  return 0;
+}
+
+int launch_conv_halo(const ipdm_conv_desc& d, cudaStream_t s) {
+  const bool pool = (d.flags & IPDM_CONV_POOL2) != 0;
+  CUtensorMap mw, mx;
+  if (int e = get_weight_map(d.w_f16, d.Cout, 9 * d.Cin, &mw)) return e;
+  if (int e = get_act_map(d.in_f16, d.N, d.H, d.W, d.Cin, HALO_SLOTS, HT_H + 2 * d.dilation, &mx)) return e;
+  if (d.stats) IPDM_CUDA(cudaMemsetAsync(d.stats, 0, (size_t)d.N * d.Cout * 2 * sizeof(float), s));
+  HaloParams hp{};
+  IgemmParams& p = hp.g;
+  p.bias = d.bias; p.residual = d.residual; p.out_f32 = d.out_f32; p.out_f16 = reinterpret_cast<__half*>(d.out_f16);
+  p.stats = d.stats;
+  p.N = d.N; p.H = d.H; p.W = d.W; p.Cin = d.Cin; p.Cout = d.Cout; p.taps = 9; p.dilation = d.dilation; p.flags = d.flags;
+  p.tiles_w = (d.W + HT_W - 1) / HT_W;
+  p.tiles_h = (d.H + HT_H - 1) / HT_H;
+  hp.mtiles = d.Cout / BLOCK_M;
+  hp.items = p.tiles_w * p.tiles_h * d.N * hp.mtiles;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    IPDM_CUDA(cudaGetDevice(&dev));
+    IPDM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int grid = hp.items < sms ? hp.items : sms;
+  const int mode = (d.residual ? 1 : 0) | (d.out_f32 ? 2 : 0) | (d.out_f16 ? 4 : 0) | (pool ? 8 : 0);
+  int e = 0;
+#define HALO_CASE(M)                                                                 \
+  case M:                                                                            \
+    e = d.dilation == 1 ? launch_variant<M, 1>(mw, mx, hp, grid, s) : launch_variant<M, 2>(mw, mx, hp, grid, s); \
+    break;
+  switch (mode) {
+    HALO_CASE(2) HALO_CASE(3) HALO_CASE(4) HALO_CASE(5) HALO_CASE(6) HALO_CASE(7)
+    HALO_CASE(10) HALO_CASE(11) HALO_CASE(12) HALO_CASE(13) HALO_CASE(14) HALO_CASE(15)
+    default:
+      set_error("conv_halo: unsupported output combination %d", mode);
+      return IPDM_E_BADARG;
+  }
+#undef HALO_CASE
+  if (e) return e;
+  return launched("k_conv_halo");
+}
+
+}  // namespace ipdm

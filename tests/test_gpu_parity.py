@@ -106,9 +106,17 @@ def _conv_pair(N, H, W, Cin, Cout, taps, dil, flags, bias, residual, want32, wan
     (1, 14, 14, 256, 256, 9, 2, 4 | 2, False, True),      # partial tile (MNIST 14x14), CRP flags
     (1, 40, 24, 128, 128, 9, 1, 1, True, True),           # ragged tiles both ways
     (3, 128, 128, 128, 128, 9, 1, 0, False, True),        # many tiles
+    (4, 256, 256, 128, 128, 9, 1, 1, False, True),        # more work items than SMs: persistent loop, both accumulators
+    (2, 64, 64, 256, 256, 9, 2, 0, True, True),           # dilation 2 in the halo kernel
 ])
-def test_conv_igemm_vs_direct(N, H, W, Cin, Cout, taps, dil, flags, bias, residual):
-    (a32, a16, ast), (b32, b16, bst) = _conv_pair(N, H, W, Cin, Cout, taps, dil, flags, bias, residual, True, True, True)
+@pytest.mark.parametrize("variant", [0, 1])      # 0: auto (persistent halo kernel where it applies), 1: per-tap tile kernel
+def test_conv_igemm_vs_direct(N, H, W, Cin, Cout, taps, dil, flags, bias, residual, variant):
+    L = _lib()
+    L.check(L.lib().ipdm_debug_option(1, variant))
+    try:
+        (a32, a16, ast), (b32, b16, bst) = _conv_pair(N, H, W, Cin, Cout, taps, dil, flags, bias, residual, True, True, True)
+    finally:
+        L.check(L.lib().ipdm_debug_option(1, 0))
     assert not torch.isnan(a32).any() and not torch.isnan(a16.float()).any()
     assert rel_l2(a32.cpu(), b32.cpu()) < 1e-5      # fp32 accumulation order over K = taps*Cin differs
     assert rel_l2(a16.float().cpu(), b16.float().cpu()) < 1e-3       # f16 rounding-boundary flips only
