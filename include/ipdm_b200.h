@@ -140,8 +140,10 @@ typedef struct {
   const float* residual;  /* f32 NHWC [N][H][W][Cout] or NULL: added before the stores                 */
   float* out_f32;         /* f32 NHWC or NULL: acc + bias + residual                                    */
   void* out_f16;          /* f16 NHWC or NULL: see flags                                                */
-  float* stats;           /* f32 [N][Cout][2] or NULL: (zeroed, then) sum / sum-of-squares of the f32 result
-                             per (n, channel), un-pivoted -- feeds InstanceNorm++ without a second pass  */
+  double* stats;          /* f64 [N][Cout][2] or NULL: (zeroed, then) sum / sum-of-squares of the f32 result
+                             per (n, channel), un-pivoted -- feeds InstanceNorm++ without a second pass.
+                             Tile partials are fp32 in a fixed order; only their combination is an fp64
+                             atomic, which keeps results run-to-run stable at fp32 precision             */
   int N, H, W, Cin, Cout;
   int taps;               /* 9 (3x3, zero padding = dilation) or 1 (1x1)                                */
   int dilation;
@@ -172,19 +174,19 @@ int ipdm_conv_direct(const ipdm_conv_desc* desc_host, void* stream);
 /* begin_conv: out f32 NHWC [N][H][W][Cout] = conv3x3(affine ? 2x-1 : x) + bias, x f32 [N][H][W]
  * (Cin == 1), w f32 [Cout][9].  Also fills `stats` like ipdm_conv_desc.stats when non-NULL.
  * Replaces ncsnv2.py:270-275. */
-int ipdm_conv_first(const float* x, const float* w, const float* bias, float* out, float* stats, int N, int H,
+int ipdm_conv_first(const float* x, const float* w, const float* bias, float* out, double* stats, int N, int H,
                     int W, int Cout, int affine, void* stream);
 
 /* end_conv: out f32 [N][H][W] = (conv3x3(in f16 NHWC [N][H][W][Cin], w f32 [9][Cin]) + bias) / sigmas[labels[n]].
- * Replaces ncsnv2.py:293-297. */
+ * workspace: f32 [N*H*W*9] scratch (per-pixel tap dot products).  Replaces ncsnv2.py:293-297. */
 int ipdm_conv_last(const void* in_f16, const float* w, const float* bias, const float* sigmas,
-                   const int64_t* labels, float* out, int N, int H, int W, int Cin, void* stream);
+                   const int64_t* labels, float* out, float* workspace, int N, int H, int W, int Cin, void* stream);
 
-/* InstanceNorm++ (normalization.py:163-176).  stats f32 [N][C][2] = per-(n,c) sum and sum of squares of
+/* InstanceNorm++ (normalization.py:163-176).  stats f64 [N][C][2] = per-(n,c) sum and sum of squares of
  * (x - pivot), pivot = x[n,0,0,c] if `pivoted` else 0 (the conv epilogues produce the un-pivoted form);
  * apply: out_f16 = f16(ELU(gamma*(IN(x) + alpha*m_hat) + beta)), `stats_pivoted` as given to stats. */
-int ipdm_instnorm_stats(const float* x, float* stats, int N, int HW, int C, int pivoted, void* stream);
-int ipdm_instnorm_apply_elu(const float* x, const float* stats, int stats_pivoted, const float* alpha,
+int ipdm_instnorm_stats(const float* x, double* stats, int N, int HW, int C, int pivoted, void* stream);
+int ipdm_instnorm_apply_elu(const float* x, const double* stats, int stats_pivoted, const float* alpha,
                             const float* gamma, const float* beta, void* out_f16, int N, int HW, int C,
                             void* stream);
 

@@ -50,7 +50,7 @@ SIGNATURES = {
     "ipdm_conv_direct": (c_int, [POINTER(ConvDesc), c_void_p]),
     "ipdm_debug_option": (c_int, [c_int, c_int]),
     "ipdm_conv_first": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "ipdm_conv_last": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "ipdm_conv_last": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "ipdm_instnorm_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "ipdm_instnorm_apply_elu": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "ipdm_act_to_f16": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p]),

@@ -17,7 +17,7 @@ struct IgemmParams {
   const float* residual;
   float* out_f32;
   __half* out_f16;
-  float* stats;
+  double* stats;
   int N, H, W, Cin, Cout, taps, dilation, flags;
   int tiles_w, tiles_h;
 };
@@ -135,8 +135,8 @@ __device__ __forceinline__ void conv_epilogue(const IgemmParams& p, float* slab,
       t1 += red[(r * 128 + te) * 2];
       t2 += red[(r * 128 + te) * 2 + 1];
     }
-    atomicAdd(&p.stats[((size_t)n * p.Cout + m0 + te) * 2], t1);
-    atomicAdd(&p.stats[((size_t)n * p.Cout + m0 + te) * 2 + 1], t2);
+    atomicAdd(&p.stats[((size_t)n * p.Cout + m0 + te) * 2], (double)t1);
+    atomicAdd(&p.stats[((size_t)n * p.Cout + m0 + te) * 2 + 1], (double)t2);
     asm volatile("bar.sync %0, 128;" ::"n"(BAR) : "memory");
   }
 }

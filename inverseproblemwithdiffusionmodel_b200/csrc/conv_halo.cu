@@ -198,7 +198,7 @@ int launch_conv_halo(const ipdm_conv_desc& d, cudaStream_t s) {
   CUtensorMap mw, mx;
   if (int e = get_weight_map(d.w_f16, d.Cout, 9 * d.Cin, &mw)) return e;
   if (int e = get_act_map(d.in_f16, d.N, d.H, d.W, d.Cin, HALO_SLOTS, HT_H + 2 * d.dilation, &mx)) return e;
-  if (d.stats) IPDM_CUDA(cudaMemsetAsync(d.stats, 0, (size_t)d.N * d.Cout * 2 * sizeof(float), s));
+  if (d.stats) IPDM_CUDA(cudaMemsetAsync(d.stats, 0, (size_t)d.N * d.Cout * 2 * sizeof(double), s));
   HaloParams hp{};
   IgemmParams& p = hp.g;
   p.bias = d.bias; p.residual = d.residual; p.out_f32 = d.out_f32; p.out_f16 = reinterpret_cast<__half*>(d.out_f16);

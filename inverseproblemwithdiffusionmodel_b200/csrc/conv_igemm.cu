@@ -224,7 +224,7 @@ extern "C" int ipdm_conv_igemm(const ipdm_conv_desc* dh, void* stream) {
   if (int e = get_act_map(d.in_f16, d.N, d.H, d.W, d.Cin, TILE_W, TILE_H, &mx)) return e;
   const int mode = (d.residual ? 1 : 0) | (d.out_f32 ? 2 : 0) | (d.out_f16 ? 4 : 0) | (pool ? 8 : 0);
   if (d.stats) {
-    IPDM_CUDA(cudaMemsetAsync(d.stats, 0, (size_t)d.N * d.Cout * 2 * sizeof(float), s));
+    IPDM_CUDA(cudaMemsetAsync(d.stats, 0, (size_t)d.N * d.Cout * 2 * sizeof(double), s));
   }
   IgemmParams p{};
   p.bias = d.bias; p.residual = d.residual; p.out_f32 = d.out_f32; p.out_f16 = reinterpret_cast<__half*>(d.out_f16);

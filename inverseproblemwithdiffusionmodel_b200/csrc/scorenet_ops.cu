@@ -14,86 +14,161 @@ static int grid1d(size_t n, int block, int cap_mult = 32) {
 }
 
 // ---------------------------------------------------------------------------- begin_conv (Cin = 1)
-// thread = (pixel, 4 output channels); the 9 taps of the pixel are shared by the C/4 threads of it.
+// thread = (4 consecutive pixels of a row, 4 output channels): 18 input values and 9 float4 weights feed 16
+// outputs.  grid (chunks, N): a block stays inside one image so the InstanceNorm++ sums can be reduced in the
+// block and added with 2 atomics per channel.
 __global__ void k_conv_first(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                             float* __restrict__ out, int N, int H, int W, int Cout, int affine) {
-  extern __shared__ float sw[];  // [9][Cout] + [Cout]
+                             float* __restrict__ out, double* __restrict__ stats, int H, int W, int Cout, int affine) {
+  extern __shared__ float sw[];  // [9][Cout] + [Cout] + per-thread stats scratch [blockDim][8]
+  float* sst = sw + 10 * Cout;
   for (int i = threadIdx.x; i < 9 * Cout; i += blockDim.x) {
     const int co = i % Cout, tap = i / Cout;
     sw[i] = w[co * 9 + tap];
   }
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[9 * Cout + i] = bias ? bias[i] : 0.f;
   __syncthreads();
+  const int n = blockIdx.y;
   const int groups = Cout / 4;
-  const size_t total = (size_t)N * H * W * groups;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int g = (int)(i % groups);
-    const size_t pix = i / groups;
+  const int g = threadIdx.x % groups;
+  const int W4 = (W + 3) / 4;
+  const size_t quads = (size_t)H * W4;                          // 4-pixel groups in the image
+  const int qper = blockDim.x / groups;
+  const float* xin = x + (size_t)n * H * W;
+  float* o = out + (size_t)n * H * W * Cout;
+  float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
+  const float4 b4 = *reinterpret_cast<const float4*>(&sw[9 * Cout + 4 * g]);
+  if (threadIdx.x / groups < qper) {
+    for (size_t q = blockIdx.x * (size_t)qper + threadIdx.x / groups; q < quads; q += (size_t)gridDim.x * qper) {
+      const int yh = (int)(q / W4), x0 = (int)(q % W4) * 4;
+      float in[3][6];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          const int yy = yh + r - 1, xx = x0 + c - 1;
+          float v = 0.f;
+          if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            v = xin[(size_t)yy * W + xx];
+            if (affine) v = 2.f * v - 1.f;
+          }
+          in[r][c] = v;
+        }
+      float4 acc[4] = {b4, b4, b4, b4};
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float4 ww = *reinterpret_cast<const float4*>(&sw[(ky * 3 + kx) * Cout + 4 * g]);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float v = in[ky][kx + p];
+            acc[p].x += v * ww.x; acc[p].y += v * ww.y; acc[p].z += v * ww.z; acc[p].w += v * ww.w;
+          }
+        }
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        if (x0 + p < W) {
+          *reinterpret_cast<float4*>(&o[((size_t)yh * W + x0 + p) * Cout + 4 * g]) = acc[p];
+          s1.x += acc[p].x; s1.y += acc[p].y; s1.z += acc[p].z; s1.w += acc[p].w;
+          s2.x += acc[p].x * acc[p].x; s2.y += acc[p].y * acc[p].y; s2.z += acc[p].z * acc[p].z; s2.w += acc[p].w * acc[p].w;
+        }
+      }
+    }
+  }
+  if (stats == nullptr) return;
+  // fixed-order block reduction (thread partials -> smem -> one thread per channel), then one fp64 atomic per
+  // value: the only order-dependent step is a double-precision add, so results are run-to-run stable in fp32
+  float* mine = sst + threadIdx.x * 8;
+  mine[0] = s1.x; mine[1] = s2.x; mine[2] = s1.y; mine[3] = s2.y; mine[4] = s1.z; mine[5] = s2.z; mine[6] = s1.w; mine[7] = s2.w;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * Cout; i += blockDim.x) {
+    const int ch = i >> 1, which = i & 1;
+    const int gg = ch >> 2, k = ch & 3;
+    float t = 0.f;
+    for (int r = 0; r < qper; ++r) t += sst[(r * groups + gg) * 8 + k * 2 + which];
+    atomicAdd(&stats[(size_t)n * Cout * 2 + i], (double)t);
+  }
+}
+
+// ---------------------------------------------------------------------------- end_conv (Cout = 1)
+// Two steps so that every input pixel (Cin f16 values) is read exactly once:
+//   dots[p][t] = sum_c in[p][c] * w[t][c]            (16 lanes per pixel, 8 channels per lane per 128)
+//   out[y][x]  = (bias + sum_t dots[(y,x) + off_t][t]) / sigma[label]     (9 reads of an L2-resident table)
+constexpr int LAST_SLOT = 76;   // floats per 8-channel weight slot (72 used)
+__global__ void k_conv_last_dots(const __half* __restrict__ in, const float* __restrict__ w, float* __restrict__ dots,
+                                 size_t npix, int Cin) {
+  // weights re-laid out per 8-channel lane slot: sw[slot][tap][8], slot stride 76 floats (conflict-free 16-byte reads)
+  extern __shared__ float sw[];
+  for (int i = threadIdx.x; i < 9 * Cin; i += blockDim.x) {
+    const int t = i / Cin, c = i % Cin;
+    sw[(c >> 3) * LAST_SLOT + t * 8 + (c & 7)] = w[i];
+  }
+  __syncthreads();
+  const int lane16 = threadIdx.x & 15;
+  const size_t gstride = (size_t)gridDim.x * (blockDim.x / 16);
+  const size_t iters = (npix + gstride - 1) / gstride;
+  size_t pix = blockIdx.x * (size_t)(blockDim.x / 16) + threadIdx.x / 16;
+  for (size_t it = 0; it < iters; ++it, pix += gstride) {
+    const bool live = pix < npix;
+    float acc[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+    if (live) {
+      const __half* p = in + pix * Cin;
+      for (int c0 = lane16 * 8; c0 < Cin; c0 += 128) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(p + c0);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 t2 = __half22float2(h2[j]);
+          f[2 * j] = t2.x;
+          f[2 * j + 1] = t2.y;
+        }
+        const float* slot = sw + (c0 >> 3) * LAST_SLOT;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const float4 w0 = *reinterpret_cast<const float4*>(slot + t * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(slot + t * 8 + 4);
+          acc[t] += f[0] * w0.x + f[1] * w0.y + f[2] * w0.z + f[3] * w0.w + f[4] * w1.x + f[5] * w1.y + f[6] * w1.z + f[7] * w1.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int off = 8; off >= 1; off >>= 1) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], off);
+    if (live && lane16 < 9) {
+      float v = acc[0];
+#pragma unroll
+      for (int t = 1; t < 9; ++t) v = lane16 == t ? acc[t] : v;
+      dots[pix * 9 + lane16] = v;
+    }
+  }
+}
+
+__global__ void k_conv_last_sum(const float* __restrict__ dots, const float* __restrict__ bias, const float* __restrict__ sigmas,
+                                const int64_t* __restrict__ labels, float* __restrict__ out, int N, int H, int W) {
+  const size_t npix = (size_t)N * H * W;
+  for (size_t pix = blockIdx.x * (size_t)blockDim.x + threadIdx.x; pix < npix; pix += (size_t)gridDim.x * blockDim.x) {
     const int xw = (int)(pix % W), yh = (int)((pix / W) % H), n = (int)(pix / ((size_t)W * H));
-    float4 acc = *reinterpret_cast<const float4*>(&sw[9 * Cout + 4 * g]);
+    float acc = bias ? bias[0] : 0.f;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
         const int yy = yh + ky - 1, xx = xw + kx - 1;
         if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-        float v = x[((size_t)n * H + yy) * W + xx];
-        if (affine) v = 2.f * v - 1.f;
-        const float4 ww = *reinterpret_cast<const float4*>(&sw[(ky * 3 + kx) * Cout + 4 * g]);
-        acc.x += v * ww.x; acc.y += v * ww.y; acc.z += v * ww.z; acc.w += v * ww.w;
+        acc += dots[(((size_t)n * H + yy) * W + xx) * 9 + ky * 3 + kx];
       }
-    *reinterpret_cast<float4*>(&out[pix * Cout + 4 * g]) = acc;
-  }
-}
-
-// ---------------------------------------------------------------------------- end_conv (Cout = 1)
-// 16 lanes per pixel, each lane 8 channels (one 16-byte load) per tap.
-__global__ void k_conv_last(const __half* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
-                            const float* __restrict__ sigmas, const int64_t* __restrict__ labels,
-                            float* __restrict__ out, int N, int H, int W, int Cin) {
-  extern __shared__ float sw[];  // [9][Cin]
-  for (int i = threadIdx.x; i < 9 * Cin; i += blockDim.x) sw[i] = w[i];
-  __syncthreads();
-  const int lane16 = threadIdx.x & 15;
-  const size_t npix = (size_t)N * H * W;
-  const size_t gstride = (size_t)gridDim.x * (blockDim.x / 16);
-  // all 16 lanes of a group (and both groups of a warp) iterate together: pad the loop so shuffles stay converged
-  const size_t iters = (npix + gstride - 1) / gstride;
-  size_t pix = blockIdx.x * (size_t)(blockDim.x / 16) + threadIdx.x / 16;
-  for (size_t it = 0; it < iters; ++it, pix += gstride) {
-    const bool live = pix < npix;
-    float acc = 0.f;
-    int n = 0;
-    if (live) {
-      const int xw = (int)(pix % W), yh = (int)((pix / W) % H);
-      n = (int)(pix / ((size_t)W * H));
-      for (int ky = 0; ky < 3; ++ky)
-        for (int kx = 0; kx < 3; ++kx) {
-          const int yy = yh + ky - 1, xx = xw + kx - 1;
-          if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-          const __half* p = in + (((size_t)n * H + yy) * W + xx) * Cin;
-          const float* wt = sw + (ky * 3 + kx) * Cin;
-          for (int c0 = lane16 * 8; c0 < Cin; c0 += 128) {
-            const uint4 raw = *reinterpret_cast<const uint4*>(p + c0);
-            const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = __half22float2(h2[j]);
-              acc += f.x * wt[c0 + 2 * j] + f.y * wt[c0 + 2 * j + 1];
-            }
-          }
-        }
-    }
-#pragma unroll
-    for (int off = 8; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (live && lane16 == 0) out[pix] = (acc + (bias ? bias[0] : 0.f)) / sigmas[labels[n]];
+    out[pix] = acc / sigmas[labels[n]];
   }
 }
 
 // ---------------------------------------------------------------------------- InstanceNorm++
 // stats[n][c] = (sum(x - p), sum((x - p)^2)) over HW, p = x[n,0,c]  (pivot kills the cancellation
 // in E[x^2] - E[x]^2).  grid (chunks, N), block 256 = (C/4 lanes) x (256/(C/4) pixel rows).
-__global__ void k_instnorm_stats(const float* __restrict__ x, float* __restrict__ stats, int HW, int C, int pivoted) {
+__global__ void k_instnorm_stats(const float* __restrict__ x, double* __restrict__ stats, int HW, int C, int pivoted) {
   const int n = blockIdx.y;
   const int lanes = C / 4;
   const int rows = blockDim.x / lanes;
@@ -118,12 +193,12 @@ __global__ void k_instnorm_stats(const float* __restrict__ x, float* __restrict_
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
     float t = 0.f;
     for (int rr = 0; rr < rows; ++rr) t += red[(size_t)rr * C * 2 + i];
-    atomicAdd(&stats[(size_t)n * C * 2 + i], t);
+    atomicAdd(&stats[(size_t)n * C * 2 + i], (double)t);
   }
 }
 
 // out = f16(ELU(gamma*((x-m)*rstd + alpha*m_hat) + beta)); per-(n,c) A,B precomputed in smem.
-__global__ void k_instnorm_apply(const float* __restrict__ x, const float* __restrict__ stats, int pivoted,
+__global__ void k_instnorm_apply(const float* __restrict__ x, const double* __restrict__ stats, int pivoted,
                                  const float* __restrict__ alpha, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, __half* __restrict__ out, int HW, int C) {
   extern __shared__ float sm[];  // A[C], B[C], mean[C], red[64]
@@ -136,9 +211,9 @@ __global__ void k_instnorm_apply(const float* __restrict__ x, const float* __res
   const float inv = 1.0f / (float)HW;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float p = pivoted ? base[c] : 0.f;
-    const float d = stats[((size_t)n * C + c) * 2] * inv;
+    const float d = (float)(stats[((size_t)n * C + c) * 2] * (double)inv);
     mean[c] = p + d;
-    const float var = fmaxf(stats[((size_t)n * C + c) * 2 + 1] * inv - d * d, 0.f);
+    const float var = fmaxf((float)(stats[((size_t)n * C + c) * 2 + 1] * (double)inv - (double)d * (double)d), 0.f);
     A[c] = rsqrtf(var + 1e-5f);  // rstd for now
   }
   __syncthreads();
@@ -168,18 +243,35 @@ __global__ void k_instnorm_apply(const float* __restrict__ x, const float* __res
     Bv[c] = g * (alpha[c] * mhat - mean[c] * rstd) + (beta ? beta[c] : 0.f);
   }
   __syncthreads();
+  // main pass: thread = 4 channels; 4 pixels in flight per thread (independent 16-byte loads)
   const int lanes = C / 4;
-  const size_t total = (size_t)HW * lanes;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % lanes) * 4;
-    const float4 v = *reinterpret_cast<const float4*>(base + (i / lanes) * C + c4);
-    const float a0 = elu1(v.x * A[c4] + Bv[c4]), a1 = elu1(v.y * A[c4 + 1] + Bv[c4 + 1]);
-    const float a2 = elu1(v.z * A[c4 + 2] + Bv[c4 + 2]), a3 = elu1(v.w * A[c4 + 3] + Bv[c4 + 3]);
-    __half2 lo = __floats2half2_rn(a0, a1), hi = __floats2half2_rn(a2, a3);
-    uint2 pk;
-    pk.x = *reinterpret_cast<unsigned*>(&lo);
-    pk.y = *reinterpret_cast<unsigned*>(&hi);
-    *reinterpret_cast<uint2*>(out + (size_t)n * HW * C + (i / lanes) * C + c4) = pk;
+  const int c4 = (int)(threadIdx.x % lanes) * 4;
+  const int rows = blockDim.x / lanes;                       // pixels per block pass
+  const int row = threadIdx.x / lanes;
+  if (row >= rows) return;
+  const float a0 = A[c4], a1 = A[c4 + 1], a2 = A[c4 + 2], a3 = A[c4 + 3];
+  const float b0 = Bv[c4], b1 = Bv[c4 + 1], b2 = Bv[c4 + 2], b3 = Bv[c4 + 3];
+  __half* obase = out + (size_t)n * HW * C;
+  const int stride = gridDim.x * rows;
+  for (int pix = blockIdx.x * rows + row; pix < HW; pix += 4 * stride) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int pp = pix + u * stride;
+      if (pp < HW) v[u] = *reinterpret_cast<const float4*>(base + (size_t)pp * C + c4);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int pp = pix + u * stride;
+      if (pp < HW) {
+        __half2 lo = __floats2half2_rn(elu1(v[u].x * a0 + b0), elu1(v[u].y * a1 + b1));
+        __half2 hi = __floats2half2_rn(elu1(v[u].z * a2 + b2), elu1(v[u].w * a3 + b3));
+        uint2 pk;
+        pk.x = *reinterpret_cast<unsigned*>(&lo);
+        pk.y = *reinterpret_cast<unsigned*>(&hi);
+        *reinterpret_cast<uint2*>(obase + (size_t)pp * C + c4) = pk;
+      }
+    }
   }
 }
 
@@ -196,33 +288,57 @@ __global__ void k_act_to_f16(const float* __restrict__ x, __half* __restrict__ o
   }
 }
 
-// thread = (pixel, 8 channels)
-__global__ void k_maxpool5(const __half* __restrict__ in, __half* __restrict__ out, int N, int H, int W, int C) {
-  const int groups = C / 8;
-  const size_t total = (size_t)N * H * W * groups;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int g = (int)(i % groups);
-    const size_t pix = i / groups;
-    const int xw = (int)(pix % W), yh = (int)((pix / W) % H), n = (int)(pix / ((size_t)W * H));
-    __half2 m[4];
-    const __half2 ninf = __float2half2_rn(-INFINITY);
-    m[0] = m[1] = m[2] = m[3] = ninf;
-    for (int dy = -2; dy <= 2; ++dy) {
-      const int yy = yh + dy;
-      if (yy < 0 || yy >= H) continue;
-      for (int dx = -2; dx <= 2; ++dx) {
-        const int xx = xw + dx;
-        if (xx < 0 || xx >= W) continue;
-        const uint4 raw = *reinterpret_cast<const uint4*>(in + (((size_t)n * H + yy) * W + xx) * C + 8 * g);
-        const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+// 5x5/s1 max-pool, separable with a register sliding window: thread = (column x, 8 channels); it walks down
+// a strip of rows, takes the horizontal 5-max of each input row (5 16-byte loads, neighbours hit L1) and keeps
+// the last five of them in registers for the vertical max -- 5 loads per output instead of 25.
+// grid (ceil(W/XT), ceil(H/YS), N * C/8/CG); block = XT * CG threads (CG channel groups of 8).
+constexpr int MP_YS = 32;   // rows per strip
+__global__ void k_maxpool5(const __half* __restrict__ in, __half* __restrict__ out, int N, int H, int W, int C, int CG, int XT) {
+  const int cg_per = C / 8 / CG;                       // channel-group blocks per image
+  const int n = blockIdx.z / cg_per;
+  const int g = (blockIdx.z % cg_per) * CG + (threadIdx.x % CG);
+  const int x = blockIdx.x * XT + threadIdx.x / CG;
+  const int y0 = blockIdx.y * MP_YS;
+  if (x >= W) return;
+  const __half2 ninf = __float2half2_rn(-INFINITY);
+  __half2 win[5][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) m[j] = __hmax2(m[j], h2[j]);
-      }
+  for (int k = 0; k < 5; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) win[k][j] = ninf;
+  const __half* base = in + (size_t)n * H * W * C + 8 * g;
+  auto hmax_row = [&](int y, __half2* m) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m[j] = ninf;
+    if (y < 0 || y >= H) return;
+#pragma unroll
+    for (int dx = -2; dx <= 2; ++dx) {
+      const int xx = x + dx;
+      if (xx < 0 || xx >= W) continue;
+      const uint4 raw = *reinterpret_cast<const uint4*>(base + ((size_t)y * W + xx) * C);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) m[j] = __hmax2(m[j], h2[j]);
     }
+  };
+  // prime the window with rows y0-2 .. y0+1
+#pragma unroll
+  for (int k = 0; k < 4; ++k) hmax_row(y0 - 2 + k, win[k + 1]);
+  const int yend = min(y0 + MP_YS, H);
+  for (int y = y0; y < yend; ++y) {
+    // shift and append row y+2
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) win[k][j] = win[k + 1][j];
+    hmax_row(y + 2, win[4]);
+    __half2 m[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m[j] = __hmax2(__hmax2(__hmax2(win[0][j], win[1][j]), __hmax2(win[2][j], win[3][j])), win[4][j]);
     uint4 o;
     o.x = *reinterpret_cast<unsigned*>(&m[0]); o.y = *reinterpret_cast<unsigned*>(&m[1]);
     o.z = *reinterpret_cast<unsigned*>(&m[2]); o.w = *reinterpret_cast<unsigned*>(&m[3]);
-    *reinterpret_cast<uint4*>(out + pix * C + 8 * g) = o;
+    *reinterpret_cast<uint4*>(out + (((size_t)n * H + y) * W + x) * C + 8 * g) = o;
   }
 }
 
@@ -355,16 +471,17 @@ int stats_after_conv(const ipdm_conv_desc& d, cudaStream_t s);
 
 using namespace ipdm;
 
-extern "C" int ipdm_instnorm_stats(const float* x, float* stats, int N, int HW, int C, int pivoted, void* stream) {
+extern "C" int ipdm_instnorm_stats(const float* x, double* stats, int N, int HW, int C, int pivoted, void* stream) {
   IPDM_REQUIRE(x && stats, IPDM_E_BADARG, "instnorm_stats: null pointer");
   IPDM_REQUIRE(C % 4 == 0 && C >= 4 && C <= 1024 && N >= 1 && HW >= 1, IPDM_E_BADARG, "instnorm_stats: C=%d must be a multiple of 4 (<=1024)", C);
   cudaStream_t s = as_stream(stream);
-  IPDM_CUDA(cudaMemsetAsync(stats, 0, (size_t)N * C * 2 * sizeof(float), s));
+  IPDM_CUDA(cudaMemsetAsync(stats, 0, (size_t)N * C * 2 * sizeof(double), s));
   const int lanes = C / 4;
   const int block = lanes >= 256 ? lanes : 256;
   const int rows = block / lanes;
   int chunks = (HW + rows * 8 - 1) / (rows * 8);
-  const int cap = (148 * 8 + N - 1) / N;
+  int cap = (148 * 4) / N;          // one resident wave (>= 4 blocks of 256 threads per SM)
+  if (cap < 1) cap = 1;
   if (chunks > cap) chunks = cap;
   if (chunks < 1) chunks = 1;
   const size_t smem = (size_t)rows * C * 2 * sizeof(float);
@@ -380,39 +497,49 @@ int ipdm::stats_after_conv(const ipdm_conv_desc& d, cudaStream_t s) {
   return ipdm_instnorm_stats(d.out_f32, d.stats, d.N, HW, d.Cout, 0, s);
 }
 
-extern "C" int ipdm_instnorm_apply_elu(const float* x, const float* stats, int stats_pivoted, const float* alpha,
+extern "C" int ipdm_instnorm_apply_elu(const float* x, const double* stats, int stats_pivoted, const float* alpha,
                                        const float* gamma, const float* beta, void* out_f16, int N, int HW, int C,
                                        void* stream) {
   IPDM_REQUIRE(x && stats && alpha && gamma && out_f16, IPDM_E_BADARG, "instnorm_apply_elu: null pointer");
   IPDM_REQUIRE(C % 4 == 0 && C >= 4 && C <= 2048, IPDM_E_BADARG, "instnorm_apply_elu: C=%d must be a multiple of 4", C);
   const size_t smem = (size_t)(3 * C + 64) * sizeof(float);
-  int chunks = grid1d((size_t)HW * (C / 4), 256, 8);
-  const int cap = (148 * 8 + N - 1) / N;
+  int chunks = grid1d((size_t)HW * (C / 4), 256 * 4, 8);
+  int cap = (148 * 4) / N;          // one resident wave
+  if (cap < 1) cap = 1;
   if (chunks > cap) chunks = cap;
   k_instnorm_apply<<<dim3(chunks, N), 256, smem, as_stream(stream)>>>(x, stats, stats_pivoted, alpha, gamma, beta,
                                                                       reinterpret_cast<__half*>(out_f16), HW, C);
   return launched("k_instnorm_apply");
 }
 
-extern "C" int ipdm_conv_first(const float* x, const float* w, const float* bias, float* out, float* stats, int N, int H,
+extern "C" int ipdm_conv_first(const float* x, const float* w, const float* bias, float* out, double* stats, int N, int H,
                                int W, int Cout, int affine, void* stream) {
   IPDM_REQUIRE(x && w && out, IPDM_E_BADARG, "conv_first: null pointer");
   IPDM_REQUIRE(Cout % 4 == 0 && Cout <= 2048, IPDM_E_BADARG, "conv_first: Cout=%d must be a multiple of 4", Cout);
-  const size_t total = (size_t)N * H * W * (Cout / 4);
-  k_conv_first<<<grid1d(total, 256), 256, (size_t)10 * Cout * sizeof(float), as_stream(stream)>>>(x, w, bias, out, N, H, W, Cout, affine);
-  if (int e = launched("k_conv_first")) return e;
-  if (stats) return ipdm_instnorm_stats(out, stats, N, H * W, Cout, 0, stream);
-  return 0;
+  IPDM_REQUIRE(Cout / 4 <= 256, IPDM_E_BADARG, "conv_first: Cout too large");
+  cudaStream_t s = as_stream(stream);
+  if (stats) IPDM_CUDA(cudaMemsetAsync(stats, 0, (size_t)N * Cout * 2 * sizeof(double), s));
+  const int groups = Cout / 4;
+  const int qper = 256 / groups;
+  const size_t quads = (size_t)H * ((W + 3) / 4);
+  int chunks = (int)((quads + qper - 1) / qper);
+  int cap = (148 * 4) / N;          // one resident wave
+  if (cap < 1) cap = 1;
+  if (chunks > cap) chunks = cap;
+  k_conv_first<<<dim3(chunks, N), 256, (size_t)(10 * Cout + 256 * 8) * sizeof(float), s>>>(x, w, bias, out, stats, H, W, Cout, affine);
+  return launched("k_conv_first");
 }
 
 extern "C" int ipdm_conv_last(const void* in_f16, const float* w, const float* bias, const float* sigmas,
-                              const int64_t* labels, float* out, int N, int H, int W, int Cin, void* stream) {
-  IPDM_REQUIRE(in_f16 && w && sigmas && labels && out, IPDM_E_BADARG, "conv_last: null pointer");
+                              const int64_t* labels, float* out, float* workspace, int N, int H, int W, int Cin, void* stream) {
+  IPDM_REQUIRE(in_f16 && w && sigmas && labels && out && workspace, IPDM_E_BADARG, "conv_last: null pointer");
   IPDM_REQUIRE(Cin % 8 == 0 && Cin <= 1024, IPDM_E_BADARG, "conv_last: Cin=%d must be a multiple of 8", Cin);
   const size_t npix = (size_t)N * H * W;
-  k_conv_last<<<grid1d(npix, 16), 256, (size_t)9 * Cin * sizeof(float), as_stream(stream)>>>(
-      reinterpret_cast<const __half*>(in_f16), w, bias, sigmas, labels, out, N, H, W, Cin);
-  return launched("k_conv_last");
+  k_conv_last_dots<<<grid1d(npix, 16, 4), 256, (size_t)(Cin / 8) * LAST_SLOT * sizeof(float), as_stream(stream)>>>(
+      reinterpret_cast<const __half*>(in_f16), w, workspace, npix, Cin);
+  if (int e = launched("k_conv_last_dots")) return e;
+  k_conv_last_sum<<<grid1d(npix, 256), 256, 0, as_stream(stream)>>>(workspace, bias, sigmas, labels, out, N, H, W);
+  return launched("k_conv_last_sum");
 }
 
 extern "C" int ipdm_act_to_f16(const float* x, void* out_f16, size_t n, int elu, void* stream) {
@@ -425,9 +552,13 @@ extern "C" int ipdm_act_to_f16(const float* x, void* out_f16, size_t n, int elu,
 extern "C" int ipdm_maxpool5_f16(const void* in_f16, void* out_f16, int N, int H, int W, int C, void* stream) {
   IPDM_REQUIRE(in_f16 && out_f16, IPDM_E_BADARG, "maxpool5: null pointer");
   IPDM_REQUIRE(C % 8 == 0, IPDM_E_BADARG, "maxpool5: C=%d must be a multiple of 8", C);
-  const size_t total = (size_t)N * H * W * (C / 8);
-  k_maxpool5<<<grid1d(total, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(in_f16),
-                                                                  reinterpret_cast<__half*>(out_f16), N, H, W, C);
+  const int groups = C / 8;
+  int CG = 16;
+  while (groups % CG != 0) CG >>= 1;                      // channel groups per block (power of two dividing C/8)
+  const int XT = 256 / CG;                                // columns per block
+  dim3 grid((W + XT - 1) / XT, (H + MP_YS - 1) / MP_YS, N * (groups / CG));
+  k_maxpool5<<<grid, XT * CG, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(in_f16),
+                                                      reinterpret_cast<__half*>(out_f16), N, H, W, C, CG, XT);
   return launched("k_maxpool5");
 }
 

@@ -162,7 +162,7 @@ class _Plan:
         return self.buf(name, (N, H, W, C), torch.float16)
 
     def stats(self, name, C):
-        return self.buf(name, (self.N, C, 2), torch.float32)
+        return self.buf(name, (self.N, C, 2), torch.float64)
 
     def pack(self):
         """(Re)build the kernel-side weight copies when any parameter changed."""
@@ -363,8 +363,9 @@ class _Plan:
         a16 = self.f16("final.a", N, H, W, ngf)
         self.norm_elu("normalizer", prev[0], fin, a16, N, H * W, ngf)
         we, be = self.w["end_conv"]
+        dots = self.buf("final.dots", (N, H, W, 9), torch.float32)
         _lib.check(self.L.ipdm_conv_last(a16.data_ptr(), we.data_ptr(), _lib.ptr(be), self.sigmas.data_ptr(), labels.data_ptr(),
-                                         out.data_ptr(), N, H, W, ngf, s), "conv_last")
+                                         out.data_ptr(), dots.data_ptr(), N, H, W, ngf, s), "conv_last")
 
 
 class _ScoreNetBase(nn.Module):

@@ -233,7 +233,7 @@ class EmuLib:
                 s = F.elu(s)
             _t(d.out_f16, (N, Ho, Wo, Cout), np.float16).copy_(s.half())
         if d.stats:
-            st = _t(d.stats, (N, Cout, 2), np.float32)
+            st = _t(d.stats, (N, Cout, 2), np.float64)
             flat = v.reshape(N, -1, Cout)
             st[:, :, 0] = flat.sum(1)
             st[:, :, 1] = (flat * flat).sum(1)
@@ -257,13 +257,13 @@ class EmuLib:
         v = F.conv2d(X, Wt, b, padding=1).permute(0, 2, 3, 1)
         _t(out, (N, H, W, Cout), np.float32).copy_(v)
         if stats is not None:
-            st = _t(stats, (N, Cout, 2), np.float32)
+            st = _t(stats, (N, Cout, 2), np.float64)
             flat = v.reshape(N, -1, Cout)
             st[:, :, 0] = flat.sum(1)
             st[:, :, 1] = (flat * flat).sum(1)
         return 0
 
-    def ipdm_conv_last(self, in16, w, bias, sigmas, labels, out, N, H, W, Cin, stream):
+    def ipdm_conv_last(self, in16, w, bias, sigmas, labels, out, ws, N, H, W, Cin, stream):
         self.launches += 1
         X = _t(in16, (N, H, W, Cin), np.float16).float().permute(0, 3, 1, 2)
         Wt = _t(w, (9, Cin), np.float32).t().reshape(1, Cin, 3, 3)
@@ -279,7 +279,7 @@ class EmuLib:
         self.launches += 1
         X = _t(x, (N, HW, C), np.float32)
         p = X[:, 0:1, :] if pivoted else 0
-        st = _t(stats, (N, C, 2), np.float32)
+        st = _t(stats, (N, C, 2), np.float64)
         st[:, :, 0] = (X - p).sum(1)
         st[:, :, 1] = ((X - p) ** 2).sum(1)
         return 0
@@ -287,7 +287,7 @@ class EmuLib:
     def ipdm_instnorm_apply_elu(self, x, stats, pivoted, alpha, gamma, beta, out16, N, HW, C, stream):
         self.launches += 1
         X = _t(x, (N, HW, C), np.float32)
-        st = _t(stats, (N, C, 2), np.float32)
+        st = _t(stats, (N, C, 2), np.float64).float()
         p = X[:, 0, :] if pivoted else 0
         d = st[:, :, 0] / HW
         mean = p + d
@@ -307,6 +307,9 @@ class EmuLib:
         self.launches += 1
         X = _t(x, (n,), np.float32)
         _t(out16, (n,), np.float16).copy_((F.elu(X) if elu else X).half())
+        return 0
+
+    def ipdm_debug_option(self, key, value):
         return 0
 
     def ipdm_maxpool5_f16(self, in16, out16, N, H, W, C, stream):

@@ -87,7 +87,7 @@ def _conv_pair(N, H, W, Cin, Cout, taps, dil, flags, bias, residual, want32, wan
     for fn in (L.lib().ipdm_conv_igemm, L.lib().ipdm_conv_direct):
         o32 = torch.full((N, Ho, Wo, Cout), float("nan"), device=DEV) if want32 else None
         o16 = torch.full((N, Ho, Wo, Cout), float("nan"), device=DEV, dtype=torch.float16) if want16 else None
-        st = torch.zeros(N, Cout, 2, device=DEV) if stats else None
+        st = torch.zeros(N, Cout, 2, device=DEV, dtype=torch.float64) if stats else None
         d = L.ConvDesc(x16.data_ptr(), w16.data_ptr(), L.ptr(b), L.ptr(res), L.ptr(o32), L.ptr(o16), L.ptr(st),
                        N, H, W, Cin, Cout, taps, dil, flags)
         L.check(fn(ctypes.byref(d), L.stream()), "conv")
@@ -122,8 +122,8 @@ def test_conv_igemm_vs_direct(N, H, W, Cin, Cout, taps, dil, flags, bias, residu
     assert rel_l2(a16.float().cpu(), b16.float().cpu()) < 1e-3       # f16 rounding-boundary flips only
     HW = a32.shape[1] * a32.shape[2]
     ref_st = torch.stack([b32.reshape(N, HW, Cout).sum(1), (b32 ** 2).reshape(N, HW, Cout).sum(1)], dim=-1)
-    assert rel_l2(ast.cpu(), ref_st.cpu()) < 1e-5
-    assert rel_l2(bst.cpu(), ref_st.cpu()) < 1e-5
+    assert rel_l2(ast.float().cpu(), ref_st.cpu()) < 1e-5
+    assert rel_l2(bst.float().cpu(), ref_st.cpu()) < 1e-5
 
 
 def test_conv_direct_vs_torch():

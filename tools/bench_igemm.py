@@ -20,7 +20,7 @@ for (H, Cin, Cout, taps, dil) in shapes:
         o32 = torch.empty(N, H, H, Cout, device=dev) if m["o32"] else None
         o16 = torch.empty(N, H, H, Cout, device=dev, dtype=torch.float16) if m["o16"] else None
         res = torch.randn(N, H, H, Cout, device=dev) if m["res"] else None
-        st = torch.zeros(N, Cout, 2, device=dev) if m["st"] else None
+        st = torch.zeros(N, Cout, 2, device=dev, dtype=torch.float64) if m["st"] else None
         d = _lib.ConvDesc(x16.data_ptr(), w16.data_ptr(), None, _lib.ptr(res), _lib.ptr(o32), _lib.ptr(o16), _lib.ptr(st),
                           N, H, H, Cin, Cout, taps, dil, m["flags"])
         for _ in range(2):
