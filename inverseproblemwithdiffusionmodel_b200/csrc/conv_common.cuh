@@ -28,7 +28,8 @@ int launch_conv_halo(const ipdm_conv_desc& d, cudaStream_t s);
 extern int g_conv_variant;       // 0 = auto, 1 = force the per-tap tile kernel (diagnostics)
 
 // Epilogue of `NCHUNK` 32-column chunks of one accumulator (128 channels x 256 pixels) by a TEAM of 4 warps
-// (128 threads, named barrier `BAR`); chunks [chunk0, chunk0 + NCHUNK).
+// (128 threads, named barrier `BAR`, a runtime value so that both teams share ONE copy of this code -- the
+// epilogue is instruction-cache bound otherwise); chunks [chunk0, chunk0 + NCHUNK).
 // TMEM lane = output channel, column = pixel j = py*TW + px of a (256/TW) x TW pixel tile at (h0, w0).
 // Each warp pulls 32 columns for its 32 channels, transposes them through the team's shared-memory slab, and
 // the team then streams the [32 pixels][128 ch] slab with 16-byte accesses: thread = 4 consecutive channels of
@@ -36,9 +37,9 @@ extern int g_conv_variant;       // 0 = auto, 1 = force the per-tap tile kernel 
 // loads of a chunk are issued before the TMEM read so their latency hides behind the staging.
 // SLABS = 2: double-buffered slab, one barrier per chunk; SLABS = 1: single slab, two barriers per chunk.
 // MODE bits: 1 = residual, 2 = fp32 output, 4 = f16 output, 8 = 2x2 mean-pool.
-template <int MODE, int TW, int BAR, int SLABS, int NCHUNK>
+template <int MODE, int TW, int SLABS, int NCHUNK>
 __device__ __forceinline__ void conv_epilogue(const IgemmParams& p, float* slab, uint32_t tmem_acc, int quad, int lane,
-                                              int n, int h0, int w0, int m0, int chunk0) {
+                                              int n, int h0, int w0, int m0, int chunk0, int BAR) {
   constexpr bool kRes = (MODE & 1) != 0, kOut32 = (MODE & 2) != 0, kOut16 = (MODE & 4) != 0, pool = (MODE & 8) != 0;
   constexpr int ROWS_PER_CHUNK = 32 / TW;       // tile rows covered by 32 columns
   constexpr int PW = TW / 2;                    // pooled pixels per pooled row
@@ -52,32 +53,32 @@ __device__ __forceinline__ void conv_epilogue(const IgemmParams& p, float* slab,
   if (p.bias) bias4 = *reinterpret_cast<const float4*>(p.bias + m0 + c4);
   float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
   const uint32_t taddr = tmem_acc + ((uint32_t)(quad * 32) << 16);
+  // this thread's pixels of a chunk are q = prow + 4*i: row i / (TW/4) of the chunk, column prow + 4*(i % (TW/4))
+  // (pooled: TW/2 columns, 8 pixels per chunk) -> offsets are a per-chunk base plus compile-time multiples
+  constexpr int CPR = (pool ? PW : TW) / 4 > 0 ? (pool ? PW : TW) / 4 : 1;      // thread-pixels per output row
+  constexpr int OROWS = pool ? ROWS_PER_CHUNK / 2 : ROWS_PER_CHUNK;             // output rows per chunk
+  const size_t row_stride = (size_t)Wo * p.Cout;
+  const size_t col_stride = (size_t)4 * p.Cout;
+  const bool col_in_tile = pool ? (prow < PW) : true;                             // PW = 4 (TW = 8): all four sub-rows valid
 #pragma unroll 1
   for (int cc = 0; cc < NCHUNK; ++cc) {
     const int chunk = chunk0 + cc;
-    // output coordinates of this thread's pixels q = prow + 4*i, and their residuals
+    const int y_base = oy0 + chunk * OROWS;
+    const size_t chunk_base = (((size_t)n * Ho + y_base) * Wo + ox0 + prow) * p.Cout + m0 + c4;
     float4 res[NPX];
     size_t off[NPX];
     bool ok[NPX];
 #pragma unroll
     for (int i = 0; i < NPX; ++i) {
-      const int q = prow + 4 * i;
-      int yy, xx;
-      if (pool) {
-        yy = oy0 + chunk * (ROWS_PER_CHUNK / 2) + q / PW;
-        xx = ox0 + q % PW;
-      } else {
-        yy = oy0 + chunk * ROWS_PER_CHUNK + q / TW;
-        xx = ox0 + q % TW;
-      }
-      ok[i] = yy < Ho && xx < Wo;
-      off[i] = (((size_t)n * Ho + yy) * Wo + xx) * p.Cout + m0 + c4;
+      const int dy = i / CPR, dx = 4 * (i % CPR);
+      ok[i] = col_in_tile && (y_base + dy) < Ho && (ox0 + prow + dx) < Wo;
+      off[i] = chunk_base + dy * row_stride + (i % CPR) * col_stride;
       if (kRes && ok[i]) res[i] = *reinterpret_cast<const float4*>(p.residual + off[i]);
     }
     float v[32];
     tmem_ld32(taddr + chunk * 32, v);
     float* buf = slab + (SLABS == 2 ? (cc & 1) * (32 * EPI_PITCH) : 0);
-    if (SLABS == 1 && cc > 0) asm volatile("bar.sync %0, 128;" ::"n"(BAR) : "memory");   // previous chunk fully consumed
+    if (SLABS == 1 && cc > 0) asm volatile("bar.sync %0, 128;" ::"r"(BAR) : "memory");   // previous chunk fully consumed
     if (!pool) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) buf[j * EPI_PITCH + te] = v[j];
@@ -90,7 +91,7 @@ __device__ __forceinline__ void conv_epilogue(const IgemmParams& p, float* slab,
         buf[qq * EPI_PITCH + te] = (((v[a] + v[b]) + v[a + 1]) + v[b + 1]) * 0.25f;
       }
     }
-    asm volatile("bar.sync %0, 128;" ::"n"(BAR) : "memory");
+    asm volatile("bar.sync %0, 128;" ::"r"(BAR) : "memory");
 #pragma unroll
     for (int i = 0; i < NPX; ++i) {
       if (ok[i]) {
@@ -119,7 +120,7 @@ __device__ __forceinline__ void conv_epilogue(const IgemmParams& p, float* slab,
     }
   }
   // the slab is reused (by the statistics below and by the next accumulator): everyone must be done reading it
-  asm volatile("bar.sync %0, 128;" ::"n"(BAR) : "memory");
+  asm volatile("bar.sync %0, 128;" ::"r"(BAR) : "memory");
   if (p.stats) {
     // combine the four pixel sub-rows that share a channel group, then 2 atomics per channel
     float* red = slab;                                    // [4][128][2]
@@ -128,7 +129,7 @@ __device__ __forceinline__ void conv_epilogue(const IgemmParams& p, float* slab,
       red[(prow * 128 + c4 + k) * 2] = s1[k];
       red[(prow * 128 + c4 + k) * 2 + 1] = s2[k];
     }
-    asm volatile("bar.sync %0, 128;" ::"n"(BAR) : "memory");
+    asm volatile("bar.sync %0, 128;" ::"r"(BAR) : "memory");
     float t1 = 0.f, t2 = 0.f;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -137,7 +138,7 @@ __device__ __forceinline__ void conv_epilogue(const IgemmParams& p, float* slab,
     }
     atomicAdd(&p.stats[((size_t)n * p.Cout + m0 + te) * 2], (double)t1);
     atomicAdd(&p.stats[((size_t)n * p.Cout + m0 + te) * 2 + 1], (double)t2);
-    asm volatile("bar.sync %0, 128;" ::"n"(BAR) : "memory");
+    asm volatile("bar.sync %0, 128;" ::"r"(BAR) : "memory");
   }
 }
 

@@ -21,6 +21,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 // Bounded wait: a wrong descriptor must surface as an error, not as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
   for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
     uint32_t done;
     asm volatile(
