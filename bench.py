@@ -282,12 +282,15 @@ def run_native(args):
     burst, sustained, hbm, peak_kind = measured_peaks()
     achieved = conv_flop / (conv_ms / 1e3) / 1e12
     step_conv_tflops = 2 * B * CONV_FLOP_PER_FORWARD_256 * (n / 256) ** 2 / (ms_total / args.steps / 1e3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "k_conv_igemm (128->128 3x3 @%dx%d, %d images, f16 ELU store)" % (n, n, N),
+    roofline = {"bound": "tensor", "kernel": "k_conv_halo<f16 store> (128->128 3x3 @%dx%d, %d images)" % (n, n, N),
                 "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "traffic": None,
                 "peak_source": f"MEASURED_PEAKS.json bf16 burst ({peak_kind}); f16 kind::f16 has the same nominal rate",
                 "ms_per_launch": conv_ms, "flop_per_launch": conv_flop,
                 "whole_step_conv_tflops": step_conv_tflops, "whole_step_frac_of_sustained": step_conv_tflops / sustained}
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     cpu = None

@@ -1,0 +1,57 @@
+"""cfg-5 microbenchmark: SENSE forward / adjoint / fused ALD step, achieved algorithmic GB/s vs the HBM roofline.
+Algorithmic bytes (SURVEY 8d, N = B*H*W): fwd/adj 8N(1+Nc) + 4*Nc*H*W ; fused step 32N + 4*Nc*H*W (Philox noise)."""
+import json, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import torch
+import parity_cases as C
+from inverseproblemwithdiffusionmodel_b200 import _lib
+L = _lib.lib()
+dev = torch.device("cuda")
+peak = 6551.7
+try:
+    peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    pass
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+def timeit(fn, reps=5):
+    fn(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()                      # evict L2 between timed iterations
+        torch.cuda.synchronize()
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return min(ts)
+
+cases = [(4, 256, 1, 40), (4, 256, 14, 40), (4, 256, 64, 40), (8, 256, 16, 16), (32, 128, 64, 4), (4, 512, 16, 40),
+         (16, 512, 16, 16), (32, 512, 64, 40), (32, 512, 16, 4), (4, 128, 64, 4)]
+if len(sys.argv) > 1 and sys.argv[1] == "quick":
+    cases = cases[:4]
+for (nc, n, B, R) in cases:
+    A = C.SENSE("exp", nc, R, 1 / 64, (1, n, n), 0)
+    A.random_under_fourier.mask = C.keep_center_mask(n, R, 1 / 64, seed=0)
+    lines = int(A.random_under_fourier.mask.sum())
+    x = torch.randn(B, 1, n, n, dtype=torch.complex64, device=dev)
+    S = A(x)
+    N = B * n * n
+    bytes_fa = 8 * N * (1 + nc) + 4 * nc * n * n
+    t_f = timeit(lambda: A(x))
+    t_a = timeit(lambda: A.conj_op(S))
+    t_am = timeit(lambda: A.conj_op_masked(S))
+    state = torch.randn(2, B, n, n, device=dev); grad = torch.randn_like(state); bvec = torch.randn_like(state)
+    mre, mim = A.device_maps(dev); m, frames = A.device_mask(dev)
+    sc = _lib.AldScalars(0.1, 0.4, 0.01, 1.0)
+    step = lambda: _lib.check(L.ipdm_ald_sense_step(state.data_ptr(), grad.data_ptr(), None, bvec.data_ptr(), mre.data_ptr(), None,
+                                                    m.data_ptr(), frames, nc, B, n, n, sc, None, None, 1, 0, _lib.stream()))
+    t_s = timeit(step)
+    bytes_s = 32 * N + 4 * nc * n * n
+    row = {"coils": nc, "size": n, "batch": B, "R": R, "lines": lines, "kspace_MB": round(8 * nc * N / 1e6, 1),
+           "fwd_ms": round(t_f, 4), "fwd_GBs": round(bytes_fa / t_f / 1e6, 1), "fwd_frac": round(bytes_fa / t_f / 1e6 / peak, 3),
+           "adj_ms": round(t_a, 4), "adj_GBs": round(bytes_fa / t_a / 1e6, 1), "adj_frac": round(bytes_fa / t_a / 1e6 / peak, 3),
+           "adj_masked_ms": round(t_am, 4), "adj_masked_GBs": round(bytes_fa / t_am / 1e6, 1),
+           "step_ms": round(t_s, 4), "step_GBs": round(bytes_s / t_s / 1e6, 1), "step_frac": round(bytes_s / t_s / 1e6 / peak, 3)}
+    print(json.dumps(row), flush=True)
+    del x, S, state, grad, bvec
