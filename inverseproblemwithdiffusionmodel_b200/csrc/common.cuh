@@ -44,6 +44,8 @@ inline int launched(const char* what) {
   } while (0)
 
 __device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v); }
+// ELU whose result is about to be rounded to f16: exp via the SFU (absolute error ~1e-7 near 0)
+__device__ __forceinline__ float elu_f16bound(float v) { return v > 0.f ? v : __expf(v) - 1.0f; }
 
 // ---- Philox4x32-10 (Salmon et al.) + Box-Muller: two N(0,1) per call -------------------------
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,

@@ -264,8 +264,8 @@ __global__ void k_instnorm_apply(const float* __restrict__ x, const double* __re
     for (int u = 0; u < 4; ++u) {
       const int pp = pix + u * stride;
       if (pp < HW) {
-        __half2 lo = __floats2half2_rn(elu1(v[u].x * a0 + b0), elu1(v[u].y * a1 + b1));
-        __half2 hi = __floats2half2_rn(elu1(v[u].z * a2 + b2), elu1(v[u].w * a3 + b3));
+        __half2 lo = __floats2half2_rn(elu_f16bound(v[u].x * a0 + b0), elu_f16bound(v[u].y * a1 + b1));
+        __half2 hi = __floats2half2_rn(elu_f16bound(v[u].z * a2 + b2), elu_f16bound(v[u].w * a3 + b3));
         uint2 pk;
         pk.x = *reinterpret_cast<unsigned*>(&lo);
         pk.y = *reinterpret_cast<unsigned*>(&hi);
@@ -279,7 +279,7 @@ __global__ void k_instnorm_apply(const float* __restrict__ x, const double* __re
 __global__ void k_act_to_f16(const float* __restrict__ x, __half* __restrict__ out, size_t n4, int elu) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 v = reinterpret_cast<const float4*>(x)[i];
-    if (elu) { v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w); }
+    if (elu) { v.x = elu_f16bound(v.x); v.y = elu_f16bound(v.y); v.z = elu_f16bound(v.z); v.w = elu_f16bound(v.w); }
     __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
     uint2 pk;
     pk.x = *reinterpret_cast<unsigned*>(&lo);
@@ -374,7 +374,7 @@ __global__ void k_bilinear_add(const float* __restrict__ src, float* __restrict_
     }
     *d = r;
     if (out16) {
-      __half2 lo = __floats2half2_rn(elu1(r.x), elu1(r.y)), hi = __floats2half2_rn(elu1(r.z), elu1(r.w));
+      __half2 lo = __floats2half2_rn(elu_f16bound(r.x), elu_f16bound(r.y)), hi = __floats2half2_rn(elu_f16bound(r.z), elu_f16bound(r.w));
       uint2 pk;
       pk.x = *reinterpret_cast<unsigned*>(&lo);
       pk.y = *reinterpret_cast<unsigned*>(&hi);

@@ -262,3 +262,43 @@ def case_sampler_cine(dev):
         # oracle.scorenet.OPERAND_ROUND) reaches x at ~3e-4; the 1e-4 bar applies to cfg-2 steps (case above)
         assert rel_l2(res[0], g[f"cine_final_{mode_T}"]) < 1e-3, mode_T
     torch.set_grad_enabled(True)
+
+
+def case_full_chain_metrics(dev, levels=40):
+    """north_star: final NRMSE / SSIM of the posterior mean within 1e-3 of the reference.  A complete chain
+    (sigma 30 -> 0.01 over `levels` levels x 3 steps + denoise) of 4 chains with identical injected noise on both
+    sides; metrics of the mean magnitude image and the mean of per-chain metrics (helpers/visualizations.py:93,117-125)."""
+    n, B = 32, 4
+    cfg = make_config("ACDC", 8, n, levels, 30.0, device=dev)
+    net, Pd = build_net(NCSNv2Deepest, "NCSNv2Deepest_ngf8", 4, cfg, dev)
+    sig = get_sigmas(cfg, mode="recons")
+    A = SENSE("exp", 4, 40, 1 / 8, (1, n, n), 0)
+    A.random_under_fourier.mask = keep_center_mask(n, 4, 1 / 8, seed=0)
+    truth = phantom(1401, 1, 1, n, n)
+    meas = A(truth.to(dev)).repeat(1, B, 1, 1, 1)
+    params = {"n_steps_each": 3, "step_lr": 9e-7, "denoise": True, "final_only": True}
+    draw = lambda shape: torch.randn(*shape)
+    sampler = ALD.ALDInvSegProximalRealImag(L2Penalty(A), 1.0, "linear", (B, 1, n, n), net, sig, params, cfg,
+                                            measurement=meas, linear_tfm=A, seg=None, device=torch.device(dev))
+    torch.manual_seed(77)
+    got = sampler(label=None, lamda=1.0, save_dir="/tmp", lr_scaled=1e6, seg_mode="full", noise_fn=draw)[0]
+    torch.set_grad_enabled(True)
+    maps, mask = A.sens_maps, A.random_under_fourier.mask
+    score = lambda x, y: SN.score_forward("NCSNv2Deepest", Pd, x, y)
+    prox = lambda z, y, a, l: M.l2_prox_sense_closed_form(z, y, maps, mask, a, l)
+    torch.manual_seed(77)
+    with torch.no_grad():
+        ref = OALD.ald_sense_real_imag(score, meas.cpu(), sig.cpu(), 3, 9e-7, 1e6, lambda s: M.sense_adjoint(s, maps), prox)
+    t = truth.abs()[0, 0]
+    rng = float(t.max() - t.min())
+    def metrics(x):
+        mags = x.abs()[:, 0]
+        mean_img = mags.mean(0)
+        per = [(OALD.nrmse(m, t), OALD.ssim(m, t, data_range=rng)) for m in mags]
+        return (OALD.nrmse(mean_img, t), OALD.ssim(mean_img, t, data_range=rng),
+                sum(p[0] for p in per) / len(per), sum(p[1] for p in per) / len(per))
+    mg, mr = metrics(got), metrics(ref)
+    for a, b in zip(mg, mr):
+        assert abs(a - b) < 1e-3, (mg, mr)
+    assert rel_l2(got, ref) < 1e-3
+    return mg, mr

@@ -313,3 +313,7 @@ def test_posterior_stats_kernel():
     for k in ("mag_mean", "mag_std", "phase_mean", "phase_std"):
         assert torch.allclose(out[k].cpu(), ref[k].reshape(16, 16), atol=2e-5), k
     assert out["n"] == 7
+
+
+def test_full_chain_posterior_metrics():
+    C.case_full_chain_metrics(DEV)
