@@ -137,6 +137,39 @@ IPDM_HD void pass_compute(int t, cf32* v, const cf32* tw) {
   }
 }
 
+// Per-thread twiddles of pass P: they depend only on (t, P), so kernels hoist them out of their coil / row loops.
+// twr[i*(R-1) + r-1] = w_L^(r*m_i), m_i = ((t + i*TPF) % Ns) * L/(Ns*R); forward table, conjugated on use.
+template <int L, int P> struct PassTw {
+  static constexpr int R = PassRadix<L, P>::value, NB = (L / R) / FftPlan<L>::TPF;
+  static constexpr int N = PassNs<L, P>::value > 1 ? NB * (R - 1) : 0;   // pass 0 has unit twiddles
+};
+template <int L, int P>
+IPDM_HD void pass_twiddles(int t, cf32* twr, const cf32* tw) {
+  constexpr int R = PassRadix<L, P>::value, TPF = FftPlan<L>::TPF, NB = (L / R) / TPF, NS = PassNs<L, P>::value;
+  if (NS == 1) return;
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    const int m = ((t + i * TPF) % NS) * (L / (NS * R));
+#pragma unroll
+    for (int r = 1; r < R; ++r) twr[i * (R - 1) + r - 1] = tw[r * m];
+  }
+}
+template <int L, int P, int DIR>
+IPDM_HD void pass_compute_regtw(cf32* v, const cf32* twr) {
+  constexpr int R = PassRadix<L, P>::value, TPF = FftPlan<L>::TPF, NB = (L / R) / TPF, NS = PassNs<L, P>::value;
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    if (NS > 1) {
+#pragma unroll
+      for (int r = 1; r < R; ++r) {
+        const cf32 w = twr[i * (R - 1) + r - 1];
+        v[i * R + r] = DIR < 0 ? cmul(v[i * R + r], w) : cmulc(v[i * R + r], w);
+      }
+    }
+    dftR<R, DIR>(v + i * R);
+  }
+}
+
 // Store the results of pass P:  dst index (j/Ns)*Ns*R + j%Ns + r*Ns.
 template <int L, int P, class StoreFn>
 IPDM_HD void pass_store(int t, const cf32* v, StoreFn store) {

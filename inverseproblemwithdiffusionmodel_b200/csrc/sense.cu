@@ -53,42 +53,65 @@ __device__ __forceinline__ void regs_to_q(const cf32* v, cf32* u) {
     for (int r = 0; r < R; ++r) u[i + r * NB] = v[i * R + r];
 }
 
-// Length-L transform of the values held in q order by the TPF threads of one row; `row` is that
-// row's smem line.  In: u[q] = input at position t+q*TPF.  Out: u[q] = output at position t+q*TPF.
-// All threads of the CTA must call it together (block-wide barriers between passes).
+// Per-thread twiddle registers for all passes of a length-L transform (filled once per kernel).
+template <int L> struct TwRegs {
+  static constexpr int N1 = PassTw<L, 1>::N, N2 = FftPlan<L>::NP > 2 ? PassTw<L, 2>::N : 0, N3 = FftPlan<L>::NP > 3 ? PassTw<L, 3>::N : 0;
+  cf32 p1[N1 > 0 ? N1 : 1], p2[N2 > 0 ? N2 : 1], p3[N3 > 0 ? N3 : 1];
+  __device__ __forceinline__ void init(int t, const cf32* tw) {
+    if constexpr (FftPlan<L>::NP > 1) pass_twiddles<L, 1>(t, p1, tw);
+    if constexpr (FftPlan<L>::NP > 2) pass_twiddles<L, 2>(t, p2, tw);
+    if constexpr (FftPlan<L>::NP > 3) pass_twiddles<L, 3>(t, p3, tw);
+  }
+};
+
+// Barrier among the TPF threads that share one transform.  TPF <= 32: they sit in one warp (tid = row*TPF + t),
+// so a warp-level sync is enough and rows / warps run decoupled; TPF = 64: two warps, named barrier 1 + row.
+template <int L>
+__device__ __forceinline__ void row_sync(int row_id) {
+  if constexpr (FftPlan<L>::TPF <= 32) {
+    __syncwarp();
+  } else {
+    asm volatile("bar.sync %0, %1;" ::"r"(row_id + 1), "n"(FftPlan<L>::TPF) : "memory");
+  }
+}
+
+// Length-L transform of the values held in q order by the TPF threads of one row; `row` is that row's private
+// smem line.  In: u[q] = input at position t+q*TPF.  Out: u[q] = output at position t+q*TPF.
+// Only the row's own threads synchronise (row_sync), so the caller needs a CTA barrier only when different
+// rows exchange data through the tile.
 template <int L, int DIR>
-__device__ __forceinline__ void fft_regs(cf32* u, cf32* row, const cf32* tw, int t) {
+__device__ __forceinline__ void fft_regs(cf32* u, cf32* row, const TwRegs<L>& T, int t, int row_id) {
   using PL = FftPlan<L>;
   constexpr int E = FftRegs<L>::E;
   cf32 v[E];
   auto ld = [&](int i) { return row[spad(i)]; };
   auto st = [&](int i, cf32 val) { row[spad(i)] = val; };
   q_to_regs<L, 0>(u, v);
-  pass_compute<L, 0, DIR>(t, v, tw);
+  pass_compute_regtw<L, 0, DIR>(v, T.p1);
   if constexpr (PL::NP == 1) {
     regs_to_q<L, 0>(v, u);
   } else {
-    __syncthreads();  // earlier readers of the tile are done
+    row_sync<L>(row_id);  // earlier readers of this row's line are done
     pass_store<L, 0>(t, v, st);
-    __syncthreads();
+    row_sync<L>(row_id);
     pass_load<L, 1>(t, v, ld);
-    pass_compute<L, 1, DIR>(t, v, tw);
+    pass_compute_regtw<L, 1, DIR>(v, T.p1);
     if constexpr (PL::NP == 2) {
       regs_to_q<L, 1>(v, u);
     } else {
-      __syncthreads();
+      row_sync<L>(row_id);
       pass_store<L, 1>(t, v, st);
-      __syncthreads();
+      row_sync<L>(row_id);
       pass_load<L, 2>(t, v, ld);
-      pass_compute<L, 2, DIR>(t, v, tw);
+      pass_compute_regtw<L, 2, DIR>(v, T.p2);
       if constexpr (PL::NP == 3) {
         regs_to_q<L, 2>(v, u);
       } else {
-        __syncthreads();
+        row_sync<L>(row_id);
         pass_store<L, 2>(t, v, st);
-        __syncthreads();
+        row_sync<L>(row_id);
         pass_load<L, 3>(t, v, ld);
-        pass_compute<L, 3, DIR>(t, v, tw);
+        pass_compute_regtw<L, 3, DIR>(v, T.p3);
         regs_to_q<L, 3>(v, u);
       }
     }
@@ -102,7 +125,7 @@ struct SenseArgs {
   const float* mre;
   const float* mim;
   const uint8_t* mask;
-  int mask_frames, ncoils, batch, H, W, ssos;
+  int mask_frames, ncoils, batch, H, W, ssos, sparse;
   float scale;  // 1/sqrt(HW) * sigma
 };
 
@@ -122,6 +145,9 @@ __global__ void __launch_bounds__(Tile<L>::NT) k_fwd_rows(SenseArgs a) {
   const int b = blockIdx.y, h0 = blockIdx.x * TL::ROWS, h = h0 + r;
   const bool valid = h < a.H;
   fill_twiddles<L>(tw, tid, TL::NT);
+  __syncthreads();
+  TwRegs<L> T;
+  T.init(t, tw);
   cf32 xq[TL::E];
 #pragma unroll
   for (int q = 0; q < TL::E; ++q) {
@@ -129,28 +155,46 @@ __global__ void __launch_bounds__(Tile<L>::NT) k_fwd_rows(SenseArgs a) {
     xq[q] = valid ? cscale(a.in[((size_t)b * a.H + h) * L + w], sgn(h + w)) : cf32{0.f, 0.f};
   }
   __syncthreads();
+  // coil maps of the next coil are fetched while the current coil is transformed
+  cf32 mnext[TL::E];
+  auto fetch_maps = [&](int c) {
+#pragma unroll
+    for (int q = 0; q < TL::E; ++q) {
+      mnext[q] = cf32{1.f, 0.f};
+      if (a.mre != nullptr && valid && c < a.ncoils) {
+        const size_t mi = ((size_t)c * a.H + h) * L + t + q * TL::TPF;
+        mnext[q] = cf32{a.mre[mi], a.mim ? a.mim[mi] : 0.f};
+      }
+    }
+  };
+  // which of this thread's k-space columns survive the mask (sparse masks: write them straight from registers)
+  bool keep[TL::E];
+#pragma unroll
+  for (int q = 0; q < TL::E; ++q) keep[q] = valid && col_on(a, b, t + q * TL::TPF);
+  fetch_maps(0);
   for (int c = 0; c < a.ncoils; ++c) {
     cf32 u[TL::E];
 #pragma unroll
-    for (int q = 0; q < TL::E; ++q) {
-      const int w = t + q * TL::TPF;
-      u[q] = xq[q];
-      if (a.mre != nullptr && valid) {
-        const size_t mi = ((size_t)c * a.H + h) * L + w;
-        const cf32 m{a.mre[mi], a.mim ? a.mim[mi] : 0.f};
-        u[q] = cmul(u[q], m);
-      }
+    for (int q = 0; q < TL::E; ++q) u[q] = a.mre != nullptr ? cmul(xq[q], mnext[q]) : xq[q];
+    fetch_maps(c + 1);
+    fft_regs<L, -1>(u, tile + r * TL::PITCH, T, t, r);
+    const size_t img = (size_t)c * a.batch + b;
+    if (a.sparse) {
+      // few sampled columns: 8-byte scattered stores of just those, no transposition through the tile
+#pragma unroll
+      for (int q = 0; q < TL::E; ++q)
+        if (keep[q]) a.ws[(img * L + t + q * TL::TPF) * a.H + h] = u[q];
+      continue;
     }
-    fft_regs<L, -1>(u, tile + r * TL::PITCH, tw, t);
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < TL::E; ++q) tile[r * TL::PITCH + spad(t + q * TL::TPF)] = u[q];
     __syncthreads();
-    const size_t img = (size_t)c * a.batch + b;
     for (int idx = tid; idx < TL::ROWS * L; idx += TL::NT) {
       const int rr = idx % TL::ROWS, k = idx / TL::ROWS;
       if (h0 + rr < a.H && col_on(a, b, k)) a.ws[(img * L + k) * a.H + h0 + rr] = tile[rr * TL::PITCH + spad(k)];
     }
+    __syncthreads();  // the gather read every row's line; the next coil's passes overwrite them
   }
 }
 
@@ -174,12 +218,15 @@ __global__ void __launch_bounds__(Tile<L>::NT) k_fwd_cols(SenseArgs a) {
     return;
   }
   fill_twiddles<L>(tw, tid, TL::NT);
+  __syncthreads();
+  TwRegs<L> T;
+  T.init(t, tw);
   cf32 u[TL::E];
 #pragma unroll
   for (int q = 0; q < TL::E; ++q)
     u[q] = active ? a.ws[(img * a.W + k) * L + t + q * TL::TPF] : cf32{0.f, 0.f};
   __syncthreads();
-  fft_regs<L, -1>(u, tile + cc * TL::PITCH, tw, t);
+  fft_regs<L, -1>(u, tile + cc * TL::PITCH, T, t, cc);
   __syncthreads();
 #pragma unroll
   for (int q = 0; q < TL::E; ++q) tile[cc * TL::PITCH + spad(t + q * TL::TPF)] = u[q];
@@ -205,6 +252,9 @@ __global__ void __launch_bounds__(Tile<L>::NT) k_adj_cols(SenseArgs a) {
   const int any = __syncthreads_or(active ? 1 : 0);
   if (!any) return;
   fill_twiddles<L>(tw, tid, TL::NT);
+  __syncthreads();
+  TwRegs<L> T;
+  T.init(t, tw);
   for (int idx = tid; idx < TL::ROWS * L; idx += TL::NT) {
     const int kk = idx % TL::ROWS, h = idx / TL::ROWS;
     cf32 v{0.f, 0.f};
@@ -215,7 +265,7 @@ __global__ void __launch_bounds__(Tile<L>::NT) k_adj_cols(SenseArgs a) {
   cf32 u[TL::E];
 #pragma unroll
   for (int q = 0; q < TL::E; ++q) u[q] = tile[cc * TL::PITCH + spad(t + q * TL::TPF)];
-  fft_regs<L, +1>(u, tile + cc * TL::PITCH, tw, t);
+  fft_regs<L, +1>(u, tile + cc * TL::PITCH, T, t, cc);
   if (active) {
 #pragma unroll
     for (int q = 0; q < TL::E; ++q) a.ws[(img * a.W + k) * L + t + q * TL::TPF] = u[q];
@@ -233,6 +283,9 @@ __global__ void __launch_bounds__(Tile<L>::NT) k_adj_rows(SenseArgs a) {
   const int b = blockIdx.y, h0 = blockIdx.x * TL::ROWS, h = h0 + r;
   const bool valid = h < a.H;
   fill_twiddles<L>(tw, tid, TL::NT);
+  __syncthreads();
+  TwRegs<L> T;
+  T.init(t, tw);
   cf32 acc[TL::E];
 #pragma unroll
   for (int q = 0; q < TL::E; ++q) acc[q] = cf32{0.f, 0.f};
@@ -249,7 +302,7 @@ __global__ void __launch_bounds__(Tile<L>::NT) k_adj_rows(SenseArgs a) {
     cf32 u[TL::E];
 #pragma unroll
     for (int q = 0; q < TL::E; ++q) u[q] = tile[r * TL::PITCH + spad(t + q * TL::TPF)];
-    fft_regs<L, +1>(u, tile + r * TL::PITCH, tw, t);
+    fft_regs<L, +1>(u, tile + r * TL::PITCH, T, t, r);
 #pragma unroll
     for (int q = 0; q < TL::E; ++q) {
       const int w = t + q * TL::TPF;
@@ -307,6 +360,9 @@ __global__ void __launch_bounds__(Tile<L>::NT) k_ald_sense(AldArgs a) {
     rstep += (uint32_t)cur;
   }
   fill_twiddles<L>(tw, tid, TL::NT);
+  __syncthreads();
+  TwRegs<L> T;
+  T.init(t, tw);
   const size_t plane = (size_t)a.batch * a.H * L;
   const size_t rowoff = ((size_t)b * a.H + (valid ? h : 0)) * L;
   const uint8_t* mrow = a.mask ? a.mask + (size_t)(b % a.mask_frames) * L : nullptr;
@@ -331,13 +387,13 @@ __global__ void __launch_bounds__(Tile<L>::NT) k_ald_sense(AldArgs a) {
       m[q] = cf32{a.mre[mi], a.mim ? a.mim[mi] : 0.f};
       u[q] = cscale(cmul(z[q], m[q]), sgn(w));
     }
-    fft_regs<L, -1>(u, tile + r * TL::PITCH, tw, t);
+    fft_regs<L, -1>(u, tile + r * TL::PITCH, T, t, r);
     if (mrow != nullptr) {
 #pragma unroll
       for (int q = 0; q < TL::E; ++q)
         if (mrow[t + q * TL::TPF] == 0) u[q] = cf32{0.f, 0.f};
     }
-    fft_regs<L, +1>(u, tile + r * TL::PITCH, tw, t);
+    fft_regs<L, +1>(u, tile + r * TL::PITCH, T, t, r);
 #pragma unroll
     for (int q = 0; q < TL::E; ++q) acc[q] = cadd(acc[q], cscale(cmulc(u[q], m[q]), sgn(t + q * TL::TPF)));
   }
@@ -575,6 +631,7 @@ extern "C" int ipdm_sense_forward(const void* x, const float* maps_re, const flo
   a.in = (const cf32*)x; a.out = (cf32*)out; a.ws = (cf32*)workspace;
   a.mre = maps_re; a.mim = maps_im; a.mask = mask; a.mask_frames = mask ? mask_frames : 1;
   a.ncoils = ncoils; a.batch = batch; a.H = H; a.W = W; a.ssos = 0;
+  a.sparse = mask != nullptr ? 1 : 0;   // masked columns are written straight from registers (any density is correct)
   a.scale = (((H / 2 + W / 2) & 1) ? -1.f : 1.f) / sqrtf((float)H * (float)W);
   if (int e = launch_rows(true, a, as_stream(stream))) return e;
   return launch_cols(true, a, as_stream(stream));

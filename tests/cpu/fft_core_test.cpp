@@ -14,7 +14,16 @@ struct RunPasses {
     constexpr int TPF = FftPlan<L>::TPF, E = FftRegs<L>::E;
     std::vector<cf32> regs(TPF * E);
     for (int t = 0; t < TPF; ++t) pass_load<L, P>(t, &regs[t * E], [&](int i) { return buf[i]; });
-    for (int t = 0; t < TPF; ++t) pass_compute<L, P, DIR>(t, &regs[t * E], tw.data());
+    // odd "threads" take the table-lookup path, even ones the hoisted register-twiddle path: both must agree
+    for (int t = 0; t < TPF; ++t) {
+      if (t & 1) {
+        pass_compute<L, P, DIR>(t, &regs[t * E], tw.data());
+      } else {
+        cf32 twr[64];
+        pass_twiddles<L, P>(t, twr, tw.data());
+        pass_compute_regtw<L, P, DIR>(&regs[t * E], twr);
+      }
+    }
     for (int t = 0; t < TPF; ++t) pass_store<L, P>(t, &regs[t * E], [&](int i, cf32 v) { buf[i] = v; });
     if constexpr (P + 1 < FftPlan<L>::NP) RunPasses<L, P + 1, DIR>::go(buf, tw);
   }
