@@ -261,31 +261,49 @@ def run_native(args):
     d2h = res[0].numel() * 8
     torch.set_grad_enabled(True)
 
-    # ---- roofline of the dominant kernel: the 128->128 3x3 igemm at 256^2 over 2*chains images ------
+    # ---- roofline of the dominant kernel -------------------------------------------------------------
+    # By launch-list share (profiles/r01_launch_breakdown.txt) the dominant kernel is k_conv_halo<7,1>: the
+    # 128->128 3x3 convolution at 256^2 with residual + f32 + f16 stores (47 of 165 launches, 36 % of the step);
+    # the f16-store-only variant of the same shape (30 launches) is timed beside it.  Same tensors as in the
+    # step: 2*chains images, far larger than L2.
     import ctypes
     N = 2 * B
     x16 = torch.randn(N, n, n, 128, device=dev).half()
     w16 = (torch.randn(128, 9, 128, device=dev) / 34).half()
     o16 = torch.empty_like(x16)
-    d = _lib.ConvDesc(x16.data_ptr(), w16.data_ptr(), None, None, None, o16.data_ptr(), None, N, n, n, 128, 128, 9, 1, _lib.CONV_F16_ELU)
-    for _ in range(3):
-        _lib.check(L.ipdm_conv_igemm(ctypes.byref(d), _lib.stream()), "igemm")
-    torch.cuda.synchronize()
-    reps = 10
-    e0.record()
-    for _ in range(reps):
-        _lib.check(L.ipdm_conv_igemm(ctypes.byref(d), _lib.stream()), "igemm")
-    e1.record()
-    torch.cuda.synchronize()
-    conv_ms = e0.elapsed_time(e1) / reps
+    o32 = torch.empty(N, n, n, 128, device=dev)
+    res = torch.randn(N, n, n, 128, device=dev)
     conv_flop = 2.0 * N * n * n * 128 * 128 * 9
+
+    def time_conv(desc, reps=10):
+        for _ in range(3):
+            _lib.check(L.ipdm_conv_igemm(ctypes.byref(desc), _lib.stream()), "igemm")
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            _lib.check(L.ipdm_conv_igemm(ctypes.byref(desc), _lib.stream()), "igemm")
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    d_res = _lib.ConvDesc(x16.data_ptr(), w16.data_ptr(), None, res.data_ptr(), o32.data_ptr(), o16.data_ptr(), None,
+                          N, n, n, 128, 128, 9, 1, _lib.CONV_F16_ELU)
+    d_f16 = _lib.ConvDesc(x16.data_ptr(), w16.data_ptr(), None, None, None, o16.data_ptr(), None, N, n, n, 128, 128, 9, 1, _lib.CONV_F16_ELU)
+    ms_res, ms_f16 = time_conv(d_res), time_conv(d_f16)
     burst, sustained, hbm, peak_kind = measured_peaks()
-    achieved = conv_flop / (conv_ms / 1e3) / 1e12
+    achieved = conv_flop / (ms_res / 1e3) / 1e12
     step_conv_tflops = 2 * B * CONV_FLOP_PER_FORWARD_256 * (n / 256) ** 2 / (ms_total / args.steps / 1e3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "k_conv_halo<f16 store> (128->128 3x3 @%dx%d, %d images)" % (n, n, N),
-                "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "traffic": None,
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this very shape
+    # (profiles/r01_ncu_conv_halo_res_mode.txt: 1.434 GB + 1.363 GB at 28 images of 256^2; algorithmic 2.58 GB)
+    traffic = 2.797738e9 if (N == 28 and n == 256) else None
+    alg_bytes = N * n * n * 128 * (2 + 4 + 4 + 2)
+    roofline = {"bound": "tensor", "kernel": "k_conv_halo<res+f32+f16> (128->128 3x3 @%dx%d, %d images)" % (n, n, N),
+                "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "traffic": traffic,
                 "peak_source": f"MEASURED_PEAKS.json bf16 burst ({peak_kind}); f16 kind::f16 has the same nominal rate",
-                "ms_per_launch": conv_ms, "flop_per_launch": conv_flop,
+                "ms_per_launch": ms_res, "flop_per_launch": conv_flop, "algorithmic_bytes_per_launch": alg_bytes,
+                "hbm_gbs_of_this_kernel": alg_bytes / ms_res / 1e6, "hbm_peak_gbs": hbm,
+                "same_shape_f16_store_only": {"ms_per_launch": ms_f16, "achieved": conv_flop / (ms_f16 / 1e3) / 1e12,
+                                              "frac": conv_flop / (ms_f16 / 1e3) / 1e12 / burst},
                 "whole_step_conv_tflops": step_conv_tflops, "whole_step_frac_of_sustained": step_conv_tflops / sustained}
 
     if world > 1:

@@ -47,6 +47,15 @@ __device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v);
 // ELU whose result is about to be rounded to f16: exp via the SFU (absolute error ~1e-7 near 0)
 __device__ __forceinline__ float elu_f16bound(float v) { return v > 0.f ? v : __expf(v) - 1.0f; }
 
+// f32 x2 -> f16 x2 with saturation: an activation beyond the f16 range degrades to +-65504 instead of turning the
+// rest of the network into inf/NaN (trained checkpoints are not available to prove the range).
+__device__ __forceinline__ unsigned pack_half2_sat(float a, float b) {
+  a = fminf(fmaxf(a, -65504.f), 65504.f);
+  b = fminf(fmaxf(b, -65504.f), 65504.f);
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<unsigned*>(&h);
+}
+
 // ---- Philox4x32-10 (Salmon et al.) + Box-Muller: two N(0,1) per call -------------------------
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                               uint32_t k1, uint32_t out[4]) {

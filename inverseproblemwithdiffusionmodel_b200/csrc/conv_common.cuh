@@ -108,10 +108,9 @@ __device__ __forceinline__ void conv_epilogue(const IgemmParams& p, float* slab,
         if (kOut16) {
           float4 h = (p.flags & IPDM_CONV_F16_PRE_RES) ? pre : a;
           if (p.flags & IPDM_CONV_F16_ELU) { h.x = elu_fast(h.x); h.y = elu_fast(h.y); h.z = elu_fast(h.z); h.w = elu_fast(h.w); }
-          __half2 lo = __floats2half2_rn(h.x, h.y), hi = __floats2half2_rn(h.z, h.w);
           uint2 pk;
-          pk.x = *reinterpret_cast<unsigned*>(&lo);
-          pk.y = *reinterpret_cast<unsigned*>(&hi);
+          pk.x = pack_half2_sat(h.x, h.y);
+          pk.y = pack_half2_sat(h.z, h.w);
           *reinterpret_cast<uint2*>(p.out_f16 + off[i]) = pk;
         }
         s1[0] += a.x; s1[1] += a.y; s1[2] += a.z; s1[3] += a.w;

@@ -264,11 +264,9 @@ __global__ void k_instnorm_apply(const float* __restrict__ x, const double* __re
     for (int u = 0; u < 4; ++u) {
       const int pp = pix + u * stride;
       if (pp < HW) {
-        __half2 lo = __floats2half2_rn(elu_f16bound(v[u].x * a0 + b0), elu_f16bound(v[u].y * a1 + b1));
-        __half2 hi = __floats2half2_rn(elu_f16bound(v[u].z * a2 + b2), elu_f16bound(v[u].w * a3 + b3));
         uint2 pk;
-        pk.x = *reinterpret_cast<unsigned*>(&lo);
-        pk.y = *reinterpret_cast<unsigned*>(&hi);
+        pk.x = pack_half2_sat(elu_f16bound(v[u].x * a0 + b0), elu_f16bound(v[u].y * a1 + b1));
+        pk.y = pack_half2_sat(elu_f16bound(v[u].z * a2 + b2), elu_f16bound(v[u].w * a3 + b3));
         *reinterpret_cast<uint2*>(obase + (size_t)pp * C + c4) = pk;
       }
     }
@@ -280,10 +278,9 @@ __global__ void k_act_to_f16(const float* __restrict__ x, __half* __restrict__ o
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 v = reinterpret_cast<const float4*>(x)[i];
     if (elu) { v.x = elu_f16bound(v.x); v.y = elu_f16bound(v.y); v.z = elu_f16bound(v.z); v.w = elu_f16bound(v.w); }
-    __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
     uint2 pk;
-    pk.x = *reinterpret_cast<unsigned*>(&lo);
-    pk.y = *reinterpret_cast<unsigned*>(&hi);
+    pk.x = pack_half2_sat(v.x, v.y);
+    pk.y = pack_half2_sat(v.z, v.w);
     reinterpret_cast<uint2*>(out)[i] = pk;
   }
 }
@@ -374,10 +371,9 @@ __global__ void k_bilinear_add(const float* __restrict__ src, float* __restrict_
     }
     *d = r;
     if (out16) {
-      __half2 lo = __floats2half2_rn(elu_f16bound(r.x), elu_f16bound(r.y)), hi = __floats2half2_rn(elu_f16bound(r.z), elu_f16bound(r.w));
       uint2 pk;
-      pk.x = *reinterpret_cast<unsigned*>(&lo);
-      pk.y = *reinterpret_cast<unsigned*>(&hi);
+      pk.x = pack_half2_sat(elu_f16bound(r.x), elu_f16bound(r.y));
+      pk.y = pack_half2_sat(elu_f16bound(r.z), elu_f16bound(r.w));
       *reinterpret_cast<uint2*>(out16 + pix * C + c4) = pk;
     }
   }
@@ -460,7 +456,7 @@ __global__ void k_conv_direct(ipdm_conv_desc d) {
     if (d.out_f16) {
       float s = (d.flags & IPDM_CONV_F16_PRE_RES) ? pre : v;
       if (d.flags & IPDM_CONV_F16_ELU) s = elu1(s);
-      reinterpret_cast<__half*>(d.out_f16)[i] = __float2half_rn(s);
+      reinterpret_cast<__half*>(d.out_f16)[i] = __float2half_rn(fminf(fmaxf(s, -65504.f), 65504.f));
     }
   }
 }

@@ -125,6 +125,52 @@ def sde_ald_corrector(score_fn, x, t, std, snr, n_steps, alpha=None, draw=_defau
     return x, x_mean
 
 
+def map_sense(score, x0, y, fwd, adj, lamda, lr, n_iters, betas=(0.5, 0.5)):
+    """MAP baseline: Adam on x with grad = -A^H(Ax - y) + lamda*(score(Re x) + i score(Im x)), label 1 throughout.
+    Reference: MAPOptimizer._step, ncsn/models/MAP_optimizers.py:97-115 (torch.optim.Adam on the complex tensor)."""
+    x = x0.clone()
+    opt = torch.optim.Adam([x], lr=lr, betas=betas)
+    labels = torch.ones(x.shape[0]).long()
+    for _ in range(n_iters):
+        grad = -adj(fwd(x) - y) + lamda * torch.complex(score(x.real, labels), score(x.imag, labels))
+        opt.zero_grad()
+        x.grad = -grad
+        opt.step()
+    return x
+
+
+def map_2dtime_tv(score, x0, y6, fwd, adj, lr, n_iters, prior_weight, w_S, w_T, betas=(0.5, 0.5)):
+    """2D+time MAP with the temporal-TV term: separate Adam optimisers on the real and imaginary parts.
+    Reference: MAPOptimizer2DTime,
+    ncsn/models/MAP_optimizers.py:154-292 (mode_T = "tv")."""
+    B, T, C, H, W = x0.shape
+    xr, xi = x0.real.clone(), x0.imag.clone()
+    o_r = torch.optim.Adam([xr], lr=lr, betas=betas)
+    o_i = torch.optim.Adam([xi], lr=lr, betas=betas)
+    y = y6.reshape(y6.shape[0], B * T, C, H, W)
+
+    def grad_of(x):
+        xf = x.reshape(B * T, C, H, W)
+        g_data = (-adj(fwd(xf) - y)).reshape(B, T, C, H, W)
+        labels = torch.ones(B * T).long()
+        g_S = torch.complex(score(xf.real, labels), score(xf.imag, labels)).reshape(B, T, C, H, W)
+        g_T = torch.complex(temporal_tv_grad(x.real, 1.0), temporal_tv_grad(x.imag, 1.0))
+        return g_data + prior_weight * (w_S * g_S + w_T * g_T)
+
+    # Quirk of the reference: x_real / x_imag are VIEWS of the initial x, so in iteration 0 the imaginary closure
+    # sees the already-updated real part; from iteration 1 on self.x is a fresh tensor that the in-place optimiser
+    # steps no longer touch, so both closures evaluate the gradient at the x of the iteration start (:175-176,206-233)
+    for it in range(n_iters):
+        x_start = torch.complex(xr, xi)
+        o_r.zero_grad()
+        xr.grad = -grad_of(x_start).real.contiguous()
+        o_r.step()
+        o_i.zero_grad()
+        xi.grad = -grad_of(torch.complex(xr, xi) if it == 0 else x_start).imag.contiguous()
+        o_i.step()
+    return torch.complex(xr, xi)
+
+
 # --------------------------------------------------------------------------- posterior statistics / metrics
 def posterior_stats(recons):
     """mean / population-std of magnitude and phase over the chain axis.

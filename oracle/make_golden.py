@@ -244,6 +244,52 @@ def gen_samplers():
     np.savez_compressed(os.path.join(OUT, "samplers.npz"), **out)
 
 
+def gen_map():
+    """MAP baselines: reference MAPOptimizer / MAPOptimizer2DTime with a no-op logger."""
+    import importlib
+    MAP = importlib.import_module(ref_shim.PKG + ".ncsn.models.MAP_optimizers")
+    from InverseProblemWithDiffusionModel.ncsn.linear_transforms.undersampling_fourier import SENSE
+    from oracle.mri_ops import keep_center_mask
+    logger = types.SimpleNamespace(add_scalar=lambda *a, **k: None, add_image=lambda *a, **k: None)
+    out = {}
+    n = 32
+    cfg = small_cfg("acdc", 8, n, 10, 30.0)
+    cfg.MAP.n_iters = 50          # plot_interval = n_iters // 50 must be >= 1
+    cfg.MAP.lr = 1e-2
+    net, _, _ = build_ref_net("NCSNv2Deepest", cfg, seed=6)
+    A = SENSE("exp", 4, 40, 1 / 8, (1, n, n), 0)
+    A.random_under_fourier.mask = keep_center_mask(n, 4, 1 / 8, seed=0)
+    meas = A(phantom(1501, 1, 1, n, n))
+    x0 = A.conj_op(meas).clone()
+    with _quiet():
+        opt = MAP.SENSEMAP(x0, meas, net, A, 0.5, cfg, logger, device=torch.device("cpu"))
+        # 6 iterations are enough to pin the arithmetic; drive _step directly (the __call__ loop only adds logging)
+        with torch.no_grad():
+            x = x0
+            for it in range(6):
+                x = opt._step(x, it)
+    out["map2d_final"] = _np(x)
+    # 2D+time with the TV temporal term
+    cfg = small_cfg("cine127", 8, n, 10, 20.0)
+    net, _, _ = build_ref_net("NCSNv2Deepest", cfg, seed=5)
+    A = SENSE("exp", 4, 16, 1 / 8, (1, n, n), 0)
+    vol = phantom(1402, 24, 1, n, n)
+    meas = A(vol).reshape(4, 1, 24, 1, n, n)
+    x0 = A.conj_op(meas.reshape(4, 24, 1, n, n)).reshape(1, 24, 1, n, n).clone()
+    net_T = types.SimpleNamespace(config=types.SimpleNamespace(data=types.SimpleNamespace(channels=64)))
+    params = dict(lr=5e-3, opt_class=torch.optim.Adam, num_iters=3, num_plot_times=1, win_size=8, prior_weight=1.0,
+                  spatial_step_weight=0.7, temporal_step_weight=0.05, save_dir="/tmp/ipdm_golden", opt_params={"betas": (0.5, 0.5)},
+                  mode_T="tv", if_random_shift=False, device=torch.device("cpu"))
+    MAP.save_vol_as_gif = lambda *a, **k: None
+    MAP.vis_images = lambda *a, **k: None
+    MAP.vis_multi_channel_signal = lambda *a, **k: None
+    MAP.normalize_phase = lambda x: x
+    with _quiet():
+        rec = MAP.MAPOptimizer2DTime(x0, meas, net, net_T, A, logger, params)()
+    out["map2dt_final"] = _np(rec)
+    np.savez_compressed(os.path.join(OUT, "map.npz"), **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
@@ -252,7 +298,8 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     os.makedirs("/tmp/ipdm_golden", exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    todo = {"linear": gen_fft_mask_coils, "sense": gen_sense_prox, "scorenet": gen_scorenet, "samplers": gen_samplers}
+    todo = {"linear": gen_fft_mask_coils, "sense": gen_sense_prox, "scorenet": gen_scorenet, "samplers": gen_samplers,
+            "map": gen_map}
     for name, fn in todo.items():
         if args.only and args.only != name:
             continue

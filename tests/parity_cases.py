@@ -29,6 +29,7 @@ from inverseproblemwithdiffusionmodel_b200.ncsn.models.ncsnv2 import NCSNv2, NCS
 from inverseproblemwithdiffusionmodel_b200.ncsn.models.proximal_op import L2Penalty, SingleCoil, Constrained, get_proximal
 from inverseproblemwithdiffusionmodel_b200.ncsn.models import ALD_optimizers as ALD
 from inverseproblemwithdiffusionmodel_b200.sde.sampling import AnnealedLangevinDynamics
+from inverseproblemwithdiffusionmodel_b200.ncsn.models import MAP_optimizers as MAP
 
 TOL32 = 1e-5
 TOL_SCORE = 5e-3
@@ -302,3 +303,29 @@ def case_full_chain_metrics(dev, levels=40):
         assert abs(a - b) < 1e-3, (mg, mr)
     assert rel_l2(got, ref) < 1e-3
     return mg, mr
+
+
+def case_map_baselines(dev):
+    """MAP baselines on the same operators, against the reference's outputs (tests/golden/map.npz).
+    Adam normalises the gradient, so a score error moves x by at most lr per step: tolerance 1e-3."""
+    g = G("map")
+    n = 32
+    cfg = make_config("ACDC", 8, n, 10, 30.0, device=dev)
+    cfg.MAP = ns(n_iters=6, lr=1e-2, complex_inner_n_steps=20)
+    net, _ = build_net(NCSNv2Deepest, "NCSNv2Deepest_ngf8", 6, cfg, dev)
+    A = SENSE("exp", 4, 40, 1 / 8, (1, n, n), 0)
+    A.random_under_fourier.mask = keep_center_mask(n, 4, 1 / 8, seed=0)
+    meas = A(phantom(1501, 1, 1, n, n).to(dev))
+    x0 = A.conj_op(meas).clone()
+    out = MAP.SENSEMAP(x0, meas, net, A, 0.5, cfg, None)()
+    assert rel_l2(out.cpu(), g["map2d_final"]) < 1e-3
+    cfg = make_config("CINE127", 8, n, 10, 20.0, device=dev)
+    net, _ = build_net(NCSNv2Deepest, "NCSNv2Deepest_ngf8", 5, cfg, dev)
+    A = SENSE("exp", 4, 16, 1 / 8, (1, n, n), 0)
+    meas = A(phantom(1402, 24, 1, n, n).to(dev)).reshape(4, 1, 24, 1, n, n)
+    x0 = A.conj_op(meas.reshape(4, 24, 1, n, n)).reshape(1, 24, 1, n, n).clone()
+    params = dict(lr=5e-3, opt_class=torch.optim.Adam, num_iters=3, num_plot_times=1, win_size=8, prior_weight=1.0,
+                  spatial_step_weight=0.7, temporal_step_weight=0.05, save_dir="/tmp", opt_params={"betas": (0.5, 0.5)},
+                  mode_T="tv", if_random_shift=False)
+    rec = MAP.MAPOptimizer2DTime(x0, meas, net, None, A, None, params)()
+    assert rel_l2(rec, g["map2dt_final"]) < 1e-3

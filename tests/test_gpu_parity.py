@@ -317,3 +317,7 @@ def test_posterior_stats_kernel():
 
 def test_full_chain_posterior_metrics():
     C.case_full_chain_metrics(DEV)
+
+
+def test_map_baselines():
+    C.case_map_baselines(DEV)

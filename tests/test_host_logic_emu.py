@@ -49,6 +49,10 @@ def test_full_chain_posterior_metrics(emu):
     C.case_full_chain_metrics("cpu", levels=12)
 
 
+def test_map_baselines(emu):
+    C.case_map_baselines("cpu")
+
+
 def test_no_cpu_fallback():
     """Without the emulator the product refuses CPU tensors instead of silently computing on the host."""
     from inverseproblemwithdiffusionmodel_b200 import _lib

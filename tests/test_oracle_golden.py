@@ -214,3 +214,28 @@ def test_posterior_stats_and_metrics():
     assert ALD.nrmse(a, a) == 0.0
     b = a + 0.1 * rrandn(2, 32, 32)
     assert 0 < ALD.ssim(b, a, data_range=1.0) < 1 and ALD.nrmse(b, a) > 0
+
+
+def test_map_baselines(golden):
+    G = golden("map")
+    n = 32
+    with torch.no_grad():
+        sig = ALD.geometric_sigmas(30.0, 0.01, 10)
+        P = _net("NCSNv2Deepest_ngf8", 6, sig)
+        score = lambda x, y: SN.score_forward("NCSNv2Deepest", P, x, y)
+        maps = M.exp_coil_maps(4, n, n, 0)
+        kc = M.keep_center_mask(n, 4, 1 / 8, seed=0)
+        fwd = lambda v: M.sense_forward(v, maps, kc)
+        adj = lambda s: M.sense_adjoint(s, maps)
+        y = fwd(phantom(1501, 1, 1, n, n))
+        out = ALD.map_sense(score, adj(y), y, fwd, adj, 0.5, 1e-2, 6)
+        assert rel_l2(out, G["map2d_final"]) < 1e-5
+        sig = ALD.geometric_sigmas(20.0, 0.01, 10)
+        P = _net("NCSNv2Deepest_ngf8", 5, sig)
+        score = lambda x, y: SN.score_forward("NCSNv2Deepest", P, x, y)
+        mask = M.live_sense_mask(n, 0)
+        fwd = lambda v: M.sense_forward(v, maps, mask)
+        y6 = fwd(phantom(1402, 24, 1, n, n)).reshape(4, 1, 24, 1, n, n)
+        x0 = adj(y6.reshape(4, 24, 1, n, n)).reshape(1, 24, 1, n, n)
+        out = ALD.map_2dtime_tv(score, x0, y6, fwd, adj, 5e-3, 3, 1.0, 0.7, 0.05)
+        assert rel_l2(out, G["map2dt_final"]) < 1e-5
