@@ -17,7 +17,7 @@ static int grid1d(size_t n, int block, int cap_mult = 32) {
 // thread = (4 consecutive pixels of a row, 4 output channels): 18 input values and 9 float4 weights feed 16
 // outputs.  grid (chunks, N): a block stays inside one image so the InstanceNorm++ sums can be reduced in the
 // block and added with 2 atomics per channel.
-__global__ void k_conv_first(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+__global__ void __launch_bounds__(256, 2) k_conv_first(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                              float* __restrict__ out, double* __restrict__ stats, int H, int W, int Cout, int affine) {
   extern __shared__ float sw[];  // [9][Cout] + [Cout] + per-thread stats scratch [blockDim][8]
   float* sst = sw + 10 * Cout;
@@ -288,9 +288,10 @@ __global__ void k_act_to_f16(const float* __restrict__ x, __half* __restrict__ o
 // 5x5/s1 max-pool, separable with a register sliding window: thread = (column x, 8 channels); it walks down
 // a strip of rows, takes the horizontal 5-max of each input row (5 16-byte loads, neighbours hit L1) and keeps
 // the last five of them in registers for the vertical max -- 5 loads per output instead of 25.
-// grid (ceil(W/XT), ceil(H/YS), N * C/8/CG); block = XT * CG threads (CG channel groups of 8).
-constexpr int MP_YS = 32;   // rows per strip
-__global__ void k_maxpool5(const __half* __restrict__ in, __half* __restrict__ out, int N, int H, int W, int C, int CG, int XT) {
+// grid (ceil(W/XT), ceil(H/YS), N * C/8/CG); block = XT * CG threads (CG channel groups of 8).  The strip length
+// YS trades redundant priming rows (4 per strip) for parallelism: 32 for large images, 8 for the 32x32 layers.
+__global__ void k_maxpool5(const __half* __restrict__ in, __half* __restrict__ out, int N, int H, int W, int C, int CG, int XT,
+                           int MP_YS /* rows per strip */) {
   const int cg_per = C / 8 / CG;                       // channel-group blocks per image
   const int n = blockIdx.z / cg_per;
   const int g = (blockIdx.z % cg_per) * CG + (threadIdx.x % CG);
@@ -346,35 +347,51 @@ __global__ void k_bilinear_add(const float* __restrict__ src, float* __restrict_
   const size_t total = (size_t)N * H * W * lanes;
   const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
   const float sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % lanes) * 4;
-    const size_t pix = i / lanes;
-    const int X = (int)(pix % W), Y = (int)((pix / W) % H), n = (int)(pix / ((size_t)W * H));
-    const float fy = sy * Y, fx = sx * X;
-    const int y0 = (int)fy, x0 = (int)fx;
-    const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
-    const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
-    const float* b = src + (size_t)n * h * w * C + c4;
-    const float4 v00 = *reinterpret_cast<const float4*>(b + ((size_t)y0 * w + x0) * C);
-    const float4 v01 = *reinterpret_cast<const float4*>(b + ((size_t)y0 * w + x1) * C);
-    const float4 v10 = *reinterpret_cast<const float4*>(b + ((size_t)y1 * w + x0) * C);
-    const float4 v11 = *reinterpret_cast<const float4*>(b + ((size_t)y1 * w + x1) * C);
-    float4 r;
-    r.x = hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
-    r.y = hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
-    r.z = hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
-    r.w = hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
-    float4* d = reinterpret_cast<float4*>(dst + pix * C + c4);
-    if (accumulate) {
-      const float4 o = *d;
-      r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+  // two independent output elements per iteration (all ten loads of both are issued before the first use)
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < total; i0 += 2 * stride) {
+    float4 v00[2], v01[2], v10[2], v11[2], old[2];
+    float ly[2], lx[2];
+    size_t dst_off[2];
+    bool live[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const size_t i = i0 + u * stride;
+      live[u] = i < total;
+      if (!live[u]) continue;
+      const int c4 = (int)(i % lanes) * 4;
+      const size_t pix = i / lanes;
+      const int X = (int)(pix % W), Y = (int)((pix / W) % H), n = (int)(pix / ((size_t)W * H));
+      const float fy = sy * Y, fx = sx * X;
+      const int y0 = (int)fy, x0 = (int)fx;
+      const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+      ly[u] = fy - y0;
+      lx[u] = fx - x0;
+      const float* b = src + (size_t)n * h * w * C + c4;
+      v00[u] = *reinterpret_cast<const float4*>(b + ((size_t)y0 * w + x0) * C);
+      v01[u] = *reinterpret_cast<const float4*>(b + ((size_t)y0 * w + x1) * C);
+      v10[u] = *reinterpret_cast<const float4*>(b + ((size_t)y1 * w + x0) * C);
+      v11[u] = *reinterpret_cast<const float4*>(b + ((size_t)y1 * w + x1) * C);
+      dst_off[u] = pix * C + c4;
+      if (accumulate) old[u] = *reinterpret_cast<const float4*>(dst + dst_off[u]);
     }
-    *d = r;
-    if (out16) {
-      uint2 pk;
-      pk.x = pack_half2_sat(elu_f16bound(r.x), elu_f16bound(r.y));
-      pk.y = pack_half2_sat(elu_f16bound(r.z), elu_f16bound(r.w));
-      *reinterpret_cast<uint2*>(out16 + pix * C + c4) = pk;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!live[u]) continue;
+      const float hy = 1.f - ly[u], hx = 1.f - lx[u];
+      float4 r;
+      r.x = hy * (hx * v00[u].x + lx[u] * v01[u].x) + ly[u] * (hx * v10[u].x + lx[u] * v11[u].x);
+      r.y = hy * (hx * v00[u].y + lx[u] * v01[u].y) + ly[u] * (hx * v10[u].y + lx[u] * v11[u].y);
+      r.z = hy * (hx * v00[u].z + lx[u] * v01[u].z) + ly[u] * (hx * v10[u].z + lx[u] * v11[u].z);
+      r.w = hy * (hx * v00[u].w + lx[u] * v01[u].w) + ly[u] * (hx * v10[u].w + lx[u] * v11[u].w);
+      if (accumulate) { r.x += old[u].x; r.y += old[u].y; r.z += old[u].z; r.w += old[u].w; }
+      *reinterpret_cast<float4*>(dst + dst_off[u]) = r;
+      if (out16) {
+        uint2 pk;
+        pk.x = pack_half2_sat(elu_f16bound(r.x), elu_f16bound(r.y));
+        pk.y = pack_half2_sat(elu_f16bound(r.z), elu_f16bound(r.w));
+        *reinterpret_cast<uint2*>(out16 + dst_off[u]) = pk;
+      }
     }
   }
 }
@@ -519,7 +536,7 @@ extern "C" int ipdm_conv_first(const float* x, const float* w, const float* bias
   const int qper = 256 / groups;
   const size_t quads = (size_t)H * ((W + 3) / 4);
   int chunks = (int)((quads + qper - 1) / qper);
-  int cap = (148 * 4) / N;          // one resident wave
+  int cap = (148 * 2) / N;          // one resident wave (2 blocks per SM at ~95 registers)
   if (cap < 1) cap = 1;
   if (chunks > cap) chunks = cap;
   k_conv_first<<<dim3(chunks, N), 256, (size_t)(10 * Cout + 256 * 8) * sizeof(float), s>>>(x, w, bias, out, stats, H, W, Cout, affine);
@@ -552,9 +569,11 @@ extern "C" int ipdm_maxpool5_f16(const void* in_f16, void* out_f16, int N, int H
   int CG = 16;
   while (groups % CG != 0) CG >>= 1;                      // channel groups per block (power of two dividing C/8)
   const int XT = 256 / CG;                                // columns per block
-  dim3 grid((W + XT - 1) / XT, (H + MP_YS - 1) / MP_YS, N * (groups / CG));
+  int ys = 32;
+  while (ys > 8 && (size_t)((W + XT - 1) / XT) * ((H + ys - 1) / ys) * N * (groups / CG) < 148 * 8) ys >>= 1;
+  dim3 grid((W + XT - 1) / XT, (H + ys - 1) / ys, N * (groups / CG));
   k_maxpool5<<<grid, XT * CG, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(in_f16),
-                                                      reinterpret_cast<__half*>(out_f16), N, H, W, C, CG, XT);
+                                                      reinterpret_cast<__half*>(out_f16), N, H, W, C, CG, XT, ys);
   return launched("k_maxpool5");
 }
 
