@@ -24,8 +24,8 @@
 namespace ipdm {
 
 constexpr int HT_H = 32, HT_W = 8;            // pixel tile
-constexpr int HALO_SLOTS = 16;                // pixel slots per halo row (8 + 2d used)
-constexpr int HALO_PITCH = HALO_SLOTS * 128;  // 2048 B
+constexpr int HALO_SLOTS = 12;                // pixel slots per halo row (8 + 2d used, d <= 2)
+constexpr int HALO_PITCH = HALO_SLOTS * 128;  // 1536 B (need not be a multiple of the 1024-byte swizzle pattern)
 constexpr int NH = 2;                         // halo ring
 constexpr int NW = 3;                         // weight ring
 constexpr int W_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
@@ -34,7 +34,7 @@ constexpr int HALO_THREADS = 352;
 template <int DIL> struct HaloCfg {
   static constexpr int ROWS = HT_H + 2 * DIL;
   static constexpr int HALO_BYTES = ROWS * HALO_PITCH;
-  static constexpr int SMEM = NH * HALO_BYTES + NW * W_BYTES + SLAB_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM = NH * HALO_BYTES + NW * W_BYTES + 2 * SLAB_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 struct HaloParams {
@@ -52,7 +52,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
   unsigned char* halo = smem;
   unsigned char* wts = smem + NH * CFG::HALO_BYTES;
   float* slab = reinterpret_cast<float*>(wts + NW * W_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(slab) + SLAB_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(slab) + 2 * SLAB_BYTES);
   uint64_t* halo_full = bars;             // [NH]
   uint64_t* halo_empty = bars + NH;       // [NH]
   uint64_t* w_full = bars + 2 * NH;       // [NW]
@@ -156,7 +156,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
     // ===== epilogue teams (TMEM lane quadrant = warp % 4): A = warps 3-6, B = warps 7-10 =====
     const int quad = warp & 3;
     const int team = warp >= 7 ? 1 : 0;
-    float* my_slab = slab + team * (32 * EPI_PITCH);
+    float* my_slab = slab + team * (2 * 32 * EPI_PITCH);      // each team: double-buffered [32 px][128 ch] slab
     uint32_t acnt = 0;
     for (int item = blockIdx.x; item < hp.items; item += gridDim.x, ++acnt) {
       int n, h0, w0, m0;
@@ -164,7 +164,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
       const int as = acnt & 1;
       mbar_wait(&acc_full[as], (acnt >> 1) & 1);
       tcgen05_fence_after();
-      conv_epilogue<MODE, HT_W, 1, 4>(p, my_slab, tmem_base + as * BLOCK_N, quad, lane, n, h0, w0, m0, team * 4, 1 + team);
+      conv_epilogue<MODE, HT_W, 2, 4>(p, my_slab, tmem_base + as * BLOCK_N, quad, lane, n, h0, w0, m0, team * 4, 1 + team);
       // all of this warp's TMEM reads are complete (tcgen05.wait::ld inside): hand the accumulator back
       tcgen05_fence_before();
       __syncwarp();
