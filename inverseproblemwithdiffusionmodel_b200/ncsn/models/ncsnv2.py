@@ -1,5 +1,5 @@
 """Mirror of `ncsn/models/ncsnv2.py` (+ the blocks of `layers.py` / `normalization.py` it uses):
-`NCSNv2` and `NCSNv2Deepest` RefineNet score networks with the reference's module tree, parameter
+`NCSNv2`, `NCSNv2Deeper` and `NCSNv2Deepest` RefineNet score networks with the reference's module tree, parameter
 names, shapes and creation order (so `load_state_dict` of a reference checkpoint works and the
 default initialisation consumes torch's RNG identically), but whose forward pass is a fixed
 sequence of hand-written sm_100a kernels:
@@ -433,6 +433,32 @@ class NCSNv2(_ScoreNetBase):
         self.refine2 = RefineBlock([2 * ngf, 2 * ngf], 2 * ngf)
         self.refine3 = RefineBlock([2 * ngf, 2 * ngf], ngf)
         self.refine4 = RefineBlock([ngf, ngf], ngf, end=True)
+
+
+class NCSNv2Deeper(_ScoreNetBase):
+    """ncsnv2.py:104-195: two pooled stages, one plain-down stage pair, then dilation 2 / 4; five refine blocks."""
+    encoder_stages = ("res1", "res2", "res3", "res4", "res5")
+    decoder_stages = ("refine1", "refine2", "refine3", "refine4", "refine5")
+
+    def __init__(self, config):
+        super().__init__()
+        self._common(config)
+        ngf = self.ngf
+        self.begin_conv = nn.Conv2d(config.data.channels, ngf, 3, stride=1, padding=1)
+        self.normalizer = self.norm(ngf)
+        self.end_conv = nn.Conv2d(ngf, config.data.channels, 3, stride=1, padding=1)
+        self.res1 = nn.ModuleList([ResidualBlock(ngf, ngf), ResidualBlock(ngf, ngf)])
+        self.res2 = nn.ModuleList([ResidualBlock(ngf, 2 * ngf, resample='down'), ResidualBlock(2 * ngf, 2 * ngf)])
+        self.res3 = nn.ModuleList([ResidualBlock(2 * ngf, 2 * ngf, resample='down'), ResidualBlock(2 * ngf, 2 * ngf)])
+        self.res4 = nn.ModuleList([ResidualBlock(2 * ngf, 4 * ngf, resample='down', dilation=2),
+                                   ResidualBlock(4 * ngf, 4 * ngf, dilation=2)])
+        self.res5 = nn.ModuleList([ResidualBlock(4 * ngf, 4 * ngf, resample='down', dilation=4),
+                                   ResidualBlock(4 * ngf, 4 * ngf, dilation=4)])
+        self.refine1 = RefineBlock([4 * ngf], 4 * ngf, start=True)
+        self.refine2 = RefineBlock([4 * ngf, 4 * ngf], 2 * ngf)
+        self.refine3 = RefineBlock([2 * ngf, 2 * ngf], 2 * ngf)
+        self.refine4 = RefineBlock([2 * ngf, 2 * ngf], ngf)
+        self.refine5 = RefineBlock([ngf, ngf], ngf, end=True)
 
 
 class NCSNv2Deepest(_ScoreNetBase):

@@ -1,8 +1,8 @@
 """Mirror of the annealed-Langevin part of `sde/sampling.py`: the 'ald' corrector
 (`AnnealedLangevinDynamics.update_fn`, sde/sampling.py:290-324), on the fused update kernel.
 
-Only what the north-star path names is here; predictors, the ODE sampler and the 'langevin'
-corrector (which needs two batch-mean norms per step) are out of scope.
+Only what the north-star path names is here (the 'ald' corrector, plus the 'langevin' corrector that shares its
+update); predictors and the ODE sampler are out of scope.
 """
 import torch
 
@@ -30,6 +30,35 @@ class Corrector:
 
     def __init__(self, sde, score_fn, snr, n_steps):
         self.sde, self.score_fn, self.snr, self.n_steps = sde, score_fn, snr, n_steps
+
+
+@register_corrector(name='langevin')
+class LangevinCorrector(Corrector):
+    """step = (snr * mean_b|noise_b| / mean_b|grad_b|)^2 * 2 * alpha, the same for every sample
+    (sde/sampling.py:258-287).  The two batch-mean norms are device-side reductions (no host sync); the update
+    itself is the fused Langevin kernel with a per-sample step."""
+
+    def update_fn(self, x, t, noise_fn=None):
+        _lib.require_cuda(x, t)
+        sde = self.sde
+        if hasattr(sde, "alphas"):
+            timestep = (t * (sde.N - 1) / sde.T).long()
+            alpha = sde.alphas.to(t.device)[timestep]
+        else:
+            alpha = torch.ones_like(t)
+        x = x.detach().float().contiguous().clone()
+        x_mean = torch.empty_like(x)
+        per = x[0].numel()
+        L = _lib.lib()
+        for i in range(self.n_steps):
+            grad = self.score_fn(x, t).contiguous()
+            noise = (torch.randn_like(x) if noise_fn is None else noise_fn(x.shape).to(x.device, torch.float32)).contiguous()
+            grad_norm = torch.norm(grad.reshape(grad.shape[0], -1), dim=-1).mean()
+            noise_norm = torch.norm(noise.reshape(noise.shape[0], -1), dim=-1).mean()
+            step = ((self.snr * noise_norm / grad_norm) ** 2 * 2 * alpha).float().contiguous()
+            _lib.check(L.ipdm_langevin_update(x.data_ptr(), grad.data_ptr(), noise.data_ptr(), x_mean.data_ptr(), x.numel(), None,
+                                              None, None, step.data_ptr(), per, 0, i, _lib.stream()), "langevin corrector")
+        return x, x_mean
 
 
 @register_corrector(name='ald')

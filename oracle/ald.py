@@ -47,7 +47,7 @@ def ald_unconditional(score, x, sigmas, n_steps_each, step_lr, denoise=True, dra
 
 
 def ald_sense_real_imag(score, measurement, sigmas, n_steps_each, step_lr, lr_scaled, adjoint, prox,
-                        denoise=True, draw=_default_draw, trace=None):
+                        denoise=True, draw=_default_draw, trace=None, guide=None):
     """cfg 2/3 sampler with guidance weight 0.  Reference: ALDInvSegProximalRealImag.__call__ and
     post_processing, ALD_optimizers.py:172-327.  x0 = A^H y; per step: score on real and imag
     separately, noise drawn in the order real, imag (:238-241), Langevin update on each part, then
@@ -62,6 +62,9 @@ def ald_sense_real_imag(score, measurement, sigmas, n_steps_each, step_lr, lr_sc
         for _ in range(n_steps_each):
             gr = score(xr, labels)
             gi = score(xi, labels)
+            if guide is not None:   # guide(x_part, c) -> seg-likelihood gradient already scaled by weight_c / sigma_c (:272-286)
+                gr = gr + guide(xr, c)
+                gi = gi + guide(xi, c)
             xr = langevin_update(xr, gr, draw(xr.shape), step)
             xi = langevin_update(xi, gi, draw(xi.shape), step)
             z = prox(xr + 1j * xi, measurement, step_lr * lr_scaled, 1.0)
@@ -123,6 +126,32 @@ def sde_ald_corrector(score_fn, x, t, std, snr, n_steps, alpha=None, draw=_defau
         x_mean = x + step[:, None, None, None] * g
         x = x_mean + noise * torch.sqrt(step * 2)[:, None, None, None]
     return x, x_mean
+
+
+def sde_langevin_corrector(score_fn, x, t, snr, n_steps, alpha=None, draw=_default_draw):
+    """'langevin' corrector: step = (snr*mean|noise|/mean|grad|)^2 * 2 * alpha (batch-mean per-sample norms).
+    Reference: LangevinCorrector.update_fn, sde/sampling.py:268-287."""
+    alpha = torch.ones_like(t) if alpha is None else alpha
+    x_mean = x
+    for _ in range(n_steps):
+        g = score_fn(x, t)
+        noise = draw(x.shape)
+        gn = torch.norm(g.reshape(g.shape[0], -1), dim=-1).mean()
+        nn_ = torch.norm(noise.reshape(noise.shape[0], -1), dim=-1).mean()
+        step = (snr * nn_ / gn) ** 2 * 2 * alpha
+        x_mean = x + step[:, None, None, None] * g
+        x = x_mean + torch.sqrt(step * 2)[:, None, None, None] * noise
+    return x, x_mean
+
+
+def seg_guidance_grad(seg, x, label, mode="full"):
+    """d/dx sum log softmax(seg(x))[label].  Reference: compute_seg_grad, ncsn/models/__init__.py:197-215."""
+    with torch.enable_grad():
+        X = x.detach().clone().requires_grad_(True)
+        prob = torch.softmax(seg(X), dim=1)
+        torch.log(torch.gather(prob, dim=1, index=label)).sum().backward()
+        g = X.grad
+    return g * label if mode == "FG" else g
 
 
 def map_sense(score, x0, y, fwd, adj, lamda, lr, n_iters, betas=(0.5, 0.5)):

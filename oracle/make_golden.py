@@ -244,6 +244,56 @@ def gen_samplers():
     np.savez_compressed(os.path.join(OUT, "samplers.npz"), **out)
 
 
+def gen_extra():
+    """NCSNv2Deeper forward, the 'langevin' corrector, segmentation-guided ALD."""
+    from InverseProblemWithDiffusionModel.ncsn.models import ALD_optimizers as ALD
+    from InverseProblemWithDiffusionModel.ncsn.models import get_sigmas
+    from InverseProblemWithDiffusionModel.ncsn.models.proximal_op import L2Penalty
+    from InverseProblemWithDiffusionModel.ncsn.linear_transforms.undersampling_fourier import SENSE
+    from InverseProblemWithDiffusionModel.sde import sampling as sde_sampling, sde_lib
+    from oracle.mri_ops import keep_center_mask
+    out = {}
+    specs_path = os.path.join(OUT, "state_dict_specs.json")
+    specs = json.load(open(specs_path))
+    with torch.no_grad():
+        cfg = small_cfg("acdc", 8, 32, 12, 30.0)
+        net, spec, _ = build_ref_net("NCSNv2Deeper", cfg, seed=8)
+        specs["NCSNv2Deeper_ngf8"] = [[k, list(s)] for k, s in spec]
+        out["deeper_out"] = _np(net(rrand(1303, 2, 1, 32, 32), torch.tensor([3, 10])))
+    json.dump(specs, open(specs_path, "w"))
+    # 'langevin' corrector
+    sde = sde_lib.VESDE(sigma_min=0.01, sigma_max=20.0, N=10)
+    cfg = small_cfg("mnist", 8, 28, 10, 20.0)
+    net, _, _ = build_ref_net("NCSNv2", cfg, seed=3)
+    score_fn = lambda x, t: net(x, torch.round((sde.T - t) * (sde.N - 1)).long())
+    corr = sde_sampling.LangevinCorrector(sde, score_fn, snr=0.16, n_steps=2)
+    torch.manual_seed(405)
+    x = torch.rand(2, 1, 28, 28)
+    with torch.no_grad():
+        xo, xm = corr.update_fn(x, torch.tensor([0.6, 0.2]))
+    out["lang_x"], out["lang_mean"] = _np(xo), _np(xm)
+    # segmentation-guided chain: weights ramp from level 0 (seg_start_time = 0), tiny seeded conv net as `seg`
+    n, B = 32, 2
+    cfg = small_cfg("acdc", 8, n, 10, 30.0)
+    net, _, _ = build_ref_net("NCSNv2Deepest", cfg, seed=4)
+    sig = get_sigmas(cfg, mode="recons")
+    A = SENSE("exp", 4, 40, 1 / 8, (1, n, n), 0)
+    A.random_under_fourier.mask = keep_center_mask(n, 4, 1 / 8, seed=0)
+    meas = A(phantom(1401, 1, 1, n, n)).repeat(1, B, 1, 1, 1)
+    torch.manual_seed(9)
+    seg = torch.nn.Conv2d(1, 3, 3, padding=1)
+    label = (rrand(1601, B, 1, n, n) * 3).long().clamp(max=2)
+    params = {"n_steps_each": 2, "step_lr": 9e-7, "denoise": True, "final_only": True}
+    sampler = ALD.ALDInvSegProximalRealImag(L2Penalty(A), 0.0, "linear", (B, 1, n, n), net, sig, params, cfg,
+                                            measurement=meas, linear_tfm=A, seg=seg, device=torch.device("cpu"))
+    torch.manual_seed(203)
+    with _quiet():
+        res = sampler(label=label, lamda=1.0, save_dir="/tmp/ipdm_golden", lr_scaled=1e6, seg_mode="full")
+    torch.set_grad_enabled(True)
+    out["seg_final"] = _np(res[0])
+    np.savez_compressed(os.path.join(OUT, "extra.npz"), **out)
+
+
 def gen_map():
     """MAP baselines: reference MAPOptimizer / MAPOptimizer2DTime with a no-op logger."""
     import importlib
@@ -299,7 +349,7 @@ def main():
     os.makedirs("/tmp/ipdm_golden", exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     todo = {"linear": gen_fft_mask_coils, "sense": gen_sense_prox, "scorenet": gen_scorenet, "samplers": gen_samplers,
-            "map": gen_map}
+            "map": gen_map, "extra": gen_extra}
     for name, fn in todo.items():
         if args.only and args.only != name:
             continue

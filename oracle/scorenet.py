@@ -113,6 +113,10 @@ ENCODERS = {
     # Reference: NCSNv2.__init__, ncsnv2.py:29-63
     "NCSNv2": [("res1", [(None, None), (None, None)]), ("res2", [("down", None), (None, None)]),
                ("res3", [("down", 2), (None, 2)]), ("res4", [("down", 4), (None, 4)])],
+    # Reference: NCSNv2Deeper.__init__, ncsnv2.py:122-154
+    "NCSNv2Deeper": [("res1", [(None, None), (None, None)]), ("res2", [("down", None), (None, None)]),
+                     ("res3", [("down", None), (None, None)]), ("res4", [("down", 2), (None, 2)]),
+                     ("res5", [("down", 4), (None, 4)])],
     # Reference: NCSNv2Deepest.__init__, ncsnv2.py:215-255
     "NCSNv2Deepest": [("res1", [(None, None), (None, None)]), ("res2", [("down", None), (None, None)]),
                       ("res3", [("down", None), (None, None)]), ("res31", [("down", None), (None, None)]),
@@ -121,6 +125,7 @@ ENCODERS = {
 # decoder: (refine name, skip stage index into the encoder list); deepest stage first
 DECODERS = {
     "NCSNv2": ["refine1", "refine2", "refine3", "refine4"],                                   # ncsnv2.py:65-68,86-89
+    "NCSNv2Deeper": ["refine1", "refine2", "refine3", "refine4", "refine5"],                   # ncsnv2.py:156-160,180-184
     "NCSNv2Deepest": ["refine1", "refine2", "refine31", "refine3", "refine4", "refine5"],      # ncsnv2.py:257-262,284-289
 }
 

@@ -25,10 +25,10 @@ from inverseproblemwithdiffusionmodel_b200.ncsn.linear_transforms.undersampling_
     SENSE, RandomUndersamplingFourier, keep_center_mask)
 from inverseproblemwithdiffusionmodel_b200.ncsn.linear_transforms.finite_diff import FiniteDiff
 from inverseproblemwithdiffusionmodel_b200.ncsn.models import get_sigmas, anneal_Langevin_dynamics
-from inverseproblemwithdiffusionmodel_b200.ncsn.models.ncsnv2 import NCSNv2, NCSNv2Deepest
+from inverseproblemwithdiffusionmodel_b200.ncsn.models.ncsnv2 import NCSNv2, NCSNv2Deeper, NCSNv2Deepest
 from inverseproblemwithdiffusionmodel_b200.ncsn.models.proximal_op import L2Penalty, SingleCoil, Constrained, get_proximal
 from inverseproblemwithdiffusionmodel_b200.ncsn.models import ALD_optimizers as ALD
-from inverseproblemwithdiffusionmodel_b200.sde.sampling import AnnealedLangevinDynamics
+from inverseproblemwithdiffusionmodel_b200.sde.sampling import AnnealedLangevinDynamics, LangevinCorrector
 from inverseproblemwithdiffusionmodel_b200.ncsn.models import MAP_optimizers as MAP
 
 TOL32 = 1e-5
@@ -329,3 +329,39 @@ def case_map_baselines(dev):
                   mode_T="tv", if_random_shift=False)
     rec = MAP.MAPOptimizer2DTime(x0, meas, net, None, A, None, params)()
     assert rel_l2(rec, g["map2dt_final"]) < 1e-3
+
+
+def case_deeper_langevin_seg(dev):
+    """NCSNv2Deeper forward, the 'langevin' corrector, and the segmentation-guidance hook (`adjust_grad`, run between
+    score and update with torch autograd on the user's seg net) against the reference's outputs."""
+    g = G("extra")
+    cfg = make_config("ACDC", 8, 32, 12, 30.0)
+    net, _ = build_net(NCSNv2Deeper, "NCSNv2Deeper_ngf8", 8, cfg, dev)
+    out = net(rrand(1303, 2, 1, 32, 32).to(dev), torch.tensor([3, 10]).to(dev))
+    assert rel_l2(out.cpu(), g["deeper_out"]) < TOL_SCORE
+    cfg = make_config("MNIST", 8, 28, 10, 20.0, device=dev)
+    net, _ = build_net(NCSNv2, "NCSNv2_ngf8_28", 3, cfg, dev)
+    sde = ns(N=10, T=1)
+    score_fn = lambda x, t: net(x, torch.round((1 - t) * 9).long())
+    torch.manual_seed(405)
+    x = torch.rand(2, 1, 28, 28).to(dev)
+    xo, xm = LangevinCorrector(sde, score_fn, snr=0.16, n_steps=2).update_fn(x, torch.tensor([0.6, 0.2]).to(dev),
+                                                                             noise_fn=lambda shape: torch.randn(*shape))
+    assert rel_l2(xo.cpu(), g["lang_x"]) < 5e-4 and rel_l2(xm.cpu(), g["lang_mean"]) < 5e-4
+    n, B = 32, 2
+    cfg = make_config("ACDC", 8, n, 10, 30.0, device=dev)
+    net, _ = build_net(NCSNv2Deepest, "NCSNv2Deepest_ngf8", 4, cfg, dev)
+    sig = get_sigmas(cfg, mode="recons")
+    A = SENSE("exp", 4, 40, 1 / 8, (1, n, n), 0)
+    A.random_under_fourier.mask = keep_center_mask(n, 4, 1 / 8, seed=0)
+    meas = A(phantom(1401, 1, 1, n, n).to(dev)).repeat(1, B, 1, 1, 1)
+    torch.manual_seed(9)
+    seg = torch.nn.Conv2d(1, 3, 3, padding=1).to(dev)
+    label = (rrand(1601, B, 1, n, n) * 3).long().clamp(max=2).to(dev)
+    params = {"n_steps_each": 2, "step_lr": 9e-7, "denoise": True, "final_only": True}
+    sampler = ALD.ALDInvSegProximalRealImag(L2Penalty(A), 0.0, "linear", (B, 1, n, n), net, sig, params, cfg,
+                                            measurement=meas, linear_tfm=A, seg=seg, device=torch.device(dev))
+    torch.manual_seed(203)
+    res = sampler(label=label, lamda=1.0, save_dir="/tmp", lr_scaled=1e6, seg_mode="full", noise_fn=lambda shape: torch.randn(*shape))
+    torch.set_grad_enabled(True)
+    assert rel_l2(res[0], g["seg_final"]) < TOL_X

@@ -321,3 +321,7 @@ def test_full_chain_posterior_metrics():
 
 def test_map_baselines():
     C.case_map_baselines(DEV)
+
+
+def test_deeper_langevin_seg():
+    C.case_deeper_langevin_seg(DEV)

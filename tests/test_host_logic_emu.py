@@ -53,6 +53,10 @@ def test_map_baselines(emu):
     C.case_map_baselines("cpu")
 
 
+def test_deeper_langevin_seg(emu):
+    C.case_deeper_langevin_seg("cpu")
+
+
 def test_no_cpu_fallback():
     """Without the emulator the product refuses CPU tensors instead of silently computing on the host."""
     from inverseproblemwithdiffusionmodel_b200 import _lib

@@ -239,3 +239,38 @@ def test_map_baselines(golden):
         x0 = adj(y6.reshape(4, 24, 1, n, n)).reshape(1, 24, 1, n, n)
         out = ALD.map_2dtime_tv(score, x0, y6, fwd, adj, 5e-3, 3, 1.0, 0.7, 0.05)
         assert rel_l2(out, G["map2dt_final"]) < 1e-5
+
+
+def test_deeper_langevin_seg_guidance(golden):
+    G = golden("extra")
+    with torch.no_grad():
+        sig = ALD.geometric_sigmas(30.0, 0.01, 12)
+        P = _net("NCSNv2Deeper_ngf8", 8, sig)
+        out = SN.score_forward("NCSNv2Deeper", P, rrand(1303, 2, 1, 32, 32), torch.tensor([3, 10]))
+        assert rel_l2(out, G["deeper_out"]) < 1e-5
+        sig = ALD.geometric_sigmas(20.0, 0.01, 10)
+        P = _net("NCSNv2_ngf8_28", 3, sig)
+        score = lambda x, y: SN.score_forward("NCSNv2", P, x, y)
+        sfn = lambda x, t: score(x, torch.round((1 - t) * 9).long())
+        torch.manual_seed(405)
+        x = torch.rand(2, 1, 28, 28)
+        xo, xm = ALD.sde_langevin_corrector(sfn, x, torch.tensor([0.6, 0.2]), 0.16, 2)
+        assert rel_l2(xo, G["lang_x"]) < 1e-5 and rel_l2(xm, G["lang_mean"]) < 1e-5
+    # segmentation-guided chain
+    n, B = 32, 2
+    sig = ALD.geometric_sigmas(30.0, 0.01, 10)
+    P = _net("NCSNv2Deepest_ngf8", 4, sig)
+    score = lambda x, y: SN.score_forward("NCSNv2Deepest", P, x, y)
+    maps = M.exp_coil_maps(4, n, n, 0)
+    kc = M.keep_center_mask(n, 4, 1 / 8, seed=0)
+    meas = M.sense_forward(phantom(1401, 1, 1, n, n), maps, kc).repeat(1, B, 1, 1, 1)
+    torch.manual_seed(9)
+    seg = torch.nn.Conv2d(1, 3, 3, padding=1)
+    label = (rrand(1601, B, 1, n, n) * 3).long().clamp(max=2)
+    w = torch.linspace(0, 1, 10)                       # get_lh_weights(sigmas, 0.0, "linear"), ALD_optimizers.py:23-38
+    guide = lambda xp, c: ALD.seg_guidance_grad(seg, xp, label) / sig[c] * w[c]
+    prox = lambda z, y, a, l: M.l2_prox_sense_closed_form(z, y, maps, kc, a, l)
+    torch.manual_seed(203)
+    with torch.no_grad():
+        out = ALD.ald_sense_real_imag(score, meas, sig, 2, 9e-7, 1e6, lambda s: M.sense_adjoint(s, maps), prox, guide=guide)
+    assert rel_l2(out, G["seg_final"]) < 2e-5
