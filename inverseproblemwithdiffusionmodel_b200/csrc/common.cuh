@@ -84,4 +84,23 @@ __device__ __forceinline__ float2 philox_normal2(uint64_t seed, uint64_t idx, ui
   return make_float2(rad * c, rad * s);
 }
 
+// Four N(0,1) per Philox call (both Box-Muller pairs), SFU log / sincos: the fused-step kernels draw the noise of
+// two complex pixels at once.  out = (re0, im0, re1, im1) for pixel pair `idx` of step `step` under `seed`.
+__device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t idx, uint32_t step, float out[4]) {
+  uint32_t r[4];
+  philox4x32_10(static_cast<uint32_t>(idx), static_cast<uint32_t>(idx >> 32), step, 0x1BD11BDBu,
+                static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const float u0 = (static_cast<float>(r[2 * p] >> 8) + 0.5f) * (1.0f / 16777216.0f);      // (0,1)
+    const float u1 = (static_cast<float>(r[2 * p + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float a2 = -2.0f * __logf(u0);             // > 0: u0 < 1
+    const float rad = a2 * rsqrtf(a2);
+    float s, c;
+    __sincosf(6.283185307179586f * u1, &s, &c);
+    out[2 * p] = rad * c;
+    out[2 * p + 1] = rad * s;
+  }
+}
+
 }  // namespace ipdm

@@ -13,6 +13,7 @@
 // kernel does update + prox (k_ald_sense).
 #include "common.cuh"
 #include "fft_core.cuh"
+#include <stdlib.h>
 
 namespace ipdm {
 
@@ -407,11 +408,78 @@ __global__ void __launch_bounds__(Tile<L>::NT) k_ald_sense(AldArgs a) {
   }
 }
 
+}  // namespace ipdm
+#include "sense_fast.cuh"
+namespace ipdm {
+
 // ---- launch helpers ---------------------------------------------------------------------------
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
   if (bytes > 48 * 1024) IPDM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   return 0;
+}
+
+// Lengths served by the two-pass engine (sense_fast.cuh); shorter transforms use the generic Stockham kernels.
+static bool fast_len(int n) { return n == 64 || n == 128 || n == 256 || n == 512; }
+static bool use_fast(int H, int W) {
+  static const bool legacy = getenv("IPDM_SENSE_LEGACY") != nullptr;   // A/B switch for profiling only
+  return !legacy && fast_len(H) && fast_len(W);
+}
+
+// per-thread twiddles in registers (true) or read from the per-CTA table (false), per kernel family
+#ifndef TWREG_FWD
+#define TWREG_FWD false
+#endif
+#ifndef TWREG_ADJ
+#define TWREG_ADJ false
+#endif
+#ifndef TWREG_ALD
+#define TWREG_ALD false
+#endif
+
+#define IPDM_FOR_FAST_LEN(LEN, MACRO) \
+  switch (LEN) {                      \
+    case 64: MACRO(64); break;        \
+    case 128: MACRO(128); break;      \
+    case 256: MACRO(256); break;      \
+    default: MACRO(512); break;       \
+  }
+
+static int launch_rows_fast(bool fwd, const SenseArgs& a, cudaStream_t s) {
+  const bool cplx = a.mim != nullptr;
+#define ROWS2_CASE(LL)                                                                              \
+  {                                                                                                 \
+    using G = Geo<LL>;                                                                              \
+    dim3 grid(a.H / G::TPC, a.batch);                                                               \
+    if (fwd) {                                                                                      \
+      if (cplx) k2_fwd_rows<LL, true, TWREG_FWD><<<grid, G::NT, G::SMEM_ROWS, s>>>(a);              \
+      else k2_fwd_rows<LL, false, TWREG_FWD><<<grid, G::NT, G::SMEM_ROWS, s>>>(a);                  \
+    } else {                                                                                        \
+      if (cplx) k2_adj_rows<LL, true, TWREG_ADJ><<<grid, G::NT, G::SMEM_ROWS, s>>>(a);              \
+      else k2_adj_rows<LL, false, TWREG_ADJ><<<grid, G::NT, G::SMEM_ROWS, s>>>(a);                  \
+    }                                                                                               \
+  }
+  IPDM_FOR_FAST_LEN(a.W, ROWS2_CASE)
+#undef ROWS2_CASE
+  return launched(fwd ? "k2_fwd_rows" : "k2_adj_rows");
+}
+
+static int launch_cols_fast(bool fwd, const SenseArgs& a, cudaStream_t s) {
+#define COLS2_CASE(LL)                                                                              \
+  {                                                                                                 \
+    using G = Geo<LL>;                                                                              \
+    dim3 grid(a.W / 16, a.ncoils * a.batch);                                                        \
+    if (fwd) {                                                                                      \
+      if (int e = set_smem(k2_fwd_cols<LL>, G::SMEM_COLS)) return e;                                \
+      k2_fwd_cols<LL><<<grid, G::NT_COLS, G::SMEM_COLS, s>>>(a);                                    \
+    } else {                                                                                        \
+      if (int e = set_smem(k2_adj_cols<LL>, G::SMEM_COLS)) return e;                                \
+      k2_adj_cols<LL><<<grid, G::NT_COLS, G::SMEM_COLS, s>>>(a);                                    \
+    }                                                                                               \
+  }
+  IPDM_FOR_FAST_LEN(a.H, COLS2_CASE)
+#undef COLS2_CASE
+  return launched(fwd ? "k2_fwd_cols" : "k2_adj_cols");
 }
 
 #define IPDM_FOR_LEN(LEN, MACRO)                                       \
@@ -633,6 +701,10 @@ extern "C" int ipdm_sense_forward(const void* x, const float* maps_re, const flo
   a.ncoils = ncoils; a.batch = batch; a.H = H; a.W = W; a.ssos = 0;
   a.sparse = mask != nullptr ? 1 : 0;   // masked columns are written straight from registers (any density is correct)
   a.scale = (((H / 2 + W / 2) & 1) ? -1.f : 1.f) / sqrtf((float)H * (float)W);
+  if (use_fast(H, W)) {
+    if (int e = launch_rows_fast(true, a, as_stream(stream))) return e;
+    return launch_cols_fast(true, a, as_stream(stream));
+  }
   if (int e = launch_rows(true, a, as_stream(stream))) return e;
   return launch_cols(true, a, as_stream(stream));
 }
@@ -649,6 +721,10 @@ extern "C" int ipdm_sense_adjoint(const void* S, const float* maps_re, const flo
   a.mask = mask; a.mask_frames = mask ? mask_frames : 1;
   a.ncoils = ncoils; a.batch = batch; a.H = H; a.W = W; a.ssos = ssos ? 1 : 0;
   a.scale = (((H / 2 + W / 2) & 1) ? -1.f : 1.f) / sqrtf((float)H * (float)W);
+  if (use_fast(H, W)) {
+    if (int e = launch_cols_fast(false, a, as_stream(stream))) return e;
+    return launch_rows_fast(false, a, as_stream(stream));
+  }
   if (int e = launch_cols(false, a, as_stream(stream))) return e;
   return launch_rows(false, a, as_stream(stream));
 }
@@ -712,6 +788,19 @@ extern "C" int ipdm_ald_sense_step(float* x, const float* grad, const float* noi
   if (scalars_host) a.sc = *scalars_host;
   a.sched = sched; a.cursor = cursor; a.seed = seed; a.rng_step = rng_step;
   cudaStream_t s = as_stream(stream);
+  if (use_fast(W, W) && H % 16 == 0) {
+    const bool cplx = maps_im != nullptr;
+#define ALD2_CASE(LL)                                                                   \
+  {                                                                                     \
+    using G = Geo<LL>;                                                                  \
+    dim3 grid(H / G::TPC, batch);                                                       \
+    if (cplx) k2_ald_sense<LL, true, TWREG_ALD><<<grid, G::NT, G::SMEM_ROWS, s>>>(a);   \
+    else k2_ald_sense<LL, false, TWREG_ALD><<<grid, G::NT, G::SMEM_ROWS, s>>>(a);       \
+  }
+    IPDM_FOR_FAST_LEN(W, ALD2_CASE)
+#undef ALD2_CASE
+    return launched("k2_ald_sense");
+  }
 #define ALD_CASE(LL)                                                         \
   {                                                                          \
     using TL = Tile<LL>;                                                     \

@@ -6,6 +6,7 @@
 #include <vector>
 #include <complex>
 #include "../../inverseproblemwithdiffusionmodel_b200/csrc/fft_core.cuh"
+#include "../../inverseproblemwithdiffusionmodel_b200/csrc/fft2p.cuh"
 using namespace ipdm;
 
 template <int L, int P, int DIR>
@@ -49,6 +50,50 @@ double check() {
   return sqrt(err / nrm);
 }
 
+// Two-pass engine (csrc/fft2p.cuh): A->B and B->A pipelines, threads run in a loop with the exchange as barrier.
+template <int L, int DIR, bool A2B>
+double check2p() {
+  using P = P2<L>;
+  std::vector<cf32> x(L), tw(L), out(L), smem(P::STRIDE + 8);
+  std::vector<std::complex<double>> xd(L);
+  for (int i = 0; i < L; ++i) {
+    x[i] = cf32{(float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f};
+    xd[i] = {x[i].x, x[i].y};
+    tw[i] = cf32{(float)cos(-2.0 * M_PI * i / L), (float)sin(-2.0 * M_PI * i / L)};
+  }
+  std::vector<cf32> regs(P::TPF * P::E);
+  cf32 twr[64];
+  if (A2B) {
+    for (int t = 0; t < P::TPF; ++t) {
+      for (int q = 0; q < P::E; ++q) regs[t * P::E + q] = x[a_pos<L>(t, q)];
+      a2b_first<L, DIR>(&regs[t * P::E], t, smem.data());
+    }
+    for (int u = 0; u < P::TPF; ++u) {
+      p2_twiddles<L>(u, twr, tw.data());
+      a2b_second<L, DIR>(&regs[u * P::E], u, smem.data(), [&](int n) { return twr[n]; });
+      for (int i = 0; i < P::E; ++i) out[b_pos<L>(u, i)] = regs[u * P::E + i];
+    }
+  } else {
+    for (int u = 0; u < P::TPF; ++u) {
+      p2_twiddles<L>(u, twr, tw.data());
+      for (int i = 0; i < P::E; ++i) regs[u * P::E + i] = x[b_pos<L>(u, i)];
+      b2a_first<L, DIR>(&regs[u * P::E], u, smem.data(), [&](int n) { return twr[n]; });
+    }
+    for (int t = 0; t < P::TPF; ++t) {
+      b2a_second<L, DIR>(&regs[t * P::E], t, smem.data());
+      for (int q = 0; q < P::E; ++q) out[a_pos<L>(t, q)] = regs[t * P::E + q];
+    }
+  }
+  double err = 0, nrm = 0;
+  for (int k = 0; k < L; ++k) {
+    std::complex<double> s = 0;
+    for (int n = 0; n < L; ++n) s += xd[n] * std::polar(1.0, DIR * 2.0 * M_PI * k * n / L);
+    err += std::norm(s - std::complex<double>(out[k].x, out[k].y));
+    nrm += std::norm(s);
+  }
+  return sqrt(err / nrm);
+}
+
 int main() {
   double worst = 0;
 #define CHK(L)                                                       \
@@ -58,6 +103,14 @@ int main() {
     worst = fmax(worst, fmax(a, b));                                 \
   }
   CHK(8) CHK(16) CHK(32) CHK(64) CHK(128) CHK(256) CHK(512) CHK(1024)
+#define CHK2(L)                                                                               \
+  {                                                                                           \
+    double a = check2p<L, -1, true>(), b = check2p<L, +1, true>();                            \
+    double c = check2p<L, -1, false>(), d = check2p<L, +1, false>();                          \
+    printf("2-pass L=%d a2b fwd %.3e inv %.3e  b2a fwd %.3e inv %.3e\n", L, a, b, c, d);      \
+    worst = fmax(worst, fmax(fmax(a, b), fmax(c, d)));                                        \
+  }
+  CHK2(8) CHK2(16) CHK2(32) CHK2(64) CHK2(128) CHK2(256) CHK2(512)
   printf("worst %.3e\n", worst);
   return worst < 2e-6 ? 0 : 1;
 }
