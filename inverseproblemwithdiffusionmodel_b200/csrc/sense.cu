@@ -464,11 +464,20 @@ static int launch_rows_fast(bool fwd, const SenseArgs& a, cudaStream_t s) {
   return launched(fwd ? "k2_fwd_rows" : "k2_adj_rows");
 }
 
+// Column CTAs walk the active-sector list in chunks of 4; with many images a few CTAs per image already fill the
+// GPU and the rest would only compile the mask and exit.
+static int cols_grid_x(const SenseArgs& a) {
+  const int chunks = a.W / 16, images = a.ncoils * a.batch;
+  int want = (148 * 8 + images - 1) / images;
+  if (want < 4) want = 4;
+  return want < chunks ? want : chunks;
+}
+
 static int launch_cols_fast(bool fwd, const SenseArgs& a, cudaStream_t s) {
 #define COLS2_CASE(LL)                                                                              \
   {                                                                                                 \
     using G = Geo<LL>;                                                                              \
-    dim3 grid(a.W / 16, a.ncoils * a.batch);                                                        \
+    dim3 grid(cols_grid_x(a), a.ncoils * a.batch);                                                  \
     if (fwd) {                                                                                      \
       if (int e = set_smem(k2_fwd_cols<LL>, G::SMEM_COLS)) return e;                                \
       k2_fwd_cols<LL><<<grid, G::NT_COLS, G::SMEM_COLS, s>>>(a);                                    \

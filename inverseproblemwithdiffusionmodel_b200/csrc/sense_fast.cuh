@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(128) k2_fwd_rows(SenseArgs a) {
 }
 
 // ---- forward, columns: transform the active sectors along H and write them (scaled, centred) ------------------
-// grid (W / 16, ncoils * batch); CTA j handles active groups 4j .. 4j+3 of its frame's list
+// grid (<= W / 16, ncoils * batch); CTA j handles active groups 4j .. 4j+3 of its frame's list, then 4(j+gridDim.x) ..
 template <int L>
 __global__ void __launch_bounds__(Geo<L>::NT_COLS) k2_fwd_cols(SenseArgs a) {
   using G = Geo<L>;
@@ -190,38 +190,40 @@ __global__ void __launch_bounds__(Geo<L>::NT_COLS) k2_fwd_cols(SenseArgs a) {
   const int b = (int)(img % a.batch);
   const uint8_t* mrow = a.mask ? a.mask + (size_t)(b % a.mask_frames) * a.W : nullptr;
   const int count = build_group_list(mrow, a.W, &gl);
-  const int g0 = blockIdx.x * 4;
-  if (g0 >= count) return;
+  if ((int)blockIdx.x * 4 >= count) return;
   fill_tws<L>(tws, tid, G::NT_COLS);
-  const int cs = tid / G::TPF, t = tid % G::TPF;
-  const bool gvalid = g0 + (cs >> 2) < count;
-  const int k = gvalid ? 4 * gl.list[g0 + (cs >> 2)] + (cs & 3) : 0;
-  const bool active = gvalid && (mrow == nullptr || mrow[k] != 0);
-  cf32* sx = xch + cs * P::STRIDE;
-  cf32 v[G::E];
-  {
-    const cf32* wp = a.ws + (img * a.W + k) * L + t;
-#pragma unroll
-    for (int q = 0; q < G::E; ++q) v[q] = active ? wp[a_off<L>(q)] : cf32{0.f, 0.f};
-  }
   __syncthreads();   // twiddle table complete
+  const int cs = tid / G::TPF, t = tid % G::TPF;
   Twid<L, (L < 512)> tw;
   tw.init(tws, t);
-  a2b_first<L, -1>(v, t, sx);
-  __syncwarp();
-  a2b_second<L, -1>(v, t, sx, tw);
-  __syncwarp();
+  cf32* sx = xch + cs * P::STRIDE;
+  for (int g0 = blockIdx.x * 4; g0 < count; g0 += gridDim.x * 4) {
+    const bool gvalid = g0 + (cs >> 2) < count;
+    const int k = gvalid ? 4 * gl.list[g0 + (cs >> 2)] + (cs & 3) : 0;
+    const bool active = gvalid && (mrow == nullptr || mrow[k] != 0);
+    cf32 v[G::E];
+    {
+      const cf32* wp = a.ws + (img * a.W + k) * L + t;
 #pragma unroll
-  for (int i = 0; i < G::E; ++i) sx[b_pos<L>(t, i)] = v[i];   // the exchange line doubles as the column's tile line
-  __syncthreads();
-  // 16-byte pieces: idx = ((gi*L + h)*2 + half)
-  for (int idx = tid; idx < 4 * L * 2; idx += G::NT_COLS) {
-    const int half = idx & 1, hh = (idx >> 1) % L, gi = (idx >> 1) / L;
-    if (g0 + gi >= count) break;
-    const int kk = 4 * gl.list[g0 + gi] + 2 * half;
-    const cf32 p0 = xch[(4 * gi + 2 * half) * P::STRIDE + hh], p1 = xch[(4 * gi + 2 * half + 1) * P::STRIDE + hh];
-    const float s0 = a.scale * sgn(hh + kk);
-    *reinterpret_cast<float4*>(a.out + (img * L + hh) * a.W + kk) = make_float4(p0.x * s0, p0.y * s0, -p1.x * s0, -p1.y * s0);
+      for (int q = 0; q < G::E; ++q) v[q] = active ? wp[a_off<L>(q)] : cf32{0.f, 0.f};
+    }
+    a2b_first<L, -1>(v, t, sx);
+    __syncwarp();
+    a2b_second<L, -1>(v, t, sx, tw);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < G::E; ++i) sx[b_pos<L>(t, i)] = v[i];   // the exchange line doubles as the column's tile line
+    __syncthreads();
+    // 16-byte pieces: idx = ((gi*L + h)*2 + half)
+    for (int idx = tid; idx < 4 * L * 2; idx += G::NT_COLS) {
+      const int half = idx & 1, hh = (idx >> 1) % L, gi = (idx >> 1) / L;
+      if (g0 + gi >= count) break;
+      const int kk = 4 * gl.list[g0 + gi] + 2 * half;
+      const cf32 p0 = xch[(4 * gi + 2 * half) * P::STRIDE + hh], p1 = xch[(4 * gi + 2 * half + 1) * P::STRIDE + hh];
+      const float s0 = a.scale * sgn(hh + kk);
+      *reinterpret_cast<float4*>(a.out + (img * L + hh) * a.W + kk) = make_float4(p0.x * s0, p0.y * s0, -p1.x * s0, -p1.y * s0);
+    }
+    __syncthreads();   // the tile is reused by the next chunk
   }
 }
 
@@ -239,41 +241,44 @@ __global__ void __launch_bounds__(Geo<L>::NT_COLS) k2_adj_cols(SenseArgs a) {
   const int b = (int)(img % a.batch);
   const uint8_t* mrow = a.mask ? a.mask + (size_t)(b % a.mask_frames) * a.W : nullptr;
   const int count = build_group_list(mrow, a.W, &gl);
-  const int g0 = blockIdx.x * 4;
-  if (g0 >= count) return;
+  if ((int)blockIdx.x * 4 >= count) return;
   fill_tws<L>(tws, tid, G::NT_COLS);
-  for (int idx = tid; idx < 4 * L * 2; idx += G::NT_COLS) {
-    const int half = idx & 1, hh = (idx >> 1) % L, gi = (idx >> 1) / L;
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (g0 + gi < count) {
-      const int kk = 4 * gl.list[g0 + gi] + 2 * half;
-      p = *reinterpret_cast<const float4*>(a.in + (img * L + hh) * a.W + kk);
-      const float s0 = sgn(hh + kk);
-      const float m0 = (mrow == nullptr || mrow[kk] != 0) ? s0 : 0.f, m1 = (mrow == nullptr || mrow[kk + 1] != 0) ? -s0 : 0.f;
-      p = make_float4(p.x * m0, p.y * m0, p.z * m1, p.w * m1);
-    }
-    xch[(4 * gi + 2 * half) * P::STRIDE + hh] = cf32{p.x, p.y};
-    xch[(4 * gi + 2 * half + 1) * P::STRIDE + hh] = cf32{p.z, p.w};
-  }
-  __syncthreads();
+  __syncthreads();   // twiddle table complete
   const int cs = tid / G::TPF, t = tid % G::TPF;
-  const bool gvalid = g0 + (cs >> 2) < count;
-  const int k = gvalid ? 4 * gl.list[g0 + (cs >> 2)] + (cs & 3) : 0;
-  const bool active = gvalid && (mrow == nullptr || mrow[k] != 0);
   Twid<L, (L < 512)> tw;
   tw.init(tws, t);
   cf32* sx = xch + cs * P::STRIDE;
-  cf32 v[G::E];
+  for (int g0 = blockIdx.x * 4; g0 < count; g0 += gridDim.x * 4) {
+    for (int idx = tid; idx < 4 * L * 2; idx += G::NT_COLS) {
+      const int half = idx & 1, hh = (idx >> 1) % L, gi = (idx >> 1) / L;
+      float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g0 + gi < count) {
+        const int kk = 4 * gl.list[g0 + gi] + 2 * half;
+        p = *reinterpret_cast<const float4*>(a.in + (img * L + hh) * a.W + kk);
+        const float s0 = sgn(hh + kk);
+        const float m0 = (mrow == nullptr || mrow[kk] != 0) ? s0 : 0.f, m1 = (mrow == nullptr || mrow[kk + 1] != 0) ? -s0 : 0.f;
+        p = make_float4(p.x * m0, p.y * m0, p.z * m1, p.w * m1);
+      }
+      xch[(4 * gi + 2 * half) * P::STRIDE + hh] = cf32{p.x, p.y};
+      xch[(4 * gi + 2 * half + 1) * P::STRIDE + hh] = cf32{p.z, p.w};
+    }
+    __syncthreads();
+    const bool gvalid = g0 + (cs >> 2) < count;
+    const int k = gvalid ? 4 * gl.list[g0 + (cs >> 2)] + (cs & 3) : 0;
+    const bool active = gvalid && (mrow == nullptr || mrow[k] != 0);
+    cf32 v[G::E];
 #pragma unroll
-  for (int q = 0; q < G::E; ++q) v[q] = sx[a_pos<L>(t, q)];
-  __syncwarp();
-  a2b_first<L, +1>(v, t, sx);
-  __syncwarp();
-  a2b_second<L, +1>(v, t, sx, tw);
-  if (active) {
-    cf32* wp = a.ws + (img * a.W + k) * L + t;
+    for (int q = 0; q < G::E; ++q) v[q] = sx[a_pos<L>(t, q)];
+    __syncwarp();
+    a2b_first<L, +1>(v, t, sx);
+    __syncwarp();
+    a2b_second<L, +1>(v, t, sx, tw);
+    if (active) {
+      cf32* wp = a.ws + (img * a.W + k) * L + t;
 #pragma unroll
-    for (int i = 0; i < G::E; ++i) wp[b_off<L>(i)] = v[i];
+      for (int i = 0; i < G::E; ++i) wp[b_off<L>(i)] = v[i];
+    }
+    __syncthreads();   // the tile is refilled by the next chunk
   }
 }
 
