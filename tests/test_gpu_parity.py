@@ -185,6 +185,24 @@ def test_conv_igemm_vs_direct(N, H, W, Cin, Cout, taps, dil, flags, bias, residu
     assert rel_l2(bst.float().cpu(), ref_st.cpu()) < 1e-5
 
 
+@pytest.mark.parametrize("want32,want16,stats", [(True, False, True), (False, True, False), (True, False, False)])
+@pytest.mark.parametrize("N,H,W,Cin,Cout,dil,flags,bias,residual", [
+    (2, 64, 64, 128, 128, 1, 1, True, True), (1, 40, 24, 128, 256, 2, 0, False, False), (1, 64, 32, 128, 128, 1, 8 | 1, True, True),
+    (3, 96, 72, 64, 128, 1, 4 | 2 | 1, False, True)])
+def test_conv_halo_output_modes(N, H, W, Cin, Cout, dil, flags, bias, residual, want32, want16, stats):
+    """Every epilogue specialisation of the persistent halo kernel (fp32-only, f16-only, with / without residual,
+    pooled) against the CUDA-core direct kernel, including tiles that overhang the image."""
+    (a32, a16, ast), (b32, b16, bst) = _conv_pair(N, H, W, Cin, Cout, 9, dil, flags, bias, residual, want32, want16, stats)
+    if want32:
+        assert not torch.isnan(a32).any()
+        assert rel_l2(a32.cpu(), b32.cpu()) < 1e-5
+    if want16:
+        assert not torch.isnan(a16.float()).any()
+        assert rel_l2(a16.float().cpu(), b16.float().cpu()) < 1e-3
+    if stats:
+        assert rel_l2(ast.float().cpu(), bst.float().cpu()) < 1e-5
+
+
 def test_conv_direct_vs_torch():
     """Anchor of the chain igemm -> direct -> torch: the CUDA-core kernel against F.conv2d on the same f16 operands."""
     import torch.nn.functional as F
