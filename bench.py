@@ -172,6 +172,45 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ native arm
+def sense_point(torch, C, _lib, L, dev, hbm, coils, size, batch, R, frac):
+    """SENSE forward / adjoint / fused ALD step at one cfg-5 sweep point: algorithmic GB/s (fwd/adj
+    8N(1+Nc) + 4*Nc*H*W, fused step 32N + 4*Nc*H*W bytes, N = B*H*W) over CUDA-event time, L2 flushed between
+    iterations, best of 5.  `adjoint` is A^H on masked data (mask applied); `conj_op_unmasked` is the reference's
+    SENSE.conj_op signature, which transforms every column (quirk Q3)."""
+    A = C.SENSE("exp", coils, R, frac, (1, size, size), 0)
+    A.random_under_fourier.mask = C.keep_center_mask(size, R, frac, seed=0)
+    x = torch.randn(batch, 1, size, size, dtype=torch.complex64, device=dev)
+    S = A(x)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def best(fn):
+        fn(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            flush.zero_(); torch.cuda.synchronize()
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return min(ts)
+
+    N = batch * size * size
+    b_fa = 8 * N * (1 + coils) + 4 * coils * size * size
+    b_st = 32 * N + 4 * coils * size * size
+    state = torch.randn(2, batch, size, size, device=dev); grad = torch.randn_like(state); bvec = torch.randn_like(state)
+    mre, _ = A.device_maps(dev); m, frames = A.device_mask(dev)
+    sc = _lib.AldScalars(0.1, 0.4, 0.01, 1.0)
+    step = lambda: _lib.check(L.ipdm_ald_sense_step(state.data_ptr(), grad.data_ptr(), None, bvec.data_ptr(), mre.data_ptr(), None,
+                                                    m.data_ptr(), frames, coils, batch, size, size, sc, None, None, 1, 0, _lib.stream()))
+    t = {"forward": best(lambda: A(x)), "adjoint": best(lambda: A.conj_op_masked(S)), "conj_op_unmasked": best(lambda: A.conj_op(S)),
+         "fused_ald_step": best(step)}
+    out = {"point": f"{coils} coils, {size}x{size}, batch {batch}, R={R} ({int(A.random_under_fourier.mask.sum())} lines), k-space {8 * coils * N / 1e6:.0f} MB",
+           "hbm_peak_gbs": hbm, "l2": "256 MB flush between iterations"}
+    for k, ms in t.items():
+        byt = b_st if k == "fused_ald_step" else b_fa
+        out[k] = {"ms": ms, "gbs": byt / ms / 1e6, "frac": byt / ms / 1e6 / hbm}
+    return out
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
@@ -297,14 +336,32 @@ def run_native(args):
     # (profiles/r01_ncu_conv_halo_res_mode.txt: 1.434 GB + 1.363 GB at 28 images of 256^2; algorithmic 2.58 GB)
     traffic = 2.797738e9 if (N == 28 and n == 256) else None
     alg_bytes = N * n * n * 128 * (2 + 4 + 4 + 2)
-    roofline = {"bound": "tensor", "kernel": "k_conv_halo<res+f32+f16> (128->128 3x3 @%dx%d, %d images)" % (n, n, N),
-                "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "traffic": traffic,
-                "peak_source": f"MEASURED_PEAKS.json bf16 burst ({peak_kind}); f16 kind::f16 has the same nominal rate",
+    # Which roofline bounds this variant?  Arithmetic intensity = 2*128*1152 FLOP / 1536 B per pixel = 192 FLOP/B, below
+    # the ridge of the measured peaks (burst tensor / HBM copy ~ 258 FLOP/B): by the roofline model it is HBM-bound,
+    # so `achieved`/`peak` are GB/s; the tensor-pipe view of the same launch and of the store-only variant
+    # (AI 576 FLOP/B, tensor-bound) are reported beside it.
+    ai = conv_flop / alg_bytes
+    ridge = burst * 1e12 / (hbm * 1e9)
+    tensor_view = {"achieved_tflops": achieved, "peak_tflops": burst, "frac": achieved / burst}
+    gbs = alg_bytes / ms_res / 1e6
+    if ai < ridge:
+        head = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm}
+    else:
+        head = {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst}
+    roofline = dict(head, **{
+                "kernel": "k_conv_halo<res+f32+f16> (128->128 3x3 @%dx%d, %d images)" % (n, n, N), "traffic": traffic,
+                "arithmetic_intensity_flop_per_byte": ai, "ridge_flop_per_byte": ridge, "tensor_view": tensor_view,
+                "peak_source": f"MEASURED_PEAKS.json HBM copy GB/s and bf16 burst TFLOP/s ({peak_kind}); f16 kind::f16 has the same nominal rate as bf16",
                 "ms_per_launch": ms_res, "flop_per_launch": conv_flop, "algorithmic_bytes_per_launch": alg_bytes,
-                "hbm_gbs_of_this_kernel": alg_bytes / ms_res / 1e6, "hbm_peak_gbs": hbm,
-                "same_shape_f16_store_only": {"ms_per_launch": ms_f16, "achieved": conv_flop / (ms_f16 / 1e3) / 1e12,
-                                              "frac": conv_flop / (ms_f16 / 1e3) / 1e12 / burst},
-                "whole_step_conv_tflops": step_conv_tflops, "whole_step_frac_of_sustained": step_conv_tflops / sustained}
+                "same_shape_f16_store_only": {"bound": "tensor", "ms_per_launch": ms_f16, "achieved": conv_flop / (ms_f16 / 1e3) / 1e12,
+                                              "peak": burst, "unit": "TFLOP/s", "frac": conv_flop / (ms_f16 / 1e3) / 1e12 / burst},
+                "whole_step_conv_tflops": step_conv_tflops, "whole_step_frac_of_sustained": step_conv_tflops / sustained})
+
+    # ---- SENSE operator GB/s (second headline metric) at a cfg-5 point whose k-space exceeds L2 ------------
+    sense = None
+    if rank == 0:
+        del x16, o16, o32, res
+        sense = sense_point(torch, C, _lib, L, dev, hbm, coils=args.coils, size=n, batch=64, R=args.R, frac=args.center_frac)
 
     if world > 1:
         dist.barrier()
@@ -325,7 +382,7 @@ def run_native(args):
                    "note": f"one bench step = one public sampler call of {call_steps} ALD steps; {n_calls} calls timed"},
            "gpu_launches": launches_per_step * args.steps,
            "launches_per_step": launches_per_step,
-           "roofline": roofline, "cpu_baseline": cpu,
+           "roofline": roofline, "sense": sense, "cpu_baseline": cpu,
            "state_finite": finite, "posterior_chains": post["n"], "my_chains": len(my_chains)}
     print(json.dumps(out), flush=True)
 

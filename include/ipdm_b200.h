@@ -128,6 +128,19 @@ int ipdm_c64_to_planar(const void* c64, float* planar, size_t n, void* stream);
  * helpers/visualizations.py:93-95,117-142. */
 int ipdm_chain_stats_accumulate(const void* x, double* acc, int chains, size_t hw, void* stream);
 
+/* sums f64 [images][4] = { sum (img-ref)^2, sum img^2, sum ref^2, sum |img-ref| } per image of n f32 values
+ * (ref_images = 1: one reference for all, else = images).  MSE, MAE and the reference's NRMSE
+ * (skimage normalized_root_mse(img, img_orig, "euclidean") = sqrt(sums[0] / sums[1]), normalised by its FIRST
+ * argument) follow on the host.  Replaces helpers/metrics.py:47-74 (numpy / skimage on the CPU). */
+int ipdm_image_sums(const float* img, const float* ref, double* sums, int images, int ref_images, size_t n, void* stream);
+
+/* out f64 [images] = SUM over the (H-6)x(W-6) interior of the skimage-default SSIM map (7x7 uniform window, sample
+ * covariance, K1 = 0.01, K2 = 0.03, C = (K * data_range)^2); divide by (H-6)*(W-6) for structural_similarity's
+ * value.  data_range must be given (skimage infers it from the dtype; the reference leaves its version unpinned).
+ * Replaces helpers/metrics.py:55-68. */
+int ipdm_ssim(const float* img, const float* ref, double* out, int images, int ref_images, int H, int W,
+              double data_range, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * NCSNv2 score network building blocks (NHWC)
  * ---------------------------------------------------------------------------------------------- */

@@ -6,7 +6,7 @@ Build the library with `python -c "import __graft_entry__ as g; g.build()"` or
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint32, c_uint64, c_ulonglong, c_void_p, POINTER
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint32, c_uint64, c_ulonglong, c_void_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libipdm_b200.so")
@@ -46,6 +46,8 @@ SIGNATURES = {
     "ipdm_planar_to_c64": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "ipdm_c64_to_planar": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "ipdm_chain_stats_accumulate": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p]),
+    "ipdm_image_sums": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_size_t, c_void_p]),
+    "ipdm_ssim": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_void_p]),
     "ipdm_conv_igemm": (c_int, [POINTER(ConvDesc), c_void_p]),
     "ipdm_conv_direct": (c_int, [POINTER(ConvDesc), c_void_p]),
     "ipdm_debug_option": (c_int, [c_int, c_int]),

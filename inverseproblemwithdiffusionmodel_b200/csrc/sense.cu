@@ -446,17 +446,21 @@ static bool use_fast(int H, int W) {
   }
 
 static int launch_rows_fast(bool fwd, const SenseArgs& a, cudaStream_t s) {
-  const bool cplx = a.mim != nullptr;
+  const bool cplx = a.mim != nullptr, dense = a.mask == nullptr;
 #define ROWS2_CASE(LL)                                                                              \
   {                                                                                                 \
     using G = Geo<LL>;                                                                              \
     dim3 grid(a.H / G::TPC, a.batch);                                                               \
     if (fwd) {                                                                                      \
-      if (cplx) k2_fwd_rows<LL, true, TWREG_FWD><<<grid, G::NT, G::SMEM_ROWS, s>>>(a);              \
-      else k2_fwd_rows<LL, false, TWREG_FWD><<<grid, G::NT, G::SMEM_ROWS, s>>>(a);                  \
+      if (cplx && dense) k2_fwd_rows<LL, true, TWREG_FWD, true><<<grid, G::NT, G::SMEM_ROWS, s>>>(a);        \
+      else if (cplx) k2_fwd_rows<LL, true, TWREG_FWD, false><<<grid, G::NT, G::SMEM_ROWS, s>>>(a);         \
+      else if (dense) k2_fwd_rows<LL, false, TWREG_FWD, true><<<grid, G::NT, G::SMEM_ROWS, s>>>(a);        \
+      else k2_fwd_rows<LL, false, TWREG_FWD, false><<<grid, G::NT, G::SMEM_ROWS, s>>>(a);                  \
     } else {                                                                                        \
-      if (cplx) k2_adj_rows<LL, true, TWREG_ADJ><<<grid, G::NT, G::SMEM_ROWS, s>>>(a);              \
-      else k2_adj_rows<LL, false, TWREG_ADJ><<<grid, G::NT, G::SMEM_ROWS, s>>>(a);                  \
+      if (cplx && dense) k2_adj_rows<LL, true, TWREG_ADJ, true><<<grid, G::NT, G::SMEM_ROWS, s>>>(a);        \
+      else if (cplx) k2_adj_rows<LL, true, TWREG_ADJ, false><<<grid, G::NT, G::SMEM_ROWS, s>>>(a);         \
+      else if (dense) k2_adj_rows<LL, false, TWREG_ADJ, true><<<grid, G::NT, G::SMEM_ROWS, s>>>(a);        \
+      else k2_adj_rows<LL, false, TWREG_ADJ, false><<<grid, G::NT, G::SMEM_ROWS, s>>>(a);                  \
     }                                                                                               \
   }
   IPDM_FOR_FAST_LEN(a.W, ROWS2_CASE)
@@ -474,16 +478,21 @@ static int cols_grid_x(const SenseArgs& a) {
 }
 
 static int launch_cols_fast(bool fwd, const SenseArgs& a, cudaStream_t s) {
+  const bool dense = a.mask == nullptr;
 #define COLS2_CASE(LL)                                                                              \
   {                                                                                                 \
     using G = Geo<LL>;                                                                              \
     dim3 grid(cols_grid_x(a), a.ncoils * a.batch);                                                  \
     if (fwd) {                                                                                      \
-      if (int e = set_smem(k2_fwd_cols<LL>, G::SMEM_COLS)) return e;                                \
-      k2_fwd_cols<LL><<<grid, G::NT_COLS, G::SMEM_COLS, s>>>(a);                                    \
+      if (int e = set_smem(k2_fwd_cols<LL, true>, G::SMEM_COLS)) return e;                          \
+      if (int e = set_smem(k2_fwd_cols<LL, false>, G::SMEM_COLS)) return e;                         \
+      if (dense) k2_fwd_cols<LL, true><<<grid, G::NT_COLS, G::SMEM_COLS, s>>>(a);                   \
+      else k2_fwd_cols<LL, false><<<grid, G::NT_COLS, G::SMEM_COLS, s>>>(a);                        \
     } else {                                                                                        \
-      if (int e = set_smem(k2_adj_cols<LL>, G::SMEM_COLS)) return e;                                \
-      k2_adj_cols<LL><<<grid, G::NT_COLS, G::SMEM_COLS, s>>>(a);                                    \
+      if (int e = set_smem(k2_adj_cols<LL, true>, G::SMEM_COLS)) return e;                          \
+      if (int e = set_smem(k2_adj_cols<LL, false>, G::SMEM_COLS)) return e;                         \
+      if (dense) k2_adj_cols<LL, true><<<grid, G::NT_COLS, G::SMEM_COLS, s>>>(a);                   \
+      else k2_adj_cols<LL, false><<<grid, G::NT_COLS, G::SMEM_COLS, s>>>(a);                        \
     }                                                                                               \
   }
   IPDM_FOR_FAST_LEN(a.H, COLS2_CASE)

@@ -98,7 +98,10 @@ template <> struct MapVal<true> {
 
 // ---- forward, rows: coil multiply, transform along W, scatter sampled columns, zero-fill inactive sectors ------
 // grid (H / TPC, batch)
-template <int L, bool CPLX, bool TWREG>
+// DENSE (no mask): every column survives, so the scratch keeps the NATURAL layout T[c][b][h][k] -- the row kernels
+// access it in runs of 8*R1 bytes and the column kernels in 16-column tiles through shared memory, every global
+// access a full line -- instead of scattering 8-byte elements into the transposed layout.
+template <int L, bool CPLX, bool TWREG, bool DENSE>
 __global__ void __launch_bounds__(128) k2_fwd_rows(SenseArgs a) {
   using G = Geo<L>;
   using P = P2<L>;
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(128) k2_fwd_rows(SenseArgs a) {
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const size_t img_stride = (size_t)a.batch * a.H * L;
   float4* zbase = reinterpret_cast<float4*>(a.out + ((size_t)b * a.H + h0) * L);
-  cf32* wsp = a.ws + ((size_t)b * L + t) * a.H + h;
+  cf32* wsp = DENSE ? a.ws + ((size_t)b * a.H + h) * L + t : a.ws + ((size_t)b * L + t) * a.H + h;
   // this thread's zero-fill pieces are the same for every coil: precompute which of them are inactive
   constexpr int ZP = G::TPC * (L / 2) / G::NT;
   uint32_t zmask = 0;
@@ -168,16 +171,21 @@ __global__ void __launch_bounds__(128) k2_fwd_rows(SenseArgs a) {
     a2b_first<L, -1>(u, t, sx);
     __syncwarp();
     a2b_second<L, -1>(u, t, sx, tw);
+    if (DENSE) {
 #pragma unroll
-    for (int i = 0; i < G::E; ++i)
-      if ((keep >> i) & 1u) wsp[(size_t)b_off<L>(i) * a.H] = u[i];
+      for (int i = 0; i < G::E; ++i) wsp[b_off<L>(i)] = u[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < G::E; ++i)
+        if ((keep >> i) & 1u) wsp[(size_t)b_off<L>(i) * a.H] = u[i];
+    }
     wsp += img_stride;
   }
 }
 
 // ---- forward, columns: transform the active sectors along H and write them (scaled, centred) ------------------
 // grid (<= W / 16, ncoils * batch); CTA j handles active groups 4j .. 4j+3 of its frame's list, then 4(j+gridDim.x) ..
-template <int L>
+template <int L, bool DENSE>
 __global__ void __launch_bounds__(Geo<L>::NT_COLS) k2_fwd_cols(SenseArgs a) {
   using G = Geo<L>;
   using P = P2<L>;
@@ -202,7 +210,20 @@ __global__ void __launch_bounds__(Geo<L>::NT_COLS) k2_fwd_cols(SenseArgs a) {
     const int k = gvalid ? 4 * gl.list[g0 + (cs >> 2)] + (cs & 3) : 0;
     const bool active = gvalid && (mrow == nullptr || mrow[k] != 0);
     cf32 v[G::E];
-    {
+    if (DENSE) {
+      // natural-layout scratch: 16-column tile -> per-column lines (16-byte loads, one 128-byte run per row)
+      for (int idx = tid; idx < 4 * L * 2; idx += G::NT_COLS) {
+        const int half = idx & 1, hh = (idx >> 1) % L, gi = (idx >> 1) / L;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g0 + gi < count) p = *reinterpret_cast<const float4*>(a.ws + (img * L + hh) * a.W + 4 * gl.list[g0 + gi] + 2 * half);
+        xch[(4 * gi + 2 * half) * P::STRIDE + hh] = cf32{p.x, p.y};
+        xch[(4 * gi + 2 * half + 1) * P::STRIDE + hh] = cf32{p.z, p.w};
+      }
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < G::E; ++q) v[q] = sx[a_pos<L>(t, q)];
+      __syncwarp();
+    } else {
       const cf32* wp = a.ws + (img * a.W + k) * L + t;
 #pragma unroll
       for (int q = 0; q < G::E; ++q) v[q] = active ? wp[a_off<L>(q)] : cf32{0.f, 0.f};
@@ -228,7 +249,7 @@ __global__ void __launch_bounds__(Geo<L>::NT_COLS) k2_fwd_cols(SenseArgs a) {
 }
 
 // ---- adjoint, columns: inverse transform of the active sectors along H into the transposed scratch ------------
-template <int L>
+template <int L, bool DENSE>
 __global__ void __launch_bounds__(Geo<L>::NT_COLS) k2_adj_cols(SenseArgs a) {
   using G = Geo<L>;
   using P = P2<L>;
@@ -273,7 +294,18 @@ __global__ void __launch_bounds__(Geo<L>::NT_COLS) k2_adj_cols(SenseArgs a) {
     a2b_first<L, +1>(v, t, sx);
     __syncwarp();
     a2b_second<L, +1>(v, t, sx, tw);
-    if (active) {
+    if (DENSE) {
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < G::E; ++i) sx[b_pos<L>(t, i)] = v[i];
+      __syncthreads();
+      for (int idx = tid; idx < 4 * L * 2; idx += G::NT_COLS) {
+        const int half = idx & 1, hh = (idx >> 1) % L, gi = (idx >> 1) / L;
+        if (g0 + gi >= count) break;
+        const cf32 p0 = xch[(4 * gi + 2 * half) * P::STRIDE + hh], p1 = xch[(4 * gi + 2 * half + 1) * P::STRIDE + hh];
+        *reinterpret_cast<float4*>(a.ws + (img * L + hh) * a.W + 4 * gl.list[g0 + gi] + 2 * half) = make_float4(p0.x, p0.y, p1.x, p1.y);
+      }
+    } else if (active) {
       cf32* wp = a.ws + (img * a.W + k) * L + t;
 #pragma unroll
       for (int i = 0; i < G::E; ++i) wp[b_off<L>(i)] = v[i];
@@ -284,7 +316,7 @@ __global__ void __launch_bounds__(Geo<L>::NT_COLS) k2_adj_cols(SenseArgs a) {
 
 // ---- adjoint, rows: gather sampled columns, inverse transform along W, conj-coil sum (or SSOS) ----------------
 // grid (H / TPC, batch)
-template <int L, bool CPLX, bool TWREG>
+template <int L, bool CPLX, bool TWREG, bool DENSE>
 __global__ void __launch_bounds__(128, (L <= 256 ? 4 : 2)) k2_adj_rows(SenseArgs a) {
   using G = Geo<L>;
   using P = P2<L>;
@@ -302,7 +334,7 @@ __global__ void __launch_bounds__(128, (L <= 256 ? 4 : 2)) k2_adj_rows(SenseArgs
   for (int q = 0; q < G::E; ++q)
     if (mrow == nullptr || mrow[a_pos<L>(t, q)] != 0) keep |= 1u << q;
   const size_t img_stride = (size_t)a.batch * a.H * L;
-  const cf32* wsp = a.ws + ((size_t)b * L + t) * a.H + h;
+  const cf32* wsp = DENSE ? a.ws + ((size_t)b * a.H + h) * L + t : a.ws + ((size_t)b * L + t) * a.H + h;
   const bool has_maps = a.mre != nullptr && !a.ssos;
   const size_t map_img = (size_t)a.H * L;
   const float* mre = a.mre + (size_t)h * L + t;
@@ -315,7 +347,11 @@ __global__ void __launch_bounds__(128, (L <= 256 ? 4 : 2)) k2_adj_rows(SenseArgs
 #pragma unroll
     for (int q = 0; q < G::E; ++q) {
       nxt[q] = cf32{0.f, 0.f};
-      if (c < a.ncoils && ((keep >> q) & 1u)) nxt[q] = wsp[(size_t)a_off<L>(q) * a.H];
+      if (DENSE) {
+        if (c < a.ncoils) nxt[q] = wsp[a_off<L>(q)];
+      } else if (c < a.ncoils && ((keep >> q) & 1u)) {
+        nxt[q] = wsp[(size_t)a_off<L>(q) * a.H];
+      }
     }
     wsp += img_stride;
   };

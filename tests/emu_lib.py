@@ -203,6 +203,23 @@ class EmuLib:
         A += torch.stack([mag.sum(0), (mag * mag).sum(0), ang.sum(0), (ang * ang).sum(0)])
         return 0
 
+    def ipdm_image_sums(self, img, ref, sums, images, ref_images, n, stream):
+        self.launches += 1
+        A = _t(img, (images, n), np.float32).double()
+        R = _t(ref, (ref_images, n), np.float32).double().expand(images, n)
+        _t(sums, (images, 4), np.float64).copy_(torch.stack([((A - R) ** 2).sum(1), (A * A).sum(1), (R * R).sum(1), (A - R).abs().sum(1)], 1))
+        return 0
+
+    def ipdm_ssim(self, img, ref, out, images, ref_images, H, W, data_range, stream):
+        self.launches += 1
+        from oracle import ald as OALD
+        A = _t(img, (images, H, W), np.float32)
+        R = _t(ref, (ref_images, H, W), np.float32)
+        o = _t(out, (images,), np.float64)
+        for i in range(images):
+            o[i] = OALD.ssim(A[i], R[0 if ref_images == 1 else i], data_range=data_range) * (H - 6) * (W - 6)
+        return 0
+
     # ---- score network
     def _conv(self, dp):
         d = _deref(dp)

@@ -365,3 +365,45 @@ def case_deeper_langevin_seg(dev):
     res = sampler(label=label, lamda=1.0, save_dir="/tmp", lr_scaled=1e6, seg_mode="full", noise_fn=lambda shape: torch.randn(*shape))
     torch.set_grad_enabled(True)
     assert rel_l2(res[0], g["seg_final"]) < TOL_X
+
+
+def case_metrics(dev):
+    """helpers.metrics / helpers.results against the oracle's restatement of the reference metrics (skimage
+    conventions) on a batch of perturbed phantoms; incl. the reference's (B,C,H,W) / (1,C,H,W) call shape."""
+    import tempfile
+    from inverseproblemwithdiffusionmodel_b200.helpers import metrics as HM, results as HR
+    B, n = 5, 72
+    g = torch.Generator().manual_seed(77)
+    orig = phantom(21, 1, 1, n, n)                                  # (1,1,H,W) complex
+    recons = orig + 0.05 * torch.complex(torch.randn(B, 1, n, n, generator=g), torch.randn(B, 1, n, n, generator=g))
+    mags, t = recons.abs(), orig.abs()
+    rng = float(t.max() - t.min())
+    got = HM.compute_metrics(["NRMSE", "SSIM", "L2", "L1"], mags.to(dev), t.to(dev), data_range=rng)
+    for i in range(B):
+        assert abs(got["NRMSE"][i] - OALD.nrmse(mags[i, 0], t[0, 0])) < 1e-6
+        assert abs(got["SSIM"][i] - OALD.ssim(mags[i, 0], t[0, 0], data_range=rng)) < 1e-6
+        assert abs(got["L2"][i] - float(((mags[i] - t[0]) ** 2).mean())) < 1e-8
+        assert abs(got["L1"][i] - float((mags[i] - t[0]).abs().mean())) < 1e-7
+    red = HM.compute_metrics(["NRMSE"], mags.to(dev), t.to(dev), reduce="mean")
+    assert abs(red["NRMSE"] - got["NRMSE"].mean()) < 1e-12
+    # multi-channel SSIM = mean of the per-channel values; per-image references
+    two = torch.cat([mags, mags.flip(-1)], 1)
+    ref2 = torch.cat([t, t.flip(-1)], 1).repeat(B, 1, 1, 1) + 0.01
+    s2 = HM.SSIM_wrapper(two.to(dev), ref2.to(dev), data_range=rng)
+    for i in range(B):
+        want = 0.5 * (OALD.ssim(two[i, 0], ref2[i, 0], data_range=rng) + OALD.ssim(two[i, 1], ref2[i, 1], data_range=rng))
+        assert abs(s2[i] - want) < 1e-6
+    mm, pm, ms, ps = HM.compute_mean_and_std(recons.to(dev))
+    st = OALD.posterior_stats(recons)
+    assert rel_l2(mm.cpu(), st["mag_mean"]) < 1e-6 and rel_l2(ms.cpu(), st["mag_std"]) < 1e-4
+    assert rel_l2(pm.cpu(), st["phase_mean"]) < 1e-5 and rel_l2(ps.cpu(), st["phase_std"]) < 1e-4
+    snr = HM.compute_snr(recons.to(dev))
+    flat = recons.abs().reshape(B, -1)
+    assert np.allclose(snr, (20 * torch.log10(flat.max(1).values / flat.std(1, unbiased=False))).numpy(), rtol=1e-5)
+    with tempfile.TemporaryDirectory() as d:
+        HR.save_reconstruction(d, orig, torch.zeros(4, 1, 1, n, n, dtype=torch.complex64), recons.to(dev), zero_filled=orig[0],
+                               args_dict={"R": 40})
+        back = HR.load_reconstruction(d)
+        assert sorted(os.listdir(d)) == ["ZF.pt", "args_dict.pkl", "measurement.pt", "original.pt", "reconstructions.pt"]
+        assert torch.equal(back["reconstructions"], recons) and back["reconstructions"].device.type == "cpu"
+        assert back["args_dict"] == {"R": 40}

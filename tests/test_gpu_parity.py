@@ -379,6 +379,10 @@ def test_sense_sampler_graph_path_matches_eager():
     assert torch.isfinite(a.abs()).all()
 
 
+def test_metrics_and_result_files():
+    C.case_metrics(DEV)
+
+
 def test_posterior_stats_kernel():
     from inverseproblemwithdiffusionmodel_b200.chains import PosteriorStats
     x = crandn(5, 7, 1, 16, 16)

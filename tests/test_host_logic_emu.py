@@ -33,6 +33,10 @@ def test_scorenet_small(emu):
     C.case_scorenet_small("cpu")
 
 
+def test_metrics_and_result_files(emu):
+    C.case_metrics("cpu")
+
+
 def test_sampler_uncond(emu):
     C.case_sampler_uncond("cpu")
 
