@@ -33,13 +33,13 @@ extern int g_conv_variant;       // 0 = auto, 1 = force the per-tap tile kernel 
 // TMEM lane = output channel, column = pixel j = py*TW + px of a (256/TW) x TW pixel tile at (h0, w0).
 // Each warp pulls 32 columns for its 32 channels, transposes them through the team's shared-memory slab, and
 // the team then streams the [32 pixels][128 ch] slab with 16-byte accesses: thread = 4 consecutive channels of
-// one pixel, so a warp touches one whole 512-byte pixel row of the NHWC tensor per instruction.  The residual
-// loads of a chunk are issued before the TMEM read so their latency hides behind the staging.
+// one pixel, so a warp touches one whole 512-byte pixel row of the NHWC tensor per instruction.  `wait_acc()` is
+// called once, after the first residual loads are in flight and before the first TMEM read.
 // SLABS = 2: double-buffered slab, one barrier per chunk; SLABS = 1: single slab, two barriers per chunk.
 // MODE bits: 1 = residual, 2 = fp32 output, 4 = f16 output, 8 = 2x2 mean-pool.
-template <int MODE, int TW, int SLABS, int NCHUNK>
+template <int MODE, int TW, int SLABS, int NCHUNK, class WaitAcc>
 __device__ __forceinline__ void conv_epilogue(const IgemmParams& p, float* slab, uint32_t tmem_acc, int quad, int lane,
-                                              int n, int h0, int w0, int m0, int chunk0, int BAR) {
+                                              int n, int h0, int w0, int m0, int chunk0, int BAR, WaitAcc wait_acc) {
   constexpr bool kRes = (MODE & 1) != 0, kOut32 = (MODE & 2) != 0, kOut16 = (MODE & 4) != 0, pool = (MODE & 8) != 0;
   constexpr int ROWS_PER_CHUNK = 32 / TW;       // tile rows covered by 32 columns
   constexpr int PW = TW / 2;                    // pooled pixels per pooled row
@@ -60,21 +60,27 @@ __device__ __forceinline__ void conv_epilogue(const IgemmParams& p, float* slab,
   const size_t row_stride = (size_t)Wo * p.Cout;
   const size_t col_stride = (size_t)4 * p.Cout;
   const bool col_in_tile = pool ? (prow < PW) : true;                             // PW = 4 (TW = 8): all four sub-rows valid
+  auto chunk_base_of = [&](int chunk) { return (((size_t)n * Ho + oy0 + chunk * OROWS) * Wo + ox0 + prow) * p.Cout + m0 + c4; };
+  auto pixel_ok = [&](int chunk, int i) {
+    return col_in_tile && (oy0 + chunk * OROWS + i / CPR) < Ho && (ox0 + prow + 4 * (i % CPR)) < Wo;
+  };
+  // Residual tiles are software-pipelined one chunk ahead: the loads of chunk c+1 are issued right after chunk c's
+  // accumulator values have been staged (their registers are dead by then), so a load has a whole chunk period to
+  // land; the first chunk's loads go out before the wait for the accumulator.
+  float4 rcur[NPX], rnext[NPX];
+  auto issue_res = [&](int chunk, float4* r) {
+    const size_t base = chunk_base_of(chunk);
+#pragma unroll
+    for (int i = 0; i < NPX; ++i) {
+      r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pixel_ok(chunk, i)) r[i] = *reinterpret_cast<const float4*>(p.residual + base + (i / CPR) * row_stride + (i % CPR) * col_stride);
+    }
+  };
+  if (kRes) issue_res(chunk0, rcur);
+  wait_acc();
 #pragma unroll 1
   for (int cc = 0; cc < NCHUNK; ++cc) {
     const int chunk = chunk0 + cc;
-    const int y_base = oy0 + chunk * OROWS;
-    const size_t chunk_base = (((size_t)n * Ho + y_base) * Wo + ox0 + prow) * p.Cout + m0 + c4;
-    float4 res[NPX];
-    size_t off[NPX];
-    bool ok[NPX];
-#pragma unroll
-    for (int i = 0; i < NPX; ++i) {
-      const int dy = i / CPR, dx = 4 * (i % CPR);
-      ok[i] = col_in_tile && (y_base + dy) < Ho && (ox0 + prow + dx) < Wo;
-      off[i] = chunk_base + dy * row_stride + (i % CPR) * col_stride;
-      if (kRes && ok[i]) res[i] = *reinterpret_cast<const float4*>(p.residual + off[i]);
-    }
     float v[32];
     tmem_ld32(taddr + chunk * 32, v);
     float* buf = slab + (SLABS == 2 ? (cc & 1) * (32 * EPI_PITCH) : 0);
@@ -92,30 +98,37 @@ __device__ __forceinline__ void conv_epilogue(const IgemmParams& p, float* slab,
       }
     }
     asm volatile("bar.sync %0, 128;" ::"r"(BAR) : "memory");
+    if (kRes && cc + 1 < NCHUNK) issue_res(chunk + 1, rnext);
+    const size_t chunk_base = chunk_base_of(chunk);
 #pragma unroll
     for (int i = 0; i < NPX; ++i) {
-      if (ok[i]) {
+      if (pixel_ok(chunk, i)) {
+        const size_t off = chunk_base + (i / CPR) * row_stride + (i % CPR) * col_stride;
         const int q = prow + 4 * i;
         float4 a = *reinterpret_cast<const float4*>(buf + q * EPI_PITCH + c4);
         a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
         const float4 pre = a;
         if (kRes) {
-          float4 r = res[i];
+          float4 r = rcur[i];
           if (p.flags & IPDM_CONV_RES_ELU) { r.x = elu_fast(r.x); r.y = elu_fast(r.y); r.z = elu_fast(r.z); r.w = elu_fast(r.w); }
           a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
         }
-        if (kOut32) *reinterpret_cast<float4*>(p.out_f32 + off[i]) = a;
+        if (kOut32) *reinterpret_cast<float4*>(p.out_f32 + off) = a;
         if (kOut16) {
           float4 h = (p.flags & IPDM_CONV_F16_PRE_RES) ? pre : a;
           if (p.flags & IPDM_CONV_F16_ELU) { h.x = elu_fast(h.x); h.y = elu_fast(h.y); h.z = elu_fast(h.z); h.w = elu_fast(h.w); }
           uint2 pk;
           pk.x = pack_half2_sat(h.x, h.y);
           pk.y = pack_half2_sat(h.z, h.w);
-          *reinterpret_cast<uint2*>(p.out_f16 + off[i]) = pk;
+          *reinterpret_cast<uint2*>(p.out_f16 + off) = pk;
         }
         s1[0] += a.x; s1[1] += a.y; s1[2] += a.z; s1[3] += a.w;
         s2[0] += a.x * a.x; s2[1] += a.y * a.y; s2[2] += a.z * a.z; s2[3] += a.w * a.w;
       }
+    }
+    if (kRes) {
+#pragma unroll
+      for (int i = 0; i < NPX; ++i) rcur[i] = rnext[i];
     }
   }
   // the slab is reused (by the statistics below and by the next accumulator): everyone must be done reading it

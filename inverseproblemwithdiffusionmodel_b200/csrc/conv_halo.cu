@@ -162,9 +162,10 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
       int n, h0, w0, m0;
       decode(item, n, h0, w0, m0);
       const int as = acnt & 1;
-      mbar_wait(&acc_full[as], (acnt >> 1) & 1);
-      tcgen05_fence_after();
-      conv_epilogue<MODE, HT_W, 2, 4>(p, my_slab, tmem_base + as * BLOCK_N, quad, lane, n, h0, w0, m0, team * 4, 1 + team);
+      conv_epilogue<MODE, HT_W, 2, 4>(p, my_slab, tmem_base + as * BLOCK_N, quad, lane, n, h0, w0, m0, team * 4, 1 + team, [&]() {
+        mbar_wait(&acc_full[as], (acnt >> 1) & 1);
+        tcgen05_fence_after();
+      });
       // all of this warp's TMEM reads are complete (tcgen05.wait::ld inside): hand the accumulator back
       tcgen05_fence_before();
       __syncwarp();

@@ -120,9 +120,10 @@ k_conv_igemm(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
     }
   } else {
     // ===== epilogue (the pipeline stages are idle once the accumulator is complete: reuse them as the slab) =====
-    mbar_wait(tmem_full_bar, 0);
-    tcgen05_fence_after();
-    conv_epilogue<MODE, TILE_W, 2, 8>(p, reinterpret_cast<float*>(smem), tmem_base, warp & 3, lane, n, h0, w0, m0, 0, 1);
+    conv_epilogue<MODE, TILE_W, 2, 8>(p, reinterpret_cast<float*>(smem), tmem_base, warp & 3, lane, n, h0, w0, m0, 0, 1, [&]() {
+      mbar_wait(tmem_full_bar, 0);
+      tcgen05_fence_after();
+    });
   }
   tcgen05_fence_before();
   __syncthreads();
