@@ -28,7 +28,7 @@ extern "C" {
 #define IPDM_E_UNSUPPORTED (-2) /* transform length not a power of two in [8,512], ... */
 #define IPDM_E_DRIVER (-3)      /* driver entry point (tensor-map encode) unavailable  */
 
-int ipdm_abi_version(void);
+int ipdm_abi_version(void);   /* 2 */
 const char* ipdm_last_error(void);
 /* number of kernels launched by this library in this process so far (bench.py's gpu_launches) */
 unsigned long long ipdm_launch_count(void);
@@ -161,6 +161,10 @@ typedef struct {
   int taps;               /* 9 (3x3, zero padding = dilation) or 1 (1x1)                                */
   int dilation;
   int flags;              /* IPDM_CONV_* below                                                          */
+  int slices;             /* 0/1: plain 2-D.  X > 1: the N images are N/X volumes of X consecutive slices
+                             ([P][X][H][W][C]); `stats` rows are then per VOLUME ([N/X][Cout][2])            */
+  int slice_shift;        /* output slice x reads input slice x + slice_shift of the same volume (zero outside
+                             [0, X)): one kx-plane of a 3x3x3 convolution (layers3d.py:38-60) = one launch   */
 } ipdm_conv_desc;
 
 #define IPDM_CONV_F16_ELU 1       /* out_f16 = f16(ELU(v)) instead of f16(v)                               */
@@ -215,6 +219,32 @@ int ipdm_bilinear_add(const float* src, float* dst, void* out_elu_f16, int N, in
 int ipdm_meanpool2(const float* in, const float* add, float* out, int N, int H, int W, int C, void* stream);
 /* f32 [Cout][Cin][kh][kw] (PyTorch OIHW) -> f16 [Cout][kh*kw][Cin] weight repack for the igemm. */
 int ipdm_pack_weights_f16(const float* w_oihw, void* w_f16, int Cout, int Cin, int taps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 3-D (patch x time) score network NCSN3DShallow: everything around its 3x3x3 convolutions, which are three
+ * ipdm_conv_igemm launches (one kx-plane each, ipdm_conv_desc.slices / slice_shift).
+ * Volume layout [P][X][T][Y][C]: P patches, X slices, each slice an NHWC image of H = T rows, W = Y columns.
+ * Reference: ncsn/models/ncsn3d.py:123-224, layers3d.py.
+ * ---------------------------------------------------------------------------------------------- */
+/* slice axis of MaxPool3d(5, stride 1, padding 2) (layers3d.py:71); the (T, Y) plane is ipdm_maxpool5_f16. */
+int ipdm_maxpool5_slices_f16(const void* in_f16, void* out_f16, int P, int X, size_t plane_elems, void* stream);
+/* begin_conv (ncsn3d.py:137): out f32 [P][X][T][Y][Cout] = Conv3d(1 -> Cout, 3, padding 1)(affine ? 2x-1 : x) + bias;
+ * x f32 [P][X][T][Y], w f32 [Cout][27] with taps ordered (kx, kt, ky). */
+int ipdm_conv3d_first(const float* x, const float* w, const float* bias, float* out, int P, int X, int T, int Y, int Cout,
+                      int affine, void* stream);
+/* end_conv + noise-level division (ncsn3d.py:141,211-215): out f32 [P][X][T][Y] = (Conv3d(C -> 1, 3)(in) + bias) /
+ * sigmas[labels[p]]; w f32 [27][C], taps ordered (kx, kt, ky). */
+int ipdm_conv3d_last(const void* in_f16, const float* w, const float* bias, const float* sigmas, const int64_t* labels,
+                     float* out, int P, int X, int T, int Y, int C, void* stream);
+/* out f16 [NS][T2][Y][K*C]: out[..][t2][y][k*C + c] = in[..][stride*t2 + offset0 + k][y][c] (0 outside [0, T)): lays the
+ * taps of conv_temporal_down / conv_temporal_up (ncsn3d.py:181-182) side by side for ONE 1x1 implicit GEMM. */
+int ipdm_gather_t_f16(const void* in_f16, void* out_f16, size_t NS, int T, int T2, int Y, int C, int stride, int offset0, int K,
+                      void* stream);
+/* out_f32 [NS][2T][Y][C] (and f16(ELU(.)) if non-NULL): out[..][2m+ph][y][c] = in[..][m][y][ph*C + c] -- the two output
+ * phases of the stride-2 ConvTranspose3d back onto the time axis. */
+int ipdm_interleave_t(const float* in, float* out_f32, void* out_elu_f16, size_t NS, int T, int Y, int C, void* stream);
+/* out = a + (elu_b ? ELU(b) : b), n f32 elements (n % 4 == 0). */
+int ipdm_add_act(const float* a, const float* b, float* out, size_t n, int elu_b, void* stream);
 
 #ifdef __cplusplus
 }

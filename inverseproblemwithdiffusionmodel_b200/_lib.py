@@ -22,7 +22,7 @@ class ConvDesc(ctypes.Structure):
     _fields_ = [("in_f16", c_void_p), ("w_f16", c_void_p), ("bias", c_void_p), ("residual", c_void_p),
                 ("out_f32", c_void_p), ("out_f16", c_void_p), ("stats", c_void_p),
                 ("N", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int), ("Cout", c_int),
-                ("taps", c_int), ("dilation", c_int), ("flags", c_int)]
+                ("taps", c_int), ("dilation", c_int), ("flags", c_int), ("slices", c_int), ("slice_shift", c_int)]
 
 
 CONV_F16_ELU, CONV_F16_PRE_RES, CONV_RES_ELU, CONV_POOL2 = 1, 2, 4, 8
@@ -60,6 +60,12 @@ SIGNATURES = {
     "ipdm_bilinear_add": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ipdm_meanpool2": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "ipdm_pack_weights_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "ipdm_maxpool5_slices_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_void_p]),
+    "ipdm_conv3d_first": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ipdm_conv3d_last": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ipdm_gather_t_f16": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ipdm_interleave_t": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),
+    "ipdm_add_act": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
 }
 
 _lib = None

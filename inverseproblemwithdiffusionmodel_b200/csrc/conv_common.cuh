@@ -20,10 +20,11 @@ struct IgemmParams {
   double* stats;
   int N, H, W, Cin, Cout, taps, dilation, flags;
   int tiles_w, tiles_h;
+  int slices, slice_shift;   // volumes of `slices` consecutive images; input slice = output slice + slice_shift
 };
 
 int get_weight_map(const void* w, int Cout, int K, CUtensorMap* out);
-int get_act_map(const void* x, int N, int H, int W, int C, int box_w, int box_h, CUtensorMap* out);
+int get_act_map(const void* x, int N, int H, int W, int C, int box_w, int box_h, int slices, CUtensorMap* out);
 int launch_conv_halo(const ipdm_conv_desc& d, cudaStream_t s);
 extern int g_conv_variant;       // 0 = auto, 1 = force the per-tap tile kernel (diagnostics)
 
@@ -148,8 +149,8 @@ __device__ __forceinline__ void conv_epilogue(const IgemmParams& p, float* slab,
       t1 += red[(r * 128 + te) * 2];
       t2 += red[(r * 128 + te) * 2 + 1];
     }
-    atomicAdd(&p.stats[((size_t)n * p.Cout + m0 + te) * 2], (double)t1);
-    atomicAdd(&p.stats[((size_t)n * p.Cout + m0 + te) * 2 + 1], (double)t2);
+    atomicAdd(&p.stats[((size_t)(n / p.slices) * p.Cout + m0 + te) * 2], (double)t1);
+    atomicAdd(&p.stats[((size_t)(n / p.slices) * p.Cout + m0 + te) * 2 + 1], (double)t2);
     asm volatile("bar.sync %0, 128;" ::"r"(BAR) : "memory");
   }
 }

@@ -100,7 +100,8 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
           const int s = cnt % NH;
           mbar_wait(&halo_empty[s], ((cnt / NH) & 1) ^ 1);
           mbar_expect_tx(&halo_full[s], CFG::ROWS * CFG::PITCH);
-          tma_load_4d(halo + s * CFG::HALO_BYTES, &tmap_x, &halo_full[s], kc * BLOCK_K, w0 - DIL, h0 - DIL, n);
+          tma_load_5d(halo + s * CFG::HALO_BYTES, &tmap_x, &halo_full[s], kc * BLOCK_K, w0 - DIL, h0 - DIL,
+                      n % p.slices + p.slice_shift, n / p.slices);
         }
       }
     }
@@ -197,13 +198,14 @@ int launch_conv_halo(const ipdm_conv_desc& d, cudaStream_t s) {
   const bool pool = (d.flags & IPDM_CONV_POOL2) != 0;
   CUtensorMap mw, mx;
   if (int e = get_weight_map(d.w_f16, d.Cout, 9 * d.Cin, &mw)) return e;
-  if (int e = get_act_map(d.in_f16, d.N, d.H, d.W, d.Cin, HT_W + 2 * d.dilation, HT_H + 2 * d.dilation, &mx)) return e;
-  if (d.stats) IPDM_CUDA(cudaMemsetAsync(d.stats, 0, (size_t)d.N * d.Cout * 2 * sizeof(double), s));
+  if (int e = get_act_map(d.in_f16, d.N, d.H, d.W, d.Cin, HT_W + 2 * d.dilation, HT_H + 2 * d.dilation, d.slices, &mx)) return e;
+  if (d.stats) IPDM_CUDA(cudaMemsetAsync(d.stats, 0, (size_t)(d.N / d.slices) * d.Cout * 2 * sizeof(double), s));
   HaloParams hp{};
   IgemmParams& p = hp.g;
   p.bias = d.bias; p.residual = d.residual; p.out_f32 = d.out_f32; p.out_f16 = reinterpret_cast<__half*>(d.out_f16);
   p.stats = d.stats;
   p.N = d.N; p.H = d.H; p.W = d.W; p.Cin = d.Cin; p.Cout = d.Cout; p.taps = 9; p.dilation = d.dilation; p.flags = d.flags;
+  p.slices = d.slices; p.slice_shift = d.slice_shift;
   p.tiles_w = (d.W + HT_W - 1) / HT_W;
   p.tiles_h = (d.H + HT_H - 1) / HT_H;
   hp.mtiles = d.Cout / BLOCK_M;

@@ -94,7 +94,7 @@ k_conv_igemm(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
         unsigned char* sb = sa + A_BYTES;
         mbar_expect_tx(&full_bar[s], STAGE_BYTES);
         tma_load_2d(sa, &tmap_w, &full_bar[s], tap * p.Cin + kc * BLOCK_K, m0);
-        tma_load_4d(sb, &tmap_x, &full_bar[s], kc * BLOCK_K, w0 + dx, h0 + dy, n);
+        tma_load_5d(sb, &tmap_x, &full_bar[s], kc * BLOCK_K, w0 + dx, h0 + dy, n % p.slices + p.slice_shift, n / p.slices);
       }
     }
   } else if (warp == 1) {
@@ -178,20 +178,21 @@ int get_weight_map(const void* w, int Cout, int K, CUtensorMap* out) {
   return 0;
 }
 
-// 4-D tiled map {C, W, H, N} over f16 NHWC activations with box {64, box_w, box_h, 1}, zero OOB fill.
-int get_act_map(const void* x, int N, int H, int W, int C, int box_w, int box_h, CUtensorMap* out) {
-  MapKey key{x, 4, ((long long)N << 32) | H, ((long long)W << 32) | C, ((long long)box_w << 32) | box_h};
+// 5-D tiled map {C, W, H, X, P} over f16 activations [P][X][H][W][C] (X = slices per volume, 1 for plain NHWC) with
+// box {64, box_w, box_h, 1, 1}, zero OOB fill -- in X too, which is what pads a 3-D convolution across slices.
+int get_act_map(const void* x, int N, int H, int W, int C, int box_w, int box_h, int slices, CUtensorMap* out) {
+  MapKey key{x, 4 + 16 * (long long)slices, ((long long)N << 32) | H, ((long long)W << 32) | C, ((long long)box_w << 32) | box_h};
   std::lock_guard<std::mutex> lk(g_maps_mu);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) { *out = it->second; return 0; }
   PFN_encodeTiled enc = get_encode();
   IPDM_REQUIRE(enc, IPDM_E_DRIVER, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)slices, (cuuint64_t)(N / slices)};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)slices * H * W * C * 2};
+  cuuint32_t box[5] = {BLOCK_K, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUtensorMap m;
-  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   IPDM_REQUIRE(r == CUDA_SUCCESS, IPDM_E_DRIVER, "cuTensorMapEncodeTiled(activations) failed: %d", (int)r);
@@ -206,7 +207,10 @@ using namespace ipdm;
 
 extern "C" int ipdm_conv_igemm(const ipdm_conv_desc* dh, void* stream) {
   IPDM_REQUIRE(dh && dh->in_f16 && dh->w_f16, IPDM_E_BADARG, "conv_igemm: null pointer");
-  const ipdm_conv_desc d = *dh;
+  ipdm_conv_desc d = *dh;
+  if (d.slices < 1) d.slices = 1;
+  IPDM_REQUIRE(d.N % d.slices == 0 && (d.slices > 1 || d.slice_shift == 0) && abs(d.slice_shift) < d.slices + (d.slices == 1),
+               IPDM_E_BADARG, "conv_igemm: N=%d slices=%d slice_shift=%d", d.N, d.slices, d.slice_shift);
   IPDM_REQUIRE(d.taps == 9 || d.taps == 1, IPDM_E_BADARG, "conv_igemm: taps must be 9 or 1");
   IPDM_REQUIRE(d.Cin % BLOCK_K == 0 && d.Cin >= BLOCK_K, IPDM_E_UNSUPPORTED, "conv_igemm: Cin=%d must be a multiple of 64", d.Cin);
   IPDM_REQUIRE(d.Cout % BLOCK_M == 0, IPDM_E_UNSUPPORTED, "conv_igemm: Cout=%d must be a multiple of 128", d.Cout);
@@ -222,12 +226,13 @@ extern "C" int ipdm_conv_igemm(const ipdm_conv_desc* dh, void* stream) {
   if (d.taps == 9 && d.dilation <= 2 && g_conv_variant != 1) return launch_conv_halo(d, s);
   CUtensorMap mw, mx;
   if (int e = get_weight_map(d.w_f16, d.Cout, d.taps * d.Cin, &mw)) return e;
-  if (int e = get_act_map(d.in_f16, d.N, d.H, d.W, d.Cin, TILE_W, TILE_H, &mx)) return e;
+  if (int e = get_act_map(d.in_f16, d.N, d.H, d.W, d.Cin, TILE_W, TILE_H, d.slices, &mx)) return e;
   const int mode = (d.residual ? 1 : 0) | (d.out_f32 ? 2 : 0) | (d.out_f16 ? 4 : 0) | (pool ? 8 : 0);
   if (d.stats) {
-    IPDM_CUDA(cudaMemsetAsync(d.stats, 0, (size_t)d.N * d.Cout * 2 * sizeof(double), s));
+    IPDM_CUDA(cudaMemsetAsync(d.stats, 0, (size_t)(d.N / d.slices) * d.Cout * 2 * sizeof(double), s));
   }
   IgemmParams p{};
+  p.slices = d.slices; p.slice_shift = d.slice_shift;
   p.bias = d.bias; p.residual = d.residual; p.out_f32 = d.out_f32; p.out_f16 = reinterpret_cast<__half*>(d.out_f16);
   p.stats = d.stats;
   p.N = d.N; p.H = d.H; p.W = d.W; p.Cin = d.Cin; p.Cout = d.Cout; p.taps = d.taps; p.dilation = d.dilation; p.flags = d.flags;

@@ -604,6 +604,7 @@ extern "C" int ipdm_pack_weights_f16(const float* w_oihw, void* w_f16, int Cout,
 extern "C" int ipdm_conv_direct(const ipdm_conv_desc* dh, void* stream) {
   IPDM_REQUIRE(dh && dh->in_f16 && dh->w_f16, IPDM_E_BADARG, "conv_direct: null pointer");
   IPDM_REQUIRE(dh->taps == 9 || dh->taps == 1, IPDM_E_BADARG, "conv_direct: taps must be 9 or 1");
+  IPDM_REQUIRE(dh->slices <= 1 && dh->slice_shift == 0, IPDM_E_UNSUPPORTED, "conv_direct: volumes (slices > 1) need the tensor-core path (Cin %% 64 == 0, Cout %% 128 == 0)");
   IPDM_REQUIRE(dh->out_f32 || dh->out_f16, IPDM_E_BADARG, "conv_direct: no output");
   const ipdm_conv_desc d = *dh;
   const bool pool = (d.flags & IPDM_CONV_POOL2) != 0;

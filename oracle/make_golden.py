@@ -340,6 +340,28 @@ def gen_map():
     np.savez_compressed(os.path.join(OUT, "map.npz"), **out)
 
 
+def gen_ncsn3d():
+    """NCSN3DShallow, the learned temporal prior: full width (ngf 128, what the tensor-core path
+    needs), two 8x8x24 patches, 5-D and flattened 3-D input conventions."""
+    from InverseProblemWithDiffusionModel.ncsn.models import ncsn3d
+    out = {}
+    specs_path = os.path.join(OUT, "state_dict_specs.json")
+    specs = json.load(open(specs_path))
+    with torch.no_grad():
+        cfg = small_cfg("cine127_1d", 128, 24, 12, 40.0)
+        net = ncsn3d.NCSN3DShallow(cfg).eval()
+        spec = [(k, tuple(v.shape)) for k, v in net.state_dict().items()]
+        P = synth_state_dict(spec, 12, net.sigmas)
+        net.load_state_dict(P)
+        specs["NCSN3DShallow_ngf128"] = [[k, list(s)] for k, s in spec]
+        x = rrand(1701, 2, 1, 8, 8, 24)
+        y = torch.tensor([2, 9])
+        out["shallow_out"] = _np(net(x, y))
+        out["shallow_out_flat"] = _np(net(x.reshape(2, 64, 24), y))
+    json.dump(specs, open(specs_path, "w"))
+    np.savez_compressed(os.path.join(OUT, "ncsn3d.npz"), **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
@@ -349,7 +371,7 @@ def main():
     os.makedirs("/tmp/ipdm_golden", exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     todo = {"linear": gen_fft_mask_coils, "sense": gen_sense_prox, "scorenet": gen_scorenet, "samplers": gen_samplers,
-            "map": gen_map, "extra": gen_extra}
+            "map": gen_map, "extra": gen_extra, "ncsn3d": gen_ncsn3d}
     for name, fn in todo.items():
         if args.only and args.only != name:
             continue

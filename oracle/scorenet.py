@@ -164,7 +164,11 @@ def synth_state_dict(spec, seed, sigmas):
         g = torch.Generator().manual_seed(seed * 100003 + idx)
         t = torch.randn(*shape, generator=g)
         if key.endswith(".weight"):
-            fan_in = shape[1] * shape[2] * shape[3]
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            if key == "conv_temporal_up.weight":       # ConvTranspose3d: (Cin, Cout, 1, 1, 4), two taps reach each output
+                fan_in = shape[0] * 2
             t = t * (0.6 / fan_in ** 0.5)
         elif key.endswith(".alpha") or key.endswith(".gamma"):
             t = 1.0 + 0.02 * t
@@ -172,3 +176,98 @@ def synth_state_dict(spec, seed, sigmas):
             t = 0.05 * t
         P[key] = t
     return P
+
+
+# ------------------------------------------------------------------------------------------------ 3-D temporal prior
+def _conv3d(P, key, x, dilation=1):
+    """3x3x3 (pad = dilation) or 1x1x1 Conv3d. Reference: conv3x3 / dilated_conv3x3 / conv1x1, layers3d.py:29-60."""
+    w = P[key + ".weight"]
+    b = P.get(key + ".bias")
+    k = w.shape[-1]
+    if OPERAND_ROUND is not None and w.shape[0] > 1 and w.shape[1] > 1:
+        x = x.to(OPERAND_ROUND).float()
+        w = w.to(OPERAND_ROUND).float()
+    return F.conv3d(x, w, b, stride=1, padding=dilation if k == 3 else 0, dilation=dilation if k == 3 else 1)
+
+
+def instance_norm3d_plus(P, key, x, eps=1e-5):
+    """Reference: InstanceNorm3dPlus.forward, normalization3d.py:164-185."""
+    mu = x.mean(dim=(2, 3, 4))
+    m_hat = (mu - mu.mean(dim=-1, keepdim=True)) / torch.sqrt(mu.var(dim=-1, keepdim=True) + eps)
+    var = x.var(dim=(2, 3, 4), unbiased=False, keepdim=True)
+    h = (x - mu[..., None, None, None]) / torch.sqrt(var + eps)
+    h = h + (m_hat * P[key + ".alpha"])[..., None, None, None]
+    out = P[key + ".gamma"].view(1, -1, 1, 1, 1) * h
+    if key + ".beta" in P:
+        out = out + P[key + ".beta"].view(1, -1, 1, 1, 1)
+    return out
+
+
+def residual_block3d(P, key, x, dilation):
+    """Reference: ResidualBlock (3-D), layers3d.py:423-476; only the un-pooled variants NCSN3DShallow builds."""
+    d = 1 if dilation is None else dilation
+    h = F.elu(instance_norm3d_plus(P, key + ".normalize1", x))
+    h = _conv3d(P, key + ".conv1", h, d)
+    h = F.elu(instance_norm3d_plus(P, key + ".normalize2", h))
+    h = _conv3d(P, key + ".conv2", h, d)
+    sc = _conv3d(P, key + ".shortcut", x, d) if key + ".shortcut.weight" in P else x
+    return sc + h
+
+
+def rcu3d(P, key, x, n_blocks, n_stages=2):
+    """Reference: RCUBlock (3-D), layers3d.py:113-135."""
+    for i in range(n_blocks):
+        r = x
+        for j in range(n_stages):
+            x = _conv3d(P, f"{key}.{i + 1}_{j + 1}_conv", F.elu(x))
+        x = x + r
+    return x
+
+
+def crp3d(P, key, x, n_stages=2):
+    """Reference: CRPBlock (3-D, MaxPool3d(5, 1, 2)), layers3d.py:63-84."""
+    x = F.elu(x)
+    path = x
+    for i in range(n_stages):
+        path = F.max_pool3d(path, kernel_size=5, stride=1, padding=2)
+        path = _conv3d(P, f"{key}.convs.{i}", path)
+        x = path + x
+    return x
+
+
+def refine3d(P, key, xs, shape, end=False):
+    """Reference: RefineBlock / MSFBlock (3-D, trilinear align_corners), layers3d.py:166-187,219-255."""
+    hs = [rcu3d(P, f"{key}.adapt_convs.{i}", xi, 2) for i, xi in enumerate(xs)]
+    if len(hs) > 1:
+        h = None
+        for i, hi in enumerate(hs):
+            t = F.interpolate(_conv3d(P, f"{key}.msf.convs.{i}", hi), size=shape, mode="trilinear", align_corners=True)
+            h = t if h is None else h + t
+    else:
+        h = hs[0]
+    h = crp3d(P, key + ".crp", h)
+    return rcu3d(P, key + ".output_convs", h, 3 if end else 1)
+
+
+def score_forward_3d_shallow(P, x, labels, logit_transform=False, rescaled=False):
+    """x (B, 1, kx, ky, T). Reference: NCSN3DShallow.forward, ncsn3d.py:186-224."""
+    h = 2 * x - 1.0 if (not logit_transform and not rescaled) else x
+    out = _conv3d(P, "begin_conv", h)
+    l1 = residual_block3d(P, "res1.1", residual_block3d(P, "res1.0", out, None), None)
+    l2 = residual_block3d(P, "res3.1", residual_block3d(P, "res3.0", l1, 2), 2)
+    wd, wu = P["conv_temporal_down.weight"], P["conv_temporal_up.weight"]
+    xd = l2
+    if OPERAND_ROUND is not None:
+        xd, wd = xd.to(OPERAND_ROUND).float(), wd.to(OPERAND_ROUND).float()
+    l3 = F.conv3d(xd, wd, P["conv_temporal_down.bias"], stride=(1, 1, 2), padding=(0, 0, 1))
+    l4 = residual_block3d(P, "res4.1", residual_block3d(P, "res4.0", l3, 4), 4)
+    r1 = refine3d(P, "refine1", [l4], l4.shape[2:])
+    r2 = refine3d(P, "refine2", [l3, r1], l3.shape[2:])
+    xu = r2
+    if OPERAND_ROUND is not None:
+        xu, wu = xu.to(OPERAND_ROUND).float(), wu.to(OPERAND_ROUND).float()
+    r3 = F.conv_transpose3d(xu, wu, P["conv_temporal_up.bias"], stride=(1, 1, 2), padding=(0, 0, 1))
+    o = refine3d(P, "refine3", [l1, r3], l1.shape[2:])
+    o = F.elu(instance_norm3d_plus(P, "normalizer", o))
+    o = _conv3d(P, "end_conv", o)
+    return o / P["sigmas"][labels].view(x.shape[0], 1, 1, 1, 1)

@@ -40,7 +40,7 @@ class EmuLib:
 
     # ---- misc
     def ipdm_abi_version(self):
-        return 1
+        return 2
 
     def ipdm_last_error(self):
         return self.err

@@ -176,6 +176,32 @@ def case_scorenet_small(dev):
     assert torch.equal(a, b)
 
 
+def case_ncsn3d_shallow(dev):
+    """NCSN3DShallow (the learned temporal prior) at full width against the reference's output:
+    5-D and flattened inputs, state-dict layout, and the f16-operand emulation of the oracle for the tight bound."""
+    from inverseproblemwithdiffusionmodel_b200.ncsn.models.ncsn3d import NCSN3DShallow
+    g = G("ncsn3d")
+    cfg = make_config("CINE127", 128, 24, 12, 40.0)
+    cfg.data.channels, cfg.data.channels_3d = 64, 1
+    net, Pd = build_net(NCSN3DShallow, "NCSN3DShallow_ngf128", 12, cfg, dev)
+    x, y = rrand(1701, 2, 1, 8, 8, 24), torch.tensor([2, 9])
+    out = net(x.to(dev), y.to(dev))
+    assert out.shape == (2, 1, 8, 8, 24)
+    e_ref = rel_l2(out.cpu(), g["shallow_out"])
+    assert e_ref < TOL_SCORE, e_ref
+    flat = net(x.reshape(2, 64, 24).to(dev), y.to(dev))
+    assert flat.shape == (2, 64, 24) and torch.equal(flat.reshape(2, 1, 8, 8, 24), out)
+    SN.OPERAND_ROUND = torch.float16
+    try:
+        with torch.no_grad():
+            emu = SN.score_forward_3d_shallow(Pd, x, y)
+    finally:
+        SN.OPERAND_ROUND = None
+    e_emu = rel_l2(out.cpu(), emu)
+    print(f"NCSN3DShallow: rel-L2 vs reference fp32 {e_ref:.2e}, vs f16-operand emulation {e_emu:.2e}")
+    assert e_emu < 2e-3, e_emu                     # same operand rounding; rounding-boundary flips and accumulation order remain
+
+
 # ------------------------------------------------------------------------------------------------ samplers
 def case_sampler_uncond(dev):
     g = G("samplers")

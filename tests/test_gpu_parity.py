@@ -21,7 +21,7 @@ def _lib():
 
 def test_library_is_native():
     L = _lib()
-    assert L.lib().ipdm_abi_version() == 1
+    assert L.lib().ipdm_abi_version() == 2
     before = L.lib().ipdm_launch_count()
     C.i2k_complex(torch.zeros(1, 1, 8, 8, dtype=torch.complex64, device=DEV))
     torch.cuda.synchronize()
@@ -377,6 +377,37 @@ def test_sense_sampler_graph_path_matches_eager():
     # chains do not interact: chain 0 of a 3-chain batch == the same chain run alone?  (Philox keys are
     # element-indexed within the batch, so only the first plane-offset-free chain is comparable)
     assert torch.isfinite(a.abs()).all()
+
+
+def test_ncsn3d_shallow_temporal_prior():
+    C.case_ncsn3d_shallow(DEV)
+
+
+def test_conv3d_via_slices_vs_torch():
+    """One 3x3x3 dilated convolution = three slice-shifted launches of the 2-D tensor-core kernels, against
+    torch.nn.functional.conv3d on the same f16-rounded operands (d = 1, 2: persistent halo kernel; d = 4: per-tap kernel)."""
+    import torch.nn.functional as F
+    L = _lib()
+    P, X, T, Y, Cin, Cout = 3, 8, 24, 8, 128, 256
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(P, X, T, Y, Cin, generator=g).half()
+    w = (torch.randn(Cout, Cin, 3, 3, 3, generator=g) / (27 * Cin) ** 0.5).half()          # (co, ci, kx, ky, kt)
+    bias = torch.randn(Cout, generator=g)
+    xd, bias_d = x.to(DEV), bias.to(DEV)
+    for d in (1, 2, 4):
+        acc = torch.full((P * X, T, Y, Cout), float("nan"), device=DEV)
+        st = torch.zeros(P, Cout, 2, dtype=torch.float64, device=DEV)
+        for order, (kx, first) in enumerate(((0, True), (2, False), (1, False))):
+            w2 = w[:, :, kx].permute(0, 3, 2, 1).contiguous().reshape(Cout, 9, Cin).to(DEV)     # [co][(kt, ky)][ci]
+            last = order == 2
+            desc = L.ConvDesc(xd.data_ptr(), w2.data_ptr(), bias_d.data_ptr() if last else None, None if first else acc.data_ptr(),
+                              acc.data_ptr(), None, st.data_ptr() if last else None, P * X, T, Y, Cin, Cout, 9, d, 0, X, (kx - 1) * d)
+            L.check(L.lib().ipdm_conv_igemm(ctypes.byref(desc), L.stream()), "conv3d plane")
+        ref = F.conv3d(x.float().permute(0, 4, 1, 3, 2), w.float(), bias, padding=d, dilation=d)      # (P, C, X, Y, T)
+        ref = ref.permute(0, 2, 4, 3, 1).reshape(P * X, T, Y, Cout)
+        assert rel_l2(acc.cpu(), ref) < 1e-5, d
+        want = torch.stack([ref.reshape(P, -1, Cout).sum(1), (ref ** 2).reshape(P, -1, Cout).sum(1)], -1)
+        assert rel_l2(st.float().cpu(), want) < 1e-5, d
 
 
 def test_metrics_and_result_files():

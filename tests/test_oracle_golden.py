@@ -142,6 +142,18 @@ def test_scorenet_forward(golden):
         assert rel_l2(out, G["v2_out"]) < 1e-5
 
 
+def test_ncsn3d_shallow_forward(golden):
+    """oracle restatement of NCSN3DShallow (temporal prior) pinned to the reference's output at full width (ngf 128)."""
+    G = golden("ncsn3d")
+    sig = ALD.geometric_sigmas(40.0, 0.01, 12)
+    with torch.no_grad():
+        P = _net("NCSN3DShallow_ngf128", 12, sig)
+        x = rrand(1701, 2, 1, 8, 8, 24)
+        out = SN.score_forward_3d_shallow(P, x, torch.tensor([2, 9]))
+    assert rel_l2(out, G["shallow_out"]) < 1e-5
+    assert rel_l2(G["shallow_out_flat"].reshape(2, 1, 8, 8, 24), G["shallow_out"]) < 1e-6
+
+
 def test_state_dict_census():
     S = _specs()
     assert len(S["NCSNv2Deepest_acdc"]) == 230 and len(S["NCSNv2_mnist28"]) == 154
