@@ -243,6 +243,11 @@ int ipdm_gather_t_f16(const void* in_f16, void* out_f16, size_t NS, int T, int T
 /* out_f32 [NS][2T][Y][C] (and f16(ELU(.)) if non-NULL): out[..][2m+ph][y][c] = in[..][m][y][ph*C + c] -- the two output
  * phases of the stride-2 ConvTranspose3d back onto the time axis. */
 int ipdm_interleave_t(const float* in, float* out_f32, void* out_elu_f16, size_t NS, int T, int Y, int C, void* stream);
+/* Patch fold of the 2D+time sampler: planar state f32 [2][B][T][H][W] <-> volumes f32 [2*B*(H/k)*(W/k)][k][T][k]
+ * (`reshape_temporal_dim`, helpers/utils.py:330-359, in the device layout of NCSN3DShallow), with the optional random
+ * roll (ALD_optimizers.py:466-470,495-499) as (shift_h, shift_w).  unfold = 0: state -> vol; 1: vol -> state. */
+int ipdm_patch_fold(float* state, float* vol, int B, int T, int H, int W, int k, int shift_h, int shift_w, int unfold,
+                    void* stream);
 /* out = a + (elu_b ? ELU(b) : b), n f32 elements (n % 4 == 0). */
 int ipdm_add_act(const float* a, const float* b, float* out, size_t n, int elu_b, void* stream);
 

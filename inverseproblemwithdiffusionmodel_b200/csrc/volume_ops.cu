@@ -156,9 +156,42 @@ __global__ void k_add_act(const float4* __restrict__ a, const float4* __restrict
   }
 }
 
+// Patch fold of the 2D+time sampler (helpers/utils.py:330-359 `reshape_temporal_dim`, with the optional random roll
+// of ALD_optimizers.py:466-470,495-499 folded in): vol[p][kx][t][ky] <-> state[pl][b][t][(h1*k + kx - sh) mod H]
+// [(w1*k + ky - sw) mod W], p = ((pl*B + b)*H/k + h1)*W/k + w1.  unfold = the inverse scatter (same index map).
+__global__ void k_patch_fold(float* __restrict__ state, float* __restrict__ vol, int B, int T, int H, int W, int k, int sh, int sw,
+                             int unfold) {
+  const int H1 = H / k, W1 = W / k;
+  const size_t total = (size_t)2 * B * T * H * W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ky = (int)(i % k);
+    size_t r = i / k;
+    const int t = (int)(r % T); r /= T;
+    const int kx = (int)(r % k); r /= k;
+    const int w1 = (int)(r % W1); r /= W1;
+    const int h1 = (int)(r % H1);
+    const size_t plb = r / H1;                                   // pl*B + b
+    int h = h1 * k + kx - sh, w = w1 * k + ky - sw;
+    h = ((h % H) + H) % H;
+    w = ((w % W) + W) % W;
+    const size_t si = ((plb * T + t) * H + h) * W + w;
+    if (unfold) state[si] = vol[i];
+    else vol[i] = state[si];
+  }
+}
+
 }  // namespace ipdm
 
 using namespace ipdm;
+
+extern "C" int ipdm_patch_fold(float* state, float* vol, int B, int T, int H, int W, int k, int shift_h, int shift_w, int unfold,
+                               void* stream) {
+  IPDM_REQUIRE(state && vol && B >= 1 && T >= 1 && k >= 1, IPDM_E_BADARG, "patch_fold: bad argument");
+  IPDM_REQUIRE(H % k == 0 && W % k == 0, IPDM_E_BADARG, "patch_fold: H=%d, W=%d must be multiples of the patch size %d", H, W, k);
+  const size_t n = (size_t)2 * B * T * H * W;
+  k_patch_fold<<<vgrid(n, 256), 256, 0, as_stream(stream)>>>(state, vol, B, T, H, W, k, shift_h, shift_w, unfold);
+  return launched("k_patch_fold");
+}
 
 extern "C" int ipdm_maxpool5_slices_f16(const void* in_f16, void* out_f16, int P, int X, size_t plane_elems, void* stream) {
   IPDM_REQUIRE(in_f16 && out_f16 && P >= 1 && X >= 1, IPDM_E_BADARG, "maxpool5_slices: bad argument");

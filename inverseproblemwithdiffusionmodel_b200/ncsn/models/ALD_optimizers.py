@@ -396,8 +396,9 @@ class ALD2DTime(_SenseChainMixin, ALDOptimizer):
         self.finite_diff = None
 
     def __call__(self, **kwargs):
-        """kwargs: save_dir, lr_scaled, mode_T in {"none","tv","tv-only"}, lamda_T, if_random_shift
-        (+ noise_fn, seed, cuda_graph).  The learned temporal prior ("diffusion1d") is not part of this path yet."""
+        """kwargs: save_dir, lr_scaled, mode_T in {"none", "tv", "tv-only", "diffusion1d", "diffusion1d-only"}, lamda_T,
+        if_random_shift (+ noise_fn, seed, cuda_graph).  "diffusion1d" = the learned temporal prior `scorenet_T`
+        (NCSN3DShallow on k x k x T patches, reference :463-502)."""
         torch.set_grad_enabled(False)
         noise_fn = kwargs.pop("noise_fn", None)
         seed = int(kwargs.pop("seed", 0))
@@ -405,12 +406,16 @@ class ALD2DTime(_SenseChainMixin, ALDOptimizer):
         mode_T = kwargs.get("mode_T", "diffusion1d")
         lamda_T = float(kwargs.get("lamda_T", 1.))
         lr_scaled = kwargs["lr_scaled"]
-        if "diffusion1d" in mode_T:
-            raise NotImplementedError("mode_T='diffusion1d' needs the NCSN3D temporal prior, which is outside the implemented hot path")
-        skip_spatial = mode_T == "tv-only"
+        diffusion = "diffusion1d" in mode_T
+        if diffusion and self.scorenet_T is None:
+            raise _lib.IpdmError("mode_T='diffusion1d' needs scorenet_T (NCSN3DShallow)")
+        random_shift = bool(kwargs.get("if_random_shift", False))
+        skip_spatial = mode_T in ("tv-only", "diffusion1d-only")
         if skip_spatial:
             self.sigmas_T = self.sigmas_T_orig
             self.sigmas = self.sigmas_T_orig
+            if self.scorenet_T is not None:
+                self.scorenet_T.sigmas = self.sigmas_T_orig
         sigmas = self.sigmas
         n_steps_each = self.params["n_steps_each"]
         step_lr = self.params["step_lr"]
@@ -427,18 +432,50 @@ class ALD2DTime(_SenseChainMixin, ALDOptimizer):
         state, bvec = self._setup_sense(y, y.device)                      # [2][B*T][H][W]
         BT = B * T
         grad = torch.zeros_like(state)
-        labels = torch.zeros(2 * BT, dtype=torch.long, device=state.device)
+        ksz = self.win_size if diffusion else 1
+        P2 = 2 * B * (H // ksz) * (W // ksz) if diffusion else 0      # temporal-prior patches (real and imaginary planes)
+        labels_all = torch.zeros(max(2 * BT, P2), dtype=torch.long, device=state.device)
+        labels = labels_all[:2 * BT]
         x_flat, g_flat = state.view(2 * BT, 1, H, W), grad.view(2 * BT, 1, H, W)
         kappa = l2_kappa(self.linear_tfm, state, step_lr * lr_scaled, 1.)
         tv = "tv" in mode_T
         prox_only = _lib.AldScalars(0.0, 0.0, float(kappa), 0.0)
-        fast = use_graph and noise_fn is None
+        fast = use_graph and noise_fn is None and not (diffusion and random_shift)
+        sig_T = self.sigmas_T.detach().float().cpu()
+        temporal_on = [diffusion and float(sig_T[c]) != -1.0 for c in range(len(sigmas))]
+        seed_T = seed ^ 0x5bd1e995
+        if diffusion:
+            vol = torch.zeros(P2, ksz, T, ksz, dtype=torch.float32, device=state.device)
+            gvol = torch.zeros_like(vol)
 
-        def one_step(c, k, noise, sched=None, cursor=None):
-            """spatial_step (:428-449) -> temporal_step (:452-462) -> proximal_step (:543-554)"""
+        def temporal_diffusion(c, k, sched_T=None, cursor=None, lab=None):
+            """fold -> scorenet_T on real and imaginary patches -> Langevin update of the patches -> unfold  (:463-502)"""
+            sh, sw = (tuple(np.random.randint(0, ksz, (2,)).tolist()) if random_shift else (0, 0))
+            _lib.check(L.ipdm_patch_fold(state.data_ptr(), vol.data_ptr(), B, T, H, W, ksz, sh, sw, 0, _lib.stream()), "patch_fold")
+            lab = labels_all[:P2] if lab is None else lab
+            if hasattr(self.scorenet_T, "forward_into"):
+                self.scorenet_T.forward_into(vol, lab, gvol)
+            else:
+                flat = vol.permute(0, 1, 3, 2).reshape(P2, ksz * ksz, T)
+                gvol.copy_(self.scorenet_T(flat, lab).reshape(P2, ksz, ksz, T).permute(0, 1, 3, 2))
+            if sched_T is not None:
+                _lib.check(L.ipdm_langevin_update(vol.data_ptr(), gvol.data_ptr(), None, None, vol.numel(), None, sched_T.data_ptr(),
+                                                  cursor.data_ptr(), None, 0, seed_T, 0, _lib.stream()), "langevin_update_T")
+            else:
+                step_T = step_lr * (self.sigmas_T[c].float().cpu() / sig_T[-1]) ** 2 * lamda_T
+                nz = None
+                if noise_fn is not None:   # reference draws (B', kx*ky, T) real then imaginary (:484-485)
+                    nr, ni = noise_fn((P2 // 2, ksz * ksz, T)), noise_fn((P2 // 2, ksz * ksz, T))
+                    nz = torch.cat([nr, ni]).reshape(P2, ksz, ksz, T).permute(0, 1, 3, 2).to(state.device, torch.float32).contiguous()
+                _lib.check(L.ipdm_langevin_update(vol.data_ptr(), gvol.data_ptr(), _lib.ptr(nz), None, vol.numel(), _scalars(step_T),
+                                                  None, None, None, 0, seed_T, k, _lib.stream()), "langevin_update_T")
+            _lib.check(L.ipdm_patch_fold(state.data_ptr(), vol.data_ptr(), B, T, H, W, ksz, sh, sw, 1, _lib.stream()), "patch_unfold")
+
+        def one_step(c, k, noise, sched=None, cursor=None, sched_T=None, with_T=None):
+            """spatial_step (:428-449) -> temporal_step (:452-502) -> proximal_step (:543-554)"""
             if not skip_spatial:
                 self._score_into(x_flat, labels, g_flat)
-            if not tv:
+            if not tv and not diffusion:
                 # Langevin update and L2-penalty step in one kernel
                 if sched is not None:
                     self._sense_step(state, grad, None, bvec, None, sched, cursor, seed, 0)
@@ -454,7 +491,10 @@ class ALD2DTime(_SenseChainMixin, ALDOptimizer):
                     step_size = step_lr * (sigmas[c] / sigmas[-1]) ** 2
                     _lib.check(L.ipdm_langevin_update(state.data_ptr(), grad.data_ptr(), _lib.ptr(noise), None, state.numel(),
                                                       _scalars(step_size), None, None, None, 0, seed, k, _lib.stream()), "langevin_update")
-            _lib.check(L.ipdm_temporal_tv_step(state.data_ptr(), B, T, H * W, lamda_T, _lib.stream()), "temporal_tv_step")
+            if tv:
+                _lib.check(L.ipdm_temporal_tv_step(state.data_ptr(), B, T, H * W, lamda_T, _lib.stream()), "temporal_tv_step")
+            elif temporal_on[c] if with_T is None else with_T:
+                temporal_diffusion(c, k, sched_T, cursor)
             # data consistency only: step = noise_scale = 0 turns the fused kernel into x - kappa*(A^H A x - b)
             self._sense_step(state, grad, None, bvec, prox_only, None, None, seed, k)
 
@@ -466,28 +506,40 @@ class ALD2DTime(_SenseChainMixin, ALDOptimizer):
             real = (state, bvec)
             if fc is None:
                 fc = {"state": torch.zeros_like(state), "grad": torch.zeros_like(state), "bvec": torch.zeros_like(state),
-                      "labels": torch.zeros_like(labels), "sched": torch.zeros_like(sched_host, device=state.device),
+                      "labels": torch.zeros_like(labels_all), "sched": torch.zeros_like(sched_host, device=state.device),
                       "cursor": torch.zeros(1, dtype=torch.int32, device=state.device)}
+                if diffusion:
+                    fc.update(vol=vol, gvol=gvol, sched_T=torch.zeros_like(sched_host, device=state.device))
                 self._fast_cache[key] = fc
-            state, grad, bvec, labels = fc["state"], fc["grad"], fc["bvec"], fc["labels"]
+            state, grad, bvec, labels_all = fc["state"], fc["grad"], fc["bvec"], fc["labels"]
+            labels = labels_all[:2 * BT]
+            if diffusion:
+                vol, gvol = fc["vol"], fc["gvol"]
             x_flat, g_flat = state.view(2 * BT, 1, H, W), grad.view(2 * BT, 1, H, W)
             if "step" not in fc:
-                def body(fc=fc):
-                    one_step(0, 0, None, fc["sched"], fc["cursor"])
-                    _lib.check(L.ipdm_ald_advance(fc["cursor"].data_ptr(), fc["labels"].data_ptr(), 2 * BT, n_steps_each, _lib.stream()), "ald_advance")
-                fc["step"] = _StepGraph(body).prime()
+                def body(with_T, fc=fc):
+                    one_step(0, 0, None, fc["sched"], fc["cursor"], fc.get("sched_T"), with_T)
+                    _lib.check(L.ipdm_ald_advance(fc["cursor"].data_ptr(), fc["labels"].data_ptr(), fc["labels"].numel(), n_steps_each,
+                                                  _lib.stream()), "ald_advance")
+                # the temporal prior is skipped on the levels whose remapped sigma_T is -1 (Q14): one captured step without
+                # it, one with it; the host picks per level
+                fc["step"] = _StepGraph(lambda: body(False)).prime()
+                if any(temporal_on):
+                    fc["step_T"] = _StepGraph(lambda: body(True)).prime()
             state.copy_(real[0])
             bvec.copy_(real[1])
             fc["sched"].copy_(sched_host)
+            if diffusion:
+                fc["sched_T"].copy_(ald_schedule(torch.where(sig_T > 0, sig_T, sig_T[-1]), n_steps_each, step_lr * lamda_T))
             fc["cursor"].zero_()
-            labels.zero_()
-            self.launches_per_step = fc["step"].launches
-            for _ in range(n_total):
-                fc["step"]()
+            labels_all.zero_()
+            self.launches_per_step = fc["step_T"].launches if "step_T" in fc else fc["step"].launches
+            for i in range(n_total):
+                fc["step_T" if temporal_on[i // n_steps_each] else "step"]()
         else:
             k = 0
             for c in range(len(sigmas)):
-                labels.fill_(c)
+                labels_all.fill_(c)
                 for s in range(n_steps_each):
                     noise = None
                     if noise_fn is not None and not skip_spatial:  # both noises are drawn before either update (:442-443)

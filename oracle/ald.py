@@ -85,11 +85,38 @@ def temporal_tv_grad(x, lamda):
     return -lamda * (torch.roll(s, 1, 1) - s)
 
 
+def remap_sigmas_T(sigmas, sigmas_T):
+    """Temporal schedule nearest-interpolated onto the tail of the spatial one; -1 = skip the temporal step.
+    Reference: ALD2DTime.__init__, ALD_optimizers.py:342-345 (quirk Q14: this vector also REPLACES the temporal
+    network's own sigmas)."""
+    import torch.nn.functional as F
+    n = int((sigmas <= sigmas_T[0]).sum())
+    out = torch.ones_like(sigmas) * (-1)
+    if n > 0:
+        out[-n:] = F.interpolate(sigmas_T.view(1, 1, -1), n, mode="nearest").squeeze()
+    return out
+
+
+def fold_patches(x, k):
+    """(N, T, H, W) -> (N*H/k*W/k, k*k, T). Reference: reshape_temporal_dim 'forward', helpers/utils.py:330-345."""
+    N, T, H, W = x.shape
+    return x.reshape(N, T, H // k, k, W // k, k).permute(0, 2, 4, 3, 5, 1).reshape(-1, k * k, T)
+
+
+def unfold_patches(p, k, H, W):
+    """Inverse of fold_patches. Reference: reshape_temporal_dim 'backward', helpers/utils.py:347-359."""
+    T = p.shape[-1]
+    return p.reshape(-1, H // k, W // k, k, k, T).permute(0, 5, 1, 3, 2, 4).reshape(-1, T, H, W)
+
+
 def ald_2dtime(score, measurement, sigmas, n_steps_each, step_lr, lr_scaled, adjoint, prox,
-               mode_T="none", lamda_T=1.0, draw=_default_draw):
-    """cfg 4 sampler for mode_T in {"none","tv"}.  Reference: ALD2DTime.__call__ / init_x_mod /
+               mode_T="none", lamda_T=1.0, draw=_default_draw, score_T=None, sigmas_T=None, win=8, random_shift=False):
+    """cfg 4 sampler for mode_T in {"none","tv","diffusion1d"}.  Reference: ALD2DTime.__call__ / init_x_mod /
     spatial_step / temporal_step / proximal_step, ALD_optimizers.py:351-554.  measurement is
-    (Nc,B,T,C,H,W); both noises are drawn before either update (:442-443); no final denoise."""
+    (Nc,B,T,C,H,W); both noises are drawn before either update (:442-443); no final denoise.
+    "diffusion1d": score_T(patches (B', win*win, T), labels) with `sigmas_T` already remapped (remap_sigmas_T),
+    skipped where it is -1, optional np.random roll of the frames before folding (:463-502)."""
+    import numpy as np
     Nc, B, T, C, H, W = measurement.shape
     y = measurement.reshape(Nc, B * T, C, H, W)
     x = adjoint(y)
@@ -109,6 +136,25 @@ def ald_2dtime(score, measurement, sigmas, n_steps_each, step_lr, lr_scaled, adj
                 xi5 = xi.reshape(B, T, C, H, W)
                 xr = (xr5 + temporal_tv_grad(xr5, lamda_T)).reshape(B * T, C, H, W)
                 xi = (xi5 + temporal_tv_grad(xi5, lamda_T)).reshape(B * T, C, H, W)
+            elif "diffusion1d" in mode_T and float(sigmas_T[c]) != -1:
+                vr = xr.reshape(B, T, C, H, W).permute(0, 2, 1, 3, 4).reshape(-1, T, H, W)
+                vi = xi.reshape(B, T, C, H, W).permute(0, 2, 1, 3, 4).reshape(-1, T, H, W)
+                if random_shift:
+                    sh = tuple(np.random.randint(0, win, (2,)).tolist())
+                    vr, vi = torch.roll(vr, sh, (-2, -1)), torch.roll(vi, sh, (-2, -1))
+                pr, pi = fold_patches(vr, win), fold_patches(vi, win)
+                lab = torch.full((pr.shape[0],), c, dtype=torch.long)
+                step_T = step_lr * (sigmas_T[c] / sigmas_T[-1]) ** 2 * lamda_T
+                sr, si = score_T(pr, lab), score_T(pi, lab)
+                n1, n2 = draw(pr.shape), draw(pi.shape)
+                pr = langevin_update(pr, sr, n1, step_T)
+                pi = langevin_update(pi, si, n2, step_T)
+                vr, vi = unfold_patches(pr, win, H, W), unfold_patches(pi, win, H, W)
+                if random_shift:
+                    back = tuple(-v for v in sh)
+                    vr, vi = torch.roll(vr, back, (-2, -1)), torch.roll(vi, back, (-2, -1))
+                xr = vr.reshape(B, C, T, H, W).permute(0, 2, 1, 3, 4).reshape(B * T, C, H, W)
+                xi = vi.reshape(B, C, T, H, W).permute(0, 2, 1, 3, 4).reshape(B * T, C, H, W)
             x = prox(xr + 1j * xi, y, step_lr * lr_scaled, 1.0)
     return x.reshape(B, T, C, H, W)
 

@@ -359,6 +359,34 @@ def gen_ncsn3d():
         out["shallow_out"] = _np(net(x, y))
         out["shallow_out_flat"] = _np(net(x.reshape(2, 64, 24), y))
     json.dump(specs, open(specs_path, "w"))
+    # ---- 2D+time chain with the learned temporal prior: 32x32 frames, T = 8, 4 coils, (1,1,W) mask; the temporal
+    # schedule starts at 0.2 so that the four last spatial levels run the temporal step and the first six skip it
+    from InverseProblemWithDiffusionModel.ncsn.models import ALD_optimizers as ALD
+    from InverseProblemWithDiffusionModel.ncsn.models import get_sigmas
+    from InverseProblemWithDiffusionModel.ncsn.models.proximal_op import L2Penalty
+    from InverseProblemWithDiffusionModel.ncsn.linear_transforms.undersampling_fourier import SENSE
+    from oracle.mri_ops import keep_center_mask
+    n, T = 32, 8
+    cfg = small_cfg("cine127", 8, n, 10, 20.0)
+    net, _, _ = build_ref_net("NCSNv2Deepest", cfg, seed=5)
+    sig = get_sigmas(cfg, mode="recons")
+    A = SENSE("exp", 4, 16, 1 / 8, (1, n, n), 0)
+    A.random_under_fourier.mask = keep_center_mask(n, 4, 1 / 8, seed=0)
+    meas = A(phantom(1702, T, 1, n, n)).reshape(4, 1, T, 1, n, n)
+    cfg_T = small_cfg("cine127_1d", 128, T, 6, 0.2)
+    sig_T = get_sigmas(cfg_T)
+    params = {"n_steps_each": 1, "step_lr": 1e-4}
+    for tag, shift in (("fixed", False), ("shift", True)):
+        net_T = ncsn3d.NCSN3DShallow(cfg_T).eval()
+        net_T.load_state_dict(synth_state_dict([(k, tuple(v.shape)) for k, v in net_T.state_dict().items()], 13, net_T.sigmas))
+        sampler = ALD.ALD2DTime(L2Penalty(A), net_T, sig_T, (1, T, 1, n, n), net, sig, params, cfg,
+                                measurement=meas, linear_tfm=A, device=torch.device("cpu"))
+        torch.manual_seed(304)
+        np.random.seed(11)
+        with _quiet():
+            res = sampler(save_dir="/tmp/ipdm_golden", lr_scaled=1e4, mode_T="diffusion1d", lamda_T=0.5, if_random_shift=shift)
+        out[f"cine_diffusion_{tag}"] = _np(res[0])
+        torch.set_grad_enabled(True)
     np.savez_compressed(os.path.join(OUT, "ncsn3d.npz"), **out)
 
 

@@ -226,6 +226,15 @@ class EmuLib:
         self.launches += 1
         N, H, W, Cin, Cout, taps = d.N, d.H, d.W, d.Cin, d.Cout, d.taps
         x = _t(d.in_f16, (N, H, W, Cin), np.float16).float().permute(0, 3, 1, 2)
+        X = max(1, d.slices)
+        if d.slice_shift:        # output slice x reads input slice x + shift of the same volume, zeros outside
+            v5 = x.reshape(N // X, X, Cin, H, W)
+            sh = torch.zeros_like(v5)
+            if d.slice_shift > 0:
+                sh[:, :X - d.slice_shift] = v5[:, d.slice_shift:]
+            else:
+                sh[:, -d.slice_shift:] = v5[:, :X + d.slice_shift]
+            x = sh.reshape(N, Cin, H, W)
         k = 3 if taps == 9 else 1
         w = _t(d.w_f16, (Cout, taps, Cin), np.float16).float().permute(0, 2, 1).reshape(Cout, Cin, k, k)
         pad = d.dilation if k == 3 else 0
@@ -250,10 +259,75 @@ class EmuLib:
                 s = F.elu(s)
             _t(d.out_f16, (N, Ho, Wo, Cout), np.float16).copy_(s.half())
         if d.stats:
-            st = _t(d.stats, (N, Cout, 2), np.float64)
-            flat = v.reshape(N, -1, Cout)
+            st = _t(d.stats, (N // X, Cout, 2), np.float64)
+            flat = v.reshape(N // X, -1, Cout)
             st[:, :, 0] = flat.sum(1)
             st[:, :, 1] = (flat * flat).sum(1)
+        return 0
+
+    # ---- 3-D (patch x time) network
+    def ipdm_maxpool5_slices_f16(self, in16, out16, P, X, plane, stream):
+        self.launches += 1
+        v = _t(in16, (P, 1, X, plane), np.float16).float()
+        _t(out16, (P, X, plane), np.float16).copy_(F.max_pool2d(v, (5, 1), 1, (2, 0))[:, 0].half())
+        return 0
+
+    def ipdm_conv3d_first(self, x, w, bias, out, P, X, T, Y, Cout, affine, stream):
+        self.launches += 1
+        v = _t(x, (P, 1, X, T, Y), np.float32)
+        if affine:
+            v = 2 * v - 1
+        wt = _t(w, (Cout, 1, 3, 3, 3), np.float32)
+        b = _t(bias, (Cout,), np.float32) if bias is not None else None
+        _t(out, (P, X, T, Y, Cout), np.float32).copy_(F.conv3d(v, wt, b, padding=1).permute(0, 2, 3, 4, 1))
+        return 0
+
+    def ipdm_conv3d_last(self, in16, w, bias, sigmas, labels, out, P, X, T, Y, C, stream):
+        self.launches += 1
+        v = _t(in16, (P, X, T, Y, C), np.float16).float().permute(0, 4, 1, 2, 3)
+        wt = _t(w, (27, C), np.float32).t().reshape(1, C, 3, 3, 3)
+        b = _t(bias, (1,), np.float32) if bias is not None else None
+        lab = _np(labels, (P,), np.int64)
+        sg = _t(sigmas, (int(lab.max()) + 1,), np.float32)[torch.from_numpy(lab.copy())]
+        _t(out, (P, X, T, Y), np.float32).copy_(F.conv3d(v, wt, b, padding=1)[:, 0] / sg.view(P, 1, 1, 1))
+        return 0
+
+    def ipdm_gather_t_f16(self, in16, out16, NS, T, T2, Y, C, stride, offset0, K, stream):
+        self.launches += 1
+        v = _t(in16, (NS, T, Y, C), np.float16)
+        o = _t(out16, (NS, T2, Y, K, C), np.float16)
+        o.zero_()
+        for t2 in range(T2):
+            for k in range(K):
+                t = stride * t2 + offset0 + k
+                if 0 <= t < T:
+                    o[:, t2, :, k, :] = v[:, t]
+        return 0
+
+    def ipdm_interleave_t(self, inp, out32, out16, NS, T, Y, C, stream):
+        self.launches += 1
+        v = _t(inp, (NS, T, Y, 2, C), np.float32).permute(0, 1, 3, 2, 4).reshape(NS, 2 * T, Y, C)
+        _t(out32, (NS, 2 * T, Y, C), np.float32).copy_(v)
+        if out16 is not None:
+            _t(out16, (NS, 2 * T, Y, C), np.float16).copy_(F.elu(v).half())
+        return 0
+
+    def ipdm_add_act(self, a, b, out, n, elu_b, stream):
+        self.launches += 1
+        B = _t(b, (n,), np.float32)
+        _t(out, (n,), np.float32).copy_(_t(a, (n,), np.float32) + (F.elu(B) if elu_b else B))
+        return 0
+
+    def ipdm_patch_fold(self, state, vol, B, T, H, W, k, sh, sw, unfold, stream):
+        self.launches += 1
+        S = _t(state, (2 * B, T, H, W), np.float32)
+        V = _t(vol, (2 * B, H // k, W // k, k, T, k), np.float32)
+        if not unfold:
+            r = torch.roll(S, (sh, sw), (-2, -1))
+            V.copy_(r.reshape(2 * B, T, H // k, k, W // k, k).permute(0, 2, 4, 3, 1, 5))
+        else:
+            r = V.permute(0, 4, 1, 3, 2, 5).reshape(2 * B, T, H, W)
+            S.copy_(torch.roll(r, (-sh, -sw), (-2, -1)))
         return 0
 
     def ipdm_conv_igemm(self, dp, stream):

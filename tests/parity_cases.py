@@ -202,6 +202,46 @@ def case_ncsn3d_shallow(dev):
     assert e_emu < 2e-3, e_emu                     # same operand rounding; rounding-boundary flips and accumulation order remain
 
 
+def case_sampler_cine_diffusion(dev):
+    """ALD2DTime with the learned temporal prior (mode_T='diffusion1d') against chains of the
+    unmodified reference: injected torch noise in the reference's draw order, np.random frame rolls, the Q14 sigma remap
+    (six spatial levels skip the temporal step, four run it)."""
+    from inverseproblemwithdiffusionmodel_b200.ncsn.models.ncsn3d import NCSN3DShallow
+    g = G("ncsn3d")
+    n, T = 32, 8
+    cfg = make_config("CINE127", 8, n, 10, 20.0, device=dev)
+    net, _ = build_net(NCSNv2Deepest, "NCSNv2Deepest_ngf8", 5, cfg, dev)
+    sig = get_sigmas(cfg, mode="recons")
+    A = SENSE("exp", 4, 16, 1 / 8, (1, n, n), 0)
+    A.random_under_fourier.mask = keep_center_mask(n, 4, 1 / 8, seed=0)
+    meas = A(phantom(1702, T, 1, n, n).to(dev)).reshape(4, 1, T, 1, n, n)
+    cfg_T = make_config("CINE127", 128, T, 6, 0.2, device=dev)
+    cfg_T.data.channels, cfg_T.data.channels_3d = 64, 1
+    sig_T = get_sigmas(cfg_T)
+    params = {"n_steps_each": 1, "step_lr": 1e-4}
+    draw = lambda shape: torch.randn(*shape)
+    for tag, shift in (("fixed", False), ("shift", True)):
+        net_T, _ = build_net(NCSN3DShallow, "NCSN3DShallow_ngf128", 13, cfg_T, dev)
+        sampler = ALD.ALD2DTime(L2Penalty(A), net_T, sig_T, (1, T, 1, n, n), net, sig, params, cfg,
+                                measurement=meas, linear_tfm=A, device=torch.device(dev))
+        assert tuple(net_T.sigmas.shape) == tuple(sig.shape) and int((net_T.sigmas == -1).sum()) == 6
+        torch.manual_seed(304)
+        np.random.seed(11)
+        res = sampler(save_dir="/tmp", lr_scaled=1e4, mode_T="diffusion1d", lamda_T=0.5, if_random_shift=shift, noise_fn=draw)
+        err = rel_l2(res[0], g[f"cine_diffusion_{tag}"])
+        assert err < 1e-3, (tag, err)                       # same tolerance and reasoning as case_sampler_cine
+    # in-kernel Philox noise + captured step graphs (one with, one without the temporal step): finite, and close to the
+    # injected-noise chain in distribution (same start, same schedule)
+    net_T, _ = build_net(NCSN3DShallow, "NCSN3DShallow_ngf128", 13, cfg_T, dev)
+    sampler = ALD.ALD2DTime(L2Penalty(A), net_T, sig_T, (1, T, 1, n, n), net, sig, params, cfg,
+                            measurement=meas, linear_tfm=A, device=torch.device(dev))
+    fast = sampler(save_dir="/tmp", lr_scaled=1e4, mode_T="diffusion1d", lamda_T=0.5, if_random_shift=False, seed=3)[0]
+    assert torch.isfinite(fast.abs()).all()
+    ref = torch.as_tensor(g["cine_diffusion_fixed"])
+    assert abs(float(fast.abs().mean()) / float(ref.abs().mean()) - 1) < 0.2
+    torch.set_grad_enabled(True)
+
+
 # ------------------------------------------------------------------------------------------------ samplers
 def case_sampler_uncond(dev):
     g = G("samplers")

@@ -383,6 +383,10 @@ def test_ncsn3d_shallow_temporal_prior():
     C.case_ncsn3d_shallow(DEV)
 
 
+def test_sampler_cine_learned_temporal_prior():
+    C.case_sampler_cine_diffusion(DEV)
+
+
 def test_conv3d_via_slices_vs_torch():
     """One 3x3x3 dilated convolution = three slice-shifted launches of the 2-D tensor-core kernels, against
     torch.nn.functional.conv3d on the same f16-rounded operands (d = 1, 2: persistent halo kernel; d = 4: per-tap kernel)."""

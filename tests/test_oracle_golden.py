@@ -154,6 +154,31 @@ def test_ncsn3d_shallow_forward(golden):
     assert rel_l2(G["shallow_out_flat"].reshape(2, 1, 8, 8, 24), G["shallow_out"]) < 1e-6
 
 
+def test_cine_chain_with_temporal_prior(golden):
+    """oracle ALD2DTime mode_T='diffusion1d' (fold, remapped sigma_T, temporal Langevin step, unfold, np.random rolls)
+    pinned to the reference's chains."""
+    G = golden("ncsn3d")
+    n, T = 32, 8
+    sig = ALD.geometric_sigmas(20.0, 0.01, 10)
+    sig_T = ALD.remap_sigmas_T(sig, ALD.geometric_sigmas(0.2, 0.01, 6))
+    maps, mask = M.exp_coil_maps(4, n, n, 0), M.keep_center_mask(n, 4, 1 / 8, seed=0)
+    meas = M.sense_forward(phantom(1702, T, 1, n, n), maps, mask).reshape(4, 1, T, 1, n, n)
+    P2 = _net("NCSNv2Deepest_ngf8", 5, sig)
+    P3 = _net("NCSN3DShallow_ngf128", 13, ALD.geometric_sigmas(0.2, 0.01, 6))
+    P3["sigmas"] = sig_T                                            # Q14
+    score = lambda x, y: SN.score_forward("NCSNv2Deepest", P2, x, y)
+    score_T = lambda p, y: SN.score_forward_3d_shallow(P3, p.reshape(-1, 1, 8, 8, T), y).reshape(-1, 64, T)
+    prox = lambda z, y, a, l: M.l2_prox_sense_closed_form(z, y, maps, mask, a, l)
+    adj = lambda s: M.sense_adjoint(s, maps)
+    for tag, shift in (("fixed", False),):
+        torch.manual_seed(304)
+        np.random.seed(11)
+        with torch.no_grad():
+            out = ALD.ald_2dtime(score, meas, sig, 1, 1e-4, 1e4, adj, prox, mode_T="diffusion1d", lamda_T=0.5,
+                                 score_T=score_T, sigmas_T=sig_T, win=8, random_shift=shift)
+        assert rel_l2(out, G[f"cine_diffusion_{tag}"]) < 1e-4, tag
+
+
 def test_state_dict_census():
     S = _specs()
     assert len(S["NCSNv2Deepest_acdc"]) == 230 and len(S["NCSNv2_mnist28"]) == 154
