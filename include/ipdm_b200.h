@@ -158,7 +158,8 @@ typedef struct {
                              Tile partials are fp32 in a fixed order; only their combination is an fp64
                              atomic, which keeps results run-to-run stable at fp32 precision             */
   int N, H, W, Cin, Cout;
-  int taps;               /* 9 (3x3, zero padding = dilation) or 1 (1x1)                                */
+  int taps;               /* 9 (3x3, zero padding = dilation), 1 (1x1) or 27 (3x3x3 over slice volumes: weights
+                             [Cout][kx][kh][kw][Cin], the kx-plane reads slice x + (kx-1)*dilation, zero outside) */
   int dilation;
   int flags;              /* IPDM_CONV_* below                                                          */
   int slices;             /* 0/1: plain 2-D.  X > 1: the N images are N/X volumes of X consecutive slices

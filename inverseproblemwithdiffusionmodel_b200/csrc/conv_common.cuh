@@ -26,9 +26,10 @@ struct IgemmParams {
 int get_weight_map(const void* w, int Cout, int K, CUtensorMap* out);
 int get_act_map(const void* x, int N, int H, int W, int C, int box_w, int box_h, int slices, CUtensorMap* out);
 int launch_conv_halo(const ipdm_conv_desc& d, cudaStream_t s);
+bool conv_halo_supports(const ipdm_conv_desc& d);
 extern int g_conv_variant;       // 0 = auto, 1 = force the per-tap tile kernel (diagnostics)
 
-// Epilogue of `NCHUNK` 32-column chunks of one accumulator (128 channels x 256 pixels) by a TEAM of 4 warps
+// Epilogue of `NCHUNK` (runtime) 32-column chunks of one accumulator (128 channels x up to 256 pixels) by a TEAM of 4 warps
 // (128 threads, named barrier `BAR`, a runtime value so that both teams share ONE copy of this code -- the
 // epilogue is instruction-cache bound otherwise); chunks [chunk0, chunk0 + NCHUNK).
 // TMEM lane = output channel, column = pixel j = py*TW + px of a (256/TW) x TW pixel tile at (h0, w0).
@@ -38,9 +39,9 @@ extern int g_conv_variant;       // 0 = auto, 1 = force the per-tap tile kernel 
 // called once, after the first residual loads are in flight and before the first TMEM read.
 // SLABS = 2: double-buffered slab, one barrier per chunk; SLABS = 1: single slab, two barriers per chunk.
 // MODE bits: 1 = residual, 2 = fp32 output, 4 = f16 output, 8 = 2x2 mean-pool.
-template <int MODE, int TW, int SLABS, int NCHUNK, class WaitAcc>
+template <int MODE, int TW, int SLABS, class WaitAcc>
 __device__ __forceinline__ void conv_epilogue(const IgemmParams& p, float* slab, uint32_t tmem_acc, int quad, int lane,
-                                              int n, int h0, int w0, int m0, int chunk0, int BAR, WaitAcc wait_acc) {
+                                              int n, int h0, int w0, int m0, int chunk0, int NCHUNK, int BAR, WaitAcc wait_acc) {
   constexpr bool kRes = (MODE & 1) != 0, kOut32 = (MODE & 2) != 0, kOut16 = (MODE & 4) != 0, pool = (MODE & 8) != 0;
   constexpr int ROWS_PER_CHUNK = 32 / TW;       // tile rows covered by 32 columns
   constexpr int PW = TW / 2;                    // pooled pixels per pooled row

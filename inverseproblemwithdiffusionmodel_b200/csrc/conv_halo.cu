@@ -23,16 +23,17 @@
 
 namespace ipdm {
 
-constexpr int HT_H = 32, HT_W = 8;            // pixel tile
+constexpr int HT_W = 8;                       // pixel tile = TH rows x 8 columns, TH = 32 (UMMA N = 256), 24 (N = 192) or
+                                              // 12 (N = 96): the short tiles fit the 24 x 8 / 12 x 8 slices of the 3-D network
 constexpr int NH = 2;                         // halo ring
 constexpr int NW = 3;                         // weight ring
 constexpr int W_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int HALO_THREADS = 352;
 
-template <int DIL> struct HaloCfg {
+template <int DIL, int TH> struct HaloCfg {
   static constexpr int SLOTS = HT_W + 2 * DIL;                // pixel slots per halo row: exactly the 8 + 2d that are used
   static constexpr int PITCH = SLOTS * 128;                   // 1280 / 1536 B (need not be a multiple of the 1024-byte swizzle pattern)
-  static constexpr int ROWS = HT_H + 2 * DIL;
+  static constexpr int ROWS = TH + 2 * DIL;
   static constexpr int HALO_BYTES = (ROWS * PITCH + 1023) / 1024 * 1024;   // every stage starts on a swizzle-pattern boundary
   static constexpr int SMEM = NH * HALO_BYTES + NW * W_BYTES + 2 * SLAB_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
@@ -42,10 +43,12 @@ struct HaloParams {
   int items, mtiles;
 };
 
-template <int MODE, int DIL>
+template <int MODE, int DIL, int TH>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, HaloParams hp) {
-  using CFG = HaloCfg<DIL>;
+  using CFG = HaloCfg<DIL, TH>;
+  constexpr int BN = TH * HT_W;                 // pixels per accumulator (UMMA N)
+  constexpr int NCH = BN / 32;                  // 32-column epilogue chunks: team A takes the first (NCH+1)/2
   const IgemmParams& p = hp.g;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -63,6 +66,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kchunks = p.Cin / BLOCK_K;
+  const int planes = p.taps == 27 ? 3 : 1;      // 27 taps: a 3x3x3 convolution over slice volumes, K loop over the 3 kx-planes
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
@@ -86,7 +90,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
     int tile = item / hp.mtiles;
     const int tw = tile % p.tiles_w; tile /= p.tiles_w;
     const int th = tile % p.tiles_h; tile /= p.tiles_h;
-    n = tile; h0 = th * HT_H; w0 = tw * HT_W; m0 = mt * BLOCK_M;
+    n = tile; h0 = th * TH; w0 = tw * HT_W; m0 = mt * BLOCK_M;
   };
 
   if (warp == 0) {
@@ -96,12 +100,14 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
       for (int item = blockIdx.x; item < hp.items; item += gridDim.x) {
         int n, h0, w0, m0;
         decode(item, n, h0, w0, m0);
-        for (int kc = 0; kc < kchunks; ++kc, ++cnt) {
-          const int s = cnt % NH;
-          mbar_wait(&halo_empty[s], ((cnt / NH) & 1) ^ 1);
-          mbar_expect_tx(&halo_full[s], CFG::ROWS * CFG::PITCH);
-          tma_load_5d(halo + s * CFG::HALO_BYTES, &tmap_x, &halo_full[s], kc * BLOCK_K, w0 - DIL, h0 - DIL,
-                      n % p.slices + p.slice_shift, n / p.slices);
+        for (int kc = 0; kc < kchunks; ++kc) {
+          for (int pl = 0; pl < planes; ++pl, ++cnt) {      // 3x3x3: one halo tile per kx-plane, from slice x + (kx-1)*d
+            const int s = cnt % NH;
+            mbar_wait(&halo_empty[s], ((cnt / NH) & 1) ^ 1);
+            mbar_expect_tx(&halo_full[s], CFG::ROWS * CFG::PITCH);
+            tma_load_5d(halo + s * CFG::HALO_BYTES, &tmap_x, &halo_full[s], kc * BLOCK_K, w0 - DIL, h0 - DIL,
+                        n % p.slices + p.slice_shift + (planes == 3 ? (pl - 1) * DIL : 0), n / p.slices);
+          }
         }
       }
     }
@@ -113,7 +119,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
         int n, h0, w0, m0;
         decode(item, n, h0, w0, m0);
         for (int kc = 0; kc < kchunks; ++kc) {
-          for (int tap = 0; tap < 9; ++tap, ++cnt) {
+          for (int tap = 0; tap < 9 * planes; ++tap, ++cnt) {     // weights [Cout][(kx,) ky, kx taps][Cin]
             const int s = cnt % NW;
             mbar_wait(&w_empty[s], ((cnt / NW) & 1) ^ 1);
             mbar_expect_tx(&w_full[s], W_BYTES);
@@ -125,30 +131,32 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+      const uint32_t idesc = make_idesc(BLOCK_M, BN);
       uint32_t hcnt = 0, wcnt = 0, acnt = 0;
       for (int item = blockIdx.x; item < hp.items; item += gridDim.x, ++acnt) {
         const int as = acnt & 1;
         mbar_wait(&acc_empty[as], ((acnt >> 1) & 1) ^ 1);
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + as * BLOCK_N;
-        for (int kc = 0; kc < kchunks; ++kc, ++hcnt) {
-          const int hs = hcnt % NH;
-          mbar_wait(&halo_full[hs], (hcnt / NH) & 1);
-          const uint32_t hbase = smem_u32(halo + hs * CFG::HALO_BYTES);
-          for (int tap = 0; tap < 9; ++tap, ++wcnt) {
-            const int ws = wcnt % NW;
-            mbar_wait(&w_full[ws], (wcnt / NW) & 1);
-            tcgen05_fence_after();
-            const int dy = (tap / 3) * DIL, dx = (tap % 3) * DIL;
-            const uint64_t adesc = make_smem_desc(smem_u32(wts + ws * W_BYTES));
-            const uint64_t bdesc = make_smem_desc(hbase + dy * CFG::PITCH + dx * 128, CFG::PITCH);
+        for (int kc = 0; kc < kchunks; ++kc) {
+          for (int pl = 0; pl < planes; ++pl, ++hcnt) {
+            const int hs = hcnt % NH;
+            mbar_wait(&halo_full[hs], (hcnt / NH) & 1);
+            const uint32_t hbase = smem_u32(halo + hs * CFG::HALO_BYTES);
+            for (int tap = 0; tap < 9; ++tap, ++wcnt) {
+              const int ws = wcnt % NW;
+              mbar_wait(&w_full[ws], (wcnt / NW) & 1);
+              tcgen05_fence_after();
+              const int dy = (tap / 3) * DIL, dx = (tap % 3) * DIL;
+              const uint64_t adesc = make_smem_desc(smem_u32(wts + ws * W_BYTES));
+              const uint64_t bdesc = make_smem_desc(hbase + dy * CFG::PITCH + dx * 128, CFG::PITCH);
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-              umma_f16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | tap | k) != 0);
-            umma_commit(&w_empty[ws]);
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                umma_f16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | pl | tap | k) != 0);
+              umma_commit(&w_empty[ws]);
+            }
+            umma_commit(&halo_empty[hs]);
           }
-          umma_commit(&halo_empty[hs]);
         }
         umma_commit(&acc_full[as]);
       }
@@ -163,7 +171,9 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
       int n, h0, w0, m0;
       decode(item, n, h0, w0, m0);
       const int as = acnt & 1;
-      conv_epilogue<MODE, HT_W, 2, 4>(p, my_slab, tmem_base + as * BLOCK_N, quad, lane, n, h0, w0, m0, team * 4, 1 + team, [&]() {
+      constexpr int NA = (NCH + 1) / 2;
+      conv_epilogue<MODE, HT_W, 2>(p, my_slab, tmem_base + as * BLOCK_N, quad, lane, n, h0, w0, m0, team ? NA : 0, team ? NCH - NA : NA,
+                                   1 + team, [&]() {
         mbar_wait(&acc_full[as], (acnt >> 1) & 1);
         tcgen05_fence_after();
       });
@@ -183,31 +193,52 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
   }
 }
 
-template <int MODE, int DIL>
+template <int MODE, int DIL, int TH>
 static int launch_variant(const CUtensorMap& mw, const CUtensorMap& mx, const HaloParams& hp, int grid, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    IPDM_CUDA(cudaFuncSetAttribute(k_conv_halo<MODE, DIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<DIL>::SMEM));
+    IPDM_CUDA(cudaFuncSetAttribute(k_conv_halo<MODE, DIL, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<DIL, TH>::SMEM));
     attr_set = true;
   }
-  k_conv_halo<MODE, DIL><<<grid, HALO_THREADS, HaloCfg<DIL>::SMEM, s>>>(mw, mx, hp);
+  k_conv_halo<MODE, DIL, TH><<<grid, HALO_THREADS, HaloCfg<DIL, TH>::SMEM, s>>>(mw, mx, hp);
   return 0;
+}
+
+// tile rows: the candidate that pads the image height least (ties -> the taller tile); pooled outputs need whole 4-row chunks of an even height
+static int pick_tile_rows(int H, bool pool) {
+  if (pool) return 32;
+  int best = 32, waste = (H + 31) / 32 * 32 - H;
+  const int cand[2] = {24, 12};
+  for (int c : cand) {
+    const int w = (H + c - 1) / c * c - H;
+    if (w < waste) { best = c; waste = w; }
+  }
+  return best;
+}
+
+// dilation 1 and 2 with every tile height; dilation 4 (halo of 16 slots x TH+8 rows per stage) only fits shared memory
+// with the 12-row tile, i.e. for the 12 x 8 slices of the 3-D network's deepest stage
+bool conv_halo_supports(const ipdm_conv_desc& d) {
+  if (d.taps < 9) return false;
+  if (d.dilation <= 2) return true;
+  return d.dilation == 4 && pick_tile_rows(d.H, (d.flags & IPDM_CONV_POOL2) != 0) == 12;
 }
 
 int launch_conv_halo(const ipdm_conv_desc& d, cudaStream_t s) {
   const bool pool = (d.flags & IPDM_CONV_POOL2) != 0;
+  const int th = pick_tile_rows(d.H, pool);
   CUtensorMap mw, mx;
-  if (int e = get_weight_map(d.w_f16, d.Cout, 9 * d.Cin, &mw)) return e;
-  if (int e = get_act_map(d.in_f16, d.N, d.H, d.W, d.Cin, HT_W + 2 * d.dilation, HT_H + 2 * d.dilation, d.slices, &mx)) return e;
+  if (int e = get_weight_map(d.w_f16, d.Cout, d.taps * d.Cin, &mw)) return e;
+  if (int e = get_act_map(d.in_f16, d.N, d.H, d.W, d.Cin, HT_W + 2 * d.dilation, th + 2 * d.dilation, d.slices, &mx)) return e;
   if (d.stats) IPDM_CUDA(cudaMemsetAsync(d.stats, 0, (size_t)(d.N / d.slices) * d.Cout * 2 * sizeof(double), s));
   HaloParams hp{};
   IgemmParams& p = hp.g;
   p.bias = d.bias; p.residual = d.residual; p.out_f32 = d.out_f32; p.out_f16 = reinterpret_cast<__half*>(d.out_f16);
   p.stats = d.stats;
-  p.N = d.N; p.H = d.H; p.W = d.W; p.Cin = d.Cin; p.Cout = d.Cout; p.taps = 9; p.dilation = d.dilation; p.flags = d.flags;
+  p.N = d.N; p.H = d.H; p.W = d.W; p.Cin = d.Cin; p.Cout = d.Cout; p.taps = d.taps; p.dilation = d.dilation; p.flags = d.flags;
   p.slices = d.slices; p.slice_shift = d.slice_shift;
   p.tiles_w = (d.W + HT_W - 1) / HT_W;
-  p.tiles_h = (d.H + HT_H - 1) / HT_H;
+  p.tiles_h = (d.H + th - 1) / th;
   hp.mtiles = d.Cout / BLOCK_M;
   hp.items = p.tiles_w * p.tiles_h * d.N * hp.mtiles;
   static int sms = 0;
@@ -219,17 +250,26 @@ int launch_conv_halo(const ipdm_conv_desc& d, cudaStream_t s) {
   const int grid = hp.items < sms ? hp.items : sms;
   const int mode = (d.residual ? 1 : 0) | (d.out_f32 ? 2 : 0) | (d.out_f16 ? 4 : 0) | (pool ? 8 : 0);
   int e = 0;
+#define HALO_TH(M, D)                                                                                     \
+  (th == 32 ? launch_variant<M, D, 32>(mw, mx, hp, grid, s)                                               \
+            : th == 24 ? launch_variant<M, D, 24>(mw, mx, hp, grid, s) : launch_variant<M, D, 12>(mw, mx, hp, grid, s))
 #define HALO_CASE(M)                                                                 \
   case M:                                                                            \
-    e = d.dilation == 1 ? launch_variant<M, 1>(mw, mx, hp, grid, s) : launch_variant<M, 2>(mw, mx, hp, grid, s); \
+    e = d.dilation == 1 ? HALO_TH(M, 1) : d.dilation == 2 ? HALO_TH(M, 2) : launch_variant<M, 4, 12>(mw, mx, hp, grid, s); \
+    break;
+#define HALO_CASE_POOL(M)                                                            \
+  case M:                                                                            \
+    e = d.dilation == 1 ? launch_variant<M, 1, 32>(mw, mx, hp, grid, s) : launch_variant<M, 2, 32>(mw, mx, hp, grid, s); \
     break;
   switch (mode) {
     HALO_CASE(2) HALO_CASE(3) HALO_CASE(4) HALO_CASE(5) HALO_CASE(6) HALO_CASE(7)
-    HALO_CASE(10) HALO_CASE(11) HALO_CASE(12) HALO_CASE(13) HALO_CASE(14) HALO_CASE(15)
+    HALO_CASE_POOL(10) HALO_CASE_POOL(11) HALO_CASE_POOL(12) HALO_CASE_POOL(13) HALO_CASE_POOL(14) HALO_CASE_POOL(15)
     default:
       set_error("conv_halo: unsupported output combination %d", mode);
       return IPDM_E_BADARG;
   }
+#undef HALO_TH
+#undef HALO_CASE_POOL
 #undef HALO_CASE
   if (e) return e;
   return launched("k_conv_halo");

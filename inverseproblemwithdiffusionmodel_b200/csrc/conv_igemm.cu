@@ -88,13 +88,14 @@ k_conv_igemm(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         const int tap = kb / kchunks, kc = kb % kchunks;
-        const int dy = p.taps == 9 ? (tap / 3 - 1) * p.dilation : 0;
-        const int dx = p.taps == 9 ? (tap % 3 - 1) * p.dilation : 0;
+        const int dy = p.taps >= 9 ? ((tap % 9) / 3 - 1) * p.dilation : 0;
+        const int dx = p.taps >= 9 ? (tap % 3 - 1) * p.dilation : 0;
+        const int dz = p.taps == 27 ? (tap / 9 - 1) * p.dilation : 0;      // 3x3x3: kx-plane = slice offset
         unsigned char* sa = smem + s * STAGE_BYTES;
         unsigned char* sb = sa + A_BYTES;
         mbar_expect_tx(&full_bar[s], STAGE_BYTES);
         tma_load_2d(sa, &tmap_w, &full_bar[s], tap * p.Cin + kc * BLOCK_K, m0);
-        tma_load_5d(sb, &tmap_x, &full_bar[s], kc * BLOCK_K, w0 + dx, h0 + dy, n % p.slices + p.slice_shift, n / p.slices);
+        tma_load_5d(sb, &tmap_x, &full_bar[s], kc * BLOCK_K, w0 + dx, h0 + dy, n % p.slices + p.slice_shift + dz, n / p.slices);
       }
     }
   } else if (warp == 1) {
@@ -120,7 +121,7 @@ k_conv_igemm(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
     }
   } else {
     // ===== epilogue (the pipeline stages are idle once the accumulator is complete: reuse them as the slab) =====
-    conv_epilogue<MODE, TILE_W, 2, 8>(p, reinterpret_cast<float*>(smem), tmem_base, warp & 3, lane, n, h0, w0, m0, 0, 1, [&]() {
+    conv_epilogue<MODE, TILE_W, 2>(p, reinterpret_cast<float*>(smem), tmem_base, warp & 3, lane, n, h0, w0, m0, 0, 8, 1, [&]() {
       mbar_wait(tmem_full_bar, 0);
       tcgen05_fence_after();
     });
@@ -211,7 +212,8 @@ extern "C" int ipdm_conv_igemm(const ipdm_conv_desc* dh, void* stream) {
   if (d.slices < 1) d.slices = 1;
   IPDM_REQUIRE(d.N % d.slices == 0 && (d.slices > 1 || d.slice_shift == 0) && abs(d.slice_shift) < d.slices + (d.slices == 1),
                IPDM_E_BADARG, "conv_igemm: N=%d slices=%d slice_shift=%d", d.N, d.slices, d.slice_shift);
-  IPDM_REQUIRE(d.taps == 9 || d.taps == 1, IPDM_E_BADARG, "conv_igemm: taps must be 9 or 1");
+  IPDM_REQUIRE(d.taps == 9 || d.taps == 1 || (d.taps == 27 && d.slices > 1), IPDM_E_BADARG,
+               "conv_igemm: taps must be 9, 1, or 27 (3x3x3 over slice volumes, slices > 1)");
   IPDM_REQUIRE(d.Cin % BLOCK_K == 0 && d.Cin >= BLOCK_K, IPDM_E_UNSUPPORTED, "conv_igemm: Cin=%d must be a multiple of 64", d.Cin);
   IPDM_REQUIRE(d.Cout % BLOCK_M == 0, IPDM_E_UNSUPPORTED, "conv_igemm: Cout=%d must be a multiple of 128", d.Cout);
   IPDM_REQUIRE(d.out_f32 || d.out_f16, IPDM_E_BADARG, "conv_igemm: no output");
@@ -223,7 +225,7 @@ extern "C" int ipdm_conv_igemm(const ipdm_conv_desc* dh, void* stream) {
   cudaStream_t s = as_stream(stream);
   // 3x3 with dilation 1 or 2: persistent halo-tile kernel (each activation tile is fetched once per 64
   // input channels instead of once per tap); everything else: the per-tap tile kernel below.
-  if (d.taps == 9 && d.dilation <= 2 && g_conv_variant != 1) return launch_conv_halo(d, s);
+  if (g_conv_variant != 1 && conv_halo_supports(d)) return launch_conv_halo(d, s);
   CUtensorMap mw, mx;
   if (int e = get_weight_map(d.w_f16, d.Cout, d.taps * d.Cin, &mw)) return e;
   if (int e = get_act_map(d.in_f16, d.N, d.H, d.W, d.Cin, TILE_W, TILE_H, d.slices, &mx)) return e;

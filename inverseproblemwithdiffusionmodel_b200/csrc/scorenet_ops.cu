@@ -595,7 +595,7 @@ extern "C" int ipdm_meanpool2(const float* in, const float* add, float* out, int
 }
 
 extern "C" int ipdm_pack_weights_f16(const float* w_oihw, void* w_f16, int Cout, int Cin, int taps, void* stream) {
-  IPDM_REQUIRE(w_oihw && w_f16 && (taps == 9 || taps == 1), IPDM_E_BADARG, "pack_weights: bad argument");
+  IPDM_REQUIRE(w_oihw && w_f16 && taps >= 1 && Cout >= 1 && Cin >= 1, IPDM_E_BADARG, "pack_weights: bad argument");
   const size_t total = (size_t)Cout * taps * Cin;
   k_pack_weights<<<grid1d(total, 256), 256, 0, as_stream(stream)>>>(w_oihw, reinterpret_cast<__half*>(w_f16), Cout, Cin, taps);
   return launched("k_pack_weights");

@@ -6,10 +6,10 @@ torch's RNG identically); the forward pass is a fixed sequence of sm_100a kernel
 Volumes are `(B, 1, kx, ky, T)` patches (8 x 8 x 24 for CINE127).  On the device they live as `[P][X][T][Y][C]`:
 every X-slice is an NHWC "image" of H = T rows and W = Y columns, so
 
-  * a 3x3x3 (dilated) convolution = THREE launches of the 2-D tcgen05 implicit GEMM, one per kx-plane, the slice
-    shifted by (kx-1)*dilation inside the volume (`ipdm_conv_desc.slices / slice_shift`, zero padding across slices
-    by the 5-D TMA box) and accumulating through the residual path; bias, the f16 copy, ELU and the InstanceNorm++
-    sums belong to the last launch (the centre plane, which touches every slice);
+  * a 3x3x3 (dilated) convolution = ONE launch of the 2-D tcgen05 implicit GEMM with a 27-tap K loop: per 64 input
+    channels the three kx-planes are three halo tiles fetched from slices x + (kx-1)*dilation of the volume
+    (`ipdm_conv_desc.taps = 27, slices = X`; the 5-D TMA box zero-pads across slices) and all 27 taps accumulate in
+    the same TMEM tile, so bias / residual / ELU / f16 copy / InstanceNorm++ sums are the ordinary epilogue;
   * InstanceNorm3dPlus is the 2-D apply kernel over X*T*Y positions; MaxPool3d(5) = the 2-D 5x5 pool + a slice-axis pool;
   * `conv_temporal_down` (Conv3d (1,1,4)/s(1,1,2)) and `conv_temporal_up` (ConvTranspose3d) are a T-gather that lays
     their taps side by side + ONE 1x1 implicit GEMM (the transposed one computes its two output phases as 2*Cout
@@ -24,7 +24,7 @@ import torch.nn as nn
 
 from . import get_sigmas
 from ... import _lib
-from ..._lib import ConvDesc, CONV_F16_ELU, CONV_F16_PRE_RES, CONV_RES_ELU
+from ..._lib import ConvDesc, CONV_F16_ELU
 from .ncsnv2 import _Plan
 
 
@@ -178,8 +178,9 @@ class _Plan3D(_Plan):
                         raise _lib.IpdmError("end_conv: only config.data.channels_3d == 1 is implemented")
                     self.w[name] = (w[0].permute(1, 3, 2, 0).reshape(27, cin).contiguous(), bias)            # [(kx, kt, ky)][C]
                 elif (kx, ky, kt) == (3, 3, 3):
-                    # one 2-D weight set per kx-plane, taps over the (T, Y) image: (kh, kw) = (kt, ky)
-                    self.w[name] = (tuple(pack2d(w[:, :, i].permute(0, 1, 3, 2)) for i in range(3)), bias)
+                    # [Cout][27][Cin], taps ordered (kx, kh = kt, kw = ky): the (T, Y) image of every kx-plane
+                    w27 = w.permute(0, 1, 2, 4, 3).reshape(cout, cin, 27, 1)
+                    self.w[name] = (pack2d(w27), bias)
                 elif (kx, ky, kt) == (1, 1, 1):
                     self.w[name] = (pack2d(w[:, :, 0]), bias)
                 elif (kx, ky) == (1, 1):
@@ -204,24 +205,10 @@ class _Plan3D(_Plan):
         _lib.check(self.L.ipdm_conv_igemm(ctypes.byref(d), _lib.stream()), what)
 
     def conv(self, wname, x16, dims, residual=None, out32=None, out16=None, stats=None, flags=0, dilation=1):
-        N, H, W, Cin, Cout = dims
-        ws, bias = self.w[wname]
-        if not isinstance(ws, tuple):      # 1x1 (shortcut of a plain block, gathered temporal convolutions)
-            return self._launch(ws, bias, x16, dims, residual, out32, out16, stats, flags, 1, 0, "conv1x1 " + wname)
-        pre_res = bool(flags & CONV_F16_PRE_RES) and residual is not None
-        acc = out32 if (out32 is not None and not pre_res) else self.f32("conv3d.acc%d_%d" % (H, Cout), N, H, W, Cout)
-        first_res = None if pre_res else residual
-        # side planes: acc = [residual +] conv(kx = 0) + conv(kx = 2)   (slices shifted by -/+ dilation; no bias)
-        self._launch(ws[0], None, x16, dims, first_res, acc, None, None, flags & CONV_RES_ELU if first_res is not None else 0,
-                     dilation, -dilation, "conv3d/-x " + wname)
-        self._launch(ws[2], None, x16, dims, acc, acc, None, None, 0, dilation, dilation, "conv3d/+x " + wname)
-        # centre plane last: it visits every slice, so bias, f16 copy and the InstanceNorm++ sums are complete
-        if pre_res:
-            self._launch(ws[1], bias, x16, dims, acc, acc, out16, None, flags & CONV_F16_ELU, dilation, 0, "conv3d/0 " + wname)
-            _lib.check(self.L.ipdm_add_act(acc.data_ptr(), residual.data_ptr(), out32.data_ptr(), acc.numel(),
-                                           1 if flags & CONV_RES_ELU else 0, _lib.stream()), "add_act " + wname)
-        else:
-            self._launch(ws[1], bias, x16, dims, acc, out32, out16, stats, flags & CONV_F16_ELU, dilation, 0, "conv3d/0 " + wname)
+        w16, bias = self.w[wname]
+        taps = w16.shape[1]           # 27: 3x3x3 over the volume; 1: shortcut of a plain block / gathered temporal convolutions
+        self._launch(w16, bias, x16, dims, residual, out32, out16, stats, flags, dilation if taps == 27 else 1, 0,
+                     ("conv3d " if taps == 27 else "conv1x1 ") + wname)
 
     def norm_elu(self, nname, x32, stats, out16, N, HW, C):
         super().norm_elu(nname, x32, stats, out16, self.P, (N // self.P) * HW, C)

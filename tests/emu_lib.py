@@ -235,10 +235,15 @@ class EmuLib:
             else:
                 sh[:, -d.slice_shift:] = v5[:, :X + d.slice_shift]
             x = sh.reshape(N, Cin, H, W)
-        k = 3 if taps == 9 else 1
-        w = _t(d.w_f16, (Cout, taps, Cin), np.float16).float().permute(0, 2, 1).reshape(Cout, Cin, k, k)
-        pad = d.dilation if k == 3 else 0
-        v = F.conv2d(x, w, None, padding=pad, dilation=d.dilation if k == 3 else 1)
+        k = 3 if taps >= 9 else 1
+        if taps == 27:           # 3x3x3 over [P][X][H][W] volumes, taps ordered (kx, kh, kw)
+            w3 = _t(d.w_f16, (Cout, 27, Cin), np.float16).float().permute(0, 2, 1).reshape(Cout, Cin, 3, 3, 3)
+            x5 = x.reshape(N // X, X, Cin, H, W).permute(0, 2, 1, 3, 4)
+            v = F.conv3d(x5, w3, None, padding=d.dilation, dilation=d.dilation).permute(0, 2, 1, 3, 4).reshape(N, Cout, H, W)
+        else:
+            w = _t(d.w_f16, (Cout, taps, Cin), np.float16).float().permute(0, 2, 1).reshape(Cout, Cin, k, k)
+            pad = d.dilation if k == 3 else 0
+            v = F.conv2d(x, w, None, padding=pad, dilation=d.dilation if k == 3 else 1)
         if d.flags & 8:
             v = (((v[:, :, ::2, ::2] + v[:, :, 1::2, ::2]) + v[:, :, ::2, 1::2]) + v[:, :, 1::2, 1::2]) * 0.25
         Ho, Wo = v.shape[2:]

@@ -412,6 +412,20 @@ def test_conv3d_via_slices_vs_torch():
         assert rel_l2(acc.cpu(), ref) < 1e-5, d
         want = torch.stack([ref.reshape(P, -1, Cout).sum(1), (ref ** 2).reshape(P, -1, Cout).sum(1)], -1)
         assert rel_l2(st.float().cpu(), want) < 1e-5, d
+        # the same convolution as ONE launch: 27-tap K loop, the three kx-planes fetched as three halo tiles
+        w27 = w.permute(0, 2, 4, 3, 1).contiguous().reshape(Cout, 27, Cin).to(DEV)                   # [co][(kx, kt, ky)][ci]
+        one = torch.full((P * X, T, Y, Cout), float("nan"), device=DEV)
+        h16 = torch.full((P * X, T, Y, Cout), float("nan"), device=DEV, dtype=torch.float16)
+        st2 = torch.zeros(P, Cout, 2, dtype=torch.float64, device=DEV)
+        res = torch.randn(P * X, T, Y, Cout, generator=g).to(DEV)
+        desc = L.ConvDesc(xd.data_ptr(), w27.data_ptr(), bias_d.data_ptr(), res.data_ptr(), one.data_ptr(), h16.data_ptr(), st2.data_ptr(),
+                          P * X, T, Y, Cin, Cout, 27, d, 1, X, 0)
+        L.check(L.lib().ipdm_conv_igemm(ctypes.byref(desc), L.stream()), "conv3d fused")
+        assert rel_l2(one.cpu(), ref + res.cpu()) < 1e-5, d
+        assert rel_l2(h16.float().cpu(), torch.nn.functional.elu(ref + res.cpu())) < 1e-3, d
+        full = ref + res.cpu()
+        want2 = torch.stack([full.reshape(P, -1, Cout).sum(1), (full ** 2).reshape(P, -1, Cout).sum(1)], -1)
+        assert rel_l2(st2.float().cpu(), want2) < 1e-5, d
 
 
 def test_metrics_and_result_files():
