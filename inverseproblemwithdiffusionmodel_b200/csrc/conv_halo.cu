@@ -26,7 +26,6 @@ namespace ipdm {
 constexpr int HT_W = 8;                       // pixel tile = TH rows x 8 columns, TH = 32 (UMMA N = 256), 24 (N = 192) or
                                               // 12 (N = 96): the short tiles fit the 24 x 8 / 12 x 8 slices of the 3-D network
 constexpr int NH = 2;                         // halo ring
-constexpr int NW = 3;                         // weight ring
 constexpr int W_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int HALO_THREADS = 352;
 
@@ -35,7 +34,11 @@ template <int DIL, int TH> struct HaloCfg {
   static constexpr int PITCH = SLOTS * 128;                   // 1280 / 1536 B (need not be a multiple of the 1024-byte swizzle pattern)
   static constexpr int ROWS = TH + 2 * DIL;
   static constexpr int HALO_BYTES = (ROWS * PITCH + 1023) / 1024 * 1024;   // every stage starts on a swizzle-pattern boundary
-  static constexpr int SMEM = NH * HALO_BYTES + NW * W_BYTES + 2 * SLAB_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int FIXED = NH * HALO_BYTES + 2 * SLAB_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  // weight ring: as deep as shared memory allows, 3 to 6 stages of 16 KB (one 128 x 64 tile per tap)
+  static constexpr int NW = (232448 - FIXED) / W_BYTES >= 6 ? 6 : (232448 - FIXED) / W_BYTES;
+  static_assert(NW >= 3, "weight ring");
+  static constexpr int SMEM = FIXED + NW * W_BYTES;
 };
 
 struct HaloParams {
@@ -47,6 +50,7 @@ template <int MODE, int DIL, int TH>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, HaloParams hp) {
   using CFG = HaloCfg<DIL, TH>;
+  constexpr int NW = CFG::NW;
   constexpr int BN = TH * HT_W;                 // pixels per accumulator (UMMA N)
   constexpr int NCH = BN / 32;                  // 32-column epilogue chunks: team A takes the first (NCH+1)/2
   const IgemmParams& p = hp.g;
