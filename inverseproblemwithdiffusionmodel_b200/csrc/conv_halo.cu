@@ -29,11 +29,14 @@ constexpr int NH = 2;                         // halo ring
 constexpr int W_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int HALO_THREADS = 352;
 
-template <int DIL, int TH> struct HaloCfg {
+// NS = images (slices) per work item: 2 for the 12-row tile, so that one streamed weight tile feeds two N = 96 MMAs
+// (a 96-pixel tile alone re-streams its 128 channels' whole weight slab: L2 -> SM bound)
+template <int DIL, int TH, int NS> struct HaloCfg {
   static constexpr int SLOTS = HT_W + 2 * DIL;                // pixel slots per halo row: exactly the 8 + 2d that are used
   static constexpr int PITCH = SLOTS * 128;                   // 1280 / 1536 B (need not be a multiple of the 1024-byte swizzle pattern)
   static constexpr int ROWS = TH + 2 * DIL;
-  static constexpr int HALO_BYTES = (ROWS * PITCH + 1023) / 1024 * 1024;   // every stage starts on a swizzle-pattern boundary
+  static constexpr int TILE_BYTES = (ROWS * PITCH + 1023) / 1024 * 1024;   // every tile starts on a swizzle-pattern boundary
+  static constexpr int HALO_BYTES = NS * TILE_BYTES;                        // one stage = the halo tiles of the item's NS images
   static constexpr int FIXED = NH * HALO_BYTES + 2 * SLAB_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   // weight ring: as deep as shared memory allows, 3 to 6 stages of 16 KB (one 128 x 64 tile per tap)
   static constexpr int NW = (232448 - FIXED) / W_BYTES >= 6 ? 6 : (232448 - FIXED) / W_BYTES;
@@ -46,11 +49,12 @@ struct HaloParams {
   int items, mtiles;
 };
 
-template <int MODE, int DIL, int TH>
+template <int MODE, int DIL, int TH, int NS>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, HaloParams hp) {
-  using CFG = HaloCfg<DIL, TH>;
+  using CFG = HaloCfg<DIL, TH, NS>;
   constexpr int NW = CFG::NW;
+  static_assert(NS * TH * HT_W <= BLOCK_N, "accumulator columns");
   constexpr int BN = TH * HT_W;                 // pixels per accumulator (UMMA N)
   constexpr int NCH = BN / 32;                  // 32-column epilogue chunks: team A takes the first (NCH+1)/2
   const IgemmParams& p = hp.g;
@@ -94,7 +98,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
     int tile = item / hp.mtiles;
     const int tw = tile % p.tiles_w; tile /= p.tiles_w;
     const int th = tile % p.tiles_h; tile /= p.tiles_h;
-    n = tile; h0 = th * TH; w0 = tw * HT_W; m0 = mt * BLOCK_M;
+    n = tile * NS; h0 = th * TH; w0 = tw * HT_W; m0 = mt * BLOCK_M;     // first of the item's NS consecutive images
   };
 
   if (warp == 0) {
@@ -108,9 +112,11 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
           for (int pl = 0; pl < planes; ++pl, ++cnt) {      // 3x3x3: one halo tile per kx-plane, from slice x + (kx-1)*d
             const int s = cnt % NH;
             mbar_wait(&halo_empty[s], ((cnt / NH) & 1) ^ 1);
-            mbar_expect_tx(&halo_full[s], CFG::ROWS * CFG::PITCH);
-            tma_load_5d(halo + s * CFG::HALO_BYTES, &tmap_x, &halo_full[s], kc * BLOCK_K, w0 - DIL, h0 - DIL,
-                        n % p.slices + p.slice_shift + (planes == 3 ? (pl - 1) * DIL : 0), n / p.slices);
+            mbar_expect_tx(&halo_full[s], NS * CFG::ROWS * CFG::PITCH);
+#pragma unroll
+            for (int sl = 0; sl < NS; ++sl)
+              tma_load_5d(halo + s * CFG::HALO_BYTES + sl * CFG::TILE_BYTES, &tmap_x, &halo_full[s], kc * BLOCK_K, w0 - DIL, h0 - DIL,
+                          (n + sl) % p.slices + p.slice_shift + (planes == 3 ? (pl - 1) * DIL : 0), (n + sl) / p.slices);
           }
         }
       }
@@ -153,10 +159,13 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
               tcgen05_fence_after();
               const int dy = (tap / 3) * DIL, dx = (tap % 3) * DIL;
               const uint64_t adesc = make_smem_desc(smem_u32(wts + ws * W_BYTES));
-              const uint64_t bdesc = make_smem_desc(hbase + dy * CFG::PITCH + dx * 128, CFG::PITCH);
 #pragma unroll
-              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                umma_f16(tacc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | pl | tap | k) != 0);
+              for (int sl = 0; sl < NS; ++sl) {
+                const uint64_t bdesc = make_smem_desc(hbase + sl * CFG::TILE_BYTES + dy * CFG::PITCH + dx * 128, CFG::PITCH);
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                  umma_f16(tacc + sl * BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | pl | tap | k) != 0);
+              }
               umma_commit(&w_empty[ws]);
             }
             umma_commit(&halo_empty[hs]);
@@ -175,9 +184,10 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
       int n, h0, w0, m0;
       decode(item, n, h0, w0, m0);
       const int as = acnt & 1;
+      // NS = 1: the two teams split the chunks of one image; NS = 2: one image (accumulator half) per team
       constexpr int NA = (NCH + 1) / 2;
-      conv_epilogue<MODE, HT_W, 2>(p, my_slab, tmem_base + as * BLOCK_N, quad, lane, n, h0, w0, m0, team ? NA : 0, team ? NCH - NA : NA,
-                                   1 + team, [&]() {
+      conv_epilogue<MODE, HT_W, 2>(p, my_slab, tmem_base + as * BLOCK_N + (NS == 2 ? team * BN : 0), quad, lane, NS == 2 ? n + team : n, h0, w0, m0,
+                                   NS == 2 ? 0 : (team ? NA : 0), NS == 2 ? NCH : (team ? NCH - NA : NA), 1 + team, [&]() {
         mbar_wait(&acc_full[as], (acnt >> 1) & 1);
         tcgen05_fence_after();
       });
@@ -197,14 +207,14 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
   }
 }
 
-template <int MODE, int DIL, int TH>
+template <int MODE, int DIL, int TH, int NS = 1>
 static int launch_variant(const CUtensorMap& mw, const CUtensorMap& mx, const HaloParams& hp, int grid, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    IPDM_CUDA(cudaFuncSetAttribute(k_conv_halo<MODE, DIL, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<DIL, TH>::SMEM));
+    IPDM_CUDA(cudaFuncSetAttribute(k_conv_halo<MODE, DIL, TH, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<DIL, TH, NS>::SMEM));
     attr_set = true;
   }
-  k_conv_halo<MODE, DIL, TH><<<grid, HALO_THREADS, HaloCfg<DIL, TH>::SMEM, s>>>(mw, mx, hp);
+  k_conv_halo<MODE, DIL, TH, NS><<<grid, HALO_THREADS, HaloCfg<DIL, TH, NS>::SMEM, s>>>(mw, mx, hp);
   return 0;
 }
 
@@ -244,7 +254,9 @@ int launch_conv_halo(const ipdm_conv_desc& d, cudaStream_t s) {
   p.tiles_w = (d.W + HT_W - 1) / HT_W;
   p.tiles_h = (d.H + th - 1) / th;
   hp.mtiles = d.Cout / BLOCK_M;
-  hp.items = p.tiles_w * p.tiles_h * d.N * hp.mtiles;
+  // two images per work item with the 12-row tile (dilation <= 2; pairs never straddle a volume: slices is even or 1 with even N)
+  const bool pair = th == 12 && d.dilation <= 2 && d.N % 2 == 0 && (d.slices == 1 || d.slices % 2 == 0);
+  hp.items = p.tiles_w * p.tiles_h * (pair ? d.N / 2 : d.N) * hp.mtiles;
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
@@ -256,7 +268,8 @@ int launch_conv_halo(const ipdm_conv_desc& d, cudaStream_t s) {
   int e = 0;
 #define HALO_TH(M, D)                                                                                     \
   (th == 32 ? launch_variant<M, D, 32>(mw, mx, hp, grid, s)                                               \
-            : th == 24 ? launch_variant<M, D, 24>(mw, mx, hp, grid, s) : launch_variant<M, D, 12>(mw, mx, hp, grid, s))
+            : th == 24 ? launch_variant<M, D, 24>(mw, mx, hp, grid, s)                                    \
+                       : pair ? launch_variant<M, D, 12, 2>(mw, mx, hp, grid, s) : launch_variant<M, D, 12>(mw, mx, hp, grid, s))
 #define HALO_CASE(M)                                                                 \
   case M:                                                                            \
     e = d.dilation == 1 ? HALO_TH(M, 1) : d.dilation == 2 ? HALO_TH(M, 2) : launch_variant<M, 4, 12>(mw, mx, hp, grid, s); \

@@ -188,7 +188,11 @@ def test_conv_igemm_vs_direct(N, H, W, Cin, Cout, taps, dil, flags, bias, residu
 @pytest.mark.parametrize("want32,want16,stats", [(True, False, True), (False, True, False), (True, False, False)])
 @pytest.mark.parametrize("N,H,W,Cin,Cout,dil,flags,bias,residual", [
     (2, 64, 64, 128, 128, 1, 1, True, True), (1, 40, 24, 128, 256, 2, 0, False, False), (1, 64, 32, 128, 128, 1, 8 | 1, True, True),
-    (3, 96, 72, 64, 128, 1, 4 | 2 | 1, False, True)])
+    (3, 96, 72, 64, 128, 1, 4 | 2 | 1, False, True),
+    (4, 12, 16, 128, 128, 1, 1, True, True),      # 12-row tile, two images per work item
+    (3, 12, 8, 128, 256, 2, 0, False, True),      # 12-row tile, odd image count: one image per item
+    (6, 24, 8, 128, 128, 2, 1, True, True),       # 24-row tile (N = 192)
+    (2, 12, 8, 256, 256, 4, 1, True, False)])     # dilation 4 on the halo kernel (12-row tile only)
 def test_conv_halo_output_modes(N, H, W, Cin, Cout, dil, flags, bias, residual, want32, want16, stats):
     """Every epilogue specialisation of the persistent halo kernel (fp32-only, f16-only, with / without residual,
     pooled) against the CUDA-core direct kernel, including tiles that overhang the image."""
