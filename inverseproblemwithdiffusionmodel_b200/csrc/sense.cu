@@ -450,7 +450,7 @@ static int launch_rows_fast(bool fwd, const SenseArgs& a, cudaStream_t s) {
 #define ROWS2_CASE(LL)                                                                              \
   {                                                                                                 \
     using G = Geo<LL>;                                                                              \
-    dim3 grid(a.H / G::TPC, a.batch);                                                               \
+    dim3 grid(a.batch, a.H / G::TPC);                                                               \
     if (fwd) {                                                                                      \
       if (cplx && dense) k2_fwd_rows<LL, true, TWREG_FWD, true><<<grid, G::NT, G::SMEM_ROWS, s>>>(a);        \
       else if (cplx) k2_fwd_rows<LL, true, TWREG_FWD, false><<<grid, G::NT, G::SMEM_ROWS, s>>>(a);         \
@@ -811,7 +811,7 @@ extern "C" int ipdm_ald_sense_step(float* x, const float* grad, const float* noi
 #define ALD2_CASE(LL)                                                                   \
   {                                                                                     \
     using G = Geo<LL>;                                                                  \
-    dim3 grid(H / G::TPC, batch);                                                       \
+    dim3 grid(batch, H / G::TPC);                                                       \
     if (cplx) k2_ald_sense<LL, true, TWREG_ALD><<<grid, G::NT, G::SMEM_ROWS, s>>>(a);   \
     else k2_ald_sense<LL, false, TWREG_ALD><<<grid, G::NT, G::SMEM_ROWS, s>>>(a);       \
   }

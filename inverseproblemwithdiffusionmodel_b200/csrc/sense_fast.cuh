@@ -97,7 +97,7 @@ template <> struct MapVal<true> {
 };
 
 // ---- forward, rows: coil multiply, transform along W, scatter sampled columns, zero-fill inactive sectors ------
-// grid (H / TPC, batch)
+// grid (batch, H / TPC)
 // DENSE (no mask): every column survives, so the scratch keeps the NATURAL layout T[c][b][h][k] -- the row kernels
 // access it in runs of 8*R1 bytes and the column kernels in 16-column tiles through shared memory, every global
 // access a full line -- instead of scattering 8-byte elements into the transposed layout.
@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(128) k2_fwd_rows(SenseArgs a) {
   __shared__ GroupList gl;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t = lane % G::TPF, r = warp * G::RPW + lane / G::TPF;
-  const int b = blockIdx.y, h0 = blockIdx.x * G::TPC, h = h0 + r;
+  // batch index fastest: CTAs that run together share the same rows of the coil maps (L2 hits instead of DRAM re-reads)
+  const int b = blockIdx.x, h0 = blockIdx.y * G::TPC, h = h0 + r;
   const uint8_t* mrow = a.mask ? a.mask + (size_t)(b % a.mask_frames) * L : nullptr;
   fill_tws<L>(tws, tid, G::NT);
   build_group_list(mrow, L, &gl);
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(Geo<L>::NT_COLS) k2_adj_cols(SenseArgs a) {
 }
 
 // ---- adjoint, rows: gather sampled columns, inverse transform along W, conj-coil sum (or SSOS) ----------------
-// grid (H / TPC, batch)
+// grid (batch, H / TPC)
 template <int L, bool CPLX, bool TWREG, bool DENSE>
 __global__ void __launch_bounds__(128, (L <= 256 ? 4 : 2)) k2_adj_rows(SenseArgs a) {
   using G = Geo<L>;
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(128, (L <= 256 ? 4 : 2)) k2_adj_rows(SenseArgs
   cf32* xch = tws + G::NTWS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t = lane % G::TPF, r = warp * G::RPW + lane / G::TPF;
-  const int b = blockIdx.y, h = blockIdx.x * G::TPC + r;
+  const int b = blockIdx.x, h = blockIdx.y * G::TPC + r;
   const uint8_t* mrow = a.mask ? a.mask + (size_t)(b % a.mask_frames) * L : nullptr;
   fill_tws<L>(tws, tid, G::NT);
   cf32* sx = xch + r * P::STRIDE;
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(128, (L <= 256 ? 3 : 2)) k2_ald_sense(AldArgs 
   cf32* xch = tws + G::NTWS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t = lane % G::TPF, r = warp * G::RPW + lane / G::TPF;
-  const int b = blockIdx.y, h = blockIdx.x * G::TPC + r;
+  const int b = blockIdx.x, h = blockIdx.y * G::TPC + r;
   ipdm_ald_scalars sc = a.sc;
   uint32_t rstep = a.rng_step;
   if (a.sched != nullptr) {
