@@ -86,7 +86,7 @@ class MAPOptimizer2DTime(object):
         p = self.params
         grad_data = self.data_step()
         grad_S = self.spatial_step()
-        grad_T = self.temporal_step(mode_T=p["mode_T"])
+        grad_T = self.temporal_step(mode_T=p["mode_T"], if_random_shift=p.get("if_random_shift", False))
         return grad_data + p["prior_weight"] * (p["spatial_step_weight"] * grad_S + p["temporal_step_weight"] * grad_T)
 
     @torch.no_grad()
@@ -123,12 +123,38 @@ class MAPOptimizer2DTime(object):
         return g.reshape(B, T, C, H, W)
 
     def temporal_step(self, mode_T="tv", if_random_shift=False):
+        if mode_T == "diffusion1d":
+            return self._temporal_diffusion(if_random_shift)
         if mode_T != "tv":
-            raise NotImplementedError("mode_T='diffusion1d' needs the NCSN3D temporal prior, which is outside the implemented hot path")
+            raise _lib.IpdmError(f"mode_T={mode_T!r}: expected 'tv' or 'diffusion1d'")
         if self.finite_diff is None:
             self.finite_diff = FiniteDiff(dims=1)
         return torch.complex(self.finite_diff.log_lh_grad(torch.real(self.x).contiguous()),
                              self.finite_diff.log_lh_grad(torch.imag(self.x).contiguous()))
+
+    def _temporal_diffusion(self, if_random_shift):
+        """score of the learned temporal prior on k x k x T patches, label 1 (reference :284-306): fold (with the optional
+        np.random roll) -> scorenet_T on the real and imaginary patches -> unfold the gradient."""
+        import numpy as np
+        B, T, C, H, W = self.x.shape
+        if C != 1:
+            raise _lib.IpdmError("MAPOptimizer2DTime: C must be 1")
+        k = int(self.params["win_size"])
+        L = _lib.lib()
+        planar = torch.stack([torch.real(self.x), torch.imag(self.x)]).reshape(2, B * T, H, W).to(torch.float32).contiguous()
+        _lib.require_cuda(planar)
+        P2 = 2 * B * (H // k) * (W // k)
+        vol = torch.empty(P2, k, T, k, dtype=torch.float32, device=planar.device)
+        gvol = torch.empty_like(vol)
+        sh, sw = (tuple(np.random.randint(0, k, (2,)).tolist()) if if_random_shift else (0, 0))
+        _lib.check(L.ipdm_patch_fold(planar.data_ptr(), vol.data_ptr(), B, T, H, W, k, sh, sw, 0, _lib.stream()), "patch_fold")
+        labels = torch.ones(P2, dtype=torch.long, device=planar.device)
+        if hasattr(self.scorenet_T, "forward_into"):
+            self.scorenet_T.forward_into(vol, labels, gvol)
+        else:
+            gvol.copy_(self.scorenet_T(vol.permute(0, 1, 3, 2).reshape(P2, k * k, T), labels).reshape(P2, k, k, T).permute(0, 1, 3, 2))
+        _lib.check(L.ipdm_patch_fold(planar.data_ptr(), gvol.data_ptr(), B, T, H, W, k, sh, sw, 1, _lib.stream()), "patch_unfold")
+        return torch.complex(planar[0], planar[1]).reshape(B, T, C, H, W)
 
     def get_reconstruction(self):
         return self.x.detach().cpu()

@@ -214,10 +214,10 @@ def map_sense(score, x0, y, fwd, adj, lamda, lr, n_iters, betas=(0.5, 0.5)):
     return x
 
 
-def map_2dtime_tv(score, x0, y6, fwd, adj, lr, n_iters, prior_weight, w_S, w_T, betas=(0.5, 0.5)):
-    """2D+time MAP with the temporal-TV term: separate Adam optimisers on the real and imaginary parts.
-    Reference: MAPOptimizer2DTime,
-    ncsn/models/MAP_optimizers.py:154-292 (mode_T = "tv")."""
+def map_2dtime_tv(score, x0, y6, fwd, adj, lr, n_iters, prior_weight, w_S, w_T, betas=(0.5, 0.5), score_T=None, win=8):
+    """2D+time MAP: separate Adam optimisers on the real and imaginary parts; temporal term = TV (score_T None) or
+    the learned patch prior with label 1 (mode_T = "diffusion1d", no roll).  Reference: MAPOptimizer2DTime,
+    ncsn/models/MAP_optimizers.py:154-306."""
     B, T, C, H, W = x0.shape
     xr, xi = x0.real.clone(), x0.imag.clone()
     o_r = torch.optim.Adam([xr], lr=lr, betas=betas)
@@ -229,7 +229,14 @@ def map_2dtime_tv(score, x0, y6, fwd, adj, lr, n_iters, prior_weight, w_S, w_T, 
         g_data = (-adj(fwd(xf) - y)).reshape(B, T, C, H, W)
         labels = torch.ones(B * T).long()
         g_S = torch.complex(score(xf.real, labels), score(xf.imag, labels)).reshape(B, T, C, H, W)
-        g_T = torch.complex(temporal_tv_grad(x.real, 1.0), temporal_tv_grad(x.imag, 1.0))
+        if score_T is None:
+            g_T = torch.complex(temporal_tv_grad(x.real, 1.0), temporal_tv_grad(x.imag, 1.0))
+        else:
+            v = x.permute(0, 2, 1, 3, 4).reshape(-1, T, H, W)
+            pr, pi = fold_patches(v.real, win), fold_patches(v.imag, win)
+            lab = torch.ones(pr.shape[0]).long()
+            g = torch.complex(unfold_patches(score_T(pr, lab), win, H, W), unfold_patches(score_T(pi, lab), win, H, W))
+            g_T = g.reshape(B, C, T, H, W).permute(0, 2, 1, 3, 4)
         return g_data + prior_weight * (w_S * g_S + w_T * g_T)
 
     # Quirk of the reference: x_real / x_imag are VIEWS of the initial x, so in iteration 0 the imaginary closure

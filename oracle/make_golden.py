@@ -387,6 +387,24 @@ def gen_ncsn3d():
             res = sampler(save_dir="/tmp/ipdm_golden", lr_scaled=1e4, mode_T="diffusion1d", lamda_T=0.5, if_random_shift=shift)
         out[f"cine_diffusion_{tag}"] = _np(res[0])
         torch.set_grad_enabled(True)
+    # ---- MAP baseline with the learned temporal prior (MAPOptimizer2DTime, mode_T = "diffusion1d"), same data ----
+    import importlib
+    MAP = importlib.import_module(ref_shim.PKG + ".ncsn.models.MAP_optimizers")
+    logger = types.SimpleNamespace(add_scalar=lambda *a, **k: None, add_image=lambda *a, **k: None)
+    MAP.save_vol_as_gif = lambda *a, **k: None
+    MAP.vis_images = lambda *a, **k: None
+    MAP.vis_multi_channel_signal = lambda *a, **k: None
+    MAP.normalize_phase = lambda x: x
+    x0 = A.conj_op(meas.reshape(4, T, 1, n, n)).reshape(1, T, 1, n, n).clone()
+    net_T = ncsn3d.NCSN3DShallow(cfg_T).eval()
+    net_T.load_state_dict(synth_state_dict([(k, tuple(v.shape)) for k, v in net_T.state_dict().items()], 13, net_T.sigmas))
+    params = dict(lr=5e-3, opt_class=torch.optim.Adam, num_iters=2, num_plot_times=1, win_size=8, prior_weight=1.0,
+                  spatial_step_weight=0.7, temporal_step_weight=0.3, save_dir="/tmp/ipdm_golden", opt_params={"betas": (0.5, 0.5)},
+                  mode_T="diffusion1d", if_random_shift=False, device=torch.device("cpu"))
+    with _quiet():
+        rec = MAP.MAPOptimizer2DTime(x0, meas, net, net_T, A, logger, params)()
+    out["map2dt_diffusion"] = _np(rec)
+    torch.set_grad_enabled(True)
     np.savez_compressed(os.path.join(OUT, "ncsn3d.npz"), **out)
 
 

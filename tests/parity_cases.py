@@ -230,6 +230,14 @@ def case_sampler_cine_diffusion(dev):
         res = sampler(save_dir="/tmp", lr_scaled=1e4, mode_T="diffusion1d", lamda_T=0.5, if_random_shift=shift, noise_fn=draw)
         err = rel_l2(res[0], g[f"cine_diffusion_{tag}"])
         assert err < 1e-3, (tag, err)                       # same tolerance and reasoning as case_sampler_cine
+    # MAP baseline with the learned temporal prior (MAPOptimizer2DTime mode_T='diffusion1d', reference :284-306)
+    net_T, _ = build_net(NCSN3DShallow, "NCSN3DShallow_ngf128", 13, cfg_T, dev)
+    x0 = A.conj_op(meas.reshape(4, T, 1, n, n)).reshape(1, T, 1, n, n).clone()
+    mp = dict(lr=5e-3, opt_class=torch.optim.Adam, num_iters=2, num_plot_times=1, win_size=8, prior_weight=1.0,
+              spatial_step_weight=0.7, temporal_step_weight=0.3, save_dir="/tmp", opt_params={"betas": (0.5, 0.5)},
+              mode_T="diffusion1d", if_random_shift=False)
+    rec = MAP.MAPOptimizer2DTime(x0, meas, net, net_T, A, None, mp)()
+    assert rel_l2(rec, g["map2dt_diffusion"]) < 1e-3
     # in-kernel Philox noise + captured step graphs (one with, one without the temporal step): finite, and close to the
     # injected-noise chain in distribution (same start, same schedule)
     net_T, _ = build_net(NCSN3DShallow, "NCSN3DShallow_ngf128", 13, cfg_T, dev)

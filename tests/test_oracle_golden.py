@@ -177,6 +177,14 @@ def test_cine_chain_with_temporal_prior(golden):
             out = ALD.ald_2dtime(score, meas, sig, 1, 1e-4, 1e4, adj, prox, mode_T="diffusion1d", lamda_T=0.5,
                                  score_T=score_T, sigmas_T=sig_T, win=8, random_shift=shift)
         assert rel_l2(out, G[f"cine_diffusion_{tag}"]) < 1e-4, tag
+    # MAP baseline with the learned temporal prior (label 1 of the temporal net's OWN schedule)
+    P3m = _net("NCSN3DShallow_ngf128", 13, ALD.geometric_sigmas(0.2, 0.01, 6))
+    score_Tm = lambda p, y: SN.score_forward_3d_shallow(P3m, p.reshape(-1, 1, 8, 8, T), y).reshape(-1, 64, T)
+    fwd = lambda x: M.sense_forward(x, maps, mask)
+    x0 = adj(meas.reshape(4, T, 1, n, n)).reshape(1, T, 1, n, n)
+    with torch.no_grad():
+        rec = ALD.map_2dtime_tv(score, x0, meas, fwd, adj, 5e-3, 2, 1.0, 0.7, 0.3, score_T=score_Tm, win=8)
+    assert rel_l2(rec, G["map2dt_diffusion"]) < 1e-4
 
 
 def test_state_dict_census():
