@@ -482,7 +482,7 @@ static int launch_cols_fast(bool fwd, const SenseArgs& a, cudaStream_t s) {
 #define COLS2_CASE(LL)                                                                              \
   {                                                                                                 \
     using G = Geo<LL>;                                                                              \
-    dim3 grid(cols_grid_x(a), a.ncoils * a.batch);                                                  \
+    dim3 grid(a.ncoils * a.batch, cols_grid_x(a));                                                  \
     if (fwd) {                                                                                      \
       if (int e = set_smem(k2_fwd_cols<LL, true>, G::SMEM_COLS)) return e;                          \
       if (int e = set_smem(k2_fwd_cols<LL, false>, G::SMEM_COLS)) return e;                         \

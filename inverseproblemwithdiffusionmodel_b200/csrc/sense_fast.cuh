@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(128) k2_fwd_rows(SenseArgs a) {
 }
 
 // ---- forward, columns: transform the active sectors along H and write them (scaled, centred) ------------------
-// grid (<= W / 16, ncoils * batch); CTA j handles active groups 4j .. 4j+3 of its frame's list, then 4(j+gridDim.x) ..
+// grid (ncoils * batch, <= W / 16); CTA (img, j) handles active groups 4j .. 4j+3 of its frame's list, then 4(j+gridDim.y) ..
 template <int L, bool DENSE>
 __global__ void __launch_bounds__(Geo<L>::NT_COLS) k2_fwd_cols(SenseArgs a) {
   using G = Geo<L>;
@@ -195,18 +195,18 @@ __global__ void __launch_bounds__(Geo<L>::NT_COLS) k2_fwd_cols(SenseArgs a) {
   cf32* xch = tws + G::NTWS;
   __shared__ GroupList gl;
   const int tid = threadIdx.x;
-  const size_t img = blockIdx.y;
+  const size_t img = blockIdx.x;
   const int b = (int)(img % a.batch);
   const uint8_t* mrow = a.mask ? a.mask + (size_t)(b % a.mask_frames) * a.W : nullptr;
   const int count = build_group_list(mrow, a.W, &gl);
-  if ((int)blockIdx.x * 4 >= count) return;
+  if ((int)blockIdx.y * 4 >= count) return;
   fill_tws<L>(tws, tid, G::NT_COLS);
   __syncthreads();   // twiddle table complete
   const int cs = tid / G::TPF, t = tid % G::TPF;
   Twid<L, (L < 512)> tw;
   tw.init(tws, t);
   cf32* sx = xch + cs * P::STRIDE;
-  for (int g0 = blockIdx.x * 4; g0 < count; g0 += gridDim.x * 4) {
+  for (int g0 = blockIdx.y * 4; g0 < count; g0 += gridDim.y * 4) {
     const bool gvalid = g0 + (cs >> 2) < count;
     const int k = gvalid ? 4 * gl.list[g0 + (cs >> 2)] + (cs & 3) : 0;
     const bool active = gvalid && (mrow == nullptr || mrow[k] != 0);
@@ -259,18 +259,18 @@ __global__ void __launch_bounds__(Geo<L>::NT_COLS) k2_adj_cols(SenseArgs a) {
   cf32* xch = tws + G::NTWS;
   __shared__ GroupList gl;
   const int tid = threadIdx.x;
-  const size_t img = blockIdx.y;
+  const size_t img = blockIdx.x;
   const int b = (int)(img % a.batch);
   const uint8_t* mrow = a.mask ? a.mask + (size_t)(b % a.mask_frames) * a.W : nullptr;
   const int count = build_group_list(mrow, a.W, &gl);
-  if ((int)blockIdx.x * 4 >= count) return;
+  if ((int)blockIdx.y * 4 >= count) return;
   fill_tws<L>(tws, tid, G::NT_COLS);
   __syncthreads();   // twiddle table complete
   const int cs = tid / G::TPF, t = tid % G::TPF;
   Twid<L, (L < 512)> tw;
   tw.init(tws, t);
   cf32* sx = xch + cs * P::STRIDE;
-  for (int g0 = blockIdx.x * 4; g0 < count; g0 += gridDim.x * 4) {
+  for (int g0 = blockIdx.y * 4; g0 < count; g0 += gridDim.y * 4) {
     for (int idx = tid; idx < 4 * L * 2; idx += G::NT_COLS) {
       const int half = idx & 1, hh = (idx >> 1) % L, gi = (idx >> 1) / L;
       float4 p = make_float4(0.f, 0.f, 0.f, 0.f);

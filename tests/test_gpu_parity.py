@@ -132,6 +132,22 @@ def test_sense_two_pass_engine_variants(H, W, nc, B, frames, cplx):
     assert rel_l2(got - z, ref - z) < 1e-4
 
 
+def test_sense_many_images():
+    """ncoils * batch beyond 65535 (the image index lives on grid.x): forward / adjoint of 20000 chains of 64x64, spot-checked."""
+    n, nc, B = 64, 4, 20000
+    A = C.SENSE("exp", nc, 8, 1 / 8, (1, n, n), 0)
+    A.random_under_fourier.mask = C.keep_center_mask(n, 8, 1 / 8, seed=0)
+    g = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.complex(torch.randn(B, 1, n, n, generator=g, device=DEV), torch.randn(B, 1, n, n, generator=g, device=DEV))
+    S = A(x)
+    back = A.conj_op_masked(S)
+    idx = [0, 1, 7777, 16383, 16384, B - 1]
+    xs = x[idx].cpu()
+    Sref = M.sense_forward(xs, A.sens_maps, A.random_under_fourier.mask)
+    assert rel_l2(S[:, idx].cpu(), Sref) < 1e-5
+    assert rel_l2(back[idx].cpu(), M.sense_adjoint(Sref, A.sens_maps)) < 1e-5
+
+
 def _conv_pair(N, H, W, Cin, Cout, taps, dil, flags, bias, residual, want32, want16, stats):
     """Run igemm and direct kernels on the same operands; return both outputs."""
     L = _lib()
