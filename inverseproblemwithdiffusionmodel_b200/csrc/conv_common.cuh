@@ -9,8 +9,6 @@ constexpr int BLOCK_M = 128;   // output channels per accumulator (TMEM lanes)
 constexpr int BLOCK_N = 256;   // pixels per accumulator (TMEM columns)
 constexpr int BLOCK_K = 64;    // f16 elements = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int EPI_PITCH = BLOCK_M + 4;          // floats per slab row: +4 keeps float4 alignment and staggers banks
-constexpr int SLAB_BYTES = 2 * 32 * EPI_PITCH * 4;   // double-buffered [32 pixels][128 ch] fp32 staging
 
 struct IgemmParams {
   const float* bias;
@@ -29,53 +27,68 @@ int launch_conv_halo(const ipdm_conv_desc& d, cudaStream_t s);
 bool conv_halo_supports(const ipdm_conv_desc& d);
 extern int g_conv_variant;       // 0 = auto, 1 = force the per-tap tile kernel (diagnostics)
 
-// Epilogue of `NCHUNK` (runtime) 32-column chunks of one accumulator (128 channels x up to 256 pixels) by a TEAM of 4 warps
-// (128 threads, named barrier `BAR`, a runtime value so that both teams share ONE copy of this code -- the
-// epilogue is instruction-cache bound otherwise); chunks [chunk0, chunk0 + NCHUNK).
-// TMEM lane = output channel, column = pixel j = py*TW + px of a (256/TW) x TW pixel tile at (h0, w0).
-// Each warp pulls 32 columns for its 32 channels, transposes them through the team's shared-memory slab, and
-// the team then streams the [32 pixels][128 ch] slab with 16-byte accesses: thread = 4 consecutive channels of
-// one pixel, so a warp touches one whole 512-byte pixel row of the NHWC tensor per instruction.  `wait_acc()` is
-// called once, after the first residual loads are in flight and before the first TMEM read.
-// SLABS = 2: double-buffered slab, one barrier per chunk; SLABS = 1: single slab, two barriers per chunk.
-// MODE bits: 1 = residual, 2 = fp32 output, 4 = f16 output, 8 = 2x2 mean-pool.
-template <int MODE, int TW, int SLABS, class WaitAcc>
-__device__ __forceinline__ void conv_epilogue(const IgemmParams& p, float* slab, uint32_t tmem_acc, int quad, int lane,
-                                              int n, int h0, int w0, int m0, int chunk0, int NCHUNK, int BAR, WaitAcc wait_acc) {
+// ---------------------------------------------------------------------------------------------------------------
+// Epilogue WITHOUT shared memory: the 32 (channel) x 32 (pixel) block a warp pulls from TMEM is re-distributed with two
+// xor-shuffle stages so that a thread ends up with 4 consecutive channels of 8 pixels -- 16-byte global accesses,
+// every 8 lanes covering one 128-byte line of the NHWC tensors -- instead of being transposed through a slab.  The
+// main loop is bound by the shared-memory port (UMMA operand reads + TMA fills); an epilogue that stays off it costs
+// the MMA nothing, needs no team barrier (every warp is independent) and frees 66 KB per CTA.  (Measured equal to the
+// slab-transposing epilogue it replaced, within noise, in all three output modes: profiles/experiments/.)
+// `wait_acc()` is called once, after the first residual loads are in flight and before the first TMEM read; residual
+// tiles are software-pipelined one chunk ahead.
+//   before: lane = (c0..c4), register j = (p0..p4)            (channel = TMEM lane, pixel = TMEM column)
+//   stage xor 1 swaps c0 <-> p0, stage xor 2 swaps c1 <-> p1
+//   after:  lane = (p0, p1, c2, c3, c4), register = (c0, c1, p2, p3, p4): float4 #i = channels 4*(lane>>2)..+3 of pixel
+//           (lane & 3) + 4*i of the chunk
+// MODE bits: 1 = residual, 2 = fp32 output, 4 = f16 output, 8 = 2x2 mean-pool (pooled before the shuffles: 8 values).
+template <int NV>
+__device__ __forceinline__ void lane_register_swap(float* v, int lane) {
+  // NV values; exchanges register bit 0 with lane bit 0, then register bit 1 with lane bit 1
+#pragma unroll
+  for (int bit = 0; bit < 2; ++bit) {
+    const bool up = (lane >> bit) & 1;
+#pragma unroll
+    for (int r = 0; r < NV; ++r) {
+      if ((r >> bit) & 1) continue;
+      const int r1 = r | (1 << bit);
+      float send = up ? v[r] : v[r1];
+      send = __shfl_xor_sync(0xffffffffu, send, 1 << bit);
+      if (up) v[r] = send; else v[r1] = send;
+    }
+  }
+}
+
+template <int MODE, int TW, class WaitAcc>
+__device__ __forceinline__ void conv_epilogue_shfl(const IgemmParams& p, uint32_t tmem_acc, int quad, int lane, int n, int h0, int w0,
+                                                   int m0, int chunk0, int NCHUNK, WaitAcc wait_acc) {
   constexpr bool kRes = (MODE & 1) != 0, kOut32 = (MODE & 2) != 0, kOut16 = (MODE & 4) != 0, pool = (MODE & 8) != 0;
-  constexpr int ROWS_PER_CHUNK = 32 / TW;       // tile rows covered by 32 columns
-  constexpr int PW = TW / 2;                    // pooled pixels per pooled row
-  constexpr int NPX = pool ? 2 : 8;             // output pixels per thread per chunk
-  const int te = quad * 32 + lane;              // 0..127 within the team
-  const int c4 = (te & 31) * 4;                 // first of this thread's 4 channels (within the 128)
-  const int prow = te >> 5;                     // pixel sub-row 0..3
+  constexpr int NPX = pool ? 2 : 8;             // float4 groups (pixels) per thread per chunk
+  constexpr int OW = pool ? TW / 2 : TW;        // output pixels per chunk row
+  constexpr int OROWS = pool ? (32 / TW) / 2 : 32 / TW;   // output rows per chunk
+  const int psub = lane & 3;                    // pixel sub-index of this thread
+  const int c4 = quad * 32 + (lane >> 2) * 4;   // first of this thread's 4 channels within the 128-channel tile
   const int Ho = pool ? p.H / 2 : p.H, Wo = pool ? p.W / 2 : p.W;
   const int oy0 = pool ? h0 / 2 : h0, ox0 = pool ? w0 / 2 : w0;
   float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (p.bias) bias4 = *reinterpret_cast<const float4*>(p.bias + m0 + c4);
   float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
   const uint32_t taddr = tmem_acc + ((uint32_t)(quad * 32) << 16);
-  // this thread's pixels of a chunk are q = prow + 4*i: row i / (TW/4) of the chunk, column prow + 4*(i % (TW/4))
-  // (pooled: TW/2 columns, 8 pixels per chunk) -> offsets are a per-chunk base plus compile-time multiples
-  constexpr int CPR = (pool ? PW : TW) / 4 > 0 ? (pool ? PW : TW) / 4 : 1;      // thread-pixels per output row
-  constexpr int OROWS = pool ? ROWS_PER_CHUNK / 2 : ROWS_PER_CHUNK;             // output rows per chunk
   const size_t row_stride = (size_t)Wo * p.Cout;
-  const size_t col_stride = (size_t)4 * p.Cout;
-  const bool col_in_tile = pool ? (prow < PW) : true;                             // PW = 4 (TW = 8): all four sub-rows valid
-  auto chunk_base_of = [&](int chunk) { return (((size_t)n * Ho + oy0 + chunk * OROWS) * Wo + ox0 + prow) * p.Cout + m0 + c4; };
-  auto pixel_ok = [&](int chunk, int i) {
-    return col_in_tile && (oy0 + chunk * OROWS + i / CPR) < Ho && (ox0 + prow + 4 * (i % CPR)) < Wo;
+  // output pixel q = psub + 4*i of a chunk: row q / OW, column q % OW
+  auto pix_off = [&](int chunk, int i, bool& ok) -> size_t {
+    const int q = psub + 4 * i;
+    const int y = oy0 + chunk * OROWS + q / OW, x = ox0 + q % OW;
+    ok = y < Ho && x < Wo;
+    return (((size_t)n * Ho + y) * Wo + x) * p.Cout + m0 + c4;
   };
-  // Residual tiles are software-pipelined one chunk ahead: the loads of chunk c+1 are issued right after chunk c's
-  // accumulator values have been staged (their registers are dead by then), so a load has a whole chunk period to
-  // land; the first chunk's loads go out before the wait for the accumulator.
   float4 rcur[NPX], rnext[NPX];
   auto issue_res = [&](int chunk, float4* r) {
-    const size_t base = chunk_base_of(chunk);
 #pragma unroll
     for (int i = 0; i < NPX; ++i) {
+      bool ok;
+      const size_t off = pix_off(chunk, i, ok);
       r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (pixel_ok(chunk, i)) r[i] = *reinterpret_cast<const float4*>(p.residual + base + (i / CPR) * row_stride + (i % CPR) * col_stride);
+      if (ok) r[i] = *reinterpret_cast<const float4*>(p.residual + off);
     }
   };
   if (kRes) issue_res(chunk0, rcur);
@@ -85,30 +98,27 @@ __device__ __forceinline__ void conv_epilogue(const IgemmParams& p, float* slab,
     const int chunk = chunk0 + cc;
     float v[32];
     tmem_ld32(taddr + chunk * 32, v);
-    float* buf = slab + (SLABS == 2 ? (cc & 1) * (32 * EPI_PITCH) : 0);
-    if (SLABS == 1 && cc > 0) asm volatile("bar.sync %0, 128;" ::"r"(BAR) : "memory");   // previous chunk fully consumed
+    if (kRes && cc + 1 < NCHUNK) issue_res(chunk + 1, rnext);
+    float w[4 * NPX];
     if (!pool) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) buf[j * EPI_PITCH + te] = v[j];
+      for (int j = 0; j < 32; ++j) w[j] = v[j];
     } else {
-      // pooled pixel q' = r*PW + cx  <-  rows 2r, 2r+1 and columns 2cx, 2cx+1 of the chunk
+      // pooled pixel q' = r*PW + cx  <-  rows 2r, 2r+1 and columns 2cx, 2cx+1 of the chunk (TW = 8: 2 x 4 pooled pixels)
 #pragma unroll
       for (int qq = 0; qq < 8; ++qq) {
-        const int r = qq / PW, cx = qq % PW;
+        const int r = qq / (TW / 2), cx = qq % (TW / 2);
         const int a = (2 * r) * TW + 2 * cx, b = (2 * r + 1) * TW + 2 * cx;
-        buf[qq * EPI_PITCH + te] = (((v[a] + v[b]) + v[a + 1]) + v[b + 1]) * 0.25f;
+        w[qq] = (((v[a] + v[b]) + v[a + 1]) + v[b + 1]) * 0.25f;
       }
     }
-    asm volatile("bar.sync %0, 128;" ::"r"(BAR) : "memory");
-    if (kRes && cc + 1 < NCHUNK) issue_res(chunk + 1, rnext);
-    const size_t chunk_base = chunk_base_of(chunk);
+    lane_register_swap<4 * NPX>(w, lane);
 #pragma unroll
     for (int i = 0; i < NPX; ++i) {
-      if (pixel_ok(chunk, i)) {
-        const size_t off = chunk_base + (i / CPR) * row_stride + (i % CPR) * col_stride;
-        const int q = prow + 4 * i;
-        float4 a = *reinterpret_cast<const float4*>(buf + q * EPI_PITCH + c4);
-        a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
+      bool ok;
+      const size_t off = pix_off(chunk, i, ok);
+      if (ok) {
+        float4 a = make_float4(w[4 * i] + bias4.x, w[4 * i + 1] + bias4.y, w[4 * i + 2] + bias4.z, w[4 * i + 3] + bias4.w);
         const float4 pre = a;
         if (kRes) {
           float4 r = rcur[i];
@@ -133,26 +143,22 @@ __device__ __forceinline__ void conv_epilogue(const IgemmParams& p, float* slab,
       for (int i = 0; i < NPX; ++i) rcur[i] = rnext[i];
     }
   }
-  // the slab is reused (by the statistics below and by the next accumulator): everyone must be done reading it
-  asm volatile("bar.sync %0, 128;" ::"r"(BAR) : "memory");
   if (p.stats) {
-    // combine the four pixel sub-rows that share a channel group, then 2 atomics per channel
-    float* red = slab;                                    // [4][128][2]
+    // the four lanes that share a channel group (lane bits 0, 1) combine, then 8 fp64 atomics from one of them
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      red[(prow * 128 + c4 + k) * 2] = s1[k];
-      red[(prow * 128 + c4 + k) * 2 + 1] = s2[k];
+      s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], 1);
+      s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], 1);
+      s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], 2);
+      s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], 2);
     }
-    asm volatile("bar.sync %0, 128;" ::"r"(BAR) : "memory");
-    float t1 = 0.f, t2 = 0.f;
+    if (psub == 0) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      t1 += red[(r * 128 + te) * 2];
-      t2 += red[(r * 128 + te) * 2 + 1];
+      for (int k = 0; k < 4; ++k) {
+        atomicAdd(&p.stats[((size_t)(n / p.slices) * p.Cout + m0 + c4 + k) * 2], (double)s1[k]);
+        atomicAdd(&p.stats[((size_t)(n / p.slices) * p.Cout + m0 + c4 + k) * 2 + 1], (double)s2[k]);
+      }
     }
-    atomicAdd(&p.stats[((size_t)(n / p.slices) * p.Cout + m0 + te) * 2], (double)t1);
-    atomicAdd(&p.stats[((size_t)(n / p.slices) * p.Cout + m0 + te) * 2 + 1], (double)t2);
-    asm volatile("bar.sync %0, 128;" ::"r"(BAR) : "memory");
   }
 }
 

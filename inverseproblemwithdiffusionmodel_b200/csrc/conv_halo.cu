@@ -17,8 +17,9 @@
 // holds two 256-column accumulators so the epilogue of item i overlaps the MMAs of item i+1, and the TMA
 // producers run ahead across item boundaries.
 //
-// Warps (352 threads): 0 = halo TMA, 1 = MMA issuer + TMEM owner, 2 = weight TMA, 3-6 = epilogue team A
-// (columns 0-127), 7-10 = epilogue team B (columns 128-255); each team has its own slab and named barrier.
+// Warps (352 threads): 0 = halo TMA, 1 = MMA issuer + TMEM owner, 2 = weight TMA, 3-6 = epilogue of the first half of
+// the accumulator's 32-column chunks, 7-10 = of the second half (warp % 4 = TMEM lane quadrant); the epilogue warps are
+// independent of each other (no shared memory, no barrier: conv_common.cuh).
 #include "conv_common.cuh"
 
 namespace ipdm {
@@ -37,7 +38,7 @@ template <int DIL, int TH, int NS> struct HaloCfg {
   static constexpr int ROWS = TH + 2 * DIL;
   static constexpr int TILE_BYTES = (ROWS * PITCH + 1023) / 1024 * 1024;   // every tile starts on a swizzle-pattern boundary
   static constexpr int HALO_BYTES = NS * TILE_BYTES;                        // one stage = the halo tiles of the item's NS images
-  static constexpr int FIXED = NH * HALO_BYTES + 2 * SLAB_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int FIXED = NH * HALO_BYTES + 1024 /*align*/ + 256 /*barriers*/;   // the epilogue uses no shared memory
   // weight ring: as deep as shared memory allows, 3 to 6 stages of 16 KB (one 128 x 64 tile per tap)
   static constexpr int NW = (232448 - FIXED) / W_BYTES >= 6 ? 6 : (232448 - FIXED) / W_BYTES;
   static_assert(NW >= 3, "weight ring");
@@ -62,8 +63,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* halo = smem;
   unsigned char* wts = smem + NH * CFG::HALO_BYTES;
-  float* slab = reinterpret_cast<float*>(wts + NW * W_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(slab) + 2 * SLAB_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wts + NW * W_BYTES);
   uint64_t* halo_full = bars;             // [NH]
   uint64_t* halo_empty = bars + NH;       // [NH]
   uint64_t* w_full = bars + 2 * NH;       // [NW]
@@ -178,16 +178,15 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
     // ===== epilogue teams (TMEM lane quadrant = warp % 4): A = warps 3-6, B = warps 7-10 =====
     const int quad = warp & 3;
     const int team = warp >= 7 ? 1 : 0;
-    float* my_slab = slab + team * (2 * 32 * EPI_PITCH);      // each team: double-buffered [32 px][128 ch] slab
     uint32_t acnt = 0;
     for (int item = blockIdx.x; item < hp.items; item += gridDim.x, ++acnt) {
       int n, h0, w0, m0;
       decode(item, n, h0, w0, m0);
       const int as = acnt & 1;
-      // NS = 1: the two teams split the chunks of one image; NS = 2: one image (accumulator half) per team
+      // NS = 1: the two warp groups split the chunks of one image; NS = 2: one image (accumulator half) per group
       constexpr int NA = (NCH + 1) / 2;
-      conv_epilogue<MODE, HT_W, 2>(p, my_slab, tmem_base + as * BLOCK_N + (NS == 2 ? team * BN : 0), quad, lane, NS == 2 ? n + team : n, h0, w0, m0,
-                                   NS == 2 ? 0 : (team ? NA : 0), NS == 2 ? NCH : (team ? NCH - NA : NA), 1 + team, [&]() {
+      conv_epilogue_shfl<MODE, HT_W>(p, tmem_base + as * BLOCK_N + (NS == 2 ? team * BN : 0), quad, lane, NS == 2 ? n + team : n, h0, w0, m0,
+                                     NS == 2 ? 0 : (team ? NA : 0), NS == 2 ? NCH : (team ? NCH - NA : NA), [&]() {
         mbar_wait(&acc_full[as], (acnt >> 1) & 1);
         tcgen05_fence_after();
       });

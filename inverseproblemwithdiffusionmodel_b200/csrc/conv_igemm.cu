@@ -120,8 +120,8 @@ k_conv_igemm(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__
       umma_commit(tmem_full_bar);    // accumulator complete
     }
   } else {
-    // ===== epilogue (the pipeline stages are idle once the accumulator is complete: reuse them as the slab) =====
-    conv_epilogue<MODE, TILE_W, 2>(p, reinterpret_cast<float*>(smem), tmem_base, warp & 3, lane, n, h0, w0, m0, 0, 8, 1, [&]() {
+    // ===== epilogue =====
+    conv_epilogue_shfl<MODE, TILE_W>(p, tmem_base, warp & 3, lane, n, h0, w0, m0, 0, 8, [&]() {
       mbar_wait(tmem_full_bar, 0);
       tcgen05_fence_after();
     });
