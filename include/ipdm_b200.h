@@ -182,7 +182,8 @@ int ipdm_conv_igemm(const ipdm_conv_desc* desc_host, void* stream);
 
 /* Diagnostics knob (tests / profiling only): key 1 = convolution kernel variant (0 auto: persistent
  * halo-tile kernel for 3x3 with dilation <= 2, per-tap tile kernel otherwise; 1 = always the per-tap
- * kernel), key 2 reserved. */
+ * kernel; 2 = TIMING EXPERIMENT: the halo kernel stops re-streaming weight tiles after the first ring fill --
+ * results are wrong, only the time is meaningful, tools/exp_weights.py). */
 int ipdm_debug_option(int key, int value);
 
 /* Same contract on CUDA cores, any Cin/Cout (used for narrow test nets and as the on-device

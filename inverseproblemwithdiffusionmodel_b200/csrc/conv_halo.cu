@@ -48,6 +48,7 @@ template <int DIL, int TH, int NS> struct HaloCfg {
 struct HaloParams {
   IgemmParams g;
   int items, mtiles;
+  int exp_skip_weights;
 };
 
 template <int MODE, int DIL, int TH, int NS>
@@ -132,6 +133,10 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
           for (int tap = 0; tap < 9 * planes; ++tap, ++cnt) {     // weights [Cout][(kx,) ky, kx taps][Cin]
             const int s = cnt % NW;
             mbar_wait(&w_empty[s], ((cnt / NW) & 1) ^ 1);
+            if (hp.exp_skip_weights && cnt >= (uint32_t)NW) {      // TIMING EXPERIMENT ONLY: stale weights, no L2 traffic
+              asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&w_full[s])) : "memory");
+              continue;
+            }
             mbar_expect_tx(&w_full[s], W_BYTES);
             tma_load_2d(wts + s * W_BYTES, &tmap_w, &w_full[s], tap * p.Cin + kc * BLOCK_K, m0);
           }
@@ -253,6 +258,7 @@ int launch_conv_halo(const ipdm_conv_desc& d, cudaStream_t s) {
   p.tiles_w = (d.W + HT_W - 1) / HT_W;
   p.tiles_h = (d.H + th - 1) / th;
   hp.mtiles = d.Cout / BLOCK_M;
+  hp.exp_skip_weights = g_conv_variant == 2;
   // two images per work item with the 12-row tile (dilation <= 2; pairs never straddle a volume: slices is even or 1 with even N)
   const bool pair = th == 12 && d.dilation <= 2 && d.N % 2 == 0 && (d.slices == 1 || d.slices % 2 == 0);
   hp.items = p.tiles_w * p.tiles_h * (pair ? d.N / 2 : d.N) * hp.mtiles;
