@@ -285,58 +285,87 @@ __global__ void k_act_to_f16(const float* __restrict__ x, __half* __restrict__ o
   }
 }
 
-// 5x5/s1 max-pool, separable with a register sliding window: thread = (column x, 8 channels); it walks down
-// a strip of rows, takes the horizontal 5-max of each input row (5 16-byte loads, neighbours hit L1) and keeps
-// the last five of them in registers for the vertical max -- 5 loads per output instead of 25.
-// grid (ceil(W/XT), ceil(H/YS), N * C/8/CG); block = XT * CG threads (CG channel groups of 8).  The strip length
-// YS trades redundant priming rows (4 per strip) for parallelism: 32 for large images, 8 for the 32x32 layers.
-__global__ void k_maxpool5(const __half* __restrict__ in, __half* __restrict__ out, int N, int H, int W, int C, int CG, int XT,
-                           int MP_YS /* rows per strip */) {
+#ifndef IPDM_MAXPOOL_NC
+#define IPDM_MAXPOOL_NC 2
+#endif
+// 5x5/s1 max-pool, separable: thread = (NC consecutive columns, 8 channels).  Per input row it loads the 8 columns
+// x-2 .. x+5 once (16 bytes each, 2 loads per output instead of 5) and forms the four horizontal 5-maxima from shared
+// partial maxima; the last five such rows live in a register ring (the row loop is unrolled by 5, so the ring index is
+// a compile-time constant and nothing is ever moved) for the vertical max.
+// grid (ceil(W / (4*XQ)), ceil(H / YS), N * C/8/CG); block = XQ * CG threads.  The strip length YS trades redundant
+// priming rows (4 per strip) for parallelism.
+// NC output columns from the NC + 4 input columns x-2 .. x+NC+1: o[j] = max(in[j .. j+4])
+template <int NC>
+__device__ __forceinline__ void hmaxN(const uint4* in, __half2 (*o)[4]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    __half2 v[NC + 4];
+#pragma unroll
+    for (int c = 0; c < NC + 4; ++c) v[c] = reinterpret_cast<const __half2*>(&in[c])[q];
+    if (NC == 4) {
+      const __half2 a = __hmax2(v[3], v[4]), b = __hmax2(v[1], v[2]), c = __hmax2(v[5], v[6]);
+      o[0][q] = __hmax2(__hmax2(v[0], b), a);
+      o[1][q] = __hmax2(__hmax2(b, a), v[5]);
+      o[2][q] = __hmax2(__hmax2(v[2], a), c);
+      o[3][q] = __hmax2(__hmax2(a, c), v[7]);
+    } else {
+      const __half2 a = __hmax2(__hmax2(v[1], v[2]), __hmax2(v[3], v[4]));
+      o[0][q] = __hmax2(v[0], a);
+      o[1][q] = __hmax2(a, v[5]);
+    }
+  }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(256, NC == 4 ? 2 : 3) k_maxpool5(const __half* __restrict__ in, __half* __restrict__ out, int N, int H, int W,
+                                                                   int C, int CG, int XQ, int MP_YS /* rows per strip */) {
   const int cg_per = C / 8 / CG;                       // channel-group blocks per image
   const int n = blockIdx.z / cg_per;
   const int g = (blockIdx.z % cg_per) * CG + (threadIdx.x % CG);
-  const int x = blockIdx.x * XT + threadIdx.x / CG;
+  const int x = (blockIdx.x * XQ + threadIdx.x / CG) * NC;    // first of this thread's NC columns
   const int y0 = blockIdx.y * MP_YS;
   if (x >= W) return;
+  const uint4 ninf4 = make_uint4(0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u);   // -inf halves
   const __half2 ninf = __float2half2_rn(-INFINITY);
-  __half2 win[5][4];
+  __half2 win[5][NC][4];                                // [ring slot][column][half2 lane]
 #pragma unroll
   for (int k = 0; k < 5; ++k)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) win[k][j] = ninf;
+    for (int j = 0; j < NC; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) win[k][j][q] = ninf;
   const __half* base = in + (size_t)n * H * W * C + 8 * g;
-  auto hmax_row = [&](int y, __half2* m) {
+  auto hrow = [&](int y, __half2 (*o)[4]) {
+    uint4 raw[NC + 4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) m[j] = ninf;
-    if (y < 0 || y >= H) return;
-#pragma unroll
-    for (int dx = -2; dx <= 2; ++dx) {
-      const int xx = x + dx;
-      if (xx < 0 || xx >= W) continue;
-      const uint4 raw = *reinterpret_cast<const uint4*>(base + ((size_t)y * W + xx) * C);
-      const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) m[j] = __hmax2(m[j], h2[j]);
+    for (int c = 0; c < NC + 4; ++c) {
+      const int xx = x - 2 + c;
+      raw[c] = ninf4;
+      if (y >= 0 && y < H && xx >= 0 && xx < W) raw[c] = *reinterpret_cast<const uint4*>(base + ((size_t)y * W + xx) * C);
     }
+    hmaxN<NC>(raw, o);
   };
-  // prime the window with rows y0-2 .. y0+1
+  // prime ring slots 1..4 with rows y0-2 .. y0+1 (slot 0 is overwritten first)
 #pragma unroll
-  for (int k = 0; k < 4; ++k) hmax_row(y0 - 2 + k, win[k + 1]);
+  for (int k = 0; k < 4; ++k) hrow(y0 - 2 + k, win[k + 1]);
   const int yend = min(y0 + MP_YS, H);
-  for (int y = y0; y < yend; ++y) {
-    // shift and append row y+2
+  for (int yb = y0; yb < yend; yb += 5) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
+    for (int s = 0; s < 5; ++s) {
+      const int y = yb + s;
+      if (y >= yend) break;
+      hrow(y + 2, win[s]);                              // row y+2 replaces row y-3: slots hold rows y-2 .. y+2
 #pragma unroll
-      for (int j = 0; j < 4; ++j) win[k][j] = win[k + 1][j];
-    hmax_row(y + 2, win[4]);
-    __half2 m[4];
+      for (int j = 0; j < NC; ++j) {
+        if (x + j >= W) continue;
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) m[j] = __hmax2(__hmax2(__hmax2(win[0][j], win[1][j]), __hmax2(win[2][j], win[3][j])), win[4][j]);
-    uint4 o;
-    o.x = *reinterpret_cast<unsigned*>(&m[0]); o.y = *reinterpret_cast<unsigned*>(&m[1]);
-    o.z = *reinterpret_cast<unsigned*>(&m[2]); o.w = *reinterpret_cast<unsigned*>(&m[3]);
-    *reinterpret_cast<uint4*>(out + (((size_t)n * H + y) * W + x) * C + 8 * g) = o;
+        for (int q = 0; q < 4; ++q)
+          oh[q] = __hmax2(__hmax2(__hmax2(win[0][j][q], win[1][j][q]), __hmax2(win[2][j][q], win[3][j][q])), win[4][j][q]);
+        *reinterpret_cast<uint4*>(out + (((size_t)n * H + y) * W + x + j) * C + 8 * g) = o;
+      }
+    }
   }
 }
 
@@ -568,12 +597,15 @@ extern "C" int ipdm_maxpool5_f16(const void* in_f16, void* out_f16, int N, int H
   const int groups = C / 8;
   int CG = 16;
   while (groups % CG != 0) CG >>= 1;                      // channel groups per block (power of two dividing C/8)
-  const int XT = 256 / CG;                                // columns per block
-  int ys = 32;
-  while (ys > 8 && (size_t)((W + XT - 1) / XT) * ((H + ys - 1) / ys) * N * (groups / CG) < 148 * 8) ys >>= 1;
+  constexpr int NC = IPDM_MAXPOOL_NC;                     // columns per thread
+  int XQ = 256 / CG;                                      // column groups per block
+  while (XQ > 1 && NC * (XQ / 2) >= W) XQ >>= 1;          // narrow images: no idle threads
+  const int XT = NC * XQ;                                 // columns per block
+  int ys = 30;                                            // multiples of 5 (the ring unroll)
+  while (ys > 10 && (size_t)((W + XT - 1) / XT) * ((H + ys - 1) / ys) * N * (groups / CG) < 148 * 4) ys -= 10;
   dim3 grid((W + XT - 1) / XT, (H + ys - 1) / ys, N * (groups / CG));
-  k_maxpool5<<<grid, XT * CG, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(in_f16),
-                                                      reinterpret_cast<__half*>(out_f16), N, H, W, C, CG, XT, ys);
+  k_maxpool5<NC><<<grid, XQ * CG, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(in_f16),
+                                                      reinterpret_cast<__half*>(out_f16), N, H, W, C, CG, XQ, ys);
   return launched("k_maxpool5");
 }
 

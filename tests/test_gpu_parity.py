@@ -223,6 +223,18 @@ def test_conv_halo_output_modes(N, H, W, Cin, Cout, dil, flags, bias, residual, 
         assert rel_l2(ast.float().cpu(), bst.float().cpu()) < 1e-5
 
 
+@pytest.mark.parametrize("N,H,W,C", [(2, 14, 14, 256), (1, 28, 28, 128), (3, 40, 24, 64), (2, 256, 256, 128), (5, 32, 32, 512), (1, 7, 5, 8)])
+def test_maxpool5_bit_exact(N, H, W, C):
+    """5x5 / stride 1 / pad 2 max-pool of the CRP blocks (layers.py:69-80): exact against torch on the same f16 values."""
+    L = _lib()
+    g = torch.Generator().manual_seed(H * 31 + W)
+    x = torch.randn(N, H, W, C, generator=g).half().to(DEV)
+    out = torch.full_like(x, float("nan"))
+    L.check(L.lib().ipdm_maxpool5_f16(x.data_ptr(), out.data_ptr(), N, H, W, C, L.stream()), "maxpool5")
+    ref = torch.nn.functional.max_pool2d(x.float().permute(0, 3, 1, 2), 5, 1, 2).permute(0, 2, 3, 1).half()
+    assert torch.equal(out, ref)
+
+
 def test_conv_direct_vs_torch():
     """Anchor of the chain igemm -> direct -> torch: the CUDA-core kernel against F.conv2d on the same f16 operands."""
     import torch.nn.functional as F
