@@ -370,56 +370,60 @@ __global__ void __launch_bounds__(256, NC == 4 ? 2 : 3) k_maxpool5(const __half*
 }
 
 // dst (+)= bilinear(src), align_corners=True, PyTorch's index arithmetic (upsample_bilinear2d).
-__global__ void k_bilinear_add(const float* __restrict__ src, float* __restrict__ dst, __half* __restrict__ out16, int N,
-                               int h, int w, int H, int W, int C, int accumulate) {
-  const int lanes = C / 4;
-  const size_t total = (size_t)N * H * W * lanes;
+// One CTA per output row (n, Y): the vertical taps / weights are per-CTA constants and all index arithmetic is 32-bit
+// (the first version spent most of its instructions on 64-bit div/mod per element); a thread handles 16-byte channel
+// quads of consecutive pixels, two per iteration so that ten independent loads are in flight.
+__global__ void __launch_bounds__(256) k_bilinear_add(const float* __restrict__ src, float* __restrict__ dst, __half* __restrict__ out16,
+                                                      int h, int w, int H, int W, int C, int accumulate) {
+  const int lanes = C >> 2;
+  const int n = blockIdx.x / H, Y = blockIdx.x % H;
   const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
   const float sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
-  // two independent output elements per iteration (all ten loads of both are issued before the first use)
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < total; i0 += 2 * stride) {
+  const float fy = sy * Y;
+  const int y0 = (int)fy, y1 = y0 + (y0 < h - 1 ? 1 : 0);
+  const float ly = fy - y0, hy = 1.f - ly;
+  const float* r0 = src + ((size_t)n * h + y0) * w * C;
+  const float* r1 = src + ((size_t)n * h + y1) * w * C;
+  float* drow = dst + ((size_t)n * H + Y) * W * C;
+  __half* hrow = out16 ? out16 + ((size_t)n * H + Y) * W * C : nullptr;
+  const int total = W * lanes;
+  for (int i0 = threadIdx.x; i0 < total; i0 += 2 * blockDim.x) {
     float4 v00[2], v01[2], v10[2], v11[2], old[2];
-    float ly[2], lx[2];
-    size_t dst_off[2];
+    float lx[2];
+    int off[2];
     bool live[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      const size_t i = i0 + u * stride;
+      const int i = i0 + u * blockDim.x;
       live[u] = i < total;
       if (!live[u]) continue;
-      const int c4 = (int)(i % lanes) * 4;
-      const size_t pix = i / lanes;
-      const int X = (int)(pix % W), Y = (int)((pix / W) % H), n = (int)(pix / ((size_t)W * H));
-      const float fy = sy * Y, fx = sx * X;
-      const int y0 = (int)fy, x0 = (int)fx;
-      const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
-      ly[u] = fy - y0;
+      const int X = i / lanes, c4 = (i - X * lanes) * 4;
+      const float fx = sx * X;
+      const int x0 = (int)fx, x1 = x0 + (x0 < w - 1 ? 1 : 0);
       lx[u] = fx - x0;
-      const float* b = src + (size_t)n * h * w * C + c4;
-      v00[u] = *reinterpret_cast<const float4*>(b + ((size_t)y0 * w + x0) * C);
-      v01[u] = *reinterpret_cast<const float4*>(b + ((size_t)y0 * w + x1) * C);
-      v10[u] = *reinterpret_cast<const float4*>(b + ((size_t)y1 * w + x0) * C);
-      v11[u] = *reinterpret_cast<const float4*>(b + ((size_t)y1 * w + x1) * C);
-      dst_off[u] = pix * C + c4;
-      if (accumulate) old[u] = *reinterpret_cast<const float4*>(dst + dst_off[u]);
+      v00[u] = *reinterpret_cast<const float4*>(r0 + x0 * C + c4);
+      v01[u] = *reinterpret_cast<const float4*>(r0 + x1 * C + c4);
+      v10[u] = *reinterpret_cast<const float4*>(r1 + x0 * C + c4);
+      v11[u] = *reinterpret_cast<const float4*>(r1 + x1 * C + c4);
+      off[u] = X * C + c4;
+      if (accumulate) old[u] = *reinterpret_cast<const float4*>(drow + off[u]);
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       if (!live[u]) continue;
-      const float hy = 1.f - ly[u], hx = 1.f - lx[u];
+      const float hx = 1.f - lx[u];
       float4 r;
-      r.x = hy * (hx * v00[u].x + lx[u] * v01[u].x) + ly[u] * (hx * v10[u].x + lx[u] * v11[u].x);
-      r.y = hy * (hx * v00[u].y + lx[u] * v01[u].y) + ly[u] * (hx * v10[u].y + lx[u] * v11[u].y);
-      r.z = hy * (hx * v00[u].z + lx[u] * v01[u].z) + ly[u] * (hx * v10[u].z + lx[u] * v11[u].z);
-      r.w = hy * (hx * v00[u].w + lx[u] * v01[u].w) + ly[u] * (hx * v10[u].w + lx[u] * v11[u].w);
+      r.x = hy * (hx * v00[u].x + lx[u] * v01[u].x) + ly * (hx * v10[u].x + lx[u] * v11[u].x);
+      r.y = hy * (hx * v00[u].y + lx[u] * v01[u].y) + ly * (hx * v10[u].y + lx[u] * v11[u].y);
+      r.z = hy * (hx * v00[u].z + lx[u] * v01[u].z) + ly * (hx * v10[u].z + lx[u] * v11[u].z);
+      r.w = hy * (hx * v00[u].w + lx[u] * v01[u].w) + ly * (hx * v10[u].w + lx[u] * v11[u].w);
       if (accumulate) { r.x += old[u].x; r.y += old[u].y; r.z += old[u].z; r.w += old[u].w; }
-      *reinterpret_cast<float4*>(dst + dst_off[u]) = r;
-      if (out16) {
+      *reinterpret_cast<float4*>(drow + off[u]) = r;
+      if (hrow) {
         uint2 pk;
         pk.x = pack_half2_sat(elu_f16bound(r.x), elu_f16bound(r.y));
         pk.y = pack_half2_sat(elu_f16bound(r.z), elu_f16bound(r.w));
-        *reinterpret_cast<uint2*>(out16 + dst_off[u]) = pk;
+        *reinterpret_cast<uint2*>(hrow + off[u]) = pk;
       }
     }
   }
@@ -613,8 +617,8 @@ extern "C" int ipdm_bilinear_add(const float* src, float* dst, void* out_elu_f16
                                  int accumulate, void* stream) {
   IPDM_REQUIRE(src && dst, IPDM_E_BADARG, "bilinear_add: null pointer");
   IPDM_REQUIRE(C % 4 == 0, IPDM_E_BADARG, "bilinear_add: C=%d must be a multiple of 4", C);
-  const size_t total = (size_t)N * H * W * (C / 4);
-  k_bilinear_add<<<grid1d(total, 256), 256, 0, as_stream(stream)>>>(src, dst, reinterpret_cast<__half*>(out_elu_f16), N, h, w, H, W, C, accumulate);
+  IPDM_REQUIRE((size_t)N * H < ((size_t)1 << 31) && (size_t)W * C < ((size_t)1 << 30), IPDM_E_UNSUPPORTED, "bilinear_add: image too large");
+  k_bilinear_add<<<N * H, 256, 0, as_stream(stream)>>>(src, dst, reinterpret_cast<__half*>(out_elu_f16), h, w, H, W, C, accumulate);
   return launched("k_bilinear_add");
 }
 

@@ -235,6 +235,22 @@ def test_maxpool5_bit_exact(N, H, W, C):
     assert torch.equal(out, ref)
 
 
+@pytest.mark.parametrize("N,h,w,H,W,C,acc", [(2, 16, 16, 32, 32, 128, 1), (1, 7, 5, 14, 10, 64, 0), (3, 64, 64, 128, 128, 128, 1), (2, 8, 8, 8, 8, 256, 1)])
+def test_bilinear_add_vs_torch(N, h, w, H, W, C, acc):
+    """MSF block: dst (+)= bilinear(src, align_corners=True) and the f16(ELU) copy (layers.py:165-184)."""
+    L = _lib()
+    g = torch.Generator().manual_seed(h * 17 + W)
+    src = torch.randn(N, h, w, C, generator=g).to(DEV)
+    dst0 = torch.randn(N, H, W, C, generator=g).to(DEV)
+    dst = dst0.clone()
+    h16 = torch.full((N, H, W, C), float("nan"), device=DEV, dtype=torch.float16)
+    L.check(L.lib().ipdm_bilinear_add(src.data_ptr(), dst.data_ptr(), h16.data_ptr(), N, h, w, H, W, C, acc, L.stream()), "bilinear_add")
+    up = torch.nn.functional.interpolate(src.permute(0, 3, 1, 2), size=(H, W), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+    ref = up + dst0 if acc else up
+    assert rel_l2(dst.cpu(), ref.cpu()) < 1e-6
+    assert rel_l2(h16.float().cpu(), torch.nn.functional.elu(ref).half().float().cpu()) < 1e-3
+
+
 def test_conv_direct_vs_torch():
     """Anchor of the chain igemm -> direct -> torch: the CUDA-core kernel against F.conv2d on the same f16 operands."""
     import torch.nn.functional as F
