@@ -31,15 +31,15 @@ __global__ void __launch_bounds__(256, 2) k_conv_first(const float* __restrict__
   const int groups = Cout / 4;
   const int g = threadIdx.x % groups;
   const int W4 = (W + 3) / 4;
-  const size_t quads = (size_t)H * W4;                          // 4-pixel groups in the image
+  const int quads = H * W4;                                     // 4-pixel groups in the image (32-bit: checked on the host)
   const int qper = blockDim.x / groups;
   const float* xin = x + (size_t)n * H * W;
   float* o = out + (size_t)n * H * W * Cout;
   float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
   const float4 b4 = *reinterpret_cast<const float4*>(&sw[9 * Cout + 4 * g]);
   if (threadIdx.x / groups < qper) {
-    for (size_t q = blockIdx.x * (size_t)qper + threadIdx.x / groups; q < quads; q += (size_t)gridDim.x * qper) {
-      const int yh = (int)(q / W4), x0 = (int)(q % W4) * 4;
+    for (int q = blockIdx.x * qper + threadIdx.x / groups; q < quads; q += gridDim.x * qper) {
+      const int yh = q / W4, x0 = (q - yh * W4) * 4;
       float in[3][6];
 #pragma unroll
       for (int r = 0; r < 3; ++r)
