@@ -71,14 +71,20 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+// 23 random bits -> a float strictly inside (0,1): (k + 0.5) 2^-23 is exact for every k < 2^23 (min 2^-24, max 1 - 2^-24).
+// With 24 bits the top value k + 0.5 = 2^24 - 0.5 is not a float, rounds to 2^24 and yields u = 1: log u = 0, and
+// a Box-Muller radius computed as a * rsqrt(a) turns into 0 * inf = NaN about once per 1.7e7 draws.
+__device__ __forceinline__ float u01_open(uint32_t r) {
+  return (static_cast<float>(r >> 9) + 0.5f) * (1.0f / 8388608.0f);
+}
+
 // (n0, n1) ~ N(0,1) for element `idx` of step `step` under `seed`.
 __device__ __forceinline__ float2 philox_normal2(uint64_t seed, uint64_t idx, uint32_t step) {
   uint32_t r[4];
   philox4x32_10(static_cast<uint32_t>(idx), static_cast<uint32_t>(idx >> 32), step, 0x1BD11BDAu,
                 static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
-  const float u0 = (static_cast<float>(r[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
-  const float u1 = (static_cast<float>(r[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  const float rad = sqrtf(-2.0f * logf(u0));
+  const float u0 = u01_open(r[0]), u1 = u01_open(r[1]);
+  const float rad = sqrtf(fmaxf(-2.0f * logf(u0), 0.0f));
   float s, c;
   sincospif(2.0f * u1, &s, &c);
   return make_float2(rad * c, rad * s);
@@ -92,9 +98,8 @@ __device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t idx, uint
                 static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
 #pragma unroll
   for (int p = 0; p < 2; ++p) {
-    const float u0 = (static_cast<float>(r[2 * p] >> 8) + 0.5f) * (1.0f / 16777216.0f);      // (0,1)
-    const float u1 = (static_cast<float>(r[2 * p + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    const float a2 = -2.0f * __logf(u0);             // > 0: u0 < 1
+    const float u0 = u01_open(r[2 * p]), u1 = u01_open(r[2 * p + 1]);
+    const float a2 = fmaxf(-2.0f * __logf(u0), 1e-12f);   // the SFU log of u0 = 1 - 2^-24 may come back as 0: keep rsqrt finite
     const float rad = a2 * rsqrtf(a2);
     float s, c;
     __sincosf(6.283185307179586f * u1, &s, &c);

@@ -395,6 +395,36 @@ def test_philox_noise_statistics_and_graph_replay():
     assert rel_l2(a, b) < 1e-5
 
 
+def test_in_kernel_noise_never_produces_nonfinite_values():
+    """3e8 in-kernel normals (fused SENSE step and plain Langevin update): every one finite.  A uniform that can round
+    to exactly 1.0 (24 random bits + 0.5 in fp32) gives radius 0 * inf = NaN about once per 1.7e7 draws -- invisible in
+    short parity cases, fatal for a 6933-step chain (found by tools/run_posterior.py)."""
+    L = _lib()
+    n, B = 256, 14
+    A = C.SENSE("exp", 4, 40, 1 / 64, (1, n, n), 0)
+    A.random_under_fourier.mask = C.keep_center_mask(n, 40, 1 / 64, seed=0)
+    mre, mim = A.device_maps(torch.device(DEV))
+    m, frames = A.device_mask(torch.device(DEV))
+    state = torch.zeros(2, B, n, n, device=DEV)
+    grad = torch.zeros_like(state)
+    bvec = torch.zeros_like(state)
+    sc = L.AldScalars(0.5, 1.0, 0.0, 0.0)
+    steps = 160
+    for k in range(steps):
+        L.check(L.lib().ipdm_ald_sense_step(state.data_ptr(), grad.data_ptr(), None, bvec.data_ptr(), mre.data_ptr(), None,
+                                            m.data_ptr(), frames, 4, B, n, n, sc, None, None, 77, k, L.stream()), "ald_sense_step")
+    assert bool(torch.isfinite(state).all())
+    v = float(state.var()) / steps            # kappa = 0: the prox is the identity, the state is a sum of unit normals
+    assert abs(v - 1) < 1e-2, v
+    x = torch.zeros(1 << 24, device=DEV)
+    g = torch.zeros_like(x)
+    for k in range(10):
+        L.check(L.lib().ipdm_langevin_update(x.data_ptr(), g.data_ptr(), None, None, x.numel(), L.AldScalars(0.0, 1.0, 0.0, 0.0),
+                                             None, None, None, 0, 5, k, L.stream()), "langevin")
+    assert bool(torch.isfinite(x).all())
+    assert abs(float(x.var()) / 10 - 1) < 1e-2
+
+
 def test_sampler_uncond():
     C.case_sampler_uncond(DEV)
 
