@@ -362,6 +362,10 @@ def run_native(args):
     if rank == 0:
         del x16, o16, o32, res
         sense = sense_point(torch, C, _lib, L, dev, hbm, coils=args.coils, size=n, batch=64, R=args.R, frac=args.center_frac)
+        if world == 1:   # the largest cfg-5 sweep point (k-space 4.3 GB >> L2): where SURVEY 8(d) evaluates the HBM fraction
+            torch.cuda.empty_cache()
+            sense["largest_sweep_point"] = sense_point(torch, C, _lib, L, dev, hbm, coils=32, size=512, batch=64, R=40.0, frac=1 / 64)
+            torch.cuda.empty_cache()
 
     if world > 1:
         dist.barrier()

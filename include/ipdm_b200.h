@@ -183,7 +183,8 @@ int ipdm_conv_igemm(const ipdm_conv_desc* desc_host, void* stream);
 /* Diagnostics knob (tests / profiling only): key 1 = convolution kernel variant (0 auto: persistent
  * halo-tile kernel for 3x3 with dilation <= 2, per-tap tile kernel otherwise; 1 = always the per-tap
  * kernel; 2 = TIMING EXPERIMENT: the halo kernel stops re-streaming weight tiles after the first ring fill --
- * results are wrong, only the time is meaningful, tools/exp_weights.py). */
+ * results are wrong, only the time is meaningful, tools/exp_weights.py).  key 2: 0 (default) / 1 = the halo kernel's L2
+ * bulk prefetch of residual tiles off / on (same results either way; A/B timing: on is 5-10 % slower). */
 int ipdm_debug_option(int key, int value);
 
 /* Same contract on CUDA cores, any Cin/Cout (used for narrow test nets and as the on-device

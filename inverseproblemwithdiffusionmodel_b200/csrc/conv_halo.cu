@@ -49,6 +49,7 @@ struct HaloParams {
   IgemmParams g;
   int items, mtiles;
   int exp_skip_weights;
+  int res_prefetch;
 };
 
 template <int MODE, int DIL, int TH, int NS>
@@ -109,6 +110,23 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
       for (int item = blockIdx.x; item < hp.items; item += gridDim.x) {
         int n, h0, w0, m0;
         decode(item, n, h0, w0, m0);
+        if ((MODE & 1) && hp.res_prefetch) {
+          // the residual tile of this item is needed by the epilogue one to two items from now: pull it into L2 now
+          // (bulk prefetch, no registers, no shared memory), so that the epilogue's loads see L2 latency, not DRAM latency
+          constexpr bool pool = (MODE & 8) != 0;
+          const int Ho = pool ? p.H / 2 : p.H, Wo = pool ? p.W / 2 : p.W;
+          const int oy0 = pool ? h0 / 2 : h0, ox0 = pool ? w0 / 2 : w0;
+          const int rows = min(pool ? TH / 2 : TH, Ho - oy0), cols = min(pool ? HT_W / 2 : HT_W, Wo - ox0);
+          for (int sl = 0; sl < NS; ++sl)
+            for (int r = 0; r < rows; ++r) {
+              const float* base = p.residual + (((size_t)(n + sl) * Ho + oy0 + r) * Wo + ox0) * p.Cout + m0;
+              if (p.Cout == BLOCK_M) {
+                prefetch_l2_bulk(base, cols * BLOCK_M * 4);
+              } else {
+                for (int c = 0; c < cols; ++c) prefetch_l2_bulk(base + (size_t)c * p.Cout, BLOCK_M * 4);
+              }
+            }
+        }
         for (int kc = 0; kc < kchunks; ++kc) {
           for (int pl = 0; pl < planes; ++pl, ++cnt) {      // 3x3x3: one halo tile per kx-plane, from slice x + (kx-1)*d
             const int s = cnt % NH;
@@ -259,6 +277,7 @@ int launch_conv_halo(const ipdm_conv_desc& d, cudaStream_t s) {
   p.tiles_h = (d.H + th - 1) / th;
   hp.mtiles = d.Cout / BLOCK_M;
   hp.exp_skip_weights = g_conv_variant == 2;
+  hp.res_prefetch = g_conv_res_prefetch;
   // two images per work item with the 12-row tile (dilation <= 2; pairs never straddle a volume: slices is even or 1 with even N)
   const bool pair = th == 12 && d.dilation <= 2 && d.N % 2 == 0 && (d.slices == 1 || d.slices % 2 == 0);
   hp.items = p.tiles_w * p.tiles_h * (pair ? d.N / 2 : d.N) * hp.mtiles;

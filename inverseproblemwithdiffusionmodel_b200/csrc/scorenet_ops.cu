@@ -37,28 +37,59 @@ __global__ void __launch_bounds__(256, 2) k_conv_first(const float* __restrict__
   float* o = out + (size_t)n * H * W * Cout;
   float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
   const float4 b4 = *reinterpret_cast<const float4*>(&sw[9 * Cout + 4 * g]);
+  float4 wt[9];                                                  // this thread's 9 x 4 weights stay in registers
+#pragma unroll
+  for (int t = 0; t < 9; ++t) wt[t] = *reinterpret_cast<const float4*>(&sw[t * Cout + 4 * g]);
+  // the 3 x 6 input patch of quad q, RAW values (the affine map 2v - 1 is applied when the patch is consumed, so that
+  // nothing waits on these loads here); outside the image the pad value maps to 0 under the same transform.  Loads of
+  // the NEXT quad are issued before the FMAs and stores of the current one.  Interior quads (all but the image border)
+  // take three unconditional loads per row: one aligned float4 and its two neighbours.
+  const float pad = affine ? 0.5f : 0.f;
+  const bool vec_ok = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  auto load_patch = [&](int q, float (&in)[3][6]) {
+    if (q >= quads) return;
+    const int yh = q / W4, x0 = (q - yh * W4) * 4;
+    if (vec_ok && yh >= 1 && yh + 1 < H && x0 >= 4 && x0 + 8 <= W) {
+      const float* r0 = xin + (size_t)(yh - 1) * W + x0;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float* rp = r0 + (size_t)r * W;
+        const float4 mid = *reinterpret_cast<const float4*>(rp);
+        in[r][0] = rp[-1]; in[r][1] = mid.x; in[r][2] = mid.y; in[r][3] = mid.z; in[r][4] = mid.w; in[r][5] = rp[4];
+      }
+      return;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int yy = yh + r - 1;
+      const bool rok = yy >= 0 && yy < H;
+      const float* rp = xin + (size_t)(rok ? yy : 0) * W;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const int xx = x0 + c - 1;
+        in[r][c] = (rok && xx >= 0 && xx < W) ? rp[xx] : pad;
+      }
+    }
+  };
   if (threadIdx.x / groups < qper) {
-    for (int q = blockIdx.x * qper + threadIdx.x / groups; q < quads; q += gridDim.x * qper) {
+    const int qstep = gridDim.x * qper;
+    int q = blockIdx.x * qper + threadIdx.x / groups;
+    float nxt[3][6];
+    load_patch(q, nxt);
+    for (; q < quads; q += qstep) {
       const int yh = q / W4, x0 = (q - yh * W4) * 4;
       float in[3][6];
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          const int yy = yh + r - 1, xx = x0 + c - 1;
-          float v = 0.f;
-          if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-            v = xin[(size_t)yy * W + xx];
-            if (affine) v = 2.f * v - 1.f;
-          }
-          in[r][c] = v;
-        }
+        for (int c = 0; c < 6; ++c) in[r][c] = affine ? 2.f * nxt[r][c] - 1.f : nxt[r][c];
+      load_patch(q + qstep, nxt);
       float4 acc[4] = {b4, b4, b4, b4};
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const float4 ww = *reinterpret_cast<const float4*>(&sw[(ky * 3 + kx) * Cout + 4 * g]);
+          const float4 ww = wt[ky * 3 + kx];
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
             const float v = in[ky][kx + p];
@@ -143,6 +174,68 @@ __global__ void k_conv_last_dots(const __half* __restrict__ in, const float* __r
 #pragma unroll
       for (int t = 1; t < 9; ++t) v = lane16 == t ? acc[t] : v;
       dots[pix * 9 + lane16] = v;
+    }
+  }
+}
+
+// Cin == 128 (the end_conv of every NCSNv2 at ngf 128): the lane's 9 x 8 weights live in registers, so a pixel costs
+// one 16-byte load, 72 FMAs and a 15-shuffle transposing reduction (lane t of the 16 ends with the sum of tap t)
+// instead of 18 shared-memory reads and 36 shuffles.  Two pixels per iteration keep two loads in flight.
+__global__ void __launch_bounds__(256, 2) k_conv_last_dots128(const __half* __restrict__ in, const float* __restrict__ w,
+                                                              float* __restrict__ dots, size_t npix) {
+  const int lane16 = threadIdx.x & 15;
+  float wr[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float4 a = *reinterpret_cast<const float4*>(w + t * 128 + lane16 * 8);
+    const float4 b = *reinterpret_cast<const float4*>(w + t * 128 + lane16 * 8 + 4);
+    wr[t][0] = a.x; wr[t][1] = a.y; wr[t][2] = a.z; wr[t][3] = a.w;
+    wr[t][4] = b.x; wr[t][5] = b.y; wr[t][6] = b.z; wr[t][7] = b.w;
+  }
+  const bool up8 = lane16 & 8, up4 = lane16 & 4, up2 = lane16 & 2, up1 = lane16 & 1;
+  const size_t gstride = (size_t)gridDim.x * (blockDim.x / 16);
+  const size_t iters = (npix + 2 * gstride - 1) / (2 * gstride);
+  size_t pix = blockIdx.x * (size_t)(blockDim.x / 16) + threadIdx.x / 16;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  uint4 nxt[2];                                  // the next iteration's two pixels are in flight while these two are reduced
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+    nxt[u] = pix + u * gstride < npix ? *reinterpret_cast<const uint4*>(in + (pix + u * gstride) * 128 + lane16 * 8) : zero4;
+  for (size_t it = 0; it < iters; ++it, pix += 2 * gstride) {
+    const size_t px[2] = {pix, pix + gstride};
+    uint4 raw[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      raw[u] = nxt[u];
+      const size_t pn = px[u] + 2 * gstride;
+      nxt[u] = pn < npix ? *reinterpret_cast<const uint4*>(in + pn * 128 + lane16 * 8) : zero4;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const __half2* h2 = reinterpret_cast<const __half2*>(&raw[u]);
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t2 = __half22float2(h2[j]);
+        f[2 * j] = t2.x;
+        f[2 * j + 1] = t2.y;
+      }
+      float v[16];
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+        v[t] = f[0] * wr[t][0] + f[1] * wr[t][1] + f[2] * wr[t][2] + f[3] * wr[t][3] + f[4] * wr[t][4] + f[5] * wr[t][5] +
+               f[6] * wr[t][6] + f[7] * wr[t][7];
+#pragma unroll
+      for (int t = 9; t < 16; ++t) v[t] = 0.f;
+      // after the step with offset o, v[t] (t < o) holds the partial sum of index t + (lane16 & ~(o - 1) & 15)
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v[t] = (up8 ? v[t + 8] : v[t]) + __shfl_xor_sync(0xffffffffu, up8 ? v[t] : v[t + 8], 8);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) v[t] = (up4 ? v[t + 4] : v[t]) + __shfl_xor_sync(0xffffffffu, up4 ? v[t] : v[t + 4], 4);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) v[t] = (up2 ? v[t + 2] : v[t]) + __shfl_xor_sync(0xffffffffu, up2 ? v[t] : v[t + 2], 2);
+      v[0] = (up1 ? v[1] : v[0]) + __shfl_xor_sync(0xffffffffu, up1 ? v[0] : v[1], 1);
+      if (px[u] < npix && lane16 < 9) dots[px[u] * 9 + lane16] = v[0];
     }
   }
 }
@@ -581,8 +674,12 @@ extern "C" int ipdm_conv_last(const void* in_f16, const float* w, const float* b
   IPDM_REQUIRE(in_f16 && w && sigmas && labels && out && workspace, IPDM_E_BADARG, "conv_last: null pointer");
   IPDM_REQUIRE(Cin % 8 == 0 && Cin <= 1024, IPDM_E_BADARG, "conv_last: Cin=%d must be a multiple of 8", Cin);
   const size_t npix = (size_t)N * H * W;
-  k_conv_last_dots<<<grid1d(npix, 16, 4), 256, (size_t)(Cin / 8) * LAST_SLOT * sizeof(float), as_stream(stream)>>>(
-      reinterpret_cast<const __half*>(in_f16), w, workspace, npix, Cin);
+  if (Cin == 128) {
+    k_conv_last_dots128<<<148 * 2, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(in_f16), w, workspace, npix);
+  } else {
+    k_conv_last_dots<<<grid1d(npix, 16, 4), 256, (size_t)(Cin / 8) * LAST_SLOT * sizeof(float), as_stream(stream)>>>(
+        reinterpret_cast<const __half*>(in_f16), w, workspace, npix, Cin);
+  }
   if (int e = launched("k_conv_last_dots")) return e;
   k_conv_last_sum<<<grid1d(npix, 256), 256, 0, as_stream(stream)>>>(workspace, bias, sigmas, labels, out, N, H, W);
   return launched("k_conv_last_sum");

@@ -6,6 +6,8 @@ from inverseproblemwithdiffusionmodel_b200 import _lib
 L = _lib.lib()
 dev = "cuda"
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 28
+if len(sys.argv) > 2:      # A/B: ipdm_debug_option(2, v): residual L2 prefetch on (1) / off (0)
+    L.ipdm_debug_option(2, int(sys.argv[2]))
 shapes = [  # (H, Cin, Cout, taps, dil)
     (256, 128, 128, 9, 1), (128, 256, 256, 9, 1), (64, 256, 256, 9, 1), (32, 512, 512, 9, 1), (128, 128, 128, 9, 1),
     (256, 128, 256, 9, 1), (32, 256, 256, 9, 1), (32, 512, 512, 9, 4), (256, 128, 256, 1, 1)]
