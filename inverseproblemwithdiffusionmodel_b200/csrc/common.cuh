@@ -50,10 +50,9 @@ __device__ __forceinline__ float elu_f16bound(float v) { return v > 0.f ? v : __
 // f32 x2 -> f16 x2 with saturation: an activation beyond the f16 range degrades to +-65504 instead of turning the
 // rest of the network into inf/NaN (trained checkpoints are not available to prove the range).
 __device__ __forceinline__ unsigned pack_half2_sat(float a, float b) {
-  a = fminf(fmaxf(a, -65504.f), 65504.f);
-  b = fminf(fmaxf(b, -65504.f), 65504.f);
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<unsigned*>(&h);
+  unsigned d;   // one F2FP.SATFINITE.F16.F32.PACK_AB: low half = a, high half = b, |x| > 65504 -> +-65504
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
 }
 
 // ---- Philox4x32-10 (Salmon et al.) + Box-Muller: two N(0,1) per call -------------------------

@@ -59,37 +59,49 @@ __device__ __forceinline__ void lane_register_swap(float* v, int lane) {
   }
 }
 
-template <int MODE, int TW, class WaitAcc>
-__device__ __forceinline__ void conv_epilogue_shfl(const IgemmParams& p, uint32_t tmem_acc, int quad, int lane, int n, int h0, int w0,
-                                                   int m0, int chunk0, int NCHUNK, WaitAcc wait_acc) {
+// The chunk loop of the epilogue.  FAST = 0: every feature read from the descriptor at run time, per-pixel bounds checks.
+// FAST = 1 / 2: the item's tile lies inside the image and the descriptor has no bias, no InstanceNorm++ sums and no ELU
+// on the residual -- every RCU / CRP convolution of the RefineNet, 82 of 113 launches -- with the f16 output being
+// ELU(result) (1, RCU) or the pre-residual value (2, CRP).  There the unused work is compiled out rather than predicated
+// and the eight pixels are one straight-line block: the epilogue warps (two per scheduler) are ISSUE-bound in the
+// residual mode, so an instruction that is not there is time.  SASS, executed instructions per 4-channel pixel:
+// ~110 in the first version (predicated ELU rescue paths, per-pixel flag tests, 64-bit index arithmetic) -> ~27.
+template <int MODE, int TW, int FAST, class WaitAcc>
+__device__ __forceinline__ void conv_epilogue_chunks(const IgemmParams& p, uint32_t tmem_acc, int quad, int lane, int n, int h0, int w0,
+                                                     int m0, int chunk0, int NCHUNK, WaitAcc wait_acc) {
   constexpr bool kRes = (MODE & 1) != 0, kOut32 = (MODE & 2) != 0, kOut16 = (MODE & 4) != 0, pool = (MODE & 8) != 0;
+  constexpr bool LEAN = FAST != 0;
   constexpr int NPX = pool ? 2 : 8;             // float4 groups (pixels) per thread per chunk
   constexpr int OW = pool ? TW / 2 : TW;        // output pixels per chunk row
   constexpr int OROWS = pool ? (32 / TW) / 2 : 32 / TW;   // output rows per chunk
+  constexpr int IPR = OW / 4;                   // of a thread's pixels q = psub + 4*i, IPR consecutive i share a row
+  static_assert(OW % 4 == 0 && NPX % IPR == 0, "chunk geometry");
   const int psub = lane & 3;                    // pixel sub-index of this thread
   const int c4 = quad * 32 + (lane >> 2) * 4;   // first of this thread's 4 channels within the 128-channel tile
   const int Ho = pool ? p.H / 2 : p.H, Wo = pool ? p.W / 2 : p.W;
   const int oy0 = pool ? h0 / 2 : h0, ox0 = pool ? w0 / 2 : w0;
+  const bool f16_elu = FAST == 1 ? true : FAST == 2 ? false : (p.flags & IPDM_CONV_F16_ELU) != 0;
+  const bool f16_pre = FAST == 1 ? false : FAST == 2 ? true : (p.flags & IPDM_CONV_F16_PRE_RES) != 0;
+  const bool res_elu = !LEAN && (p.flags & IPDM_CONV_RES_ELU) != 0;
   float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (p.bias) bias4 = *reinterpret_cast<const float4*>(p.bias + m0 + c4);
+  if (!LEAN && p.bias) bias4 = *reinterpret_cast<const float4*>(p.bias + m0 + c4);
   float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
   const uint32_t taddr = tmem_acc + ((uint32_t)(quad * 32) << 16);
-  const size_t row_stride = (size_t)Wo * p.Cout;
-  // output pixel q = psub + 4*i of a chunk: row q / OW, column q % OW
-  auto pix_off = [&](int chunk, int i, bool& ok) -> size_t {
-    const int q = psub + 4 * i;
-    const int y = oy0 + chunk * OROWS + q / OW, x = ox0 + q % OW;
-    ok = y < Ho && x < Wo;
-    return (((size_t)n * Ho + y) * Wo + x) * p.Cout + m0 + c4;
-  };
+  // element offset of this thread's first pixel of chunk 0 (row oy0, column ox0 + psub); pixel i of a chunk adds
+  // i/IPR rows and 4*(i%IPR) pixels: a 32-bit element offset eo(i), so an address is one IMAD.WIDE on the chunk's base
+  const uint32_t row_stride = (uint32_t)Wo * p.Cout, col_stride = 4u * p.Cout;
+  const size_t off0 = (((size_t)n * Ho + oy0) * Wo + ox0 + psub) * p.Cout + m0 + c4;
+  const int cols_left = Wo - ox0 - psub;        // pixel i is inside the image iff 4*(i%IPR) < cols_left and its row < Ho
+  auto eo = [&](int i) -> uint32_t { return (uint32_t)(i / IPR) * row_stride + (uint32_t)(i % IPR) * col_stride; };
+  auto inside = [&](int i, int rows_left) -> bool { return LEAN || (i / IPR < rows_left && 4 * (i % IPR) < cols_left); };
   float4 rcur[NPX], rnext[NPX];
   auto issue_res = [&](int chunk, float4* r) {
+    const char* rp = reinterpret_cast<const char*>(p.residual + off0 + (size_t)(chunk * OROWS) * row_stride);
+    const int rows_left = Ho - oy0 - chunk * OROWS;
 #pragma unroll
     for (int i = 0; i < NPX; ++i) {
-      bool ok;
-      const size_t off = pix_off(chunk, i, ok);
       r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ok) r[i] = *reinterpret_cast<const float4*>(p.residual + off);
+      if (inside(i, rows_left)) r[i] = *reinterpret_cast<const float4*>(rp + (size_t)eo(i) * 4);
     }
   };
   if (kRes) issue_res(chunk0, rcur);
@@ -114,29 +126,34 @@ __device__ __forceinline__ void conv_epilogue_shfl(const IgemmParams& p, uint32_
       }
     }
     lane_register_swap<4 * NPX>(w, lane);
+    const size_t offc = off0 + (size_t)(chunk * OROWS) * row_stride;
+    char* o32 = reinterpret_cast<char*>(p.out_f32 + offc);
+    char* o16 = reinterpret_cast<char*>(p.out_f16 + offc);
+    const int rows_left = Ho - oy0 - chunk * OROWS;
 #pragma unroll
     for (int i = 0; i < NPX; ++i) {
-      bool ok;
-      const size_t off = pix_off(chunk, i, ok);
-      if (ok) {
-        float4 a = make_float4(w[4 * i] + bias4.x, w[4 * i + 1] + bias4.y, w[4 * i + 2] + bias4.z, w[4 * i + 3] + bias4.w);
+      if (inside(i, rows_left)) {
+        float4 a = make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+        if (!LEAN) { a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w; }
         const float4 pre = a;
         if (kRes) {
           float4 r = rcur[i];
-          if (p.flags & IPDM_CONV_RES_ELU) { r.x = elu_fast(r.x); r.y = elu_fast(r.y); r.z = elu_fast(r.z); r.w = elu_fast(r.w); }
+          if (res_elu) { r.x = elu_fast(r.x); r.y = elu_fast(r.y); r.z = elu_fast(r.z); r.w = elu_fast(r.w); }
           a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
         }
-        if (kOut32) *reinterpret_cast<float4*>(p.out_f32 + off) = a;
+        if (kOut32) *reinterpret_cast<float4*>(o32 + (size_t)eo(i) * 4) = a;
         if (kOut16) {
-          float4 h = (p.flags & IPDM_CONV_F16_PRE_RES) ? pre : a;
-          if (p.flags & IPDM_CONV_F16_ELU) { h.x = elu_fast(h.x); h.y = elu_fast(h.y); h.z = elu_fast(h.z); h.w = elu_fast(h.w); }
+          float4 h = (kRes && f16_pre) ? pre : a;
+          if (f16_elu) { h.x = elu_fast(h.x); h.y = elu_fast(h.y); h.z = elu_fast(h.z); h.w = elu_fast(h.w); }
           uint2 pk;
           pk.x = pack_half2_sat(h.x, h.y);
           pk.y = pack_half2_sat(h.z, h.w);
-          *reinterpret_cast<uint2*>(p.out_f16 + off) = pk;
+          *reinterpret_cast<uint2*>(o16 + (size_t)eo(i) * 2) = pk;
         }
-        s1[0] += a.x; s1[1] += a.y; s1[2] += a.z; s1[3] += a.w;
-        s2[0] += a.x * a.x; s2[1] += a.y * a.y; s2[2] += a.z * a.z; s2[3] += a.w * a.w;
+        if (!LEAN) {
+          s1[0] += a.x; s1[1] += a.y; s1[2] += a.z; s1[3] += a.w;
+          s2[0] += a.x * a.x; s2[1] += a.y * a.y; s2[2] += a.z * a.z; s2[3] += a.w * a.w;
+        }
       }
     }
     if (kRes) {
@@ -144,7 +161,7 @@ __device__ __forceinline__ void conv_epilogue_shfl(const IgemmParams& p, uint32_
       for (int i = 0; i < NPX; ++i) rcur[i] = rnext[i];
     }
   }
-  if (p.stats) {
+  if (!LEAN && p.stats) {
     // the four lanes that share a channel group (lane bits 0, 1) combine, then 8 fp64 atomics from one of them
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -161,6 +178,25 @@ __device__ __forceinline__ void conv_epilogue_shfl(const IgemmParams& p, uint32_
       }
     }
   }
+}
+
+template <int MODE, int TW, class WaitAcc>
+__device__ __forceinline__ void conv_epilogue_shfl(const IgemmParams& p, uint32_t tmem_acc, int quad, int lane, int n, int h0, int w0,
+                                                   int m0, int chunk0, int NCHUNK, WaitAcc wait_acc) {
+  constexpr bool kRes = (MODE & 1) != 0, kOut16 = (MODE & 4) != 0, pool = (MODE & 8) != 0;
+  constexpr int OROWS = pool ? (32 / TW) / 2 : 32 / TW, OW = pool ? TW / 2 : TW;
+  const int Ho = pool ? p.H / 2 : p.H, Wo = pool ? p.W / 2 : p.W;
+  const int oy0 = pool ? h0 / 2 : h0, ox0 = pool ? w0 / 2 : w0;
+  // warp-uniform: the chunks [chunk0, chunk0 + NCHUNK) of this item lie inside the image and nothing optional is asked for
+  const bool lean = p.bias == nullptr && p.stats == nullptr && (p.flags & IPDM_CONV_RES_ELU) == 0 &&
+                    oy0 + (chunk0 + NCHUNK) * OROWS <= Ho && ox0 + OW <= Wo;
+  const bool elu = (p.flags & IPDM_CONV_F16_ELU) != 0, pre = kRes && (p.flags & IPDM_CONV_F16_PRE_RES) != 0;
+  if (lean && (!kOut16 || (elu && !pre)))
+    conv_epilogue_chunks<MODE, TW, 1>(p, tmem_acc, quad, lane, n, h0, w0, m0, chunk0, NCHUNK, wait_acc);
+  else if (lean && !elu && (pre || !kRes))
+    conv_epilogue_chunks<MODE, TW, 2>(p, tmem_acc, quad, lane, n, h0, w0, m0, chunk0, NCHUNK, wait_acc);
+  else
+    conv_epilogue_chunks<MODE, TW, 0>(p, tmem_acc, quad, lane, n, h0, w0, m0, chunk0, NCHUNK, wait_acc);
 }
 
 }  // namespace ipdm

@@ -17,9 +17,11 @@
 // holds two 256-column accumulators so the epilogue of item i overlaps the MMAs of item i+1, and the TMA
 // producers run ahead across item boundaries.
 //
-// Warps (352 threads): 0 = halo TMA, 1 = MMA issuer + TMEM owner, 2 = weight TMA, 3-6 = epilogue of the first half of
-// the accumulator's 32-column chunks, 7-10 = of the second half (warp % 4 = TMEM lane quadrant); the epilogue warps are
-// independent of each other (no shared memory, no barrier: conv_common.cuh).
+// Warps (384 threads = 3 warpgroups): 0 = halo TMA, 1 = MMA issuer + TMEM owner, 2 = weight TMA, 3 = idle; 4-7 = epilogue
+// of the first half of the accumulator's 32-column chunks, 8-11 = of the second half (warp % 4 = TMEM lane quadrant);
+// the epilogue warps are independent of each other (no shared memory, no barrier: conv_common.cuh).  The launch gives
+// every thread 168 registers; warpgroup 0 hands most of its share to the epilogue warpgroups (`setmaxnreg` 64 / 216), whose
+// residual variant keeps two 32-value residual tiles, the accumulator chunk and its addresses live at once.
 #include "conv_common.cuh"
 
 namespace ipdm {
@@ -28,7 +30,8 @@ constexpr int HT_W = 8;                       // pixel tile = TH rows x 8 column
                                               // 12 (N = 96): the short tiles fit the 24 x 8 / 12 x 8 slices of the 3-D network
 constexpr int NH = 2;                         // halo ring
 constexpr int W_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-constexpr int HALO_THREADS = 352;
+constexpr int HALO_THREADS = 384;            // three warpgroups: 0 = producers + MMA issuer, 1 and 2 = epilogue teams
+constexpr int HALO_REGS_LOW = 64, HALO_REGS_HIGH = 216;   // setmaxnreg: 64*128 + 216*256 <= 168*384 (the launch allocation)
 
 // NS = images (slices) per work item: 2 for the 12-row tile, so that one streamed weight tile feeds two N = 96 MMAs
 // (a 96-pixel tile alone re-streams its 128 channels' whole weight slab: L2 -> SM bound)
@@ -103,6 +106,8 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
     n = tile * NS; h0 = th * TH; w0 = tw * HT_W; m0 = mt * BLOCK_M;     // first of the item's NS consecutive images
   };
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HALO_REGS_LOW));   // (role code below keeps its indentation)
   if (warp == 0) {
     // ===== halo producer: one TMA box per (item, 64-channel chunk) =====
     if (lane == 0) {
@@ -197,10 +202,12 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
         umma_commit(&acc_full[as]);
       }
     }
+  }
   } else {
-    // ===== epilogue teams (TMEM lane quadrant = warp % 4): A = warps 3-6, B = warps 7-10 =====
+    // ===== epilogue teams (TMEM lane quadrant = warp % 4): A = warps 4-7, B = warps 8-11 =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(HALO_REGS_HIGH));
     const int quad = warp & 3;
-    const int team = warp >= 7 ? 1 : 0;
+    const int team = warp >= 8 ? 1 : 0;
     uint32_t acnt = 0;
     for (int item = blockIdx.x; item < hp.items; item += gridDim.x, ++acnt) {
       int n, h0, w0, m0;
