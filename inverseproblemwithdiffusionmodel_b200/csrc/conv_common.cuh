@@ -26,6 +26,7 @@ int get_act_map(const void* x, int N, int H, int W, int C, int box_w, int box_h,
 int launch_conv_halo(const ipdm_conv_desc& d, cudaStream_t s);
 bool conv_halo_supports(const ipdm_conv_desc& d);
 extern int g_conv_res_prefetch;  // halo kernel: L2 bulk prefetch of the residual tile by the producer warp (0 = off, the default: measured 5-10 % SLOWER when on)
+extern int g_conv_pdl;           // halo kernel launched with programmatic stream serialization (PDL)
 extern int g_conv_variant;       // 0 = auto, 1 = force the per-tap tile kernel (diagnostics)
 
 // ---------------------------------------------------------------------------------------------------------------

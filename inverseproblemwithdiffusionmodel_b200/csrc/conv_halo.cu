@@ -22,6 +22,7 @@
 // the epilogue warps are independent of each other (no shared memory, no barrier: conv_common.cuh).  The launch gives
 // every thread 168 registers; warpgroup 0 hands most of its share to the epilogue warpgroups (`setmaxnreg` 64 / 216), whose
 // residual variant keeps two 32-value residual tiles, the accumulator chunk and its addresses live at once.
+#include <cstdlib>
 #include "conv_common.cuh"
 
 namespace ipdm {
@@ -53,6 +54,7 @@ struct HaloParams {
   int items, mtiles;
   int exp_skip_weights;
   int res_prefetch;
+  int pdl;
 };
 
 template <int MODE, int DIL, int TH, int NS>
@@ -97,6 +99,10 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch (no-ops in a plain launch): let the NEXT kernel's CTAs be scheduled as ours retire, and
+  // keep everything that reads or overwrites the PREVIOUS kernel's tensors (activation TMA, residual, outputs) behind
+  // griddepcontrol.wait; the weight ring (static data) and the set-up above run ahead of it.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   auto decode = [&](int item, int& n, int& h0, int& w0, int& m0) {
     const int mt = item % hp.mtiles;
@@ -111,6 +117,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
   if (warp == 0) {
     // ===== halo producer: one TMA box per (item, 64-channel chunk) =====
     if (lane == 0) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");
       uint32_t cnt = 0;
       for (int item = blockIdx.x; item < hp.items; item += gridDim.x) {
         int n, h0, w0, m0;
@@ -208,6 +215,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(HALO_REGS_HIGH));
     const int quad = warp & 3;
     const int team = warp >= 8 ? 1 : 0;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     uint32_t acnt = 0;
     for (int item = blockIdx.x; item < hp.items; item += gridDim.x, ++acnt) {
       int n, h0, w0, m0;
@@ -242,6 +250,18 @@ static int launch_variant(const CUtensorMap& mw, const CUtensorMap& mx, const Ha
   if (!attr_set) {
     IPDM_CUDA(cudaFuncSetAttribute(k_conv_halo<MODE, DIL, TH, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<DIL, TH, NS>::SMEM));
     attr_set = true;
+  }
+  if (hp.pdl) {
+    // programmatic dependent launch: this grid's CTAs may start (set-up, weight ring fill) as the previous kernel's CTAs
+    // retire; everything that touches the previous kernel's data sits behind griddepcontrol.wait in the kernel
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(HALO_THREADS); cfg.dynamicSmemBytes = HaloCfg<DIL, TH, NS>::SMEM; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    IPDM_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<MODE, DIL, TH, NS>, mw, mx, hp));
+    return 0;
   }
   k_conv_halo<MODE, DIL, TH, NS><<<grid, HALO_THREADS, HaloCfg<DIL, TH, NS>::SMEM, s>>>(mw, mx, hp);
   return 0;
@@ -285,6 +305,8 @@ int launch_conv_halo(const ipdm_conv_desc& d, cudaStream_t s) {
   hp.mtiles = d.Cout / BLOCK_M;
   hp.exp_skip_weights = g_conv_variant == 2;
   hp.res_prefetch = g_conv_res_prefetch;
+  static const int env_pdl = getenv("IPDM_CONV_PDL") ? atoi(getenv("IPDM_CONV_PDL")) : -1;   // A/B runs of whole programs
+  hp.pdl = env_pdl >= 0 ? env_pdl : g_conv_pdl;
   // two images per work item with the 12-row tile (dilation <= 2; pairs never straddle a volume: slices is even or 1 with even N)
   const bool pair = th == 12 && d.dilation <= 2 && d.N % 2 == 0 && (d.slices == 1 || d.slices % 2 == 0);
   hp.items = p.tiles_w * p.tiles_h * (pair ? d.N / 2 : d.N) * hp.mtiles;

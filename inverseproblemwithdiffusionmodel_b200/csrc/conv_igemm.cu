@@ -158,6 +158,7 @@ static std::mutex g_maps_mu;
 
 int g_conv_variant = 0;
 int g_conv_res_prefetch = 0;
+int g_conv_pdl = 0;
 
 int get_weight_map(const void* w, int Cout, int K, CUtensorMap* out) {
   MapKey key{w, 2, Cout, K, 0};
@@ -266,6 +267,7 @@ extern "C" int ipdm_debug_option(int key, int value) {
   switch (key) {
     case 1: g_conv_variant = value; return 0;
     case 2: g_conv_res_prefetch = value; return 0;
+    case 3: g_conv_pdl = value; return 0;
     default: set_error("debug_option: unknown key %d", key); return IPDM_E_BADARG;
   }
 }
