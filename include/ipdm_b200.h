@@ -184,7 +184,8 @@ int ipdm_conv_igemm(const ipdm_conv_desc* desc_host, void* stream);
  * halo-tile kernel for 3x3 with dilation <= 2, per-tap tile kernel otherwise; 1 = always the per-tap
  * kernel; 2 = TIMING EXPERIMENT: the halo kernel stops re-streaming weight tiles after the first ring fill --
  * results are wrong, only the time is meaningful, tools/exp_weights.py).  key 2: 0 (default) / 1 = the halo kernel's L2
- * bulk prefetch of residual tiles off / on (same results either way; A/B timing: on is 5-10 % slower). */
+ * bulk prefetch of residual tiles off / on (same results either way; A/B timing: on is 5-10 % slower).  key 3: 0 (default) /
+ * 1 = launch the halo kernel with programmatic stream serialization (PDL; also env IPDM_CONV_PDL; measured +0.4 %). */
 int ipdm_debug_option(int key, int value);
 
 /* Same contract on CUDA cores, any Cin/Cout (used for narrow test nets and as the on-device

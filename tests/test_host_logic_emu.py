@@ -89,3 +89,18 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(handle, name), name
     assert _lib.lib().ipdm_abi_version() == 2
     assert _lib.lib().ipdm_sense_workspace_bytes(4, 2, 256, 256) == 4 * 2 * 256 * 256 * 8
+
+
+def test_noise_uniform_conversion_stays_inside_the_open_interval():
+    """The in-kernel Box-Muller draws take u = (k + 0.5) * 2^-23 from 23 random bits (csrc/common.cuh:u01_open).  In fp32
+    that is exact for every k, so 0 < u < 1 and log(u) < 0 always.  The first version used 24 bits: k + 0.5 is not
+    representable above 2^23, the top value rounds to 2^24 and u = 1.0 -- radius 0 * rsqrt(0) = NaN about once per 1.7e7
+    draws, which no short parity case can see (found by a full 6933-step chain).  This pins the arithmetic fact."""
+    import numpy as np
+    k = np.arange(1 << 23, dtype=np.uint32)
+    u = (k.astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 8388608.0)
+    assert u.dtype == np.float32
+    assert float(u.min()) == 2.0 ** -24 and float(u.max()) == 1.0 - 2.0 ** -24
+    assert np.array_equal(u.astype(np.float64), (k.astype(np.float64) + 0.5) / 8388608.0)      # exact, no rounding anywhere
+    top24 = (np.float32((1 << 24) - 1) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)      # what 24 bits would give
+    assert float(top24) == 1.0
