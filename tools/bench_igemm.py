@@ -14,6 +14,12 @@ shapes = [  # (H, Cin, Cout, taps, dil)
 modes = {"f16elu": dict(o32=False, o16=True, res=False, st=False, flags=1),
          "f32+stats": dict(o32=True, o16=False, res=False, st=True, flags=0),
          "res+f32+f16elu": dict(o32=True, o16=True, res=True, st=False, flags=1)}
+if os.environ.get("IGEMM_ALL_MODES"):     # which stream costs what: every combination of the three epilogue streams, first shape only
+    shapes = shapes[:1]
+    modes.update({"f32": dict(o32=True, o16=False, res=False, st=False, flags=0),
+                  "f32+f16elu": dict(o32=True, o16=True, res=False, st=False, flags=1),
+                  "res+f32": dict(o32=True, o16=False, res=True, st=False, flags=0),
+                  "res+f16elu": dict(o32=False, o16=True, res=True, st=False, flags=1)})
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for (H, Cin, Cout, taps, dil) in shapes:
     x16 = torch.randn(N, H, H, Cin, device=dev).half()
