@@ -252,6 +252,12 @@ int ipdm_interleave_t(const float* in, float* out_f32, void* out_elu_f16, size_t
  * roll (ALD_optimizers.py:466-470,495-499) as (shift_h, shift_w).  unfold = 0: state -> vol; 1: vol -> state. */
 int ipdm_patch_fold(float* state, float* vol, int B, int T, int H, int W, int k, int shift_h, int shift_w, int unfold,
                     void* stream);
+
+/* Same fold / unfold with the shifts of the current step read on the device: shifts = int32 [steps][2] (shift_h, shift_w per
+ * ALD step, drawn by the host in the reference's np.random order, ALD_optimizers.py:466-470), cursor = the step counter
+ * that ipdm_ald_advance increments -- so that a captured step graph can run the random-roll variant (if_random_shift). */
+int ipdm_patch_fold_sched(float* state, float* vol, int B, int T, int H, int W, int k, const int* shifts, const int* cursor,
+                          int unfold, void* stream);
 /* out = a + (elu_b ? ELU(b) : b), n f32 elements (n % 4 == 0). */
 int ipdm_add_act(const float* a, const float* b, float* out, size_t n, int elu_b, void* stream);
 

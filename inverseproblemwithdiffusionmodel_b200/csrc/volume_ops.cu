@@ -160,7 +160,12 @@ __global__ void k_add_act(const float4* __restrict__ a, const float4* __restrict
 // of ALD_optimizers.py:466-470,495-499 folded in): vol[p][kx][t][ky] <-> state[pl][b][t][(h1*k + kx - sh) mod H]
 // [(w1*k + ky - sw) mod W], p = ((pl*B + b)*H/k + h1)*W/k + w1.  unfold = the inverse scatter (same index map).
 __global__ void k_patch_fold(float* __restrict__ state, float* __restrict__ vol, int B, int T, int H, int W, int k, int sh, int sw,
-                             int unfold) {
+                             const int* __restrict__ shifts, const int* __restrict__ cursor, int unfold) {
+  if (shifts != nullptr) {                                       // per-step shifts from a device table (captured graphs)
+    const int c = *cursor;
+    sh = shifts[2 * c];
+    sw = shifts[2 * c + 1];
+  }
   const int H1 = H / k, W1 = W / k;
   const size_t total = (size_t)2 * B * T * H * W;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -189,7 +194,16 @@ extern "C" int ipdm_patch_fold(float* state, float* vol, int B, int T, int H, in
   IPDM_REQUIRE(state && vol && B >= 1 && T >= 1 && k >= 1, IPDM_E_BADARG, "patch_fold: bad argument");
   IPDM_REQUIRE(H % k == 0 && W % k == 0, IPDM_E_BADARG, "patch_fold: H=%d, W=%d must be multiples of the patch size %d", H, W, k);
   const size_t n = (size_t)2 * B * T * H * W;
-  k_patch_fold<<<vgrid(n, 256), 256, 0, as_stream(stream)>>>(state, vol, B, T, H, W, k, shift_h, shift_w, unfold);
+  k_patch_fold<<<vgrid(n, 256), 256, 0, as_stream(stream)>>>(state, vol, B, T, H, W, k, shift_h, shift_w, nullptr, nullptr, unfold);
+  return launched("k_patch_fold");
+}
+
+extern "C" int ipdm_patch_fold_sched(float* state, float* vol, int B, int T, int H, int W, int k, const int* shifts, const int* cursor,
+                                     int unfold, void* stream) {
+  IPDM_REQUIRE(state && vol && shifts && cursor && B >= 1 && T >= 1 && k >= 1, IPDM_E_BADARG, "patch_fold_sched: bad argument");
+  IPDM_REQUIRE(H % k == 0 && W % k == 0, IPDM_E_BADARG, "patch_fold_sched: H=%d, W=%d must be multiples of the patch size %d", H, W, k);
+  const size_t n = (size_t)2 * B * T * H * W;
+  k_patch_fold<<<vgrid(n, 256), 256, 0, as_stream(stream)>>>(state, vol, B, T, H, W, k, 0, 0, shifts, cursor, unfold);
   return launched("k_patch_fold");
 }
 

@@ -440,7 +440,7 @@ class ALD2DTime(_SenseChainMixin, ALDOptimizer):
         kappa = l2_kappa(self.linear_tfm, state, step_lr * lr_scaled, 1.)
         tv = "tv" in mode_T
         prox_only = _lib.AldScalars(0.0, 0.0, float(kappa), 0.0)
-        fast = use_graph and noise_fn is None and not (diffusion and random_shift)
+        fast = use_graph and noise_fn is None
         sig_T = self.sigmas_T.detach().float().cpu()
         temporal_on = [diffusion and float(sig_T[c]) != -1.0 for c in range(len(sigmas))]
         seed_T = seed ^ 0x5bd1e995
@@ -448,10 +448,17 @@ class ALD2DTime(_SenseChainMixin, ALDOptimizer):
             vol = torch.zeros(P2, ksz, T, ksz, dtype=torch.float32, device=state.device)
             gvol = torch.zeros_like(vol)
 
-        def temporal_diffusion(c, k, sched_T=None, cursor=None, lab=None):
+        def fold(unfold, sh, sw, shifts, cursor):
+            if shifts is not None:      # captured step: this step's roll comes from the device table
+                _lib.check(L.ipdm_patch_fold_sched(state.data_ptr(), vol.data_ptr(), B, T, H, W, ksz, shifts.data_ptr(), cursor.data_ptr(),
+                                                   unfold, _lib.stream()), "patch_fold_sched")
+            else:
+                _lib.check(L.ipdm_patch_fold(state.data_ptr(), vol.data_ptr(), B, T, H, W, ksz, sh, sw, unfold, _lib.stream()), "patch_fold")
+
+        def temporal_diffusion(c, k, sched_T=None, cursor=None, lab=None, shifts=None):
             """fold -> scorenet_T on real and imaginary patches -> Langevin update of the patches -> unfold  (:463-502)"""
-            sh, sw = (tuple(np.random.randint(0, ksz, (2,)).tolist()) if random_shift else (0, 0))
-            _lib.check(L.ipdm_patch_fold(state.data_ptr(), vol.data_ptr(), B, T, H, W, ksz, sh, sw, 0, _lib.stream()), "patch_fold")
+            sh, sw = (tuple(np.random.randint(0, ksz, (2,)).tolist()) if random_shift and shifts is None else (0, 0))
+            fold(0, sh, sw, shifts, cursor)
             lab = labels_all[:P2] if lab is None else lab
             if hasattr(self.scorenet_T, "forward_into"):
                 self.scorenet_T.forward_into(vol, lab, gvol)
@@ -469,9 +476,9 @@ class ALD2DTime(_SenseChainMixin, ALDOptimizer):
                     nz = torch.cat([nr, ni]).reshape(P2, ksz, ksz, T).permute(0, 1, 3, 2).to(state.device, torch.float32).contiguous()
                 _lib.check(L.ipdm_langevin_update(vol.data_ptr(), gvol.data_ptr(), _lib.ptr(nz), None, vol.numel(), _scalars(step_T),
                                                   None, None, None, 0, seed_T, k, _lib.stream()), "langevin_update_T")
-            _lib.check(L.ipdm_patch_fold(state.data_ptr(), vol.data_ptr(), B, T, H, W, ksz, sh, sw, 1, _lib.stream()), "patch_unfold")
+            fold(1, sh, sw, shifts, cursor)
 
-        def one_step(c, k, noise, sched=None, cursor=None, sched_T=None, with_T=None):
+        def one_step(c, k, noise, sched=None, cursor=None, sched_T=None, with_T=None, shifts=None):
             """spatial_step (:428-449) -> temporal_step (:452-502) -> proximal_step (:543-554)"""
             if not skip_spatial:
                 self._score_into(x_flat, labels, g_flat)
@@ -494,14 +501,14 @@ class ALD2DTime(_SenseChainMixin, ALDOptimizer):
             if tv:
                 _lib.check(L.ipdm_temporal_tv_step(state.data_ptr(), B, T, H * W, lamda_T, _lib.stream()), "temporal_tv_step")
             elif temporal_on[c] if with_T is None else with_T:
-                temporal_diffusion(c, k, sched_T, cursor)
+                temporal_diffusion(c, k, sched_T, cursor, shifts=shifts)
             # data consistency only: step = noise_scale = 0 turns the fused kernel into x - kappa*(A^H A x - b)
             self._sense_step(state, grad, None, bvec, prox_only, None, None, seed, k)
 
         if fast and not skip_spatial:
             sched_host = ald_schedule(sigmas, n_steps_each, step_lr, kappa)
             n_total = sched_host.shape[0]
-            key = ("cine", B, T, H, W, n_total, n_steps_each, seed, mode_T, lamda_T, float(kappa), state.device)
+            key = ("cine", B, T, H, W, n_total, n_steps_each, seed, mode_T, lamda_T, float(kappa), bool(diffusion and random_shift), state.device)
             fc = self._fast_cache.get(key)
             real = (state, bvec)
             if fc is None:
@@ -510,6 +517,8 @@ class ALD2DTime(_SenseChainMixin, ALDOptimizer):
                       "cursor": torch.zeros(1, dtype=torch.int32, device=state.device)}
                 if diffusion:
                     fc.update(vol=vol, gvol=gvol, sched_T=torch.zeros_like(sched_host, device=state.device))
+                    if random_shift:
+                        fc["shifts"] = torch.zeros(n_total, 2, dtype=torch.int32, device=state.device)
                 self._fast_cache[key] = fc
             state, grad, bvec, labels_all = fc["state"], fc["grad"], fc["bvec"], fc["labels"]
             labels = labels_all[:2 * BT]
@@ -518,7 +527,7 @@ class ALD2DTime(_SenseChainMixin, ALDOptimizer):
             x_flat, g_flat = state.view(2 * BT, 1, H, W), grad.view(2 * BT, 1, H, W)
             if "step" not in fc:
                 def body(with_T, fc=fc):
-                    one_step(0, 0, None, fc["sched"], fc["cursor"], fc.get("sched_T"), with_T)
+                    one_step(0, 0, None, fc["sched"], fc["cursor"], fc.get("sched_T"), with_T, fc.get("shifts"))
                     _lib.check(L.ipdm_ald_advance(fc["cursor"].data_ptr(), fc["labels"].data_ptr(), fc["labels"].numel(), n_steps_each,
                                                   _lib.stream()), "ald_advance")
                 # the temporal prior is skipped on the levels whose remapped sigma_T is -1 (Q14): one captured step without
@@ -531,6 +540,14 @@ class ALD2DTime(_SenseChainMixin, ALDOptimizer):
             fc["sched"].copy_(sched_host)
             if diffusion:
                 fc["sched_T"].copy_(ald_schedule(torch.where(sig_T > 0, sig_T, sig_T[-1]), n_steps_each, step_lr * lamda_T))
+            if "shifts" in fc:
+                # the rolls of the whole chain, drawn in the order the per-step path (and the reference, :466-470) draws them:
+                # one np.random.randint(0, k, (2,)) per step that runs the temporal prior
+                tab = np.zeros((n_total, 2), dtype=np.int32)
+                for i in range(n_total):
+                    if temporal_on[i // n_steps_each]:
+                        tab[i] = np.random.randint(0, ksz, (2,))
+                fc["shifts"].copy_(torch.from_numpy(tab))
             fc["cursor"].zero_()
             labels_all.zero_()
             self.launches_per_step = fc["step_T"].launches if "step_T" in fc else fc["step"].launches

@@ -335,6 +335,11 @@ class EmuLib:
             S.copy_(torch.roll(r, (-sh, -sw), (-2, -1)))
         return 0
 
+    def ipdm_patch_fold_sched(self, state, vol, B, T, H, W, k, shifts, cursor, unfold, stream):
+        c = int(_np(cursor, (1,), np.int32)[0])
+        sh, sw = (int(v) for v in _np(shifts + 8 * c, (2,), np.int32))
+        return self.ipdm_patch_fold(state, vol, B, T, H, W, k, sh, sw, unfold, stream)
+
     def ipdm_conv_igemm(self, dp, stream):
         d = _deref(dp)
         assert d.Cin % 64 == 0 and d.Cout % 128 == 0

@@ -250,6 +250,38 @@ def case_sampler_cine_diffusion(dev):
     torch.set_grad_enabled(True)
 
 
+def case_cine_diffusion_shift_graph(dev):
+    """if_random_shift=True on the captured-graph path (per-step rolls read from a device table, ipdm_patch_fold_sched)
+    against the per-step path that draws np.random.randint at every temporal step: same np.random seed, same Philox keys
+    => the same chain; a different np.random seed => a different one (the rolls are really applied)."""
+    from inverseproblemwithdiffusionmodel_b200.ncsn.models.ncsn3d import NCSN3DShallow
+    n, T = 32, 8
+    cfg = make_config("CINE127", 8, n, 10, 20.0, device=dev)
+    net, _ = build_net(NCSNv2Deepest, "NCSNv2Deepest_ngf8", 5, cfg, dev)
+    sig = get_sigmas(cfg, mode="recons")
+    A = SENSE("exp", 4, 16, 1 / 8, (1, n, n), 0)
+    A.random_under_fourier.mask = keep_center_mask(n, 4, 1 / 8, seed=0)
+    meas = A(phantom(1702, T, 1, n, n).to(dev)).reshape(4, 1, T, 1, n, n)
+    cfg_T = make_config("CINE127", 128, T, 6, 0.2, device=dev)
+    cfg_T.data.channels, cfg_T.data.channels_3d = 64, 1
+    sig_T = get_sigmas(cfg_T)
+    params = {"n_steps_each": 2, "step_lr": 1e-4}
+    outs = {}
+    for tag, graph, npseed in (("graph", True, 21), ("eager", False, 21), ("graph_other_rolls", True, 22)):
+        net_T, _ = build_net(NCSN3DShallow, "NCSN3DShallow_ngf128", 13, cfg_T, dev)
+        sampler = ALD.ALD2DTime(L2Penalty(A), net_T, sig_T, (1, T, 1, n, n), net, sig, params, cfg,
+                                measurement=meas, linear_tfm=A, device=torch.device(dev))
+        np.random.seed(npseed)
+        outs[tag] = sampler(save_dir="/tmp", lr_scaled=1e4, mode_T="diffusion1d", lamda_T=0.5, if_random_shift=True, seed=3,
+                            cuda_graph=graph)[0]
+        torch.set_grad_enabled(True)
+    assert torch.isfinite(outs["graph"].abs()).all()
+    err = rel_l2(outs["graph"], outs["eager"])
+    assert err < 1e-5, err
+    assert rel_l2(outs["graph_other_rolls"], outs["graph"]) > 1e-4
+    return err
+
+
 # ------------------------------------------------------------------------------------------------ samplers
 def case_sampler_uncond(dev):
     g = G("samplers")

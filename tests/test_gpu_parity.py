@@ -465,6 +465,10 @@ def test_sampler_cine_learned_temporal_prior():
     C.case_sampler_cine_diffusion(DEV)
 
 
+def test_cine_random_shift_graph_path_matches_per_step_path():
+    C.case_cine_diffusion_shift_graph(DEV)
+
+
 def test_conv3d_via_slices_vs_torch():
     """One 3x3x3 dilated convolution = three slice-shifted launches of the 2-D tensor-core kernels, against
     torch.nn.functional.conv3d on the same f16-rounded operands (d = 1, 2: persistent halo kernel; d = 4: per-tap kernel)."""
