@@ -23,7 +23,10 @@ cfg_T.data.channels, cfg_T.data.channels_3d = 64, 1
 torch.manual_seed(1)
 net_T = NCSN3DShallow(cfg_T).to(dev).eval()
 sig_T = C.get_sigmas(cfg_T)
+only = sys.argv[2].split(",") if len(sys.argv) > 2 else None
 for mode_T, lam in (("tv", 0.01), ("diffusion1d", 1.0)):
+    if only and mode_T not in only:
+        continue
     smp = C.ALD.ALD2DTime(C.L2Penalty(A), net_T, sig_T, (1, 24, 1, n, n), net, sig, {"n_steps_each": 3, "step_lr": 1e-4}, cfg,
                           measurement=meas, linear_tfm=A, device=dev)
     torch.cuda.synchronize(); t0 = time.perf_counter()
