@@ -333,8 +333,9 @@ def run_native(args):
     achieved = conv_flop / (ms_res / 1e3) / 1e12
     step_conv_tflops = 2 * B * CONV_FLOP_PER_FORWARD_256 * (n / 256) ** 2 / (ms_total / args.steps / 1e3) / 1e12
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this very shape
-    # (profiles/r01_ncu_conv_halo_res_mode.txt: 1.434 GB + 1.363 GB at 28 images of 256^2; algorithmic 2.58 GB)
-    traffic = 2.797738e9 if (N == 28 and n == 256) else None
+    # (profiles/r01_ncu_conv_halo_res_mode.txt: 1.412 GB read + 1.359 GB written at 28 images of 256^2; algorithmic 2.82 GB:
+    # a little of the f16 input is still L2-resident from the previous launch)
+    traffic = 2.770720e9 if (N == 28 and n == 256) else None
     alg_bytes = N * n * n * 128 * (2 + 4 + 4 + 2)
     # Which roofline bounds this variant?  Arithmetic intensity = 2*128*1152 FLOP / 1536 B per pixel = 192 FLOP/B, below
     # the ridge of the measured peaks (burst tensor / HBM copy ~ 258 FLOP/B): by the roofline model it is HBM-bound,
