@@ -199,8 +199,9 @@ def sense_point(torch, C, _lib, L, dev, hbm, coils, size, batch, R, frac):
     state = torch.randn(2, batch, size, size, device=dev); grad = torch.randn_like(state); bvec = torch.randn_like(state)
     mre, _ = A.device_maps(dev); m, frames = A.device_mask(dev)
     sc = _lib.AldScalars(0.1, 0.4, 0.01, 1.0)
-    step = lambda: _lib.check(L.ipdm_ald_sense_step(state.data_ptr(), grad.data_ptr(), None, bvec.data_ptr(), mre.data_ptr(), None,
-                                                    m.data_ptr(), frames, coils, batch, size, size, sc, None, None, 1, 0, _lib.stream()))
+    plan = A.device_plan(dev, size)
+    step = lambda: _lib.check(L.ipdm_ald_sense_step_plan(plan.handle, state.data_ptr(), grad.data_ptr(), None, bvec.data_ptr(), mre.data_ptr(), None,
+                                                         coils, batch, size, sc, None, None, _lib.rng(1, 0), _lib.stream()))
     t = {"forward": best(lambda: A(x)), "adjoint": best(lambda: A.conj_op_masked(S)), "conj_op_unmasked": best(lambda: A.conj_op(S)),
          "fused_ald_step": best(step)}
     out = {"point": f"{coils} coils, {size}x{size}, batch {batch}, R={R} ({int(A.random_under_fourier.mask.sum())} lines), k-space {8 * coils * N / 1e6:.0f} MB",

@@ -28,7 +28,7 @@ extern "C" {
 #define IPDM_E_UNSUPPORTED (-2) /* transform length not a power of two in [8,512], ... */
 #define IPDM_E_DRIVER (-3)      /* driver entry point (tensor-map encode) unavailable  */
 
-int ipdm_abi_version(void);   /* 2 */
+int ipdm_abi_version(void);   /* 3 */
 const char* ipdm_last_error(void);
 /* number of kernels launched by this library in this process so far (bench.py's gpu_launches) */
 unsigned long long ipdm_launch_count(void);
@@ -62,6 +62,28 @@ int ipdm_sense_adjoint(const void* S, const float* maps_re, const float* maps_im
                        int mask_frames, void* out, int ncoils, int batch, int H, int W, int ssos,
                        void* workspace, void* stream);
 
+/* ---- mask plans: the column mask compiled once, on the host, into the tables the fast kernels read ------------
+ * A plan belongs to one (mask, H, W) and to the device that was current at creation; it is immutable afterwards and
+ * may be used from any number of streams / threads at once.  plan_create allocates device memory and copies
+ * synchronously (call it outside graph capture); every *_plan operation below is asynchronous like the rest.
+ *   mask_host  u8 [mask_frames][W] in HOST memory (non-zero = sampled column)
+ * When every frame keeps few columns (<= 32 of W in {256, 512}, <= 16 of 128) and H is in {64,128,256,512} the plan
+ * is "pruned": row transforms compute / consume the sampled columns only and the scratch is compact; otherwise the
+ * *_plan calls run the general masked kernels with the plan's device copy of the mask.  Same results either way.
+ * Replaces nothing in the reference (its mask is a tensor multiplied after a full FFT,
+ * undersampling_fourier.py:77-82); it is the `*_plan_create/_destroy` cache SURVEY 8(b) asks for. */
+int ipdm_sense_plan_create(const uint8_t* mask_host, int mask_frames, int H, int W, void** plan_out);
+int ipdm_sense_plan_destroy(void* plan);
+/* info[8] = { pruned (rows and columns), max sampled columns per frame, compact scratch row length, max active
+ * 32-byte sectors per row, mask_frames, H, W, pruned_rows (the fused step only needs the row transforms) } */
+int ipdm_sense_plan_info(const void* plan, int* info);
+/* ipdm_sense_forward with the plan's mask (x c64 [batch][H][W] -> out c64 [ncoils][batch][H][W]). */
+int ipdm_sense_forward_plan(const void* plan, const void* x, const float* maps_re, const float* maps_im, void* out,
+                            int ncoils, int batch, void* workspace, void* stream);
+/* ipdm_sense_adjoint on data that is zero off the plan's mask (columns off the mask are not read). */
+int ipdm_sense_adjoint_plan(const void* plan, const void* S, const float* maps_re, const float* maps_im, void* out,
+                            int ncoils, int batch, int ssos, void* workspace, void* stream);
+
 /* k-space elementwise helpers for SingleCoil / projection (proximal_op.py:72-94,
  * undersampling_fourier.py:89-97):  mode 0: S *= 1/(1 + a*mask);
  * mode 1: S = a*Y + (1-a)*mask*S + (1-mask)*S   (Y = measured k-space, a = lamda);  mode 2: S *= mask.
@@ -85,16 +107,29 @@ typedef struct {
   float sigma;       /* sigma of this level (informational)                                          */
 } ipdm_ald_scalars;
 
-/* x <- x + step*grad + noise_scale*noise, n floats.  noise == NULL => in-kernel Philox4x32-10 N(0,1)
- * keyed by (seed, element index, *cursor or rng_step).  step_per_sample (f32 [batch], may be NULL)
+/* In-kernel noise: Philox4x32-10 with key = seed (^ *seed_dev) and counter = (position inside the chain, chain id,
+ * step, tag), so the stream of a chain depends on its GLOBAL id only -- not on the rank, the number of ranks or its
+ * slot in the batch (reference draw site ALD_optimizers.py:238-241, per-sample randn_like).  Passed by host
+ * pointer; NULL = all zero. */
+typedef struct {
+  uint64_t seed;
+  const uint64_t* seed_dev; /* device, may be NULL: XORed into `seed` when the kernel runs, so that a captured graph can
+                               be replayed with a fresh stream (successive sampler calls must not repeat their noise) */
+  uint32_t rng_step;        /* step counter; with a device schedule the kernel adds *cursor                         */
+  int32_t chain_base;       /* chain id of sample i = chain_ids ? chain_ids[i] : chain_base + i                      */
+  const int32_t* chain_ids; /* device int32 [samples], may be NULL                                                  */
+  size_t chain_elems;       /* ipdm_langevin_update only: floats per sample (0: the whole buffer is one chain)       */
+} ipdm_rng;
+
+/* x <- x + step*grad + noise_scale*noise, n floats.  noise == NULL => in-kernel N(0,1) (see ipdm_rng; element pairs
+ * (2p, 2p+1) of a sample share one Philox call).  step_per_sample (f32 [batch], may be NULL)
  * overrides `step`/`noise_scale` per sample (sde corrector, sde/sampling.py:320-322); per_sample_elems
  * = elements per sample.  x_mean (may be NULL) receives x + step*grad.
  * Replaces: ALDOptimizer.__call__ update (ncsn/models/ALD_optimizers.py:114-117),
  *   anneal_Langevin_dynamics (ncsn/models/__init__.py:58-61), AnnealedLangevinDynamics.update_fn. */
 int ipdm_langevin_update(float* x, const float* grad, const float* noise, float* x_mean, size_t n,
                          const ipdm_ald_scalars* scalars_host, const ipdm_ald_scalars* sched, const int* cursor,
-                         const float* step_per_sample, size_t per_sample_elems, uint64_t seed, uint32_t rng_step,
-                         void* stream);
+                         const float* step_per_sample, size_t per_sample_elems, const ipdm_rng* rng_host, void* stream);
 
 /* One fused data-consistency ALD step on the planar state x f32 [2][batch][H][W]:
  *     z = x + step*grad + noise_scale*noise          (real and imaginary planes, independent noises)
@@ -102,14 +137,20 @@ int ipdm_langevin_update(float* x, const float* grad, const float* noise, float*
  * with A the SENSE operator (maps, column mask).  Because the mask acts on W only, the H-axis
  * transform cancels in A^H A and the kernel needs only length-W row FFTs.
  * grad planar f32 [2][batch][H][W] (score of the real plane, score of the imaginary plane);
- * noise planar or NULL (Philox).  tv_lamda is reserved (0).
+ * noise planar or NULL (in-kernel: image i of the batch is chain ipdm_rng.chain_ids[i]; the pixels w and w + W/2 of a
+ * row share one Philox call).
  * Replaces: the loop body of ALDInvSegProximalRealImag.__call__ + post_processing
  *   (ALD_optimizers.py:238-241,288-327), ALD2DTime.spatial_step update + proximal_step (:442-449,
  *   543-554) with L2Penalty.__call__ (proximal_op.py:19-51). */
 int ipdm_ald_sense_step(float* x, const float* grad, const float* noise, const float* b, const float* maps_re,
                         const float* maps_im, const uint8_t* mask, int mask_frames, int ncoils, int batch, int H,
                         int W, const ipdm_ald_scalars* scalars_host, const ipdm_ald_scalars* sched,
-                        const int* cursor, uint64_t seed, uint32_t rng_step, void* stream);
+                        const int* cursor, const ipdm_rng* rng_host, void* stream);
+/* The same step with the mask given as a plan (pruned row transforms when the plan allows); H = rows per image. */
+int ipdm_ald_sense_step_plan(const void* plan, float* x, const float* grad, const float* noise, const float* b,
+                             const float* maps_re, const float* maps_im, int ncoils, int batch, int H,
+                             const ipdm_ald_scalars* scalars_host, const ipdm_ald_scalars* sched, const int* cursor,
+                             const ipdm_rng* rng_host, void* stream);
 
 /* labels[i] = *cursor / n_steps_each for i < batch, then (*cursor)++  (one tiny launch per step). */
 int ipdm_ald_advance(int* cursor, int64_t* labels, int batch, int n_steps_each, void* stream);

@@ -25,6 +25,19 @@ class ConvDesc(ctypes.Structure):
                 ("taps", c_int), ("dilation", c_int), ("flags", c_int), ("slices", c_int), ("slice_shift", c_int)]
 
 
+class Rng(ctypes.Structure):
+    """mirror of `ipdm_rng`"""
+    _fields_ = [("seed", c_uint64), ("seed_dev", c_void_p), ("rng_step", c_uint32), ("chain_base", ctypes.c_int32),
+                ("chain_ids", c_void_p), ("chain_elems", c_size_t)]
+
+
+def rng(seed=0, rng_step=0, chain_ids=None, chain_elems=0, seed_dev=None, chain_base=0):
+    """`ipdm_rng` for one call.  chain_ids: int32 device tensor of GLOBAL chain ids (one per sample) or None
+    (sample i is chain chain_base + i); seed_dev: uint64/int64 device tensor[1] XORed into `seed` on the device."""
+    return Rng(int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(seed_dev), int(rng_step) & 0xFFFFFFFF, int(chain_base), ptr(chain_ids),
+               int(chain_elems))
+
+
 CONV_F16_ELU, CONV_F16_PRE_RES, CONV_RES_ELU, CONV_POOL2 = 1, 2, 4, 8
 
 # name -> (restype, argtypes); every symbol of include/ipdm_b200.h
@@ -37,10 +50,17 @@ SIGNATURES = {
     "ipdm_sense_adjoint": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ipdm_kspace_combine": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_int, c_int, c_int, c_void_p]),
     "ipdm_caxpy": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_size_t, c_void_p]),
+    "ipdm_sense_plan_create": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_void_p)]),
+    "ipdm_sense_plan_destroy": (c_int, [c_void_p]),
+    "ipdm_sense_plan_info": (c_int, [c_void_p, POINTER(c_int)]),
+    "ipdm_sense_forward_plan": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "ipdm_sense_adjoint_plan": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ipdm_langevin_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, POINTER(AldScalars), c_void_p, c_void_p,
-                                     c_void_p, c_size_t, c_uint64, c_uint32, c_void_p]),
+                                     c_void_p, c_size_t, POINTER(Rng), c_void_p]),
     "ipdm_ald_sense_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
-                                    c_int, c_int, POINTER(AldScalars), c_void_p, c_void_p, c_uint64, c_uint32, c_void_p]),
+                                    c_int, c_int, POINTER(AldScalars), c_void_p, c_void_p, POINTER(Rng), c_void_p]),
+    "ipdm_ald_sense_step_plan": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                         POINTER(AldScalars), c_void_p, c_void_p, POINTER(Rng), c_void_p]),
     "ipdm_ald_advance": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "ipdm_temporal_tv_step": (c_int, [c_void_p, c_int, c_int, c_size_t, c_float, c_void_p]),
     "ipdm_planar_to_c64": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -101,6 +121,37 @@ def check(rc, what=""):
 def ptr(t):
     """device pointer of a torch tensor (None -> NULL)"""
     return None if t is None else t.data_ptr()
+
+
+def fresh_seed():
+    """A seed drawn from torch's global generator -- what a sampler uses when the caller passes none, so that
+    successive calls draw fresh noise (like the reference's torch.randn_like) and torch.manual_seed reproduces a run."""
+    import torch
+    return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+
+class SensePlan:
+    """Owner of one `ipdm_sense_plan_*` handle (a column mask compiled for one device and one (H, W))."""
+
+    def __init__(self, mask_u8_host, H, W):
+        import numpy as np
+        m = np.ascontiguousarray(mask_u8_host, dtype=np.uint8).reshape(-1, W)
+        self.frames, self.H, self.W = int(m.shape[0]), int(H), int(W)
+        handle = c_void_p()
+        check(lib().ipdm_sense_plan_create(m.ctypes.data, self.frames, self.H, self.W, ctypes.byref(handle)), "sense_plan_create")
+        self.handle = handle
+        info = (c_int * 8)()
+        check(lib().ipdm_sense_plan_info(self.handle, info), "sense_plan_info")
+        self.pruned, self.ns_max, self.ns_pad, self.groups_max = bool(info[0]), info[1], info[2], info[3]
+        self.pruned_rows = bool(info[7])
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) and _lib is not None:
+                _lib.ipdm_sense_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
 
 
 def stream():

@@ -77,10 +77,26 @@ __device__ __forceinline__ float u01_open(uint32_t r) {
   return (static_cast<float>(r >> 9) + 0.5f) * (1.0f / 8388608.0f);
 }
 
-// (n0, n1) ~ N(0,1) for element `idx` of step `step` under `seed`.
-__device__ __forceinline__ float2 philox_normal2(uint64_t seed, uint64_t idx, uint32_t step) {
+// ---- noise streams keyed by CHAIN -------------------------------------------------------------------------------
+// chain i draws from Philox(key = seed, counter = (position inside the chain, chain id, step, tag)), so a
+// chain's noise does not depend on the rank it runs on, on the number of ranks or on its slot in the rank's batch
+// (reference draw site: ncsn/models/ALD_optimizers.py:238-241, per-sample torch.randn_like).
+struct RngArgs {
+  uint64_t seed;
+  const unsigned long long* seed_dev;   // optional: XORed into seed at run time (a captured graph replays with fresh streams)
+  uint32_t step;                        // step counter (added to *cursor when the step comes from a device schedule)
+  int chain_base;                       // chain id of sample i = chain_ids ? chain_ids[i] : chain_base + i
+  const int* chain_ids;
+};
+__device__ __forceinline__ uint64_t rng_seed(const RngArgs& r) { return r.seed_dev ? (r.seed ^ *r.seed_dev) : r.seed; }
+__device__ __forceinline__ uint32_t rng_chain(const RngArgs& r, size_t i) {
+  return (uint32_t)(r.chain_ids ? r.chain_ids[i] : r.chain_base + (int)i);
+}
+
+// (n0, n1) ~ N(0,1) for the element pair `pair` of chain `chain` at step `step` under `seed` (generic Langevin kernel).
+__device__ __forceinline__ float2 philox_normal2(uint64_t seed, uint32_t chain, uint64_t pair, uint32_t step) {
   uint32_t r[4];
-  philox4x32_10(static_cast<uint32_t>(idx), static_cast<uint32_t>(idx >> 32), step, 0x1BD11BDAu,
+  philox4x32_10(static_cast<uint32_t>(pair), chain, step, 0x1BD11BDAu ^ static_cast<uint32_t>(pair >> 32),
                 static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
   const float u0 = u01_open(r[0]), u1 = u01_open(r[1]);
   const float rad = sqrtf(fmaxf(-2.0f * logf(u0), 0.0f));
@@ -89,12 +105,12 @@ __device__ __forceinline__ float2 philox_normal2(uint64_t seed, uint64_t idx, ui
   return make_float2(rad * c, rad * s);
 }
 
-// Four N(0,1) per Philox call (both Box-Muller pairs), SFU log / sincos: the fused-step kernels draw the noise of
-// two complex pixels at once.  out = (re0, im0, re1, im1) for pixel pair `idx` of step `step` under `seed`.
-__device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t idx, uint32_t step, float out[4]) {
+// Four N(0,1) per Philox call (both Box-Muller pairs), SFU log / sincos: the noise of the complex pixels `pix` and
+// `pix + W/2` of one image row -- out = (re, im, re', im').  Every fused-step kernel family (pruned, two-pass,
+// Stockham) pairs pixels the same way, so the in-kernel noise of a chain does not depend on which one runs.
+__device__ __forceinline__ void philox_chain_normal4(uint64_t seed, uint32_t chain, uint32_t pix, uint32_t step, float out[4]) {
   uint32_t r[4];
-  philox4x32_10(static_cast<uint32_t>(idx), static_cast<uint32_t>(idx >> 32), step, 0x1BD11BDBu,
-                static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
+  philox4x32_10(pix, chain, step, 0x1BD11BDBu, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
 #pragma unroll
   for (int p = 0; p < 2; ++p) {
     const float u0 = u01_open(r[2 * p]), u1 = u01_open(r[2 * p + 1]);

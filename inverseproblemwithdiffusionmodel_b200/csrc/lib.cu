@@ -17,6 +17,6 @@ void set_error(const char* fmt, ...) {
 
 }  // namespace ipdm
 
-extern "C" int ipdm_abi_version(void) { return 2; }
+extern "C" int ipdm_abi_version(void) { return 3; }
 extern "C" const char* ipdm_last_error(void) { return ipdm::g_err; }
 extern "C" unsigned long long ipdm_launch_count(void) { return ipdm::g_launches.load(); }

@@ -13,7 +13,9 @@
 // kernel does update + prox (k_ald_sense).
 #include "common.cuh"
 #include "fft_core.cuh"
+#include "sense_plan.h"
 #include <stdlib.h>
+#include <string.h>
 
 namespace ipdm {
 
@@ -340,8 +342,7 @@ struct AldArgs {
   ipdm_ald_scalars sc;
   const ipdm_ald_scalars* sched;
   const int* cursor;
-  uint64_t seed;
-  uint32_t rng_step;
+  RngArgs rng;
 };
 
 template <int L>
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(Tile<L>::NT) k_ald_sense(AldArgs a) {
   const int b = blockIdx.y, h = blockIdx.x * TL::ROWS + r;
   const bool valid = h < a.H;
   ipdm_ald_scalars sc = a.sc;
-  uint32_t rstep = a.rng_step;
+  uint32_t rstep = a.rng.step;
   if (a.sched != nullptr) {
     const int cur = *a.cursor;
     sc = a.sched[cur];
@@ -371,12 +372,26 @@ __global__ void __launch_bounds__(Tile<L>::NT) k_ald_sense(AldArgs a) {
 #pragma unroll
   for (int q = 0; q < TL::E; ++q) {
     const size_t o = rowoff + t + q * TL::TPF;
-    float2 n;
-    if (a.noise != nullptr) n = make_float2(a.noise[o], a.noise[plane + o]);
-    else n = philox_normal2(a.seed, o, rstep);
-    z[q].x = a.x[o] + sc.step * a.grad[o] + sc.noise_scale * n.x;
-    z[q].y = a.x[plane + o] + sc.step * a.grad[plane + o] + sc.noise_scale * n.y;
+    z[q].x = a.x[o] + sc.step * a.grad[o];
+    z[q].y = a.x[plane + o] + sc.step * a.grad[plane + o];
+    if (a.noise != nullptr) {
+      z[q].x += sc.noise_scale * a.noise[o];
+      z[q].y += sc.noise_scale * a.noise[plane + o];
+    }
     acc[q] = cf32{0.f, 0.f};
+  }
+  if (a.noise == nullptr && sc.noise_scale != 0.f) {
+    const uint64_t seed = rng_seed(a.rng);
+    const uint32_t chain = rng_chain(a.rng, b);
+#pragma unroll
+    for (int q = 0; q < TL::E / 2; ++q) {   // pixels w and w + W/2 share one Philox call, as in every kernel family
+      float n[4];
+      philox_chain_normal4(seed, chain, (uint32_t)((valid ? h : 0) * L + t + q * TL::TPF), rstep, n);
+      z[q].x += sc.noise_scale * n[0];
+      z[q].y += sc.noise_scale * n[1];
+      z[q + TL::E / 2].x += sc.noise_scale * n[2];
+      z[q + TL::E / 2].y += sc.noise_scale * n[3];
+    }
   }
   __syncthreads();
   for (int c = 0; c < a.ncoils; ++c) {
@@ -410,6 +425,7 @@ __global__ void __launch_bounds__(Tile<L>::NT) k_ald_sense(AldArgs a) {
 
 }  // namespace ipdm
 #include "sense_fast.cuh"
+#include "sense_pruned.cuh"
 namespace ipdm {
 
 // ---- launch helpers ---------------------------------------------------------------------------
@@ -550,6 +566,93 @@ static int launch_cols(bool fwd, const SenseArgs& a, cudaStream_t s) {
   return launched(fwd ? "k_fwd_cols" : "k_adj_cols");
 }
 
+
+// ---- mask plans -----------------------------------------------------------------------------------------------
+struct SensePlan {
+  uint32_t magic;
+  int device, frames, H, W, ns_max, ns_pad, ng_max, nout;
+  bool pruned_rows, pruned_2d;
+  unsigned char* buf;       // one device allocation holding every table
+  const uint8_t* mask_dev;  // [frames][W]
+  PlanView view;
+};
+static constexpr uint32_t PLAN_MAGIC = 0x53504c4eu;   // "SPLN"
+
+static const SensePlan* as_plan(const void* p) {
+  const SensePlan* pl = static_cast<const SensePlan*>(p);
+  return (pl != nullptr && pl->magic == PLAN_MAGIC) ? pl : nullptr;
+}
+
+template <int LH> static std::vector<float> tws_for() { return build_tws_host(LH, P2<LH>::R0, P2<LH>::R1); }
+
+template <int L, int NOUT>
+static int launch_pruned_rows(bool fwd, const SenseArgs& a, const PlanView& v, cudaStream_t s) {
+  using G = PGeo<L>;
+  dim3 grid(a.batch, a.H / G::TPC);
+  const bool cplx = a.mim != nullptr;
+  if (fwd) {
+    if (cplx) kp_fwd_rows<L, NOUT, true><<<grid, G::NT, 0, s>>>(a, v);
+    else kp_fwd_rows<L, NOUT, false><<<grid, G::NT, 0, s>>>(a, v);
+  } else {
+    if (cplx) kp_adj_rows<L, NOUT, true><<<grid, G::NT, 0, s>>>(a, v);
+    else kp_adj_rows<L, NOUT, false><<<grid, G::NT, 0, s>>>(a, v);
+  }
+  return launched(fwd ? "kp_fwd_rows" : "kp_adj_rows");
+}
+
+static int launch_pruned_rows_any(bool fwd, const SenseArgs& a, const SensePlan* pl, cudaStream_t s) {
+  const int key = a.W * 10 + pl->nout;
+  switch (key) {
+    case 5121: return launch_pruned_rows<512, 1>(fwd, a, pl->view, s);
+    case 2561: return launch_pruned_rows<256, 1>(fwd, a, pl->view, s);
+    case 2562: return launch_pruned_rows<256, 2>(fwd, a, pl->view, s);
+    case 1281: return launch_pruned_rows<128, 1>(fwd, a, pl->view, s);
+    case 1282: return launch_pruned_rows<128, 2>(fwd, a, pl->view, s);
+  }
+  set_error("pruned rows: no kernel for W=%d with %d outputs per thread", a.W, pl->nout);
+  return IPDM_E_UNSUPPORTED;
+}
+
+static int launch_pruned_cols(bool fwd, const SenseArgs& a, const SensePlan* pl, cudaStream_t s) {
+  const int chunks = (pl->ng_max + 3) / 4;
+#define PCOLS_CASE(LL)                                                                   \
+  {                                                                                      \
+    using G = Geo<LL>;                                                                   \
+    dim3 grid(a.ncoils * a.batch, chunks);                                               \
+    if (fwd) {                                                                           \
+      if (int e = set_smem(kp_fwd_cols<LL>, G::SMEM_COLS)) return e;                     \
+      kp_fwd_cols<LL><<<grid, G::NT_COLS, G::SMEM_COLS, s>>>(a, pl->view);               \
+    } else {                                                                             \
+      if (int e = set_smem(kp_adj_cols<LL>, G::SMEM_COLS)) return e;                     \
+      kp_adj_cols<LL><<<grid, G::NT_COLS, G::SMEM_COLS, s>>>(a, pl->view);               \
+    }                                                                                    \
+  }
+  IPDM_FOR_FAST_LEN(a.H, PCOLS_CASE)
+#undef PCOLS_CASE
+  return launched(fwd ? "kp_fwd_cols" : "kp_adj_cols");
+}
+
+template <int L, int NOUT>
+static int launch_pruned_ald(const AldArgs& a, const PlanView& v, cudaStream_t s) {
+  using G = PGeo<L>;
+  dim3 grid(a.batch, a.H / G::TPC);
+  if (a.mim != nullptr) kp_ald_sense<L, NOUT, true><<<grid, G::NT, 0, s>>>(a, v);
+  else kp_ald_sense<L, NOUT, false><<<grid, G::NT, 0, s>>>(a, v);
+  return launched("kp_ald_sense");
+}
+
+static RngArgs rng_args(const ipdm_rng* r) {
+  RngArgs o{};
+  if (r != nullptr) {
+    o.seed = r->seed;
+    o.seed_dev = reinterpret_cast<const unsigned long long*>(r->seed_dev);
+    o.step = r->rng_step;
+    o.chain_base = r->chain_base;
+    o.chain_ids = r->chain_ids;
+  }
+  return o;
+}
+
 static bool pow2_ok(int n) { return n >= 8 && n <= 512 && (n & (n - 1)) == 0; }
 
 // ---- small elementwise kernels ------------------------------------------------------------------
@@ -604,30 +707,36 @@ struct LangevinArgs {
   const int* cursor;
   const float* step_per_sample;
   size_t per_sample;
-  uint64_t seed;
-  uint32_t rng_step;
+  RngArgs rng;
+  size_t chain_elems;   // floats per chain (0: the whole buffer is chain rng_chain(0))
 };
 
 __global__ void k_langevin(LangevinArgs a) {
   ipdm_ald_scalars sc = a.sc;
-  uint32_t rstep = a.rng_step;
+  uint32_t rstep = a.rng.step;
   if (a.sched != nullptr) {
     const int cur = *a.cursor;
     sc = a.sched[cur];
     rstep += (uint32_t)cur;
   }
-  // two elements per thread so one Philox call feeds both
-  const size_t pairs = (a.n + 1) / 2;
-  for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < pairs; p += (size_t)gridDim.x * blockDim.x) {
-    const size_t i0 = 2 * p, i1 = 2 * p + 1;
-    float2 nz;
-    if (a.noise != nullptr) nz = make_float2(a.noise[i0], i1 < a.n ? a.noise[i1] : 0.f);
-    else nz = philox_normal2(a.seed, p, rstep);
+  const bool draw = a.noise == nullptr && (sc.noise_scale != 0.f || a.step_per_sample != nullptr);
+  const uint64_t seed = draw ? rng_seed(a.rng) : 0;
+  // two elements per thread so one Philox call feeds both; pairs never straddle two chains
+  const size_t ce = a.chain_elems ? a.chain_elems : a.n;
+  const size_t ppc = (ce + 1) / 2, nchains = (a.n + ce - 1) / ce;
+  for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < ppc * nchains; p += (size_t)gridDim.x * blockDim.x) {
+    const size_t ci = p / ppc, pl = p % ppc;
+    const size_t i0 = ci * ce + 2 * pl, i1 = i0 + 1;
+    const bool has1 = 2 * pl + 1 < ce && i1 < a.n;
+    if (i0 >= a.n) continue;
+    float2 nz = make_float2(0.f, 0.f);
+    if (a.noise != nullptr) nz = make_float2(a.noise[i0], has1 ? a.noise[i1] : 0.f);
+    else if (draw) nz = philox_normal2(seed, rng_chain(a.rng, ci), pl, rstep);
     float st0 = sc.step, ns0 = sc.noise_scale, st1 = sc.step, ns1 = sc.noise_scale;
     if (a.step_per_sample != nullptr) {
       st0 = a.step_per_sample[i0 / a.per_sample];
       ns0 = sqrtf(2.f * st0);
-      if (i1 < a.n) {
+      if (has1) {
         st1 = a.step_per_sample[i1 / a.per_sample];
         ns1 = sqrtf(2.f * st1);
       }
@@ -635,7 +744,7 @@ __global__ void k_langevin(LangevinArgs a) {
     const float m0 = a.x[i0] + st0 * a.grad[i0];
     if (a.x_mean) a.x_mean[i0] = m0;
     a.x[i0] = m0 + ns0 * nz.x;
-    if (i1 < a.n) {
+    if (has1) {
       const float m1 = a.x[i1] + st1 * a.grad[i1];
       if (a.x_mean) a.x_mean[i1] = m1;
       a.x[i1] = m1 + ns1 * nz.y;
@@ -777,37 +886,26 @@ extern "C" int ipdm_c64_to_planar(const void* c64, float* planar, size_t n, void
 extern "C" int ipdm_langevin_update(float* x, const float* grad, const float* noise, float* x_mean, size_t n,
                                     const ipdm_ald_scalars* scalars_host, const ipdm_ald_scalars* sched,
                                     const int* cursor, const float* step_per_sample, size_t per_sample_elems,
-                                    uint64_t seed, uint32_t rng_step, void* stream) {
+                                    const ipdm_rng* rng_host, void* stream) {
   IPDM_REQUIRE(x && grad, IPDM_E_BADARG, "langevin_update: null pointer");
   IPDM_REQUIRE(scalars_host || (sched && cursor) || step_per_sample, IPDM_E_BADARG, "langevin_update: no step size given");
   IPDM_REQUIRE(!step_per_sample || per_sample_elems > 0, IPDM_E_BADARG, "langevin_update: per_sample_elems");
+  if (n == 0) return 0;
   LangevinArgs a{};
   a.x = x; a.grad = grad; a.noise = noise; a.x_mean = x_mean; a.n = n;
   if (scalars_host) a.sc = *scalars_host;
   a.sched = sched; a.cursor = cursor; a.step_per_sample = step_per_sample; a.per_sample = per_sample_elems;
-  a.seed = seed; a.rng_step = rng_step;
+  a.rng = rng_args(rng_host);
+  a.chain_elems = rng_host ? rng_host->chain_elems : 0;
+  IPDM_REQUIRE(a.chain_elems == 0 || n % a.chain_elems == 0, IPDM_E_BADARG, "langevin_update: n is not a multiple of chain_elems");
   k_langevin<<<grid_for((n + 1) / 2, 256), 256, 0, as_stream(stream)>>>(a);
   return launched("k_langevin");
 }
 
-extern "C" int ipdm_ald_sense_step(float* x, const float* grad, const float* noise, const float* b,
-                                   const float* maps_re, const float* maps_im, const uint8_t* mask, int mask_frames,
-                                   int ncoils, int batch, int H, int W, const ipdm_ald_scalars* scalars_host,
-                                   const ipdm_ald_scalars* sched, const int* cursor, uint64_t seed, uint32_t rng_step,
-                                   void* stream) {
-  IPDM_REQUIRE(x && grad && b && maps_re, IPDM_E_BADARG, "ald_sense_step: null pointer");
-  IPDM_REQUIRE(scalars_host || (sched && cursor), IPDM_E_BADARG, "ald_sense_step: no scalars given");
-  IPDM_REQUIRE(pow2_ok(W), IPDM_E_UNSUPPORTED, "ald_sense_step: W=%d must be a power of two in [8,512]", W);
-  IPDM_REQUIRE(ncoils >= 1 && batch >= 1 && H >= 1, IPDM_E_BADARG, "ald_sense_step: bad shape");
-  AldArgs a{};
-  a.x = x; a.grad = grad; a.noise = noise; a.bvec = b; a.mre = maps_re; a.mim = maps_im;
-  a.mask = mask; a.mask_frames = mask ? mask_frames : 1;
-  a.ncoils = ncoils; a.batch = batch; a.H = H; a.W = W;
-  if (scalars_host) a.sc = *scalars_host;
-  a.sched = sched; a.cursor = cursor; a.seed = seed; a.rng_step = rng_step;
-  cudaStream_t s = as_stream(stream);
+static int ald_sense_general(const AldArgs& a, cudaStream_t s) {
+  const int H = a.H, W = a.W, batch = a.batch;
   if (use_fast(W, W) && H % 16 == 0) {
-    const bool cplx = maps_im != nullptr;
+    const bool cplx = a.mim != nullptr;
 #define ALD2_CASE(LL)                                                                   \
   {                                                                                     \
     using G = Geo<LL>;                                                                  \
@@ -831,6 +929,53 @@ extern "C" int ipdm_ald_sense_step(float* x, const float* grad, const float* noi
   return launched("k_ald_sense");
 }
 
+extern "C" int ipdm_ald_sense_step(float* x, const float* grad, const float* noise, const float* b,
+                                   const float* maps_re, const float* maps_im, const uint8_t* mask, int mask_frames,
+                                   int ncoils, int batch, int H, int W, const ipdm_ald_scalars* scalars_host,
+                                   const ipdm_ald_scalars* sched, const int* cursor, const ipdm_rng* rng_host,
+                                   void* stream) {
+  IPDM_REQUIRE(x && grad && b && maps_re, IPDM_E_BADARG, "ald_sense_step: null pointer");
+  IPDM_REQUIRE(scalars_host || (sched && cursor), IPDM_E_BADARG, "ald_sense_step: no scalars given");
+  IPDM_REQUIRE(pow2_ok(W), IPDM_E_UNSUPPORTED, "ald_sense_step: W=%d must be a power of two in [8,512]", W);
+  IPDM_REQUIRE(ncoils >= 1 && batch >= 1 && H >= 1, IPDM_E_BADARG, "ald_sense_step: bad shape");
+  AldArgs a{};
+  a.x = x; a.grad = grad; a.noise = noise; a.bvec = b; a.mre = maps_re; a.mim = maps_im;
+  a.mask = mask; a.mask_frames = mask ? mask_frames : 1;
+  a.ncoils = ncoils; a.batch = batch; a.H = H; a.W = W;
+  if (scalars_host) a.sc = *scalars_host;
+  a.sched = sched; a.cursor = cursor; a.rng = rng_args(rng_host);
+  return ald_sense_general(a, as_stream(stream));
+}
+
+extern "C" int ipdm_ald_sense_step_plan(const void* plan, float* x, const float* grad, const float* noise, const float* b,
+                                        const float* maps_re, const float* maps_im, int ncoils, int batch, int H,
+                                        const ipdm_ald_scalars* scalars_host, const ipdm_ald_scalars* sched,
+                                        const int* cursor, const ipdm_rng* rng_host, void* stream) {
+  const SensePlan* pl = as_plan(plan);
+  IPDM_REQUIRE(pl, IPDM_E_BADARG, "ald_sense_step_plan: not a plan");
+  IPDM_REQUIRE(x && grad && b && maps_re, IPDM_E_BADARG, "ald_sense_step_plan: null pointer");
+  IPDM_REQUIRE(scalars_host || (sched && cursor), IPDM_E_BADARG, "ald_sense_step_plan: no scalars given");
+  IPDM_REQUIRE(ncoils >= 1 && batch >= 1 && H >= 1, IPDM_E_BADARG, "ald_sense_step_plan: bad shape");
+  AldArgs a{};
+  a.x = x; a.grad = grad; a.noise = noise; a.bvec = b; a.mre = maps_re; a.mim = maps_im;
+  a.mask = pl->mask_dev; a.mask_frames = pl->frames;
+  a.ncoils = ncoils; a.batch = batch; a.H = H; a.W = pl->W;
+  if (scalars_host) a.sc = *scalars_host;
+  a.sched = sched; a.cursor = cursor; a.rng = rng_args(rng_host);
+  cudaStream_t s = as_stream(stream);
+  static const bool no_pruned = getenv("IPDM_SENSE_NO_PRUNED") != nullptr;   // A/B switch for profiling only
+  if (pl->pruned_rows && !no_pruned && H % 16 == 0) {
+    switch (pl->W * 10 + pl->nout) {
+      case 5121: return launch_pruned_ald<512, 1>(a, pl->view, s);
+      case 2561: return launch_pruned_ald<256, 1>(a, pl->view, s);
+      case 2562: return launch_pruned_ald<256, 2>(a, pl->view, s);
+      case 1281: return launch_pruned_ald<128, 1>(a, pl->view, s);
+      case 1282: return launch_pruned_ald<128, 2>(a, pl->view, s);
+    }
+  }
+  return ald_sense_general(a, s);
+}
+
 extern "C" int ipdm_ald_advance(int* cursor, int64_t* labels, int batch, int n_steps_each, void* stream) {
   IPDM_REQUIRE(cursor && n_steps_each >= 1, IPDM_E_BADARG, "ald_advance: bad argument");
   k_advance<<<1, 128, 0, as_stream(stream)>>>(cursor, labels, batch, n_steps_each);
@@ -848,4 +993,149 @@ extern "C" int ipdm_chain_stats_accumulate(const void* x, double* acc, int chain
   IPDM_REQUIRE(x && acc && chains >= 1, IPDM_E_BADARG, "chain_stats_accumulate: bad argument");
   k_chain_stats<<<grid_for(hw, 256), 256, 0, as_stream(stream)>>>((const cf32*)x, acc, chains, hw);
   return launched("k_chain_stats");
+}
+
+// ---- plans ------------------------------------------------------------------------------------------------------
+extern "C" int ipdm_sense_plan_create(const uint8_t* mask_host, int mask_frames, int H, int W, void** plan_out) {
+  IPDM_REQUIRE(mask_host && plan_out && mask_frames >= 1, IPDM_E_BADARG, "sense_plan_create: bad argument");
+  IPDM_REQUIRE(pow2_ok(W) && H >= 1, IPDM_E_UNSUPPORTED, "sense_plan_create: W=%d must be a power of two in [8,512]", W);
+  PlanHost ph = build_plan_host(mask_host, mask_frames, W);
+  SensePlan* pl = new SensePlan();
+  memset(pl, 0, sizeof(*pl));
+  pl->magic = PLAN_MAGIC;
+  pl->frames = mask_frames; pl->H = H; pl->W = W;
+  pl->ns_max = ph.ns_max; pl->ns_pad = ph.ns_pad; pl->ng_max = ph.ng_max;
+  pl->pruned_rows = ph.pruned;
+  pl->pruned_2d = ph.pruned && fast_len(H);
+  pl->nout = ph.pruned ? (ph.ns_max + ph.R1 - 1) / ph.R1 : 0;
+  if (pl->nout > 2) { pl->pruned_rows = pl->pruned_2d = false; }
+  cudaError_t ce = cudaGetDevice(&pl->device);
+  if (ce != cudaSuccess) { delete pl; set_error("sense_plan_create: %s", cudaGetErrorString(ce)); return (int)ce; }
+  std::vector<float> tws;
+  if (pl->pruned_2d) {
+    switch (H) {
+      case 64: tws = tws_for<64>(); break;
+      case 128: tws = tws_for<128>(); break;
+      case 256: tws = tws_for<256>(); break;
+      default: tws = tws_for<512>(); break;
+    }
+  }
+  // one allocation, every table 256-byte aligned
+  struct Piece { const void* src; size_t bytes; size_t off; };
+  std::vector<Piece> pieces;
+  size_t total = 0;
+  auto add = [&](const void* src, size_t bytes) {
+    pieces.push_back(Piece{src, bytes, total});
+    total += (bytes + 255) & ~(size_t)255;
+    return pieces.size() - 1;
+  };
+  const size_t i_mask = add(ph.mask.data(), ph.mask.size());
+  size_t i_ns = 0, i_ng = 0, i_kcol = 0, i_nat = 0, i_k0c = 0, i_cls = 0, i_tw = 0, i_groups = 0, i_gslot = 0, i_gbm = 0, i_tws = 0;
+  std::vector<uint32_t> cls_words;
+  if (pl->pruned_rows) {
+    i_ns = add(ph.ns.data(), ph.ns.size() * sizeof(int));
+    i_ng = add(ph.ngroups.data(), ph.ngroups.size() * sizeof(int));
+    i_kcol = add(ph.kcol.data(), ph.kcol.size() * sizeof(uint16_t));
+    i_nat = add(ph.nat.data(), ph.nat.size());
+    i_k0c = add(ph.k0c.data(), ph.k0c.size());
+    cls_words.resize((size_t)mask_frames * 5);
+    memcpy(cls_words.data(), ph.cls.data(), cls_words.size() * 4);
+    i_cls = add(cls_words.data(), cls_words.size() * 4);
+    i_tw = add(ph.tw.data(), ph.tw.size() * sizeof(float));
+    i_groups = add(ph.groups.data(), ph.groups.size());
+    i_gslot = add(ph.gslot.data(), ph.gslot.size());
+    i_gbm = add(ph.gbitmap.data(), ph.gbitmap.size() * sizeof(uint32_t));
+    if (!tws.empty()) i_tws = add(tws.data(), tws.size() * sizeof(float));
+  }
+  ce = cudaMalloc(reinterpret_cast<void**>(&pl->buf), total);
+  if (ce != cudaSuccess) { delete pl; set_error("sense_plan_create: cudaMalloc: %s", cudaGetErrorString(ce)); return (int)ce; }
+  for (const Piece& pc : pieces) {
+    if (pc.bytes == 0) continue;
+    ce = cudaMemcpy(pl->buf + pc.off, pc.src, pc.bytes, cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) {
+      cudaFree(pl->buf);
+      delete pl;
+      set_error("sense_plan_create: cudaMemcpy: %s", cudaGetErrorString(ce));
+      return (int)ce;
+    }
+  }
+  auto at = [&](size_t i) { return pl->buf + pieces[i].off; };
+  pl->mask_dev = at(i_mask);
+  if (pl->pruned_rows) {
+    PlanView& v = pl->view;
+    v.frames = mask_frames; v.W = W; v.ns_pad = ph.ns_pad; v.ng_all = W / 4;
+    v.ns = reinterpret_cast<const int*>(at(i_ns));
+    v.ngroups = reinterpret_cast<const int*>(at(i_ng));
+    v.kcol = reinterpret_cast<const uint16_t*>(at(i_kcol));
+    v.nat = at(i_nat);
+    v.k0c = at(i_k0c);
+    v.cls = reinterpret_cast<const uint32_t*>(at(i_cls));
+    v.tw = reinterpret_cast<const cf32*>(at(i_tw));
+    v.groups = at(i_groups);
+    v.gslot = at(i_gslot);
+    v.gbitmap = reinterpret_cast<const uint32_t*>(at(i_gbm));
+    v.tws_h = tws.empty() ? nullptr : reinterpret_cast<const cf32*>(at(i_tws));
+  }
+  *plan_out = pl;
+  return 0;
+}
+
+extern "C" int ipdm_sense_plan_destroy(void* plan) {
+  SensePlan* pl = const_cast<SensePlan*>(as_plan(plan));
+  IPDM_REQUIRE(pl, IPDM_E_BADARG, "sense_plan_destroy: not a plan");
+  pl->magic = 0;
+  cudaFree(pl->buf);
+  delete pl;
+  return 0;
+}
+
+extern "C" int ipdm_sense_plan_info(const void* plan, int* info) {
+  const SensePlan* pl = as_plan(plan);
+  IPDM_REQUIRE(pl && info, IPDM_E_BADARG, "sense_plan_info: bad argument");
+  info[0] = pl->pruned_2d; info[1] = pl->ns_max; info[2] = pl->ns_pad; info[3] = pl->ng_max;
+  info[4] = pl->frames; info[5] = pl->H; info[6] = pl->W; info[7] = pl->pruned_rows;
+  return 0;
+}
+
+static bool plan_pruned_2d(const SensePlan* pl) {
+  static const bool no_pruned = getenv("IPDM_SENSE_NO_PRUNED") != nullptr;   // A/B switch for profiling only
+  return pl->pruned_2d && !no_pruned;
+}
+
+extern "C" int ipdm_sense_forward_plan(const void* plan, const void* x, const float* maps_re, const float* maps_im, void* out,
+                                       int ncoils, int batch, void* workspace, void* stream) {
+  const SensePlan* pl = as_plan(plan);
+  IPDM_REQUIRE(pl, IPDM_E_BADARG, "sense_forward_plan: not a plan");
+  if (!plan_pruned_2d(pl))
+    return ipdm_sense_forward(x, maps_re, maps_im, pl->mask_dev, pl->frames, out, ncoils, batch, pl->H, pl->W, workspace, stream);
+  IPDM_REQUIRE(x && out && workspace, IPDM_E_BADARG, "sense_forward_plan: null pointer");
+  IPDM_REQUIRE(ncoils >= 1 && batch >= 1, IPDM_E_BADARG, "sense_forward_plan: bad ncoils/batch");
+  IPDM_REQUIRE(maps_re != nullptr || ncoils == 1, IPDM_E_BADARG, "sense_forward_plan: maps NULL needs ncoils == 1");
+  const int H = pl->H, W = pl->W;
+  SenseArgs a{};
+  a.in = (const cf32*)x; a.out = (cf32*)out; a.ws = (cf32*)workspace;
+  a.mre = maps_re; a.mim = maps_im; a.mask = pl->mask_dev; a.mask_frames = pl->frames;
+  a.ncoils = ncoils; a.batch = batch; a.H = H; a.W = W; a.ssos = 0; a.sparse = 1;
+  a.scale = (((H / 2 + W / 2) & 1) ? -1.f : 1.f) / sqrtf((float)H * (float)W);
+  if (int e = launch_pruned_rows_any(true, a, pl, as_stream(stream))) return e;
+  return launch_pruned_cols(true, a, pl, as_stream(stream));
+}
+
+extern "C" int ipdm_sense_adjoint_plan(const void* plan, const void* S, const float* maps_re, const float* maps_im, void* out,
+                                       int ncoils, int batch, int ssos, void* workspace, void* stream) {
+  const SensePlan* pl = as_plan(plan);
+  IPDM_REQUIRE(pl, IPDM_E_BADARG, "sense_adjoint_plan: not a plan");
+  if (!plan_pruned_2d(pl))
+    return ipdm_sense_adjoint(S, maps_re, maps_im, pl->mask_dev, pl->frames, out, ncoils, batch, pl->H, pl->W, ssos, workspace, stream);
+  IPDM_REQUIRE(S && out && workspace, IPDM_E_BADARG, "sense_adjoint_plan: null pointer");
+  IPDM_REQUIRE(ncoils >= 1 && batch >= 1, IPDM_E_BADARG, "sense_adjoint_plan: bad ncoils/batch");
+  const int H = pl->H, W = pl->W;
+  SenseArgs a{};
+  a.in = (const cf32*)S; a.out = (cf32*)out; a.ws = (cf32*)workspace;
+  a.mre = ssos ? nullptr : maps_re; a.mim = ssos ? nullptr : maps_im;
+  a.mask = pl->mask_dev; a.mask_frames = pl->frames;
+  a.ncoils = ncoils; a.batch = batch; a.H = H; a.W = W; a.ssos = ssos ? 1 : 0;
+  a.scale = (((H / 2 + W / 2) & 1) ? -1.f : 1.f) / sqrtf((float)H * (float)W);
+  if (int e = launch_pruned_cols(false, a, pl, as_stream(stream))) return e;
+  return launch_pruned_rows_any(false, a, pl, as_stream(stream));
 }

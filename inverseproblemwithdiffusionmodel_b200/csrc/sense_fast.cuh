@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(128, (L <= 256 ? 3 : 2)) k2_ald_sense(AldArgs 
   const int t = lane % G::TPF, r = warp * G::RPW + lane / G::TPF;
   const int b = blockIdx.x, h = blockIdx.y * G::TPC + r;
   ipdm_ald_scalars sc = a.sc;
-  uint32_t rstep = a.rng_step;
+  uint32_t rstep = a.rng.step;
   if (a.sched != nullptr) {
     const int cur = *a.cursor;
     sc = a.sched[cur];
@@ -457,15 +457,17 @@ __global__ void __launch_bounds__(128, (L <= 256 ? 3 : 2)) k2_ald_sense(AldArgs 
         z[q].x += sc.noise_scale * nr[a_off<L>(q)];
         z[q].y += sc.noise_scale * ni[a_off<L>(q)];
       }
-    } else {
+    } else if (sc.noise_scale != 0.f) {
+      const uint64_t seed = rng_seed(a.rng);
+      const uint32_t chain = rng_chain(a.rng, b);
 #pragma unroll
-      for (int q = 0; q < G::E; q += 2) {
+      for (int q = 0; q < G::E / 2; ++q) {   // pixels w and w + W/2 share one Philox call, as in every kernel family
         float n[4];
-        philox_normal4(a.seed, rowoff + a_off<L>(q), rstep, n);   // keyed by the first pixel of the pair
+        philox_chain_normal4(seed, chain, (uint32_t)(h * L + a_off<L>(q) + t), rstep, n);
         z[q].x += sc.noise_scale * n[0];
         z[q].y += sc.noise_scale * n[1];
-        z[q + 1].x += sc.noise_scale * n[2];
-        z[q + 1].y += sc.noise_scale * n[3];
+        z[q + G::E / 2].x += sc.noise_scale * n[2];
+        z[q + G::E / 2].y += sc.noise_scale * n[3];
       }
     }
   }

@@ -53,15 +53,23 @@ def _as_c64(X):
     return X.contiguous()
 
 
-def fft2c(X, inverse=False, mask_u8=None, mask_frames=1):
-    """Centred orthonormal 2-D DFT of the last two axes of a CUDA tensor (any leading shape)."""
+def fft2c(X, inverse=False, mask_u8=None, mask_frames=1, plan=None):
+    """Centred orthonormal 2-D DFT of the last two axes of a CUDA tensor (any leading shape).  A column mask is
+    given as a compiled plan (`_lib.SensePlan`) or as a raw u8 [frames][W] device tensor."""
     X = _as_c64(X)
     H, W = X.shape[-2:]
     batch = X.numel() // (H * W)
     out = torch.empty_like(X)
     L = _lib.lib()
     ws = workspace(X.device, L.ipdm_sense_workspace_bytes(1, batch, H, W))
-    if inverse:
+    if plan is not None:
+        if inverse:
+            _lib.check(L.ipdm_sense_adjoint_plan(plan.handle, X.data_ptr(), None, None, out.data_ptr(), 1, batch, 0, ws.data_ptr(),
+                                                 _lib.stream()), "k2i_complex")
+        else:
+            _lib.check(L.ipdm_sense_forward_plan(plan.handle, X.data_ptr(), None, None, out.data_ptr(), 1, batch, ws.data_ptr(),
+                                                 _lib.stream()), "i2k_complex")
+    elif inverse:
         _lib.check(L.ipdm_sense_adjoint(X.data_ptr(), None, None, _lib.ptr(mask_u8), mask_frames, out.data_ptr(),
                                         1, batch, H, W, 0, ws.data_ptr(), _lib.stream()), "k2i_complex")
     else:

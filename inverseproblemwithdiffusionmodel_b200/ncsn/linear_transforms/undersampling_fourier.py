@@ -7,6 +7,7 @@ parity are kept on purpose: the live mask ignores `R` / `center_
 (24,1,1,W) (Q1/Q2), `conj_op` applies no mask (Q3), the coil maps are real float64 (Q4).  The mask
 is a plain attribute that callers may overwrite (e.g. with a (1,1,W) keep-centre mask).
 """
+import contextlib
 import warnings
 
 import numpy as np
@@ -28,12 +29,15 @@ def keep_center_mask(W, R, center_lines_frac, seed):
 
 
 class _MaskCache:
-    """uint8 [frames][W] device copy of a broadcastable column mask, rebuilt when the attribute changes."""
+    """uint8 [frames][W] device copy of a broadcastable column mask and its compiled plans (one per image height),
+    rebuilt when the attribute changes."""
 
     def __init__(self):
         self.key = None
         self.dev = None
+        self.host = None
         self.frames = 1
+        self.plans = {}
 
     def get(self, mask, device):
         key = (id(mask), mask._version, device)
@@ -42,10 +46,22 @@ class _MaskCache:
             if mask.numel() % W != 0 or (mask.dim() >= 2 and mask.shape[-2] != 1 and mask.numel() != W):
                 raise _lib.IpdmError(f"mask of shape {tuple(mask.shape)} is not a column mask (…,1,W)")
             flat = (mask.reshape(-1, W) != 0).to(torch.uint8)
+            self.host = flat.cpu().contiguous()
             self.dev = flat.to(device).contiguous()
             self.frames = flat.shape[0]
             self.key = key
+            self.plans = {}
         return self.dev, self.frames
+
+    def plan(self, mask, device, H):
+        """`_lib.SensePlan` of this mask for images of H rows on `device` (created on first use, outside graph capture)."""
+        self.get(mask, device)
+        pl = self.plans.get(H)
+        if pl is None:
+            with (torch.cuda.device(device) if torch.device(device).type == "cuda" else contextlib.nullcontext()):
+                pl = _lib.SensePlan(self.host.numpy(), H, self.host.shape[-1])
+            self.plans[H] = pl
+        return pl
 
 
 def _frames_vs_batch(frames, X):
@@ -77,13 +93,16 @@ class RandomUndersamplingFourier(LinearTransform):
     def device_mask(self, device):
         return self._mc.get(self.mask, device)
 
+    def device_plan(self, device, H):
+        return self._mc.plan(self.mask, device, H)
+
     def __call__(self, X: torch.Tensor) -> torch.Tensor:
         X = _as_c64(X)
         m, frames = self.device_mask(X.device)
         X = _frames_vs_batch(frames, X).contiguous()
         if frames > 1 and X.shape[1] != 1:
             raise _lib.IpdmError("per-frame masks need C == 1")
-        return fft2c(X, inverse=False, mask_u8=m, mask_frames=frames)
+        return fft2c(X, inverse=False, plan=self.device_plan(X.device, X.shape[-2]))
 
     def conj_op(self, S: torch.Tensor) -> torch.Tensor:
         return fft2c(S, inverse=True)
@@ -142,6 +161,9 @@ class SENSE(LinearTransform):
     def device_mask(self, device):
         return self.random_under_fourier.device_mask(device)
 
+    def device_plan(self, device, H):
+        return self.random_under_fourier.device_plan(device, H)
+
     # ---- operator -------------------------------------------------------------------------------
     def __call__(self, X: torch.Tensor) -> torch.Tensor:
         """X: (B, C, H, W) -> (num_sens, B, C, H, W)   (reference :140-150)"""
@@ -157,8 +179,9 @@ class SENSE(LinearTransform):
         out = torch.empty((Nc,) + tuple(X.shape), dtype=torch.complex64, device=X.device)
         L = _lib.lib()
         ws = workspace(X.device, L.ipdm_sense_workspace_bytes(Nc, batch, H, W))
-        _lib.check(L.ipdm_sense_forward(X.data_ptr(), mre.data_ptr(), _lib.ptr(mim), m.data_ptr(), frames, out.data_ptr(),
-                                        Nc, batch, H, W, ws.data_ptr(), _lib.stream()), "SENSE.__call__")
+        plan = self.device_plan(X.device, H)
+        _lib.check(L.ipdm_sense_forward_plan(plan.handle, X.data_ptr(), mre.data_ptr(), _lib.ptr(mim), out.data_ptr(),
+                                             Nc, batch, ws.data_ptr(), _lib.stream()), "SENSE.__call__")
         return out
 
     def _adjoint(self, S, ssos, masked):
@@ -169,14 +192,16 @@ class SENSE(LinearTransform):
             raise _lib.IpdmError(f"SENSE: got {Nc} coil images for {mre.shape[0]} coil maps")
         H, W = S.shape[-2:]
         batch = S[0].numel() // (H * W)
-        m, frames = (None, 1)
-        if masked:
-            m, frames = self.device_mask(S.device)
         out = torch.empty(S.shape[1:], dtype=torch.float32 if ssos else torch.complex64, device=S.device)
         L = _lib.lib()
         ws = workspace(S.device, L.ipdm_sense_workspace_bytes(Nc, batch, H, W))
-        _lib.check(L.ipdm_sense_adjoint(S.data_ptr(), mre.data_ptr(), _lib.ptr(mim), _lib.ptr(m), frames, out.data_ptr(),
-                                        Nc, batch, H, W, 1 if ssos else 0, ws.data_ptr(), _lib.stream()), "SENSE.conj_op")
+        if masked:
+            plan = self.device_plan(S.device, H)
+            _lib.check(L.ipdm_sense_adjoint_plan(plan.handle, S.data_ptr(), mre.data_ptr(), _lib.ptr(mim), out.data_ptr(),
+                                                 Nc, batch, 1 if ssos else 0, ws.data_ptr(), _lib.stream()), "SENSE.conj_op_masked")
+        else:
+            _lib.check(L.ipdm_sense_adjoint(S.data_ptr(), mre.data_ptr(), _lib.ptr(mim), None, 1, out.data_ptr(),
+                                            Nc, batch, H, W, 1 if ssos else 0, ws.data_ptr(), _lib.stream()), "SENSE.conj_op")
         return out
 
     def conj_op(self, S: torch.Tensor) -> torch.Tensor:

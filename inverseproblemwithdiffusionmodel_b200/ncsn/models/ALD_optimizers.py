@@ -11,11 +11,15 @@ imaginary plane), so that
   * a whole step (forward + update + schedule advance) is captured once in a CUDA graph and replayed
     for all L*n_steps_each steps; per-level scalars are read on the device from a schedule table.
 
-Noise is drawn in-kernel (Philox4x32-10 keyed by seed / element / step, so a chain does not depend
-on how chains are spread over GPUs) unless `noise_fn(shape)` is given, which injects host-chosen
-tensors in the reference's draw order -- that is how the parity tests feed identical noise.
+Noise is drawn in-kernel -- Philox4x32-10 with key = seed and counter = (pixel, GLOBAL chain id, step): pass
+`chain_ids` (one id per chain of the batch; default 0..B-1) and the same `seed` on every rank and chain i is the same
+chain whether it runs alone, inside any batch, or on any rank of any world size -- unless `noise_fn(shape)` is given,
+which injects host-chosen tensors in the reference's draw order (that is how the parity tests feed identical noise).
+Without `seed` each call draws a fresh one from torch's global generator, like the reference's `torch.randn_like`
+(so repeated calls give different chains and `torch.manual_seed` reproduces a run); a captured step graph reads the
+seed from device memory and is not re-captured.
 The reference's per-step prints (host syncs) and PNG snapshots are side effects, not results, and
-are not reproduced.  Extra keyword arguments accepted by every `__call__`: `noise_fn`, `seed`,
+are not reproduced.  Extra keyword arguments accepted by every `__call__`: `noise_fn`, `seed`, `chain_ids`,
 `cuda_graph` (default True), `x_init` (override the initial state).
 """
 import abc
@@ -50,6 +54,41 @@ def _default_device():
 def _scalars(step, kappa=0.0, sigma=0.0, noise_on=True):
     step32 = torch.tensor(float(step), dtype=torch.float32)
     return _lib.AldScalars(float(step32), float(torch.sqrt(step32 * 2)) if noise_on else 0.0, float(kappa), float(sigma))
+
+
+def _seed_and_chains(kwargs, n_chains, device, injected):
+    """(seed, int32 device tensor of global chain ids) from the `seed` / `chain_ids` keyword arguments.  With
+    injected noise no seed is needed and torch's global generator is left untouched (the injected draws come from it)."""
+    seed = kwargs.pop("seed", None)
+    seed = (0 if injected else _lib.fresh_seed()) if seed is None else int(seed)
+    ids = kwargs.pop("chain_ids", None)
+    ids = torch.arange(n_chains, dtype=torch.int32) if ids is None else torch.as_tensor(ids, dtype=torch.int32).reshape(-1)
+    if ids.numel() != n_chains:
+        raise ValueError(f"chain_ids has {ids.numel()} entries for {n_chains} chains")
+    return seed, ids.to(device)
+
+
+def _seed_tensor(seed, device):
+    return torch.tensor([seed], dtype=torch.int64, device=device)
+
+
+def data_transform(config, X):
+    """Initial-state transform of the generic sampler (reference helpers/utils.py:212-226): dequantisation noise, the
+    2x-1 rescale or the logit transform, image-mean subtraction.  The identity for every shipped config."""
+    d = config.data
+    if getattr(d, "uniform_dequantization", False):
+        X = X / 256. * 255. + torch.rand_like(X) / 256.
+    if getattr(d, "gaussian_dequantization", False):
+        X = X + torch.randn_like(X) * 0.01
+    if getattr(d, "rescaled", False):
+        X = 2 * X - 1.
+    elif getattr(d, "logit_transform", False):
+        lam = 1e-6
+        X = lam + (1 - 2 * lam) * X
+        X = torch.log(X) - torch.log1p(-X)
+    if hasattr(config, 'image_mean'):
+        return X - config.image_mean.to(X.device)[None, ...]
+    return X
 
 
 def _to_planar(xc):
@@ -139,7 +178,6 @@ class ALDOptimizer(abc.ABC):
     def __call__(self, **kwargs):
         torch.set_grad_enabled(False)
         noise_fn = kwargs.pop("noise_fn", None)
-        seed = int(kwargs.pop("seed", 0))
         use_graph = bool(kwargs.pop("cuda_graph", True))
         x_init = kwargs.pop("x_init", None)
         sigmas = self.sigmas
@@ -148,10 +186,12 @@ class ALDOptimizer(abc.ABC):
         L = _lib.lib()
 
         x_mod = self.init_x_mod() if x_init is None else x_init
-        x_mod = x_mod.to(self.device, torch.float32).contiguous().clone()
+        x_mod = data_transform(self.config, x_mod.to(self.device, torch.float32)).contiguous().clone()   # reference :86
         _lib.require_cuda(x_mod)
-        self.preprocessing_steps(**kwargs)
         B = x_mod.shape[0]
+        seed, chain_ids = _seed_and_chains(kwargs, B, x_mod.device, noise_fn is not None)
+        per_chain = x_mod[0].numel()
+        self.preprocessing_steps(**kwargs)
         grad = torch.empty_like(x_mod)
         labels = torch.zeros(B, dtype=torch.long, device=x_mod.device)
         images = []
@@ -160,21 +200,25 @@ class ALDOptimizer(abc.ABC):
         if fast:
             sched_host = ald_schedule(sigmas, n_steps_each, step_lr)
             n_total = sched_host.shape[0]
-            key = ("uncond", tuple(x_mod.shape), n_total, n_steps_each, seed, x_mod.device)
+            key = ("uncond", tuple(x_mod.shape), n_total, n_steps_each, x_mod.device)
             fc = self._fast_cache.get(key)
             if fc is None:
                 fc = {"x": torch.zeros_like(x_mod), "grad": torch.zeros_like(x_mod), "labels": torch.zeros_like(labels),
                       "sched": torch.zeros_like(sched_host, device=x_mod.device),
-                      "cursor": torch.zeros(1, dtype=torch.int32, device=x_mod.device)}
+                      "cursor": torch.zeros(1, dtype=torch.int32, device=x_mod.device),
+                      "seed": _seed_tensor(0, x_mod.device), "chain_ids": torch.zeros_like(chain_ids)}
 
                 def body(fc=fc):
                     self._score_into(fc["x"], fc["labels"], fc["grad"])
                     _lib.check(L.ipdm_langevin_update(fc["x"].data_ptr(), fc["grad"].data_ptr(), None, None, fc["x"].numel(), None,
-                                                      fc["sched"].data_ptr(), fc["cursor"].data_ptr(), None, 0, seed, 0, _lib.stream()), "langevin_update")
+                                                      fc["sched"].data_ptr(), fc["cursor"].data_ptr(), None, 0,
+                                                      _lib.rng(0, 0, fc["chain_ids"], per_chain, fc["seed"]), _lib.stream()), "langevin_update")
                     _lib.check(L.ipdm_ald_advance(fc["cursor"].data_ptr(), fc["labels"].data_ptr(), B, n_steps_each, _lib.stream()), "ald_advance")
 
                 fc["step"] = _StepGraph(body).prime()
                 self._fast_cache[key] = fc
+            fc["seed"].fill_(seed)
+            fc["chain_ids"].copy_(chain_ids)
             fc["x"].copy_(x_mod)
             fc["sched"].copy_(sched_host)
             fc["cursor"].zero_()
@@ -194,8 +238,8 @@ class ALDOptimizer(abc.ABC):
                     g = self.adjust_grad(grad, x_mod, sigma=sigma, **kwargs)
                     noise = None if noise_fn is None else noise_fn(x_mod.shape).to(x_mod.device, torch.float32).contiguous()
                     _lib.check(L.ipdm_langevin_update(x_mod.data_ptr(), g.contiguous().data_ptr(), _lib.ptr(noise), None,
-                                                      x_mod.numel(), _scalars(step_size), None, None, None, 0, seed, k,
-                                                      _lib.stream()), "langevin_update")
+                                                      x_mod.numel(), _scalars(step_size), None, None, None, 0,
+                                                      _lib.rng(seed, k, chain_ids, per_chain), _lib.stream()), "langevin_update")
                     k += 1
                     if not self.params["final_only"]:
                         images.append(x_mod.to('cpu'))
@@ -203,7 +247,7 @@ class ALDOptimizer(abc.ABC):
             labels.fill_(len(sigmas) - 1)
             self._score_into(x_mod, labels, grad)
             _lib.check(L.ipdm_langevin_update(x_mod.data_ptr(), grad.data_ptr(), None, None, x_mod.numel(),
-                                              _scalars(sigmas[-1] ** 2, noise_on=False), None, None, None, 0, seed, 0,
+                                              _scalars(sigmas[-1] ** 2, noise_on=False), None, None, None, 0, None,
                                               _lib.stream()), "denoise")
             images.append(x_mod.to('cpu'))
         if self.params["final_only"]:
@@ -232,16 +276,17 @@ class _SenseChainMixin:
             b = x0
         return _to_planar(x0), _to_planar(b)
 
-    def _sense_step(self, state, grad, noise, bvec, scalars=None, sched=None, cursor=None, seed=0, rng_step=0):
+    def _sense_step(self, state, grad, noise, bvec, scalars=None, sched=None, cursor=None, rng=None):
         A = self.linear_tfm
         mre, mim = A.device_maps(state.device)
-        m, frames = A.device_mask(state.device)
+        _, frames = A.device_mask(state.device)
         _, Bp, H, W = state.shape
         if frames not in (1, Bp):
             raise RuntimeError(f"mask has {frames} frames but the batch holds {Bp} images")
-        _lib.check(_lib.lib().ipdm_ald_sense_step(state.data_ptr(), grad.data_ptr(), _lib.ptr(noise), bvec.data_ptr(),
-                                                  mre.data_ptr(), _lib.ptr(mim), m.data_ptr(), frames, mre.shape[0], Bp, H, W,
-                                                  scalars, _lib.ptr(sched), _lib.ptr(cursor), seed, rng_step, _lib.stream()),
+        plan = A.device_plan(state.device, H)
+        _lib.check(_lib.lib().ipdm_ald_sense_step_plan(plan.handle, state.data_ptr(), grad.data_ptr(), _lib.ptr(noise), bvec.data_ptr(),
+                                                       mre.data_ptr(), _lib.ptr(mim), mre.shape[0], Bp, H,
+                                                       scalars, _lib.ptr(sched), _lib.ptr(cursor), rng, _lib.stream()),
                    "ald_sense_step")
 
 
@@ -285,7 +330,6 @@ class ALDInvSegProximalRealImag(_SenseChainMixin, ALDOptimizer):
         replays one captured ALD step on the loaded state -- instead of running the schedule."""
         torch.set_grad_enabled(False)
         noise_fn = kwargs.pop("noise_fn", None)
-        seed = int(kwargs.pop("seed", 0))
         use_graph = bool(kwargs.pop("cuda_graph", True))
         return_chain = bool(kwargs.pop("return_chain", False))
         sigmas = self.sigmas
@@ -298,6 +342,8 @@ class ALDInvSegProximalRealImag(_SenseChainMixin, ALDOptimizer):
         Nc, B, C, H, W = y.shape
         if C != 1:
             raise _lib.IpdmError("ALDInvSegProximalRealImag: C must be 1")
+        seed, chain_ids = _seed_and_chains(kwargs, B, y.device, noise_fn is not None)
+        plane_ids = torch.cat([2 * chain_ids, 2 * chain_ids + 1])      # the non-fused path updates the two planes as 2B samples
         state, bvec = self._setup_sense(y.to(torch.complex64).contiguous(), y.device)   # [2][B][H][W]
         self.preprocessing_steps(**kwargs)
         grad = torch.empty_like(state)
@@ -313,20 +359,24 @@ class ALDInvSegProximalRealImag(_SenseChainMixin, ALDOptimizer):
             kappa = l2_kappa(self.linear_tfm, state, step_lr * lr_scaled, 1.)
             sched_host = ald_schedule(sigmas, n_steps_each, step_lr, kappa)
             n_total = sched_host.shape[0]
-            key = ("sense", B, H, W, n_total, n_steps_each, seed, state.device)
+            key = ("sense", B, H, W, n_total, n_steps_each, state.device)
             fc = self._fast_cache.get(key)
             if fc is None:
                 fc = {"state": torch.zeros_like(state), "grad": torch.zeros_like(state), "bvec": torch.zeros_like(state),
                       "labels": torch.zeros_like(labels), "sched": torch.zeros_like(sched_host, device=state.device),
-                      "cursor": torch.zeros(1, dtype=torch.int32, device=state.device)}
+                      "cursor": torch.zeros(1, dtype=torch.int32, device=state.device),
+                      "seed": _seed_tensor(0, state.device), "chain_ids": torch.zeros_like(chain_ids)}
 
                 def body(fc=fc):
                     self._score_into(fc["state"].view(2 * B, 1, H, W), fc["labels"], fc["grad"].view(2 * B, 1, H, W))
-                    self._sense_step(fc["state"], fc["grad"], None, fc["bvec"], None, fc["sched"], fc["cursor"], seed, 0)
+                    self._sense_step(fc["state"], fc["grad"], None, fc["bvec"], None, fc["sched"], fc["cursor"],
+                                     _lib.rng(0, 0, fc["chain_ids"], 0, fc["seed"]))
                     _lib.check(L.ipdm_ald_advance(fc["cursor"].data_ptr(), fc["labels"].data_ptr(), 2 * B, n_steps_each, _lib.stream()), "ald_advance")
 
                 fc["step"] = _StepGraph(body).prime()
                 self._fast_cache[key] = fc
+            fc["seed"].fill_(seed)
+            fc["chain_ids"].copy_(chain_ids)
             fc["state"].copy_(state)
             fc["bvec"].copy_(bvec)
             fc["sched"].copy_(sched_host)
@@ -359,10 +409,12 @@ class ALDInvSegProximalRealImag(_SenseChainMixin, ALDOptimizer):
                         noise = torch.stack([nr.reshape(B, H, W), ni.reshape(B, H, W)], 0).to(state.device, torch.float32).contiguous()
                     if fused:
                         kappa = l2_kappa(self.linear_tfm, state, step_lr * lr_scaled, 1.)
-                        self._sense_step(state, grad, noise, bvec, _scalars(step_size, kappa, sigma), None, None, seed, k)
+                        self._sense_step(state, grad, noise, bvec, _scalars(step_size, kappa, sigma), None, None,
+                                         _lib.rng(seed, k, chain_ids))
                     else:
                         _lib.check(L.ipdm_langevin_update(state.data_ptr(), grad.data_ptr(), _lib.ptr(noise), None, state.numel(),
-                                                          _scalars(step_size), None, None, None, 0, seed, k, _lib.stream()), "langevin_update")
+                                                          _scalars(step_size), None, None, None, 0,
+                                                          _lib.rng(seed, k, plane_ids, H * W), _lib.stream()), "langevin_update")
                         xr, xi = self.post_processing(state[0].unsqueeze(1), state[1].unsqueeze(1), alpha=step_lr, sigma=sigma, **kwargs)
                         state[0].copy_(xr.squeeze(1))
                         state[1].copy_(xi.squeeze(1))
@@ -371,7 +423,7 @@ class ALDInvSegProximalRealImag(_SenseChainMixin, ALDOptimizer):
             labels.fill_(len(sigmas) - 1)
             self._score_into(x_flat, labels, g_flat)
             _lib.check(L.ipdm_langevin_update(state.data_ptr(), grad.data_ptr(), None, None, state.numel(),
-                                              _scalars(sigmas[-1] ** 2, noise_on=False), None, None, None, 0, seed, 0,
+                                              _scalars(sigmas[-1] ** 2, noise_on=False), None, None, None, 0, None,
                                               _lib.stream()), "denoise")
         x_mod = _to_complex(state, (B, 1, H, W))
         self.final_state = x_mod
@@ -401,7 +453,6 @@ class ALD2DTime(_SenseChainMixin, ALDOptimizer):
         (NCSN3DShallow on k x k x T patches, reference :463-502)."""
         torch.set_grad_enabled(False)
         noise_fn = kwargs.pop("noise_fn", None)
-        seed = int(kwargs.pop("seed", 0))
         use_graph = bool(kwargs.pop("cuda_graph", True))
         mode_T = kwargs.get("mode_T", "diffusion1d")
         lamda_T = float(kwargs.get("lamda_T", 1.))
@@ -429,8 +480,12 @@ class ALD2DTime(_SenseChainMixin, ALDOptimizer):
         if not self._fused_ok():
             raise _lib.IpdmError("ALD2DTime: only L2Penalty over SENSE is implemented")
         y = y6.reshape(Nc, B * T, C, H, W).contiguous()
+        seed, chain_ids = _seed_and_chains(kwargs, B, y.device, noise_fn is not None)
         state, bvec = self._setup_sense(y, y.device)                      # [2][B*T][H][W]
         BT = B * T
+        # noise streams: frame t of chain i is sample i*T + t; the generic update sees the two planes as 2*B*T samples
+        frame_ids = (chain_ids.view(B, 1) * T + torch.arange(T, dtype=torch.int32, device=y.device).view(1, T)).reshape(-1).contiguous()
+        plane_ids = torch.cat([2 * frame_ids, 2 * frame_ids + 1])
         grad = torch.zeros_like(state)
         ksz = self.win_size if diffusion else 1
         P2 = 2 * B * (H // ksz) * (W // ksz) if diffusion else 0      # temporal-prior patches (real and imaginary planes)
@@ -443,10 +498,22 @@ class ALD2DTime(_SenseChainMixin, ALDOptimizer):
         fast = use_graph and noise_fn is None
         sig_T = self.sigmas_T.detach().float().cpu()
         temporal_on = [diffusion and float(sig_T[c]) != -1.0 for c in range(len(sigmas))]
-        seed_T = seed ^ 0x5bd1e995
+        SEED_T = 0x5bd1e995                                            # the temporal prior's stream: seed ^ SEED_T
         if diffusion:
             vol = torch.zeros(P2, ksz, T, ksz, dtype=torch.float32, device=state.device)
             gvol = torch.zeros_like(vol)
+            npp = (H // ksz) * (W // ksz)                               # patches per plane and chain, volumes ordered (plane, chain, patch)
+            vol_ids = ((2 * chain_ids.view(1, B, 1) + torch.arange(2, dtype=torch.int32, device=y.device).view(2, 1, 1)) * npp
+                       + torch.arange(npp, dtype=torch.int32, device=y.device).view(1, 1, npp)).reshape(-1).contiguous()
+        ids = {"frame": frame_ids, "plane": plane_ids, "vol": vol_ids if diffusion else None, "seed_dev": None}
+
+        def rng_for(kind, k, temporal=False):
+            """ipdm_rng of one launch: eager steps pass the seed by value, captured steps read it from device memory"""
+            elems = {"frame": 0, "plane": H * W, "vol": ksz * T * ksz}[kind]
+            base = SEED_T if temporal else 0
+            if ids["seed_dev"] is not None:
+                return _lib.rng(base, 0, ids[kind], elems, ids["seed_dev"])
+            return _lib.rng(seed ^ base, k, ids[kind], elems)
 
         def fold(unfold, sh, sw, shifts, cursor):
             if shifts is not None:      # captured step: this step's roll comes from the device table
@@ -467,7 +534,7 @@ class ALD2DTime(_SenseChainMixin, ALDOptimizer):
                 gvol.copy_(self.scorenet_T(flat, lab).reshape(P2, ksz, ksz, T).permute(0, 1, 3, 2))
             if sched_T is not None:
                 _lib.check(L.ipdm_langevin_update(vol.data_ptr(), gvol.data_ptr(), None, None, vol.numel(), None, sched_T.data_ptr(),
-                                                  cursor.data_ptr(), None, 0, seed_T, 0, _lib.stream()), "langevin_update_T")
+                                                  cursor.data_ptr(), None, 0, rng_for("vol", 0, True), _lib.stream()), "langevin_update_T")
             else:
                 step_T = step_lr * (self.sigmas_T[c].float().cpu() / sig_T[-1]) ** 2 * lamda_T
                 nz = None
@@ -475,7 +542,7 @@ class ALD2DTime(_SenseChainMixin, ALDOptimizer):
                     nr, ni = noise_fn((P2 // 2, ksz * ksz, T)), noise_fn((P2 // 2, ksz * ksz, T))
                     nz = torch.cat([nr, ni]).reshape(P2, ksz, ksz, T).permute(0, 1, 3, 2).to(state.device, torch.float32).contiguous()
                 _lib.check(L.ipdm_langevin_update(vol.data_ptr(), gvol.data_ptr(), _lib.ptr(nz), None, vol.numel(), _scalars(step_T),
-                                                  None, None, None, 0, seed_T, k, _lib.stream()), "langevin_update_T")
+                                                  None, None, None, 0, rng_for("vol", k, True), _lib.stream()), "langevin_update_T")
             fold(1, sh, sw, shifts, cursor)
 
         def one_step(c, k, noise, sched=None, cursor=None, sched_T=None, with_T=None, shifts=None):
@@ -485,42 +552,51 @@ class ALD2DTime(_SenseChainMixin, ALDOptimizer):
             if not tv and not diffusion:
                 # Langevin update and L2-penalty step in one kernel
                 if sched is not None:
-                    self._sense_step(state, grad, None, bvec, None, sched, cursor, seed, 0)
+                    self._sense_step(state, grad, None, bvec, None, sched, cursor, rng_for("frame", 0))
                 else:
                     step_size = step_lr * (sigmas[c] / sigmas[-1]) ** 2
-                    self._sense_step(state, grad, noise, bvec, _scalars(step_size, kappa, sigmas[c]), None, None, seed, k)
+                    self._sense_step(state, grad, noise, bvec, _scalars(step_size, kappa, sigmas[c]), None, None, rng_for("frame", k))
                 return
             if not skip_spatial:
                 if sched is not None:
                     _lib.check(L.ipdm_langevin_update(state.data_ptr(), grad.data_ptr(), None, None, state.numel(), None,
-                                                      sched.data_ptr(), cursor.data_ptr(), None, 0, seed, 0, _lib.stream()), "langevin_update")
+                                                      sched.data_ptr(), cursor.data_ptr(), None, 0, rng_for("plane", 0), _lib.stream()), "langevin_update")
                 else:
                     step_size = step_lr * (sigmas[c] / sigmas[-1]) ** 2
                     _lib.check(L.ipdm_langevin_update(state.data_ptr(), grad.data_ptr(), _lib.ptr(noise), None, state.numel(),
-                                                      _scalars(step_size), None, None, None, 0, seed, k, _lib.stream()), "langevin_update")
+                                                      _scalars(step_size), None, None, None, 0, rng_for("plane", k), _lib.stream()), "langevin_update")
             if tv:
                 _lib.check(L.ipdm_temporal_tv_step(state.data_ptr(), B, T, H * W, lamda_T, _lib.stream()), "temporal_tv_step")
             elif temporal_on[c] if with_T is None else with_T:
                 temporal_diffusion(c, k, sched_T, cursor, shifts=shifts)
             # data consistency only: step = noise_scale = 0 turns the fused kernel into x - kappa*(A^H A x - b)
-            self._sense_step(state, grad, None, bvec, prox_only, None, None, seed, k)
+            self._sense_step(state, grad, None, bvec, prox_only, None, None, None)
 
         if fast and not skip_spatial:
             sched_host = ald_schedule(sigmas, n_steps_each, step_lr, kappa)
             n_total = sched_host.shape[0]
-            key = ("cine", B, T, H, W, n_total, n_steps_each, seed, mode_T, lamda_T, float(kappa), bool(diffusion and random_shift), state.device)
+            key = ("cine", B, T, H, W, n_total, n_steps_each, mode_T, lamda_T, float(kappa), bool(diffusion and random_shift), state.device)
             fc = self._fast_cache.get(key)
             real = (state, bvec)
             if fc is None:
                 fc = {"state": torch.zeros_like(state), "grad": torch.zeros_like(state), "bvec": torch.zeros_like(state),
                       "labels": torch.zeros_like(labels_all), "sched": torch.zeros_like(sched_host, device=state.device),
-                      "cursor": torch.zeros(1, dtype=torch.int32, device=state.device)}
+                      "cursor": torch.zeros(1, dtype=torch.int32, device=state.device),
+                      "seed": _seed_tensor(0, state.device), "frame": torch.zeros_like(frame_ids), "plane": torch.zeros_like(plane_ids)}
+                if diffusion:
+                    fc["vol_ids"] = torch.zeros_like(vol_ids)
                 if diffusion:
                     fc.update(vol=vol, gvol=gvol, sched_T=torch.zeros_like(sched_host, device=state.device))
                     if random_shift:
                         fc["shifts"] = torch.zeros(n_total, 2, dtype=torch.int32, device=state.device)
                 self._fast_cache[key] = fc
             state, grad, bvec, labels_all = fc["state"], fc["grad"], fc["bvec"], fc["labels"]
+            fc["seed"].fill_(seed)
+            fc["frame"].copy_(frame_ids)
+            fc["plane"].copy_(plane_ids)
+            if diffusion:
+                fc["vol_ids"].copy_(vol_ids)
+            ids.update(frame=fc["frame"], plane=fc["plane"], vol=fc.get("vol_ids"), seed_dev=fc["seed"])
             labels = labels_all[:2 * BT]
             if diffusion:
                 vol, gvol = fc["vol"], fc["gvol"]

@@ -30,22 +30,26 @@ def ald_schedule(sigmas, n_steps_each, step_lr, kappa=0.0):
     return rows.repeat_interleave(n_steps_each, dim=0).contiguous()
 
 
-def langevin_update_(x, grad, step, noise=None, seed=0, rng_step=0, x_mean=None):
-    """In place x += step*grad + sqrt(2*step)*noise on float32 CUDA tensors (Philox noise if None)."""
+def langevin_update_(x, grad, step, noise=None, seed=0, rng_step=0, x_mean=None, chain_ids=None):
+    """In place x += step*grad + sqrt(2*step)*noise on float32 CUDA tensors (B, ...).  noise None: in-kernel Philox,
+    sample i drawing the stream of chain chain_ids[i] (default i)."""
     _lib.require_cuda(x, grad)
     sc = _lib.AldScalars(float(step), float(torch.sqrt(torch.tensor(float(step), dtype=torch.float32) * 2)), 0.0, 0.0)
+    per = x[0].numel() if x.dim() > 1 else 0
     _lib.check(_lib.lib().ipdm_langevin_update(x.data_ptr(), grad.data_ptr(), _lib.ptr(noise), _lib.ptr(x_mean), x.numel(),
-                                               sc, None, None, None, 0, int(seed), int(rng_step), _lib.stream()),
+                                               sc, None, None, None, 0, _lib.rng(seed, rng_step, chain_ids, per), _lib.stream()),
                "langevin_update")
     return x
 
 
 @torch.no_grad()
 def anneal_Langevin_dynamics(x_mod, scorenet, sigmas, n_steps_each=200, step_lr=0.000008,
-                             final_only=False, verbose=False, denoise=True, noise_fn=None, seed=0):
+                             final_only=False, verbose=False, denoise=True, noise_fn=None, seed=None):
     """Reference ncsn/models/__init__.py:40-82.  `noise_fn(shape) -> Tensor` injects noise (parity
-    tests); otherwise noise comes from the in-kernel Philox stream `seed`."""
+    tests); otherwise noise comes from the in-kernel Philox stream `seed` (None: a fresh seed from torch's
+    global generator per call, like the reference's randn_like)."""
     _lib.require_cuda(x_mod)
+    seed = (0 if noise_fn is not None else _lib.fresh_seed()) if seed is None else int(seed)
     x_mod = x_mod.detach().float().contiguous().clone()
     images = []
     k = 0

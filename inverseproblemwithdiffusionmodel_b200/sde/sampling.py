@@ -57,7 +57,7 @@ class LangevinCorrector(Corrector):
             noise_norm = torch.norm(noise.reshape(noise.shape[0], -1), dim=-1).mean()
             step = ((self.snr * noise_norm / grad_norm) ** 2 * 2 * alpha).float().contiguous()
             _lib.check(L.ipdm_langevin_update(x.data_ptr(), grad.data_ptr(), noise.data_ptr(), x_mean.data_ptr(), x.numel(), None,
-                                              None, None, step.data_ptr(), per, 0, i, _lib.stream()), "langevin corrector")
+                                              None, None, step.data_ptr(), per, None, _lib.stream()), "langevin corrector")
         return x, x_mean
 
 
@@ -66,8 +66,11 @@ class AnnealedLangevinDynamics(Corrector):
     """step = (snr*std_t)^2 * 2 * alpha_t ;  x_mean = x + step*score ;  x = x_mean + sqrt(2 step)*noise.
     `sde` needs `.marginal_prob(x, t)[1]` (and `.alphas`, `.N`, `.T` for VP-type SDEs, detected by attribute)."""
 
-    def update_fn(self, x, t, noise_fn=None, seed=0):
+    def update_fn(self, x, t, noise_fn=None, seed=None):
+        """seed None: every call draws a fresh seed from torch's global generator (the reference draws fresh
+        torch.randn_like noise at every call, sde/sampling.py:316); pass a seed to pin the stream of ONE call."""
         _lib.require_cuda(x, t)
+        seed = (0 if noise_fn is not None else _lib.fresh_seed()) if seed is None else int(seed)
         sde = self.sde
         if hasattr(sde, "alphas"):
             timestep = (t * (sde.N - 1) / sde.T).long()
@@ -84,5 +87,5 @@ class AnnealedLangevinDynamics(Corrector):
             step = ((self.snr * std) ** 2 * 2 * alpha).float().contiguous()
             noise = None if noise_fn is None else noise_fn(x.shape).to(x.device, torch.float32).contiguous()
             _lib.check(L.ipdm_langevin_update(x.data_ptr(), grad.data_ptr(), _lib.ptr(noise), x_mean.data_ptr(), x.numel(), None,
-                                              None, None, step.data_ptr(), per, int(seed), i, _lib.stream()), "ald corrector")
+                                              None, None, step.data_ptr(), per, _lib.rng(seed, i, None, per), _lib.stream()), "ald corrector")
         return x, x_mean

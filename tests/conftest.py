@@ -15,6 +15,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu`-marked tests need a CUDA device and the built library: skip them (instead of erroring) where either is missing."""
+    import torch
+    lib = os.path.join(ROOT, "inverseproblemwithdiffusionmodel_b200", "libipdm_b200.so")
+    why = None
+    if not torch.cuda.is_available():
+        why = "no CUDA device"
+    elif not os.path.exists(lib):
+        why = "libipdm_b200.so is not built"
+    if why:
+        skip = pytest.mark.skip(reason=why)
+        for item in items:
+            if "gpu" in item.keywords:
+                item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def golden():
     def load(name):

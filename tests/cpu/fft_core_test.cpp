@@ -7,6 +7,9 @@
 #include <complex>
 #include "../../inverseproblemwithdiffusionmodel_b200/csrc/fft_core.cuh"
 #include "../../inverseproblemwithdiffusionmodel_b200/csrc/fft2p.cuh"
+#include "../../inverseproblemwithdiffusionmodel_b200/csrc/fftpr.cuh"
+#include "../../inverseproblemwithdiffusionmodel_b200/csrc/sense_plan.h"
+#include <cstring>
 using namespace ipdm;
 
 template <int L, int P, int DIR>
@@ -94,6 +97,94 @@ double check2p() {
   return sqrt(err / nrm);
 }
 
+// Pruned row transforms (csrc/fftpr.cuh) driven by the tables of csrc/sense_plan.h: forward = the sampled columns of a
+// full DFT, adjoint = the inverse DFT of a spectrum that is zero off the sampled columns.  Two mask frames with
+// different column sets, a centre window plus scattered lines as the keep-centre masks have them.
+template <int L>
+double check_pruned(int ns_target, unsigned seed) {
+  using P = PR<L>;
+  srand(seed);
+  const int frames = 2;
+  std::vector<uint8_t> mask(frames * L, 0);
+  for (int f = 0; f < frames; ++f) {
+    int n = 0;
+    const int win = ns_target / 3;
+    for (int k = L / 2 - win / 2; k < L / 2 - win / 2 + win; ++k) { mask[f * L + k] = 1; ++n; }
+    while (n < ns_target - f) { const int k = rand() % L; if (!mask[f * L + k]) { mask[f * L + k] = 1; ++n; } }
+  }
+  PlanHost pl = build_plan_host(mask.data(), frames, L);
+  if (!pl.pruned || pl.R1 != P::R1) { printf("plan not pruned for L=%d ns=%d\n", L, ns_target); return 1.0; }
+  double worst = 0;
+  for (int f = 0; f < frames; ++f) {
+    const int ns = pl.ns[f], NP = pl.ns_pad;
+    // structure checks: natural order ascending and matching the mask, classes sorted, group slots consistent
+    int cnt = 0;
+    for (int k = 0; k < L; ++k) if (mask[f * L + k]) { if (pl.kcol[f * NP + cnt] != k) return 2.0; ++cnt; }
+    if (cnt != ns) return 3.0;
+    const uint8_t* cls = &pl.cls[f * PlanHost::CLS_PITCH];
+    if (cls[0] != 0 || cls[16] != ns) return 4.0;
+    for (int jj = 0; jj < ns; ++jj) {
+      const int k = pl.kcol[f * NP + pl.nat[f * NP + jj]];
+      if ((k & 15) != pl.k0c[f * NP + jj] || jj < cls[k & 15] || jj >= cls[(k & 15) + 1]) return 5.0;
+    }
+    for (int g = 0; g < pl.ngroups[f]; ++g) {
+      const int q = pl.groups[f * (L / 4) + g];
+      if (!((pl.gbitmap[f * 4 + (q >> 5)] >> (q & 31)) & 1u)) return 6.0;
+      for (int i = 0; i < 4; ++i) {
+        const int s = pl.gslot[(f * (L / 4) + g) * 4 + i];
+        if ((s != 255) != (mask[f * L + 4 * q + i] != 0)) return 7.0;
+        if (s != 255 && pl.kcol[f * NP + s] != 4 * q + i) return 8.0;
+      }
+    }
+    uint32_t cw[5];
+    memcpy(cw, cls, 20);
+    const cf32* tw = reinterpret_cast<const cf32*>(pl.tw.data()) + (size_t)f * NP * P::R1;
+    // ---- forward
+    std::vector<cf32> x(L), line(P::LINE + 8);
+    std::vector<std::complex<double>> xd(L);
+    for (int i = 0; i < L; ++i) {
+      x[i] = cf32{(float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f};
+      xd[i] = {x[i].x, x[i].y};
+    }
+    for (int t = 0; t < P::R1; ++t) {
+      cf32 v[P::R0];
+      for (int q = 0; q < P::R0; ++q) v[q] = x[P::R1 * q + t];
+      pr_first<L, -1>(v, t, line.data());
+    }
+    double err = 0, nrm = 0;
+    for (int jj = 0; jj < ns; ++jj) {
+      const cf32 o = pr_gather<L, -1>(line.data(), pl.k0c[f * NP + jj], tw + jj * P::R1);
+      const int k = pl.kcol[f * NP + pl.nat[f * NP + jj]];
+      std::complex<double> s = 0;
+      for (int n = 0; n < L; ++n) s += xd[n] * std::polar(1.0, -2.0 * M_PI * k * n / L);
+      err += std::norm(s - std::complex<double>(o.x, o.y));
+      nrm += std::norm(s);
+    }
+    worst = fmax(worst, sqrt(err / nrm));
+    // ---- adjoint
+    std::vector<cf32> Y(pl.ns_pad), out(L);
+    std::vector<std::complex<double>> Yd(L, 0.0);
+    for (int jj = 0; jj < ns; ++jj) {
+      Y[jj] = cf32{(float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f};
+      Yd[pl.kcol[f * NP + pl.nat[f * NP + jj]]] = {Y[jj].x, Y[jj].y};
+    }
+    for (int t = 0; t < P::R1; ++t) {
+      cf32 v[P::R0];
+      pr_scatter<L, +1>(v, t, Y.data(), tw, P::R1, cw);
+      for (int q = 0; q < P::R0; ++q) out[P::R1 * q + t] = v[q];
+    }
+    err = 0; nrm = 0;
+    for (int n = 0; n < L; ++n) {
+      std::complex<double> s = 0;
+      for (int k = 0; k < L; ++k) s += Yd[k] * std::polar(1.0, 2.0 * M_PI * k * n / L);
+      err += std::norm(s - std::complex<double>(out[n].x, out[n].y));
+      nrm += std::norm(s);
+    }
+    worst = fmax(worst, sqrt(err / nrm));
+  }
+  return worst;
+}
+
 int main() {
   double worst = 0;
 #define CHK(L)                                                       \
@@ -111,6 +202,13 @@ int main() {
     worst = fmax(worst, fmax(fmax(a, b), fmax(c, d)));                                        \
   }
   CHK2(8) CHK2(16) CHK2(32) CHK2(64) CHK2(128) CHK2(256) CHK2(512)
+#define CHKP(L, NS)                                                   \
+  {                                                                   \
+    double a = check_pruned<L>(NS, 17 * L + NS);                      \
+    printf("pruned L=%d ns=%d worst %.3e\n", L, NS, a);               \
+    worst = fmax(worst, a);                                           \
+  }
+  CHKP(128, 8) CHKP(128, 16) CHKP(256, 11) CHKP(256, 20) CHKP(256, 32) CHKP(512, 21) CHKP(512, 32) CHKP(512, 3)
   printf("worst %.3e\n", worst);
   return worst < 2e-6 ? 0 : 1;
 }

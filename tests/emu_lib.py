@@ -40,7 +40,7 @@ class EmuLib:
 
     # ---- misc
     def ipdm_abi_version(self):
-        return 2
+        return 3
 
     def ipdm_last_error(self):
         return self.err
@@ -98,6 +98,42 @@ class EmuLib:
             _t(out, (B, H, W), np.complex64).copy_(acc)
         return 0
 
+    # ---- mask plans: the emulator keeps the host mask and forwards to the mask-pointer entry points
+    def ipdm_sense_plan_create(self, mask_host, frames, H, W, plan_out):
+        if not hasattr(self, "plans"):
+            self.plans = {}
+        m = np.array(_np(mask_host, (frames, W), np.uint8), copy=True)
+        key = 0x1000 + len(self.plans)
+        self.plans[key] = (m, frames, H, W)
+        _deref(plan_out).value = key
+        return 0
+
+    def _plan(self, plan):
+        return self.plans[plan.value if hasattr(plan, "value") else plan]
+
+    def ipdm_sense_plan_destroy(self, plan):
+        return 0
+
+    def ipdm_sense_plan_info(self, plan, info):
+        m, frames, H, W = self._plan(plan)
+        ns = int(m.sum(axis=1).max())
+        groups = int(m.reshape(frames, W // 4, 4).any(axis=2).sum(axis=1).max()) if W % 4 == 0 else 0
+        for i, v in enumerate([0, ns, (ns + 3) // 4 * 4, groups, frames, H, W, 0]):
+            info[i] = v
+        return 0
+
+    def ipdm_sense_forward_plan(self, plan, x, mre, mim, out, nc, B, ws, stream):
+        m, frames, H, W = self._plan(plan)
+        return self.ipdm_sense_forward(x, mre, mim, m.ctypes.data, frames, out, nc, B, H, W, ws, stream)
+
+    def ipdm_sense_adjoint_plan(self, plan, S, mre, mim, out, nc, B, ssos, ws, stream):
+        m, frames, H, W = self._plan(plan)
+        return self.ipdm_sense_adjoint(S, mre, mim, m.ctypes.data, frames, out, nc, B, H, W, ssos, ws, stream)
+
+    def ipdm_ald_sense_step_plan(self, plan, x, grad, noise, b, mre, mim, nc, B, H, sc, sched, cursor, rng, stream):
+        m, frames, _, W = self._plan(plan)
+        return self.ipdm_ald_sense_step(x, grad, noise, b, mre, mim, m.ctypes.data, frames, nc, B, H, W, sc, sched, cursor, rng, stream)
+
     def ipdm_kspace_combine(self, S, Y, mask, frames, a, mode, batch, H, W, stream):
         self.launches += 1
         Sx = _t(S, (batch, H, W), np.complex64)
@@ -125,7 +161,7 @@ class EmuLib:
         sc = _deref(sc)
         return sc.step, sc.noise_scale, sc.kappa
 
-    def ipdm_langevin_update(self, x, grad, noise, x_mean, n, sc, sched, cursor, sps, per, seed, rng_step, stream):
+    def ipdm_langevin_update(self, x, grad, noise, x_mean, n, sc, sched, cursor, sps, per, rng, stream):
         self.launches += 1
         X, G = _t(x, (n,), np.float32), _t(grad, (n,), np.float32)
         Nz = _t(noise, (n,), np.float32) if noise is not None else None
@@ -142,7 +178,7 @@ class EmuLib:
         X.copy_(mean if Nz is None else mean + ns * Nz)
         return 0
 
-    def ipdm_ald_sense_step(self, x, grad, noise, b, mre, mim, mask, frames, nc, B, H, W, sc, sched, cursor, seed, rng_step, stream):
+    def ipdm_ald_sense_step(self, x, grad, noise, b, mre, mim, mask, frames, nc, B, H, W, sc, sched, cursor, rng, stream):
         self.launches += 1
         st, ns, kappa = self._scalars(sc, sched, cursor)
         X, G, Bv = (_t(p, (2, B, H, W), np.float32) for p in (x, grad, b))

@@ -32,7 +32,8 @@ from inverseproblemwithdiffusionmodel_b200.sde.sampling import AnnealedLangevinD
 from inverseproblemwithdiffusionmodel_b200.ncsn.models import MAP_optimizers as MAP
 
 TOL32 = 1e-5
-TOL_SCORE = 5e-3
+TOL_SCORE = 2e-3        # score vs the fp32 oracle / reference: f16 conv operands cost ~8e-4
+TOL_SCORE_EMU = 1.5e-3   # score vs the oracle with f16-rounded conv operands (same arithmetic as the kernels up to summation order)
 TOL_X = 1e-4
 
 

@@ -21,7 +21,7 @@ def _lib():
 
 def test_library_is_native():
     L = _lib()
-    assert L.lib().ipdm_abi_version() == 2
+    assert L.lib().ipdm_abi_version() == 3
     before = L.lib().ipdm_launch_count()
     C.i2k_complex(torch.zeros(1, 1, 8, 8, dtype=torch.complex64, device=DEV))
     torch.cuda.synchronize()
@@ -73,47 +73,83 @@ def test_sense_full_size(n, nc, B, R):
     assert rel_l2((A(x.to(DEV) + 2 * x2)).cpu(), (S + 2 * A(x2)).cpu()) < 1e-5
 
 
-@pytest.mark.parametrize("H,W,nc,B,frames,cplx", [(128, 128, 4, 24, 24, False), (64, 256, 3, 5, 1, True), (512, 128, 2, 2, 1, False),
-                                                  (256, 64, 5, 6, 3, True), (512, 512, 3, 2, 1, True)])
-def test_sense_two_pass_engine_variants(H, W, nc, B, frames, cplx):
-    """The 64..512 kernels (csrc/sense_fast.cuh) through the C ABI: per-frame masks, complex coil maps, non-square
-    images, SSOS, unmasked / masked adjoint and the fused step, each against the oracle."""
+def _sparse_mask(g, frames, W, lines):
+    """`lines` sampled columns per frame: a centre window plus scattered ones (frame f keeps lines - (f % 3))."""
+    mask = torch.zeros(frames, 1, 1, W, dtype=torch.bool)
+    for f in range(frames):
+        n = max(2, lines - (f % 3))
+        win = max(2, n // 3)
+        mask[f, ..., W // 2 - win // 2:W // 2 - win // 2 + win] = True
+        while int(mask[f].sum()) < n:
+            mask[f, ..., int(torch.randint(0, W, (1,), generator=g))] = True
+    return mask
+
+
+def _sense_battery(H, W, nc, B, frames, cplx, lines, use_plan):
+    """Forward, unmasked / masked adjoint, dirty input, SSOS and the fused step through the C ABI against the oracle:
+    mask given as a raw device mask (general kernels) or as a compiled plan (pruned kernels when it allows)."""
     L = _lib()
-    g = torch.Generator().manual_seed(H + 3 * W + nc)
+    lib = L.lib()
+    g = torch.Generator().manual_seed(H + 3 * W + nc + (lines or 0))
     maps = torch.rand(nc, H, W, generator=g, dtype=torch.float64) + 0.2
     if cplx:
         maps = maps * torch.exp(1j * torch.rand(nc, H, W, generator=g, dtype=torch.float64))
-    mask = torch.rand(frames, 1, 1, W, generator=g) < 0.15
-    mask[..., W // 2 - 2:W // 2 + 2] = True
-    m8 = mask.reshape(frames, W).to(torch.uint8).contiguous().to(DEV)
+    if lines is None:
+        mask = torch.rand(frames, 1, 1, W, generator=g) < 0.15
+        mask[..., W // 2 - 2:W // 2 + 2] = True
+    else:
+        mask = _sparse_mask(g, frames, W, lines)
+    m8h = mask.reshape(frames, W).to(torch.uint8).contiguous()
+    m8 = m8h.to(DEV)
+    plan = L.SensePlan(m8h.numpy(), H, W) if use_plan else None
+    if use_plan and lines is not None:
+        assert plan.pruned and plan.ns_max == lines
     mask = mask[0] if frames == 1 else mask.repeat(B // frames, 1, 1, 1)     # kernel: frame = b % frames
     x = crandn(H + W, B, 1, H, W)
     mre = maps.real.float().contiguous().to(DEV)
     mim = maps.imag.float().contiguous().to(DEV) if cplx else None
-    ws = torch.empty(L.lib().ipdm_sense_workspace_bytes(nc, B, H, W), dtype=torch.uint8, device=DEV)
+    ws = torch.empty(lib.ipdm_sense_workspace_bytes(nc, B, H, W), dtype=torch.uint8, device=DEV)
+    st = L.stream()
+
+    def fwd(xd, out):
+        if use_plan:
+            L.check(lib.ipdm_sense_forward_plan(plan.handle, xd.data_ptr(), mre.data_ptr(), L.ptr(mim), out.data_ptr(), nc, B, ws.data_ptr(), st), "fwd")
+        else:
+            L.check(lib.ipdm_sense_forward(xd.data_ptr(), mre.data_ptr(), L.ptr(mim), m8.data_ptr(), frames, out.data_ptr(), nc, B, H, W, ws.data_ptr(), st), "fwd")
+
+    def adj_masked(yd, out, ssos=0):
+        if use_plan:
+            L.check(lib.ipdm_sense_adjoint_plan(plan.handle, yd.data_ptr(), L.ptr(None if ssos else mre), L.ptr(None if ssos else mim), out.data_ptr(),
+                                                nc, B, ssos, ws.data_ptr(), st), "adj")
+        else:
+            L.check(lib.ipdm_sense_adjoint(yd.data_ptr(), L.ptr(None if ssos else mre), L.ptr(None if ssos else mim), m8.data_ptr(), frames,
+                                           out.data_ptr(), nc, B, H, W, ssos, ws.data_ptr(), st), "adj")
+
     S = torch.full((nc, B, 1, H, W), float("nan"), dtype=torch.complex64, device=DEV)
     xd = x.to(DEV).contiguous()
-    L.check(L.lib().ipdm_sense_forward(xd.data_ptr(), mre.data_ptr(), L.ptr(mim), m8.data_ptr(), frames, S.data_ptr(), nc, B, H, W,
-                                       ws.data_ptr(), L.stream()), "fwd")
+    fwd(xd, S)
     Sref = M.sense_forward(x, maps, mask)
     assert rel_l2(S.cpu(), Sref) < 1e-5
     assert float((S.cpu() * (~mask)).abs().max()) == 0.0          # every unsampled column is written, with exact zeros
     y = (mask * crandn(H + W + 1, nc, B, 1, H, W)).to(torch.complex64)
     yd = y.to(DEV).contiguous()
     ref_adj = M.sense_adjoint(y, maps.to(torch.complex64) if cplx else maps)
-    for mk in (None, m8):
-        out = torch.full((B, 1, H, W), float("nan"), dtype=torch.complex64, device=DEV)
-        L.check(L.lib().ipdm_sense_adjoint(yd.data_ptr(), mre.data_ptr(), L.ptr(mim), L.ptr(mk), frames, out.data_ptr(), nc, B, H, W, 0,
-                                           ws.data_ptr(), L.stream()), "adj")
-        assert rel_l2(out.cpu(), ref_adj) < 1e-5
+    out = torch.full((B, 1, H, W), float("nan"), dtype=torch.complex64, device=DEV)
+    L.check(lib.ipdm_sense_adjoint(yd.data_ptr(), mre.data_ptr(), L.ptr(mim), None, 1, out.data_ptr(), nc, B, H, W, 0, ws.data_ptr(), st), "adj")
+    assert rel_l2(out.cpu(), ref_adj) < 1e-5
+    out.fill_(float("nan"))
+    adj_masked(yd, out)
+    assert rel_l2(out.cpu(), ref_adj) < 1e-5
     # an input that is NOT zero off the mask: the masked adjoint must ignore the unsampled columns
     dirty = crandn(H + W + 2, nc, B, 1, H, W).to(DEV)
     out2 = torch.empty((B, 1, H, W), dtype=torch.complex64, device=DEV)
-    L.check(L.lib().ipdm_sense_adjoint(dirty.data_ptr(), mre.data_ptr(), L.ptr(mim), m8.data_ptr(), frames, out2.data_ptr(), nc, B, H, W, 0,
-                                       ws.data_ptr(), L.stream()), "adj")
+    adj_masked(dirty, out2)
     assert rel_l2(out2.cpu(), M.sense_adjoint((mask * dirty.cpu()).to(torch.complex64), maps.to(torch.complex64) if cplx else maps)) < 1e-5
     ss = torch.empty((B, 1, H, W), dtype=torch.float32, device=DEV)
-    L.check(L.lib().ipdm_sense_adjoint(yd.data_ptr(), None, None, None, 1, ss.data_ptr(), nc, B, H, W, 1, ws.data_ptr(), L.stream()), "ssos")
+    L.check(lib.ipdm_sense_adjoint(yd.data_ptr(), None, None, None, 1, ss.data_ptr(), nc, B, H, W, 1, ws.data_ptr(), st), "ssos")
+    assert rel_l2(ss.cpu(), M.sense_ssos(y)) < 1e-5
+    ss.fill_(float("nan"))
+    adj_masked(yd, ss, ssos=1)
     assert rel_l2(ss.cpu(), M.sense_ssos(y)) < 1e-5
     # fused Langevin + data-consistency step
     gr, nz = crandn(7, B, 1, H, W), crandn(8, B, 1, H, W)
@@ -125,11 +161,54 @@ def test_sense_two_pass_engine_variants(H, W, nc, B, frames, cplx):
     planar = lambda c: torch.stack([c.real.reshape(B, H, W), c.imag.reshape(B, H, W)]).contiguous().to(DEV)
     state, grad, noise, bvec = planar(x), planar(gr), planar(nz), planar(ref_adj)
     sc = L.AldScalars(step, nsc, kappa, 0.0)
-    L.check(L.lib().ipdm_ald_sense_step(state.data_ptr(), grad.data_ptr(), noise.data_ptr(), bvec.data_ptr(), mre.data_ptr(), L.ptr(mim),
-                                        m8.data_ptr(), frames, nc, B, H, W, sc, None, None, 0, 0, L.stream()), "ald_sense_step")
+    if use_plan:
+        L.check(lib.ipdm_ald_sense_step_plan(plan.handle, state.data_ptr(), grad.data_ptr(), noise.data_ptr(), bvec.data_ptr(), mre.data_ptr(),
+                                             L.ptr(mim), nc, B, H, sc, None, None, None, st), "ald_sense_step_plan")
+    else:
+        L.check(lib.ipdm_ald_sense_step(state.data_ptr(), grad.data_ptr(), noise.data_ptr(), bvec.data_ptr(), mre.data_ptr(), L.ptr(mim),
+                                        m8.data_ptr(), frames, nc, B, H, W, sc, None, None, None, st), "ald_sense_step")
     got = torch.complex(state[0], state[1]).cpu().reshape(B, 1, H, W)
     assert rel_l2(got, ref) < 1e-5
     assert rel_l2(got - z, ref - z) < 1e-4
+    # in-kernel noise: the pruned and the general kernels draw the same stream for the same (seed, chain, pixel, step)
+    if use_plan:
+        s1, s2 = planar(x), planar(x)
+        ids = torch.arange(100, 100 + B, dtype=torch.int32, device=DEV)
+        L.check(lib.ipdm_ald_sense_step_plan(plan.handle, s1.data_ptr(), grad.data_ptr(), None, bvec.data_ptr(), mre.data_ptr(),
+                                             L.ptr(mim), nc, B, H, sc, None, None, L.rng(11, 3, ids), st), "ald_sense_step_plan")
+        L.check(lib.ipdm_ald_sense_step(s2.data_ptr(), grad.data_ptr(), None, bvec.data_ptr(), mre.data_ptr(), L.ptr(mim),
+                                        m8.data_ptr(), frames, nc, B, H, W, sc, None, None, L.rng(11, 3, ids), st), "ald_sense_step")
+        assert rel_l2(s1.cpu(), s2.cpu()) < 1e-5
+        assert rel_l2(s1.cpu(), state.cpu()) > 1e-2      # and it is noise, not the injected tensor
+
+
+@pytest.mark.parametrize("H,W,nc,B,frames,cplx", [(128, 128, 4, 24, 24, False), (64, 256, 3, 5, 1, True), (512, 128, 2, 2, 1, False),
+                                                  (256, 64, 5, 6, 3, True), (512, 512, 3, 2, 1, True)])
+def test_sense_two_pass_engine_variants(H, W, nc, B, frames, cplx):
+    """The 64..512 kernels (csrc/sense_fast.cuh) through the C ABI: per-frame masks, complex coil maps, non-square
+    images, SSOS, unmasked / masked adjoint and the fused step, each against the oracle."""
+    _sense_battery(H, W, nc, B, frames, cplx, None, use_plan=False)
+
+
+@pytest.mark.parametrize("H,W,nc,B,frames,cplx,lines", [
+    (128, 128, 4, 24, 24, False, 8), (128, 128, 2, 3, 1, True, 16), (64, 256, 3, 5, 1, True, 11), (512, 128, 2, 2, 1, False, 9),
+    (256, 256, 4, 6, 3, True, 20), (256, 256, 4, 14, 1, False, 11), (256, 256, 2, 2, 1, False, 32), (512, 512, 3, 2, 1, True, 21),
+    (256, 512, 16, 4, 1, False, 21), (512, 512, 32, 4, 1, False, 32), (64, 512, 2, 3, 1, False, 2)])
+def test_sense_pruned_plan_variants(H, W, nc, B, frames, cplx, lines):
+    """The pruned kernels (csrc/sense_pruned.cuh, masks that keep <= 32 columns) through the plan entry points: one and two
+    outputs per thread, every row length, per-frame masks with different line counts, complex maps, non-square images,
+    16 and 32 coils at 512 columns (cfg 5), each against the oracle."""
+    _sense_battery(H, W, nc, B, frames, cplx, lines, use_plan=True)
+
+
+def test_sense_plan_falls_back_to_the_general_kernels():
+    """A mask that keeps too many columns for the pruned kernels (141 of 512 at R = 4) still works through a plan."""
+    _sense_battery(128, 512, 2, 2, 1, False, None, use_plan=True)
+    L = _lib()
+    m = (torch.rand(1, 256) < 0.3).to(torch.uint8)
+    assert not L.SensePlan(m.numpy(), 256, 256).pruned
+    m = torch.zeros(1, 64, dtype=torch.uint8); m[0, 30:34] = 1
+    assert not L.SensePlan(m.numpy(), 64, 64).pruned          # W = 64 is served by the general kernels
 
 
 def test_sense_many_images():
@@ -292,14 +371,28 @@ def test_scorenet_ngf128_tensor_core_path():
     out = net(x.to(DEV), y.to(DEV)).cpu()
     with torch.no_grad():
         ref = SN.score_forward("NCSNv2Deepest", Pd, x, y)
+        SN.OPERAND_ROUND = torch.float16          # the oracle with conv operands rounded to f16 like the kernels' (fp32 accumulate)
+        try:
+            emu = SN.score_forward("NCSNv2Deepest", Pd, x, y)
+        finally:
+            SN.OPERAND_ROUND = None
+    print("ngf128 Deepest score: vs fp32 oracle %.2e, vs f16-operand oracle %.2e" % (rel_l2(out, ref), rel_l2(out, emu)))
     assert rel_l2(out, ref) < C.TOL_SCORE
+    assert rel_l2(out, emu) < C.TOL_SCORE_EMU
     assert L.lib().ipdm_launch_count() - before > 150
     net2, Pd2, _ = _full_width_net(C.NCSNv2, "NCSNv2", 28, 22)
     x = rrand(78, 2, 1, 28, 28)
     out = net2(x.to(DEV), y.to(DEV)).cpu()
     with torch.no_grad():
         ref = SN.score_forward("NCSNv2", Pd2, x, y)
+        SN.OPERAND_ROUND = torch.float16
+        try:
+            emu = SN.score_forward("NCSNv2", Pd2, x, y)
+        finally:
+            SN.OPERAND_ROUND = None
+    print("ngf128 NCSNv2 score: vs fp32 oracle %.2e, vs f16-operand oracle %.2e" % (rel_l2(out, ref), rel_l2(out, emu)))
     assert rel_l2(out, ref) < C.TOL_SCORE
+    assert rel_l2(out, emu) < C.TOL_SCORE_EMU
 
 
 def test_single_ald_step_ngf128():
@@ -336,6 +429,193 @@ def test_single_ald_step_ngf128():
         assert rel_l2(got, ref) < 1e-4, float(levels[0])
 
 
+def test_single_ald_step_ngf128_bench_config():
+    """The benchmarked configuration itself: 256x256, 14 chains (28 images per forward: work items >> SMs), 4 coils, R = 40,
+    ngf 128 on the tensor-core path.  One ALD step (2 score forwards + update + prox) with injected noise at the first
+    level from x0 = A^H y and at a middle level; chains are independent, so the oracle runs the first and the last
+    chain only (14 chains x 2 forwards at 256^2 would take minutes of CPU).  north_star bar: 1e-4 relative L2."""
+    n, B = 256, 14
+    net, Pd, cfg = _full_width_net(C.NCSNv2Deepest, "NCSNv2Deepest", n, 29, num_classes=2311, sigma_begin=348.0)
+    sig = C.get_sigmas(cfg, mode="recons")
+    A = C.SENSE("exp", 4, 40, 1 / 64, (1, n, n), 0)
+    A.random_under_fourier.mask = C.keep_center_mask(n, 40, 1 / 64, seed=0)
+    assert A.device_plan(torch.device(DEV, 0), n).pruned
+    meas = A(phantom(12, B, 1, n, n).to(DEV))                       # 14 different images
+    maps, mask = A.sens_maps, A.random_under_fourier.mask
+    score = lambda x, y: SN.score_forward("NCSNv2Deepest", Pd, x, y)
+    prox = lambda z, y, a, l: M.l2_prox_sense_closed_form(z, y, maps, mask, a, l)
+    adj = lambda s: M.sense_adjoint(s, maps)
+    params = {"n_steps_each": 1, "step_lr": 9e-7, "denoise": False, "final_only": True}
+    sub = [0, B - 1]
+    for li in (0, 1155):
+        lv = sig[li:li + 1]
+        net.sigmas = lv.to(DEV)
+        Pd["sigmas"] = lv.cpu()
+        ratio2 = float((lv[0] / sig[-1]) ** 2)
+        g = torch.Generator().manual_seed(600 + li)
+        noises = [torch.randn(B, 1, n, n, generator=g) for _ in range(2)]     # real, then imaginary (:238-241)
+        it = iter(noises)
+        sampler = C.ALD.ALDInvSegProximalRealImag(C.L2Penalty(A), 1.0, "linear", (B, 1, n, n), net, lv.to(DEV),
+                                                  dict(params, step_lr=9e-7 * ratio2), cfg,
+                                                  measurement=meas, linear_tfm=A, seg=None, device=torch.device(DEV))
+        got = sampler(label=None, lamda=1.0, save_dir="/tmp", lr_scaled=1e6 / ratio2, seg_mode="full", noise_fn=lambda shape: next(it))[0]
+        it2 = iter([nz[sub] for nz in noises])
+        with torch.no_grad():
+            ref = OALD.ald_sense_real_imag(score, meas.cpu()[:, sub], lv.cpu(), 1, 9e-7 * ratio2, 1e6 / ratio2, adj, prox, denoise=False,
+                                           draw=lambda shape: next(it2))
+        torch.set_grad_enabled(True)
+        assert rel_l2(got[sub], ref) < 1e-4, (li, rel_l2(got[sub], ref))
+
+
+def test_full_chain_metrics_ngf128_tensor_core_path():
+    """north_star bar 3 on the TENSOR-CORE path: a complete chain (12 levels x 3 steps + denoise) of 2 chains at 64x64 with
+    ngf 128 and identical injected noise; NRMSE / SSIM of the posterior mean and the mean of per-chain metrics within 1e-3 of
+    the oracle's, and the samples themselves within 1e-3."""
+    n, B, levels = 64, 2, 12
+    net, Pd, cfg = _full_width_net(C.NCSNv2Deepest, "NCSNv2Deepest", n, 31, num_classes=levels, sigma_begin=30.0)
+    sig = C.get_sigmas(cfg, mode="recons")
+    A = C.SENSE("exp", 4, 40, 1 / 8, (1, n, n), 0)
+    A.random_under_fourier.mask = C.keep_center_mask(n, 4, 1 / 8, seed=0)
+    truth = phantom(1402, 1, 1, n, n)
+    meas = A(truth.to(DEV)).repeat(1, B, 1, 1, 1)
+    params = {"n_steps_each": 3, "step_lr": 9e-7, "denoise": True, "final_only": True}
+    draw = lambda shape: torch.randn(*shape)
+    sampler = C.ALD.ALDInvSegProximalRealImag(C.L2Penalty(A), 1.0, "linear", (B, 1, n, n), net, sig, params, cfg,
+                                              measurement=meas, linear_tfm=A, seg=None, device=torch.device(DEV))
+    torch.manual_seed(78)
+    got = sampler(label=None, lamda=1.0, save_dir="/tmp", lr_scaled=1e6, seg_mode="full", noise_fn=draw)[0]
+    torch.set_grad_enabled(True)
+    maps, mask = A.sens_maps, A.random_under_fourier.mask
+    score = lambda x, y: SN.score_forward("NCSNv2Deepest", Pd, x, y)
+    prox = lambda z, y, a, l: M.l2_prox_sense_closed_form(z, y, maps, mask, a, l)
+    torch.manual_seed(78)
+    with torch.no_grad():
+        ref = OALD.ald_sense_real_imag(score, meas.cpu(), sig.cpu(), 3, 9e-7, 1e6, lambda s_: M.sense_adjoint(s_, maps), prox)
+    t = truth.abs()[0, 0]
+    rng = float(t.max() - t.min())
+
+    def metrics(x):
+        mags = x.abs()[:, 0]
+        mean_img = mags.mean(0)
+        per = [(OALD.nrmse(m, t), OALD.ssim(m, t, data_range=rng)) for m in mags]
+        return (OALD.nrmse(mean_img, t), OALD.ssim(mean_img, t, data_range=rng),
+                sum(p_[0] for p_ in per) / len(per), sum(p_[1] for p_ in per) / len(per))
+    mg, mr = metrics(got), metrics(ref)
+    for a, b in zip(mg, mr):
+        assert abs(a - b) < 1e-3, (mg, mr)
+    assert rel_l2(got, ref) < 1e-3, rel_l2(got, ref)
+
+
+@pytest.mark.parametrize("N,HW,Cc,offset", [(3, 32 * 32, 128, 0.0), (2, 64 * 64, 256, 50.0), (1, 17 * 9, 512, -3.0)])
+def test_instnorm_plus_isolated(N, HW, Cc, offset):
+    """InstanceNorm2dPlus (normalization.py:150-176) on its own: `ipdm_instnorm_stats` (pivoted and un-pivoted sums) and
+    `ipdm_instnorm_apply_elu` (per-channel normalisation + the cross-channel m_hat term + gamma / beta + ELU) against the
+    oracle; a large common offset makes the un-pivoted E[x^2] - E[x]^2 form lose digits, the pivoted one must not."""
+    L = _lib()
+    lib = L.lib()
+    g = torch.Generator().manual_seed(N * 1000 + Cc)
+    x = torch.randn(N, Cc, HW, 1, generator=g) * (0.5 + torch.rand(1, Cc, 1, 1, generator=g)) + torch.randn(1, Cc, 1, 1, generator=g) + offset
+    Pn = {"n.alpha": 1 + 0.02 * torch.randn(Cc, generator=g), "n.gamma": 1 + 0.02 * torch.randn(Cc, generator=g),
+          "n.beta": 0.1 * torch.randn(Cc, generator=g)}
+    ref = torch.nn.functional.elu(SN.instance_norm_plus(Pn, "n", x.double()).float())          # (N, C, HW, 1)
+    xd = x.reshape(N, Cc, HW).permute(0, 2, 1).contiguous().to(DEV)                             # NHWC
+    a, gm, bt = (Pn[k].to(DEV) for k in ("n.alpha", "n.gamma", "n.beta"))
+    for pivoted in (0, 1):
+        stats = torch.zeros(N, Cc, 2, dtype=torch.float64, device=DEV)
+        L.check(lib.ipdm_instnorm_stats(xd.data_ptr(), stats.data_ptr(), N, HW, Cc, pivoted, L.stream()), "stats")
+        piv = xd[:, 0, :].double() if pivoted else torch.zeros(N, Cc, dtype=torch.float64, device=DEV)
+        d = xd.double() - piv[:, None, :]
+        assert rel_l2(stats[..., 0].cpu(), d.sum(1).cpu()) < 1e-5
+        assert rel_l2(stats[..., 1].cpu(), (d * d).sum(1).cpu()) < 1e-5
+        out = torch.empty(N, HW, Cc, dtype=torch.float16, device=DEV)
+        L.check(lib.ipdm_instnorm_apply_elu(xd.data_ptr(), stats.data_ptr(), pivoted, a.data_ptr(), gm.data_ptr(), bt.data_ptr(),
+                                            out.data_ptr(), N, HW, Cc, L.stream()), "apply")
+        got = out.float().permute(0, 2, 1).reshape(N, Cc, HW, 1).cpu()
+        tol = 1.5e-3 if (pivoted or offset == 0.0) else 2e-2      # f16 output rounding ~5e-4; un-pivoted sums at offset 50 lose ~3 digits
+        assert rel_l2(got, ref) < tol, (pivoted, rel_l2(got, ref))
+    # beta may be absent (the kernel accepts NULL)
+    out = torch.empty(N, HW, Cc, dtype=torch.float16, device=DEV)
+    L.check(lib.ipdm_instnorm_apply_elu(xd.data_ptr(), stats.data_ptr(), 1, a.data_ptr(), gm.data_ptr(), None, out.data_ptr(), N, HW, Cc,
+                                        L.stream()), "apply")
+    Pn.pop("n.beta")
+    ref2 = torch.nn.functional.elu(SN.instance_norm_plus(Pn, "n", x.double()).float())
+    assert rel_l2(out.float().permute(0, 2, 1).reshape(N, Cc, HW, 1).cpu(), ref2) < 1.5e-3
+
+
+def test_chain_noise_is_keyed_by_global_chain_id():
+    """chain i draws Philox(seed, chain i) -- the same chain whether it runs alone, at any slot of any batch, or
+    on any rank of any world size.  Kernel level (bit-identical) for the fused step and the generic update, then through the
+    public sampler: chain 5 alone == chain 5 inside the 14-chain batch of a single GPU == chain 5 on rank 5 of 8."""
+    from inverseproblemwithdiffusionmodel_b200 import chains as CH
+    L = _lib()
+    lib = L.lib()
+    n, nc = 128, 4
+    A = C.SENSE("exp", nc, 40, 1 / 16, (1, n, n), 0)
+    A.random_under_fourier.mask = C.keep_center_mask(n, 40, 1 / 16, seed=0)
+    mre, _ = A.device_maps(torch.device(DEV))
+    plan = A.device_plan(torch.device(DEV), n)
+    m8, frames = A.device_mask(torch.device(DEV))
+    sc = L.AldScalars(0.1, 0.45, 0.02, 1.0)
+    g = torch.Generator().manual_seed(5)
+    per_chain = {i: (torch.randn(2, n, n, generator=g), torch.randn(2, n, n, generator=g), torch.randn(2, n, n, generator=g)) for i in range(16)}
+
+    def run(ids, fused_plan=True):
+        st, gr, bv = (torch.stack([per_chain[i][k] for i in ids], 1).contiguous().to(DEV) for k in range(3))
+        idt = torch.tensor(ids, dtype=torch.int32, device=DEV)
+        if fused_plan:
+            L.check(lib.ipdm_ald_sense_step_plan(plan.handle, st.data_ptr(), gr.data_ptr(), None, bv.data_ptr(), mre.data_ptr(), None, nc, len(ids), n,
+                                                 sc, None, None, L.rng(99, 7, idt), L.stream()), "step")
+        else:
+            L.check(lib.ipdm_ald_sense_step(st.data_ptr(), gr.data_ptr(), None, bv.data_ptr(), mre.data_ptr(), None, m8.data_ptr(), frames, nc, len(ids),
+                                            n, n, sc, None, None, L.rng(99, 7, idt), L.stream()), "step")
+        return st.cpu()
+    for fused_plan in (True, False):
+        alone = run([5], fused_plan)
+        batch = run(list(range(14)), fused_plan)
+        rank5 = run(CH.chain_partition(16, 8, 5), fused_plan)           # chains 5, 13
+        assert torch.equal(alone[:, 0], batch[:, 5]) and torch.equal(alone[:, 0], rank5[:, 0])
+        assert not torch.equal(batch[:, 5], batch[:, 6])
+    # generic update (cfg 1 / sde corrector): per-sample streams
+    xs = {i: torch.randn(1, 28, 28, generator=g) for i in range(16)}
+
+    def run_l(ids):
+        x = torch.stack([xs[i] for i in ids]).contiguous().to(DEV)
+        gz = torch.zeros_like(x)
+        idt = torch.tensor(ids, dtype=torch.int32, device=DEV)
+        L.check(lib.ipdm_langevin_update(x.data_ptr(), gz.data_ptr(), None, None, x.numel(), L.AldScalars(0.0, 1.0, 0.0, 0.0), None, None, None, 0,
+                                         L.rng(4, 2, idt, 28 * 28), L.stream()), "langevin")
+        return x.cpu()
+    assert torch.equal(run_l([5])[0], run_l(list(range(14)))[5]) and torch.equal(run_l([5])[0], run_l([13, 5])[1])
+    # public sampler, captured-graph path with in-kernel noise
+    n2 = 32
+    cfg = C.make_config("ACDC", 8, n2, 10, 30.0, device=DEV)
+    net, _ = C.build_net(C.NCSNv2Deepest, "NCSNv2Deepest_ngf8", 4, cfg, DEV)
+    sig = C.get_sigmas(cfg, mode="recons")
+    A2 = C.SENSE("exp", 4, 40, 1 / 8, (1, n2, n2), 0)
+    A2.random_under_fourier.mask = C.keep_center_mask(n2, 4, 1 / 8, seed=0)
+    y1 = A2(phantom(1403, 1, 1, n2, n2).to(DEV))
+    params = {"n_steps_each": 2, "step_lr": 9e-7, "denoise": True, "final_only": True}
+
+    def sample(ids):
+        Bn = len(ids)
+        s_ = C.ALD.ALDInvSegProximalRealImag(C.L2Penalty(A2), 1.0, "linear", (Bn, 1, n2, n2), net, sig, params, cfg,
+                                             measurement=y1.repeat(1, Bn, 1, 1, 1), linear_tfm=A2, seg=None, device=torch.device(DEV))
+        out = s_(label=None, lamda=1.0, save_dir="/tmp", lr_scaled=1e6, seg_mode="full", seed=2024, chain_ids=ids)[0]
+        torch.set_grad_enabled(True)
+        return out
+    alone, batch, rank5 = sample([5]), sample(list(range(14))), sample(CH.chain_partition(105, 8, 5))
+    assert rel_l2(alone[0], batch[5]) < 1e-6 and rel_l2(alone[0], rank5[0]) < 1e-6
+    assert rel_l2(batch[5], batch[6]) > 1e-3
+    # and without a seed two calls differ (fresh stream per call), with torch.manual_seed they repeat
+    s_ = C.ALD.ALDInvSegProximalRealImag(C.L2Penalty(A2), 1.0, "linear", (2, 1, n2, n2), net, sig, params, cfg,
+                                         measurement=y1.repeat(1, 2, 1, 1, 1), linear_tfm=A2, seg=None, device=torch.device(DEV))
+    kw = dict(label=None, lamda=1.0, save_dir="/tmp", lr_scaled=1e6, seg_mode="full")
+    torch.manual_seed(1); a1 = s_(**kw)[0]; a2 = s_(**kw)[0]
+    torch.manual_seed(1); a3 = s_(**kw)[0]
+    torch.set_grad_enabled(True)
+    assert rel_l2(a1, a2) > 1e-3 and torch.equal(a1, a3)
+
+
 def test_fused_step_kernel_vs_oracle_256():
     """ipdm_ald_sense_step on a cfg-2 sized state (256x256, 4 coils, R=40) against the closed form."""
     L = _lib()
@@ -357,7 +637,7 @@ def test_fused_step_kernel_vs_oracle_256():
     m, frames = A.device_mask(torch.device(DEV))
     sc = L.AldScalars(step, ns, kappa, 0.0)
     L.check(L.lib().ipdm_ald_sense_step(state.data_ptr(), grad.data_ptr(), noise.data_ptr(), bvec.data_ptr(), mre.data_ptr(), None,
-                                        m.data_ptr(), frames, 4, B, n, n, sc, None, None, 0, 0, L.stream()), "ald_sense_step")
+                                        m.data_ptr(), frames, 4, B, n, n, sc, None, None, None, L.stream()), "ald_sense_step")
     got = torch.complex(state[0], state[1]).cpu().reshape(B, 1, n, n)
     assert rel_l2(got, ref) < 1e-5
     assert rel_l2(got - z, ref - z) < 1e-4
@@ -371,7 +651,7 @@ def test_philox_noise_statistics_and_graph_replay():
     x = torch.zeros(n, device=DEV)
     g = torch.zeros(n, device=DEV)
     sc = L.AldScalars(0.5, 1.0, 0.0, 0.0)
-    call = lambda buf, seed, k: L.check(L.lib().ipdm_langevin_update(buf.data_ptr(), g.data_ptr(), None, None, n, sc, None, None, None, 0, seed, k, L.stream()), "langevin")
+    call = lambda buf, seed, k: L.check(L.lib().ipdm_langevin_update(buf.data_ptr(), g.data_ptr(), None, None, n, sc, None, None, None, 0, L.rng(seed, k), L.stream()), "langevin")
     call(x, 42, 0)
     assert abs(float(x.mean())) < 5e-3 and abs(float(x.var()) - 1) < 1e-2
     assert abs(float((x ** 4).mean()) - 3) < 0.1
@@ -412,7 +692,7 @@ def test_in_kernel_noise_never_produces_nonfinite_values():
     steps = 160
     for k in range(steps):
         L.check(L.lib().ipdm_ald_sense_step(state.data_ptr(), grad.data_ptr(), None, bvec.data_ptr(), mre.data_ptr(), None,
-                                            m.data_ptr(), frames, 4, B, n, n, sc, None, None, 77, k, L.stream()), "ald_sense_step")
+                                            m.data_ptr(), frames, 4, B, n, n, sc, None, None, L.rng(77, k), L.stream()), "ald_sense_step")
     assert bool(torch.isfinite(state).all())
     v = float(state.var()) / steps            # kappa = 0: the prox is the identity, the state is a sum of unit normals
     assert abs(v - 1) < 1e-2, v
@@ -420,7 +700,7 @@ def test_in_kernel_noise_never_produces_nonfinite_values():
     g = torch.zeros_like(x)
     for k in range(10):
         L.check(L.lib().ipdm_langevin_update(x.data_ptr(), g.data_ptr(), None, None, x.numel(), L.AldScalars(0.0, 1.0, 0.0, 0.0),
-                                             None, None, None, 0, 5, k, L.stream()), "langevin")
+                                             None, None, None, 0, L.rng(5, k), L.stream()), "langevin")
     assert bool(torch.isfinite(x).all())
     assert abs(float(x.var()) / 10 - 1) < 1e-2
 

@@ -87,7 +87,7 @@ def test_library_exports_every_declared_symbol():
     handle = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(handle, name), name
-    assert _lib.lib().ipdm_abi_version() == 2
+    assert _lib.lib().ipdm_abi_version() == 3
     assert _lib.lib().ipdm_sense_workspace_bytes(4, 2, 256, 256) == 4 * 2 * 256 * 256 * 8
 
 

@@ -44,11 +44,12 @@ for (nc, n, B, R) in cases:
     state = torch.randn(2, B, n, n, device=dev); grad = torch.randn_like(state); bvec = torch.randn_like(state)
     mre, mim = A.device_maps(dev); m, frames = A.device_mask(dev)
     sc = _lib.AldScalars(0.1, 0.4, 0.01, 1.0)
-    step = lambda: _lib.check(L.ipdm_ald_sense_step(state.data_ptr(), grad.data_ptr(), None, bvec.data_ptr(), mre.data_ptr(), None,
-                                                    m.data_ptr(), frames, nc, B, n, n, sc, None, None, 1, 0, _lib.stream()))
+    plan = A.device_plan(dev, n)
+    step = lambda: _lib.check(L.ipdm_ald_sense_step_plan(plan.handle, state.data_ptr(), grad.data_ptr(), None, bvec.data_ptr(), mre.data_ptr(), None,
+                                                         nc, B, n, sc, None, None, _lib.rng(1, 0), _lib.stream()))
     t_s = timeit(step)
     bytes_s = 32 * N + 4 * nc * n * n
-    row = {"coils": nc, "size": n, "batch": B, "R": R, "lines": lines, "kspace_MB": round(8 * nc * N / 1e6, 1),
+    row = {"coils": nc, "size": n, "batch": B, "R": R, "lines": lines, "pruned": plan.pruned, "kspace_MB": round(8 * nc * N / 1e6, 1),
            "fwd_ms": round(t_f, 4), "fwd_GBs": round(bytes_fa / t_f / 1e6, 1), "fwd_frac": round(bytes_fa / t_f / 1e6 / peak, 3),
            "adj_ms": round(t_a, 4), "adj_GBs": round(bytes_fa / t_a / 1e6, 1), "adj_frac": round(bytes_fa / t_a / 1e6 / peak, 3),
            "adj_masked_ms": round(t_am, 4), "adj_masked_GBs": round(bytes_fa / t_am / 1e6, 1),

@@ -19,7 +19,7 @@ for _ in range(reps):
     S = A(x)
     A.conj_op_masked(S)
     A.conj_op(S)
-    _lib.check(L.ipdm_ald_sense_step(state.data_ptr(), grad.data_ptr(), None, bvec.data_ptr(), mre.data_ptr(), None,
-                                     m.data_ptr(), frames, nc, B, n, n, sc, None, None, 1, 0, _lib.stream()))
+    _lib.check(L.ipdm_ald_sense_step_plan(A.device_plan(dev, n).handle, state.data_ptr(), grad.data_ptr(), None, bvec.data_ptr(), mre.data_ptr(), None,
+                                          nc, B, n, sc, None, None, _lib.rng(1, 0), _lib.stream()))
 torch.cuda.synchronize()
 print("ok")
