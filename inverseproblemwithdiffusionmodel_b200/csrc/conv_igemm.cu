@@ -268,6 +268,7 @@ extern "C" int ipdm_debug_option(int key, int value) {
     case 1: g_conv_variant = value; return 0;
     case 2: g_conv_res_prefetch = value; return 0;
     case 3: g_conv_pdl = value; return 0;
+    case 4: IPDM_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value)); return 0;
     default: set_error("debug_option: unknown key %d", key); return IPDM_E_BADARG;
   }
 }

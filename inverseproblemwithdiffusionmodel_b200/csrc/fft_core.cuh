@@ -21,7 +21,8 @@
 
 namespace ipdm {
 
-struct cf32 {
+// 8-byte aligned: complex64 tensors, scratch and shared-memory lines all are, and it lets one 64-bit access move a value
+struct alignas(8) cf32 {
   float x, y;
 };
 

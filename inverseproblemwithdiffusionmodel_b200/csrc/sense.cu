@@ -570,7 +570,7 @@ static int launch_cols(bool fwd, const SenseArgs& a, cudaStream_t s) {
 // ---- mask plans -----------------------------------------------------------------------------------------------
 struct SensePlan {
   uint32_t magic;
-  int device, frames, H, W, ns_max, ns_pad, ng_max, nout;
+  int device, frames, H, W, ns_max, ns_pad, ng_max, nout, cmax, nchunks_max;
   bool pruned_rows, pruned_2d;
   unsigned char* buf;       // one device allocation holding every table
   const uint8_t* mask_dev;  // [frames][W]
@@ -585,46 +585,42 @@ static const SensePlan* as_plan(const void* p) {
 
 template <int LH> static std::vector<float> tws_for() { return build_tws_host(LH, P2<LH>::R0, P2<LH>::R1); }
 
-template <int L, int NOUT>
-static int launch_pruned_rows(bool fwd, const SenseArgs& a, const PlanView& v, cudaStream_t s) {
-  using G = PGeo<L>;
-  dim3 grid(a.batch, a.H / G::TPC);
-  const bool cplx = a.mim != nullptr;
-  if (fwd) {
-    if (cplx) kp_fwd_rows<L, NOUT, true><<<grid, G::NT, 0, s>>>(a, v);
-    else kp_fwd_rows<L, NOUT, false><<<grid, G::NT, 0, s>>>(a, v);
-  } else {
-    if (cplx) kp_adj_rows<L, NOUT, true><<<grid, G::NT, 0, s>>>(a, v);
-    else kp_adj_rows<L, NOUT, false><<<grid, G::NT, 0, s>>>(a, v);
+// (row length, outputs per thread, entries per residue class) -> kernel instance
+#define IPDM_PRUNED_SWITCH(W_, NOUT_, CMAX_, MACRO)                                          \
+  switch ((W_) * 100 + (NOUT_) * 10 + (CMAX_)) {                                             \
+    case 51212: MACRO(512, 1, 2); break;  case 51214: MACRO(512, 1, 4); break;               \
+    case 25612: MACRO(256, 1, 2); break;  case 25614: MACRO(256, 1, 4); break;               \
+    case 25622: MACRO(256, 2, 2); break;  case 25624: MACRO(256, 2, 4); break;               \
+    case 12812: MACRO(128, 1, 2); break;  case 12814: MACRO(128, 1, 4); break;               \
+    case 12822: MACRO(128, 2, 2); break;  case 12824: MACRO(128, 2, 4); break;               \
+    default:                                                                                 \
+      set_error("pruned SENSE: no kernel for W=%d, %d outputs per thread, classes of %d", W_, NOUT_, CMAX_); \
+      return IPDM_E_UNSUPPORTED;                                                             \
   }
+
+static int launch_pruned_rows_any(bool fwd, const SenseArgs& a, const SensePlan* pl, cudaStream_t s) {
+#define PROWS_CASE(LL, NO, CM)                                                               \
+  {                                                                                          \
+    using G = PGeo<LL>;                                                                      \
+    dim3 grid(a.batch, a.H / G::TPC);                                                        \
+    if (fwd) kp_fwd_rows<LL, NO><<<grid, G::NT, 0, s>>>(a, pl->view);                        \
+    else kp_adj_rows<LL, NO, CM><<<grid, G::NT, 0, s>>>(a, pl->view);                        \
+  }
+  IPDM_PRUNED_SWITCH(a.W, pl->nout, pl->cmax, PROWS_CASE)
+#undef PROWS_CASE
   return launched(fwd ? "kp_fwd_rows" : "kp_adj_rows");
 }
 
-static int launch_pruned_rows_any(bool fwd, const SenseArgs& a, const SensePlan* pl, cudaStream_t s) {
-  const int key = a.W * 10 + pl->nout;
-  switch (key) {
-    case 5121: return launch_pruned_rows<512, 1>(fwd, a, pl->view, s);
-    case 2561: return launch_pruned_rows<256, 1>(fwd, a, pl->view, s);
-    case 2562: return launch_pruned_rows<256, 2>(fwd, a, pl->view, s);
-    case 1281: return launch_pruned_rows<128, 1>(fwd, a, pl->view, s);
-    case 1282: return launch_pruned_rows<128, 2>(fwd, a, pl->view, s);
-  }
-  set_error("pruned rows: no kernel for W=%d with %d outputs per thread", a.W, pl->nout);
-  return IPDM_E_UNSUPPORTED;
-}
-
 static int launch_pruned_cols(bool fwd, const SenseArgs& a, const SensePlan* pl, cudaStream_t s) {
-  const int chunks = (pl->ng_max + 3) / 4;
 #define PCOLS_CASE(LL)                                                                   \
   {                                                                                      \
-    using G = Geo<LL>;                                                                   \
-    dim3 grid(a.ncoils * a.batch, chunks);                                               \
+    dim3 grid(a.ncoils * a.batch, pl->nchunks_max);                                      \
     if (fwd) {                                                                           \
-      if (int e = set_smem(kp_fwd_cols<LL>, G::SMEM_COLS)) return e;                     \
-      kp_fwd_cols<LL><<<grid, G::NT_COLS, G::SMEM_COLS, s>>>(a, pl->view);               \
+      if (int e = set_smem(kp_fwd_cols<LL>, CGeo<LL>::SMEM)) return e;                   \
+      kp_fwd_cols<LL><<<grid, CGeo<LL>::NT, CGeo<LL>::SMEM, s>>>(a, pl->view);           \
     } else {                                                                             \
-      if (int e = set_smem(kp_adj_cols<LL>, G::SMEM_COLS)) return e;                     \
-      kp_adj_cols<LL><<<grid, G::NT_COLS, G::SMEM_COLS, s>>>(a, pl->view);               \
+      if (int e = set_smem(kp_adj_cols<LL>, CGeo<LL>::SMEM)) return e;                   \
+      kp_adj_cols<LL><<<grid, CGeo<LL>::NT, CGeo<LL>::SMEM, s>>>(a, pl->view);           \
     }                                                                                    \
   }
   IPDM_FOR_FAST_LEN(a.H, PCOLS_CASE)
@@ -632,12 +628,15 @@ static int launch_pruned_cols(bool fwd, const SenseArgs& a, const SensePlan* pl,
   return launched(fwd ? "kp_fwd_cols" : "kp_adj_cols");
 }
 
-template <int L, int NOUT>
-static int launch_pruned_ald(const AldArgs& a, const PlanView& v, cudaStream_t s) {
-  using G = PGeo<L>;
-  dim3 grid(a.batch, a.H / G::TPC);
-  if (a.mim != nullptr) kp_ald_sense<L, NOUT, true><<<grid, G::NT, 0, s>>>(a, v);
-  else kp_ald_sense<L, NOUT, false><<<grid, G::NT, 0, s>>>(a, v);
+static int launch_pruned_ald(const AldArgs& a, const SensePlan* pl, cudaStream_t s) {
+#define PALD_CASE(LL, NO, CM)                                                                \
+  {                                                                                          \
+    using G = PGeo<LL>;                                                                      \
+    dim3 grid(a.batch, a.H / G::TPC);                                                        \
+    kp_ald_sense<LL, NO, CM><<<grid, G::NT, 0, s>>>(a, pl->view);                            \
+  }
+  IPDM_PRUNED_SWITCH(a.W, pl->nout, pl->cmax, PALD_CASE)
+#undef PALD_CASE
   return launched("kp_ald_sense");
 }
 
@@ -964,15 +963,7 @@ extern "C" int ipdm_ald_sense_step_plan(const void* plan, float* x, const float*
   a.sched = sched; a.cursor = cursor; a.rng = rng_args(rng_host);
   cudaStream_t s = as_stream(stream);
   static const bool no_pruned = getenv("IPDM_SENSE_NO_PRUNED") != nullptr;   // A/B switch for profiling only
-  if (pl->pruned_rows && !no_pruned && H % 16 == 0) {
-    switch (pl->W * 10 + pl->nout) {
-      case 5121: return launch_pruned_ald<512, 1>(a, pl->view, s);
-      case 2561: return launch_pruned_ald<256, 1>(a, pl->view, s);
-      case 2562: return launch_pruned_ald<256, 2>(a, pl->view, s);
-      case 1281: return launch_pruned_ald<128, 1>(a, pl->view, s);
-      case 1282: return launch_pruned_ald<128, 2>(a, pl->view, s);
-    }
-  }
+  if (pl->pruned_rows && !no_pruned && H % 16 == 0 && maps_im == nullptr) return launch_pruned_ald(a, pl, s);
   return ald_sense_general(a, s);
 }
 
@@ -1008,6 +999,8 @@ extern "C" int ipdm_sense_plan_create(const uint8_t* mask_host, int mask_frames,
   pl->pruned_rows = ph.pruned;
   pl->pruned_2d = ph.pruned && fast_len(H);
   pl->nout = ph.pruned ? (ph.ns_max + ph.R1 - 1) / ph.R1 : 0;
+  pl->cmax = ph.cmax;
+  pl->nchunks_max = ph.nchunks_max;
   if (pl->nout > 2) { pl->pruned_rows = pl->pruned_2d = false; }
   cudaError_t ce = cudaGetDevice(&pl->device);
   if (ce != cudaSuccess) { delete pl; set_error("sense_plan_create: %s", cudaGetErrorString(ce)); return (int)ce; }
@@ -1030,21 +1023,23 @@ extern "C" int ipdm_sense_plan_create(const uint8_t* mask_host, int mask_frames,
     return pieces.size() - 1;
   };
   const size_t i_mask = add(ph.mask.data(), ph.mask.size());
-  size_t i_ns = 0, i_ng = 0, i_kcol = 0, i_nat = 0, i_k0c = 0, i_cls = 0, i_tw = 0, i_groups = 0, i_gslot = 0, i_gbm = 0, i_tws = 0;
-  std::vector<uint32_t> cls_words;
+  size_t i_ns = 0, i_ng = 0, i_nc = 0, i_kcol = 0, i_nat = 0, i_k0c = 0, i_ppos = 0, i_tw = 0, i_twh = 0, i_groups = 0, i_gslot = 0,
+         i_chunks = 0, i_gbm = 0, i_big = 0, i_tws = 0;
   if (pl->pruned_rows) {
     i_ns = add(ph.ns.data(), ph.ns.size() * sizeof(int));
     i_ng = add(ph.ngroups.data(), ph.ngroups.size() * sizeof(int));
+    i_nc = add(ph.nchunks.data(), ph.nchunks.size() * sizeof(int));
     i_kcol = add(ph.kcol.data(), ph.kcol.size() * sizeof(uint16_t));
     i_nat = add(ph.nat.data(), ph.nat.size());
     i_k0c = add(ph.k0c.data(), ph.k0c.size());
-    cls_words.resize((size_t)mask_frames * 5);
-    memcpy(cls_words.data(), ph.cls.data(), cls_words.size() * 4);
-    i_cls = add(cls_words.data(), cls_words.size() * 4);
+    i_ppos = add(ph.ppos.data(), ph.ppos.size());
     i_tw = add(ph.tw.data(), ph.tw.size() * sizeof(float));
+    i_twh = add(ph.twh.data(), ph.twh.size() * sizeof(float));
+    i_chunks = add(ph.chunks.data(), ph.chunks.size());
     i_groups = add(ph.groups.data(), ph.groups.size());
     i_gslot = add(ph.gslot.data(), ph.gslot.size());
     i_gbm = add(ph.gbitmap.data(), ph.gbitmap.size() * sizeof(uint32_t));
+    i_big = add(ph.big.data(), ph.big.size() * sizeof(uint32_t));
     if (!tws.empty()) i_tws = add(tws.data(), tws.size() * sizeof(float));
   }
   ce = cudaMalloc(reinterpret_cast<void**>(&pl->buf), total);
@@ -1063,17 +1058,21 @@ extern "C" int ipdm_sense_plan_create(const uint8_t* mask_host, int mask_frames,
   pl->mask_dev = at(i_mask);
   if (pl->pruned_rows) {
     PlanView& v = pl->view;
-    v.frames = mask_frames; v.W = W; v.ns_pad = ph.ns_pad; v.ng_all = W / 4;
+    v.frames = mask_frames; v.W = W; v.ns_pad = ph.ns_pad; v.ng_all = W / 4; v.cmax = ph.cmax;
     v.ns = reinterpret_cast<const int*>(at(i_ns));
     v.ngroups = reinterpret_cast<const int*>(at(i_ng));
+    v.nchunks = reinterpret_cast<const int*>(at(i_nc));
     v.kcol = reinterpret_cast<const uint16_t*>(at(i_kcol));
     v.nat = at(i_nat);
     v.k0c = at(i_k0c);
-    v.cls = reinterpret_cast<const uint32_t*>(at(i_cls));
+    v.ppos = at(i_ppos);
     v.tw = reinterpret_cast<const cf32*>(at(i_tw));
+    v.twh = reinterpret_cast<const cf32*>(at(i_twh));
+    v.chunks = at(i_chunks);
     v.groups = at(i_groups);
     v.gslot = at(i_gslot);
     v.gbitmap = reinterpret_cast<const uint32_t*>(at(i_gbm));
+    v.big = reinterpret_cast<const uint32_t*>(at(i_big));
     v.tws_h = tws.empty() ? nullptr : reinterpret_cast<const cf32*>(at(i_tws));
   }
   *plan_out = pl;
@@ -1106,7 +1105,7 @@ extern "C" int ipdm_sense_forward_plan(const void* plan, const void* x, const fl
                                        int ncoils, int batch, void* workspace, void* stream) {
   const SensePlan* pl = as_plan(plan);
   IPDM_REQUIRE(pl, IPDM_E_BADARG, "sense_forward_plan: not a plan");
-  if (!plan_pruned_2d(pl))
+  if (!plan_pruned_2d(pl) || maps_im != nullptr)   // the pruned kernels take real coil maps (the reference's, quirk Q4) or none
     return ipdm_sense_forward(x, maps_re, maps_im, pl->mask_dev, pl->frames, out, ncoils, batch, pl->H, pl->W, workspace, stream);
   IPDM_REQUIRE(x && out && workspace, IPDM_E_BADARG, "sense_forward_plan: null pointer");
   IPDM_REQUIRE(ncoils >= 1 && batch >= 1, IPDM_E_BADARG, "sense_forward_plan: bad ncoils/batch");
@@ -1125,14 +1124,14 @@ extern "C" int ipdm_sense_adjoint_plan(const void* plan, const void* S, const fl
                                        int ncoils, int batch, int ssos, void* workspace, void* stream) {
   const SensePlan* pl = as_plan(plan);
   IPDM_REQUIRE(pl, IPDM_E_BADARG, "sense_adjoint_plan: not a plan");
-  if (!plan_pruned_2d(pl))
+  if (!plan_pruned_2d(pl) || (maps_im != nullptr && !ssos))
     return ipdm_sense_adjoint(S, maps_re, maps_im, pl->mask_dev, pl->frames, out, ncoils, batch, pl->H, pl->W, ssos, workspace, stream);
   IPDM_REQUIRE(S && out && workspace, IPDM_E_BADARG, "sense_adjoint_plan: null pointer");
   IPDM_REQUIRE(ncoils >= 1 && batch >= 1, IPDM_E_BADARG, "sense_adjoint_plan: bad ncoils/batch");
   const int H = pl->H, W = pl->W;
   SenseArgs a{};
   a.in = (const cf32*)S; a.out = (cf32*)out; a.ws = (cf32*)workspace;
-  a.mre = ssos ? nullptr : maps_re; a.mim = ssos ? nullptr : maps_im;
+  a.mre = ssos ? nullptr : maps_re; a.mim = nullptr;
   a.mask = pl->mask_dev; a.mask_frames = pl->frames;
   a.ncoils = ncoils; a.batch = batch; a.H = H; a.W = W; a.ssos = ssos ? 1 : 0;
   a.scale = (((H / 2 + W / 2) & 1) ? -1.f : 1.f) / sqrtf((float)H * (float)W);

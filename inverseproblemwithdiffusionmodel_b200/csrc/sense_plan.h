@@ -8,9 +8,15 @@
 //   nat[f][jj], k0c[f][jj], cls[f][0..16], tw[f][jj][t]
 //                      the same columns in CLASS order (sorted by k mod 16, then k): natural slot, class k mod 16,
 //                      class boundaries, and the twiddle vectors w_W^(t*k) = exp(-2*pi*i*t*k/W), t < W/16
+//   ppos[f][jj]        position of class entry jj in the PADDED class layout k0*cmax + e (cmax = largest class of any
+//                      frame): the inverse transforms read their classes with static indices, pads hold zeros
+//   twh[f][jj][10]     the twiddle vector in factored form, w^(t*k) = w^((t&3)*k) * w^(4*(t>>2)*k): entries
+//                      w^k, w^2k, w^3k, then w^(4m*k) for m = 1 .. W/64-1 (20 registers instead of 2*W/16)
 //   ngroups[f], groups[f][g], gslot[f][g][0..3], gbitmap[f][4]
 //                      the active 4-column groups (one 32-byte sector of a k-space row each), for every group the
 //                      natural slot of each of its columns (255 = not sampled), and the bitmap over all W/4 groups
+//   nchunks[f], chunks[f][c] = {first group, groups, first slot, slots}
+//                      work items of the column kernels: runs of whole groups holding at most 8 sampled columns
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -20,14 +26,16 @@
 namespace ipdm {
 
 struct PlanHost {
-  int frames = 0, W = 0, R1 = 0, ns_max = 0, ns_pad = 0, ng_max = 0;
-  bool pruned = false;   // every frame keeps <= the limit the pruned kernels are built for
-  std::vector<int> ns, ngroups;
+  int frames = 0, W = 0, R1 = 0, ns_max = 0, ns_pad = 0, ng_max = 0, cmax = 0, nchunks_max = 0;
+  bool pruned = false;   // every frame keeps <= the limit the pruned kernels are built for and no residue class holds > 4 columns
+  std::vector<int> ns, ngroups, nchunks;
   std::vector<uint16_t> kcol;
-  std::vector<uint8_t> nat, k0c, cls, groups, gslot, mask;
-  std::vector<uint32_t> gbitmap;
-  std::vector<float> tw;   // interleaved (re, im)
+  std::vector<uint8_t> nat, k0c, cls, ppos, groups, gslot, chunks, mask;
+  std::vector<uint32_t> gbitmap, big;   // big[f][2]: classes with >= 3 / == 4 entries, one bit per class
+  std::vector<float> tw, twh;   // interleaved (re, im)
   static constexpr int CLS_PITCH = 20;   // 17 boundaries padded to five 32-bit words
+  static constexpr int TWH = 10;         // factored twiddle entries per column
+  static constexpr int CHUNK_SLOTS = 8;  // sampled columns per work item of the column kernels
 };
 
 // Largest ns the pruned row kernels take for a row length W (0: W not served).  One register-resident twiddle vector
@@ -54,9 +62,13 @@ inline PlanHost build_plan_host(const uint8_t* mask, int frames, int W) {
     p.ngroups[f] = g;
     p.ns_max = std::max(p.ns_max, n);
     p.ng_max = std::max(p.ng_max, g);
+    int cnt[16] = {0};   // largest residue class (column mod 16) over all frames
+    for (int k = 0; k < W; ++k)
+      if (mask[(size_t)f * W + k]) p.cmax = std::max(p.cmax, ++cnt[k & 15]);
   }
   const int limit = pruned_ns_limit(W);
-  p.pruned = limit > 0 && p.ns_max >= 1 && p.ns_max <= limit;
+  p.pruned = limit > 0 && p.ns_max >= 1 && p.ns_max <= limit && p.cmax <= 4;
+  p.cmax = p.cmax <= 2 ? 2 : 4;   // padded class size the kernels are built for
   p.ns_pad = std::max(4, (p.ns_max + 3) & ~3);
   if (!p.pruned) return p;
   const int NP = p.ns_pad, R1 = p.R1;
@@ -64,10 +76,15 @@ inline PlanHost build_plan_host(const uint8_t* mask, int frames, int W) {
   p.nat.assign((size_t)frames * NP, 0);
   p.k0c.assign((size_t)frames * NP, 0);
   p.cls.assign((size_t)frames * PlanHost::CLS_PITCH, 0);
+  p.ppos.assign((size_t)frames * NP, 0);
   p.tw.assign((size_t)frames * NP * R1 * 2, 0.f);
+  p.twh.assign((size_t)frames * NP * PlanHost::TWH * 2, 0.f);
+  p.nchunks.assign(frames, 0);
+  p.chunks.assign((size_t)frames * ng_all * 4, 0);
   p.groups.assign((size_t)frames * ng_all, 0);
   p.gslot.assign((size_t)frames * ng_all * 4, 255);
   p.gbitmap.assign((size_t)frames * 4, 0u);
+  p.big.assign((size_t)frames * 2, 0u);
   for (int f = 0; f < frames; ++f) {
     const uint8_t* m = mask + (size_t)f * W;
     std::vector<int> cols;
@@ -85,16 +102,25 @@ inline PlanHost build_plan_host(const uint8_t* mask, int frames, int W) {
       while (jj < order.size() && (cols[order[jj]] & 15) == k0) ++jj;
     }
     cls[16] = (uint8_t)jj;
+    for (int k0 = 0; k0 < 16; ++k0) {
+      if (cls[k0 + 1] - cls[k0] >= 3) p.big[(size_t)f * 2] |= 1u << k0;
+      if (cls[k0 + 1] - cls[k0] >= 4) p.big[(size_t)f * 2 + 1] |= 1u << k0;
+    }
     for (size_t j = 0; j < order.size(); ++j) {
       const int s = order[j], k = cols[s];
       p.nat[(size_t)f * NP + j] = (uint8_t)s;
       p.k0c[(size_t)f * NP + j] = (uint8_t)(k & 15);
-      for (int t = 0; t < R1; ++t) {
+      p.ppos[(size_t)f * NP + j] = (uint8_t)((k & 15) * p.cmax + ((int)j - cls[k & 15]));
+      auto tw_of = [&](int t, float* out) {
         const int e = (int)(((long long)t * k) % W);
         const double ang = -2.0 * M_PI * (double)e / (double)W;
-        p.tw[(((size_t)f * NP + j) * R1 + t) * 2] = (float)cos(ang);
-        p.tw[(((size_t)f * NP + j) * R1 + t) * 2 + 1] = (float)sin(ang);
-      }
+        out[0] = (float)cos(ang);
+        out[1] = (float)sin(ang);
+      };
+      for (int t = 0; t < R1; ++t) tw_of(t, &p.tw[(((size_t)f * NP + j) * R1 + t) * 2]);
+      float* th = &p.twh[((size_t)f * NP + j) * PlanHost::TWH * 2];
+      for (int i = 1; i <= 3; ++i) tw_of(i, th + 2 * (i - 1));
+      for (int m = 1; m < R1 / 4; ++m) tw_of(4 * m, th + 2 * (2 + m));
     }
     int g = 0;
     for (int q = 0; q < ng_all; ++q) {
@@ -108,6 +134,25 @@ inline PlanHost build_plan_host(const uint8_t* mask, int frames, int W) {
       }
       ++g;
     }
+    // column-kernel work items: consecutive whole groups, at most CHUNK_SLOTS sampled columns each
+    int c = 0, g_lo = 0, s_lo = 0;
+    while (g_lo < g) {
+      int g_hi = g_lo, s_hi = s_lo;
+      while (g_hi < g) {
+        int in_group = 0;
+        for (int i = 0; i < 4; ++i) in_group += p.gslot[((size_t)f * ng_all + g_hi) * 4 + i] != 255;
+        if (s_hi - s_lo + in_group > PlanHost::CHUNK_SLOTS) break;
+        s_hi += in_group;
+        ++g_hi;
+      }
+      uint8_t* ch = &p.chunks[((size_t)f * ng_all + c) * 4];
+      ch[0] = (uint8_t)g_lo; ch[1] = (uint8_t)(g_hi - g_lo); ch[2] = (uint8_t)s_lo; ch[3] = (uint8_t)(s_hi - s_lo);
+      g_lo = g_hi;
+      s_lo = s_hi;
+      ++c;
+    }
+    p.nchunks[f] = c;
+    p.nchunks_max = std::max(p.nchunks_max, c);
   }
   return p;
 }

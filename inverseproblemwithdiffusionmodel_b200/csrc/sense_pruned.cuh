@@ -20,30 +20,34 @@
 namespace ipdm {
 
 struct PlanView {
-  int frames, W, ns_pad, ng_all;
+  int frames, W, ns_pad, ng_all, cmax;
   const int* ns;
   const int* ngroups;
+  const int* nchunks;
   const uint16_t* kcol;
-  const uint8_t* nat;
-  const uint8_t* k0c;
-  const uint32_t* cls;      // [frames][5]
+  const uint8_t* nat;       // [frames][ns_pad]  class position -> natural slot
+  const uint8_t* k0c;       // [frames][ns_pad]  class position -> k mod 16
+  const uint8_t* ppos;      // [frames][ns_pad]  class position -> position in the padded class layout (k0*cmax + e)
   const cf32* tw;           // [frames][ns_pad][W/16], class order
+  const cf32* twh;          // [frames][ns_pad][10], class order, factored form
   const uint8_t* groups;    // [frames][W/4]
   const uint8_t* gslot;     // [frames][W/4][4]
+  const uint8_t* chunks;    // [frames][W/4][4] = {first group, groups, first slot, slots}
   const uint32_t* gbitmap;  // [frames][4]
+  const uint32_t* big;      // [frames][2]  classes with >= 3 / 4 sampled columns
   const cf32* tws_h;        // layout-B twiddles of the H transform (Geo<H>::NTWS entries)
 };
+constexpr int PLAN_TWH = 10;
 
 template <int L> struct PGeo {
   using P = PR<L>;
   static constexpr int RPW = 32 / P::R1, WARPS = 4, NT = 128, TPC = RPW * WARPS;   // rows per CTA: 4, 8, 16
-  static constexpr int YP = 32;                                                    // per-row spectrum line (class order)
   static constexpr int ZP = TPC * (L / 2) / NT;                                    // 16-byte zero-fill pieces per thread and coil
 };
 
 // The outputs (forward) / inputs (adjoint) of thread t: class positions jj = t + R1*o, o < NOUT.
 template <int L, int NOUT> struct MySlots {
-  int k0[NOUT], slot[NOUT];
+  int k0[NOUT], slot[NOUT], pp[NOUT];
   __device__ __forceinline__ void init(const PlanView& p, int f, int ns, int t) {
 #pragma unroll
     for (int o = 0; o < NOUT; ++o) {
@@ -51,32 +55,32 @@ template <int L, int NOUT> struct MySlots {
       const bool on = jj < ns;
       k0[o] = on ? p.k0c[f * p.ns_pad + jj] : 0;
       slot[o] = on ? p.nat[f * p.ns_pad + jj] : -1;
+      pp[o] = on ? p.ppos[f * p.ns_pad + jj] : 0;
     }
   }
 };
 
-// twr[o][tt] = w_W^(tt * k) for the thread's outputs; ALT multiplies by (-1)^tt (the fused step works on the
-// un-centred spectrum: column k of the mask sits at plain index k ^ (W/2)).
+// Factored twiddle vectors of the thread's outputs; ALT folds (-1)^t in (the fused step works on the un-centred spectrum:
+// column k of the mask sits at plain index k ^ (W/2), i.e. w^(t*k) picks up (-1)^t = (-1)^(t&3): w^k and w^3k change sign).
 template <int L, int NOUT, bool ALT>
-__device__ __forceinline__ void load_my_twiddles(cf32 (&twr)[NOUT][PR<L>::R1], const PlanView& p, int f, int ns, int t) {
+__device__ __forceinline__ void load_my_twiddles(cf32 (&twh)[NOUT][PR<L>::NTWH], const PlanView& p, int f, int ns, int t) {
   using P = PR<L>;
 #pragma unroll
   for (int o = 0; o < NOUT; ++o) {
     const int jj = t + P::R1 * o;
-    const cf32x2* src = reinterpret_cast<const cf32x2*>(p.tw + ((size_t)f * p.ns_pad + (jj < ns ? jj : 0)) * P::R1);
+    const cf32* src = p.twh + ((size_t)f * p.ns_pad + (jj < ns ? jj : 0)) * PLAN_TWH;
 #pragma unroll
-    for (int i = 0; i < P::R1 / 2; ++i) {
-      const cf32x2 w = src[i];
-      twr[o][2 * i] = w.a;
-      twr[o][2 * i + 1] = ALT ? cf32{-w.b.x, -w.b.y} : w.b;
+    for (int i = 0; i < P::NTWH; ++i) {
+      const cf32 w = src[i];
+      twh[o][i] = (ALT && (i == 0 || i == 2)) ? cf32{-w.x, -w.y} : w;
     }
   }
 }
 
 // ---- forward, rows: coil multiply, pruned transform along W, compact scratch, zero-fill -------------------------
-// grid (batch, H / TPC)
-template <int L, int NOUT, bool CPLX>
-__global__ void __launch_bounds__(128) kp_fwd_rows(SenseArgs a, PlanView p) {
+// grid (batch, H / TPC).  Real coil maps (or none).
+template <int L, int NOUT>
+__global__ void __launch_bounds__(128, 3) kp_fwd_rows(SenseArgs a, PlanView p) {
   using G = PGeo<L>;
   using P = PR<L>;
   __shared__ __align__(16) cf32 xch[G::TPC * P::LINE];
@@ -88,8 +92,8 @@ __global__ void __launch_bounds__(128) kp_fwd_rows(SenseArgs a, PlanView p) {
   cf32* sx = xch + r * P::LINE;
   MySlots<L, NOUT> my;
   my.init(p, f, ns, t);
-  cf32 twr[NOUT][P::R1];
-  load_my_twiddles<L, NOUT, false>(twr, p, f, ns, t);
+  cf32 twh[NOUT][P::NTWH];
+  load_my_twiddles<L, NOUT, false>(twh, p, f, ns, t);
   cf32 xq[P::R0];
   {
     const cf32* xp = a.in + ((size_t)b * a.H + h) * L + t;
@@ -100,14 +104,12 @@ __global__ void __launch_bounds__(128) kp_fwd_rows(SenseArgs a, PlanView p) {
   const bool has_maps = a.mre != nullptr;
   const size_t map_img = (size_t)a.H * L;
   const float* mre = a.mre + (size_t)h * L + t;
-  const float* mim = a.mim + (size_t)h * L + t;
-  MapVal<CPLX> mnext[P::R0];
+  float mnext[P::R0];
   auto fetch_maps = [&](int c) {
     if (has_maps && c < a.ncoils) {
 #pragma unroll
-      for (int q = 0; q < P::R0; ++q) mnext[q].load(mre, mim, P::R1 * q);
+      for (int q = 0; q < P::R0; ++q) mnext[q] = mre[P::R1 * q];
       mre += map_img;
-      mim += map_img;
     }
   };
   fetch_maps(0);
@@ -124,9 +126,11 @@ __global__ void __launch_bounds__(128) kp_fwd_rows(SenseArgs a, PlanView p) {
   cf32* wsp = a.ws + ((size_t)b * a.H + h) * p.ns_pad;
   const size_t ws_stride = (size_t)a.batch * a.H * p.ns_pad;
   for (int c = 0; c < a.ncoils; ++c) {
+    // (re-reading the row per coil instead of keeping it would free 32 registers for a fourth resident CTA, but this
+    // kernel is bound by the L1 / shared-memory data pipe -- ncu: 95 % -- and the re-reads land exactly there)
     cf32 u[P::R0];
 #pragma unroll
-    for (int q = 0; q < P::R0; ++q) u[q] = has_maps ? mnext[q].mul(xq[q]) : xq[q];
+    for (int q = 0; q < P::R0; ++q) u[q] = has_maps ? cscale(xq[q], mnext[q]) : xq[q];
     fetch_maps(c + 1);
 #pragma unroll
     for (int z = 0; z < G::ZP; ++z)
@@ -137,21 +141,31 @@ __global__ void __launch_bounds__(128) kp_fwd_rows(SenseArgs a, PlanView p) {
     __syncwarp();
 #pragma unroll
     for (int o = 0; o < NOUT; ++o)
-      if (my.slot[o] >= 0) wsp[my.slot[o]] = pr_gather<L, -1>(sx, my.k0[o], twr[o]);
+      if (my.slot[o] >= 0) wsp[my.slot[o]] = pr_gather<L, -1>(sx, my.k0[o], twh[o]);
     wsp += ws_stride;
   }
 }
 
 // ---- column kernels: full two-pass transforms along H of the sampled columns ------------------------------------
-// grid (ncoils * batch, chunks); a chunk = 4 consecutive active groups = 16 column positions, one transform each
-// (positions that are not sampled idle).
+// grid (ncoils * batch, chunks); a chunk = a run of whole active groups holding at most 8 sampled columns (plan table),
+// one transform per sampled column.  The compact scratch rows of a chunk are contiguous (<= 64 bytes per image row).
 template <int LH>
 __device__ __forceinline__ void copy_tws(cf32* tws, const cf32* src, int tid, int nt) {
   for (int e = tid; e < Geo<LH>::NTWS; e += nt) tws[e] = src[e];
 }
+// line pitch of the column kernels: odd, so that the 16 lanes that fill / drain 16 different lines at the same row
+// (the coalesced side of the compact scratch) hit 16 different bank pairs
+// 8 lines (sampled columns) per CTA: half the shared memory of a 16-line CTA, twice the resident CTAs -- these kernels
+// move little data and wait on its latency, so residency is what they need
+template <int LH> struct CGeo {
+  static constexpr int CL = 8;
+  static constexpr int NT = CL * Geo<LH>::TPF;
+  static constexpr int CSTRIDE = P2<LH>::STRIDE | 1;
+  static constexpr size_t SMEM = (size_t)(Geo<LH>::NTWS + CL * CSTRIDE) * sizeof(cf32);
+};
 
 template <int LH>
-__global__ void __launch_bounds__(Geo<LH>::NT_COLS) kp_fwd_cols(SenseArgs a, PlanView p) {
+__global__ void __launch_bounds__(CGeo<LH>::NT) kp_fwd_cols(SenseArgs a, PlanView p) {
   using G = Geo<LH>;
   using P = P2<LH>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -160,43 +174,54 @@ __global__ void __launch_bounds__(Geo<LH>::NT_COLS) kp_fwd_cols(SenseArgs a, Pla
   const int tid = threadIdx.x;
   const size_t img = blockIdx.x;
   const int b = (int)(img % a.batch), f = b % p.frames;
-  const int ng = p.ngroups[f], g0 = blockIdx.y * 4;
-  if (g0 >= ng) return;
-  copy_tws<LH>(tws, p.tws_h, tid, G::NT_COLS);
-  const int cs = tid / G::TPF, t = tid % G::TPF;
-  cf32* sx = xch + cs * P::STRIDE;
-  const bool gvalid = g0 + (cs >> 2) < ng;
-  const int slot = gvalid ? p.gslot[((size_t)f * p.ng_all + g0 + (cs >> 2)) * 4 + (cs & 3)] : 255;
-  cf32 v[G::E];
+  if ((int)blockIdx.y >= p.nchunks[f]) return;
+  const uchar4 ch = *reinterpret_cast<const uchar4*>(p.chunks + ((size_t)f * p.ng_all + blockIdx.y) * 4);
+  const int g_lo = ch.x, g_cnt = ch.y, s_lo = ch.z, s_cnt = ch.w;
+  copy_tws<LH>(tws, p.tws_h, tid, CGeo<LH>::NT);
+  // compact scratch rows -> one line per sampled column (lanes along the slots: contiguous runs of 8*s_cnt bytes)
   {
-    const cf32* wp = a.ws + (img * LH + t) * p.ns_pad + (slot != 255 ? slot : 0);
-#pragma unroll
-    for (int q = 0; q < G::E; ++q) v[q] = slot != 255 ? wp[(size_t)a_off<LH>(q) * p.ns_pad] : cf32{0.f, 0.f};
+    const cf32* wp = a.ws + img * LH * p.ns_pad + s_lo;
+#pragma unroll 4
+    for (int idx = tid; idx < CGeo<LH>::CL * LH; idx += CGeo<LH>::NT) {
+      const int si = idx % CGeo<LH>::CL, hh = idx / CGeo<LH>::CL;
+      if (si < s_cnt) xch[si * CGeo<LH>::CSTRIDE + hh] = wp[(size_t)hh * p.ns_pad + si];
+    }
   }
-  __syncthreads();   // twiddle table complete
-  Twid<LH, (LH < 512)> tw;
-  tw.init(tws, t);
-  a2b_first<LH, -1>(v, t, sx);
-  __syncwarp();
-  a2b_second<LH, -1>(v, t, sx, tw);
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < G::E; ++i) sx[b_pos<LH>(t, i)] = v[i];   // the exchange line doubles as the column's tile line
   __syncthreads();
-  // 16-byte pieces: idx = ((gi*LH + h)*2 + half)
-  for (int idx = tid; idx < 4 * LH * 2; idx += G::NT_COLS) {
-    const int half = idx & 1, hh = (idx >> 1) % LH, gi = (idx >> 1) / LH;
-    if (g0 + gi >= ng) break;
-    const int kk = 4 * p.groups[f * p.ng_all + g0 + gi] + 2 * half;
-    const cf32 p0 = xch[(4 * gi + 2 * half) * P::STRIDE + hh], p1 = xch[(4 * gi + 2 * half + 1) * P::STRIDE + hh];
-    const float s0 = a.scale * sgn(hh + kk);
-    *reinterpret_cast<float4*>(a.out + (img * LH + hh) * a.W + kk) = make_float4(p0.x * s0, p0.y * s0, -p1.x * s0, -p1.y * s0);
+  const int cs = tid / G::TPF, t = tid % G::TPF;
+  cf32* sx = xch + cs * CGeo<LH>::CSTRIDE;
+  {   // every line is transformed (lines past s_cnt hold stale data nobody reads): no divergence around __syncwarp
+    Twid<LH, (LH < 512)> tw;
+    tw.init(tws, t);
+    cf32 v[G::E];
+#pragma unroll
+    for (int q = 0; q < G::E; ++q) v[q] = sx[a_pos<LH>(t, q)];
+    __syncwarp();
+    a2b_first<LH, -1>(v, t, sx);
+    __syncwarp();
+    a2b_second<LH, -1>(v, t, sx, tw);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < G::E; ++i) sx[b_pos<LH>(t, i)] = v[i];   // the exchange line doubles as the column's tile line
+  }
+  __syncthreads();
+  // active sectors, 16-byte pieces: idx = (h * g_cnt + gi) * 2 + half -- consecutive lanes walk the sectors of one image row
+  for (int idx = tid; idx < LH * g_cnt * 2; idx += CGeo<LH>::NT) {
+    const int half = idx & 1, gi = (idx >> 1) % g_cnt, hh = (idx >> 1) / g_cnt;
+    const int g = g_lo + gi;
+    const int kk = 4 * p.groups[f * p.ng_all + g] + 2 * half;
+    const uint8_t* gs = p.gslot + ((size_t)f * p.ng_all + g) * 4 + 2 * half;
+    const int s0 = gs[0], s1 = gs[1];
+    const cf32 p0 = s0 != 255 ? xch[(s0 - s_lo) * CGeo<LH>::CSTRIDE + hh] : cf32{0.f, 0.f};
+    const cf32 p1 = s1 != 255 ? xch[(s1 - s_lo) * CGeo<LH>::CSTRIDE + hh] : cf32{0.f, 0.f};
+    const float sc0 = a.scale * sgn(hh + kk);
+    *reinterpret_cast<float4*>(a.out + (img * LH + hh) * a.W + kk) = make_float4(p0.x * sc0, p0.y * sc0, -p1.x * sc0, -p1.y * sc0);
   }
 }
 
 // adjoint, columns: inverse transform of the sampled columns along H into the compact scratch
 template <int LH>
-__global__ void __launch_bounds__(Geo<LH>::NT_COLS) kp_adj_cols(SenseArgs a, PlanView p) {
+__global__ void __launch_bounds__(CGeo<LH>::NT) kp_adj_cols(SenseArgs a, PlanView p) {
   using G = Geo<LH>;
   using P = P2<LH>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -205,111 +230,145 @@ __global__ void __launch_bounds__(Geo<LH>::NT_COLS) kp_adj_cols(SenseArgs a, Pla
   const int tid = threadIdx.x;
   const size_t img = blockIdx.x;
   const int b = (int)(img % a.batch), f = b % p.frames;
-  const int ng = p.ngroups[f], g0 = blockIdx.y * 4;
-  if (g0 >= ng) return;
-  copy_tws<LH>(tws, p.tws_h, tid, G::NT_COLS);
-  for (int idx = tid; idx < 4 * LH * 2; idx += G::NT_COLS) {
-    const int half = idx & 1, hh = (idx >> 1) % LH, gi = (idx >> 1) / LH;
-    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (g0 + gi < ng) {
-      const int g = g0 + gi, kk = 4 * p.groups[f * p.ng_all + g] + 2 * half;
-      const uint8_t* gs = p.gslot + ((size_t)f * p.ng_all + g) * 4 + 2 * half;
-      q = *reinterpret_cast<const float4*>(a.in + (img * LH + hh) * a.W + kk);
-      const float s0 = sgn(hh + kk);
-      const float m0 = gs[0] != 255 ? s0 : 0.f, m1 = gs[1] != 255 ? -s0 : 0.f;
-      q = make_float4(q.x * m0, q.y * m0, q.z * m1, q.w * m1);
+  if ((int)blockIdx.y >= p.nchunks[f]) return;
+  const uchar4 ch = *reinterpret_cast<const uchar4*>(p.chunks + ((size_t)f * p.ng_all + blockIdx.y) * 4);
+  const int g_lo = ch.x, g_cnt = ch.y, s_lo = ch.z, s_cnt = ch.w;
+  copy_tws<LH>(tws, p.tws_h, tid, CGeo<LH>::NT);
+  // active sectors of this chunk -> lines of the sampled columns; four independent 16-byte loads in flight per thread
+  {
+    const int total = LH * g_cnt * 2;
+    for (int base = tid; base < total; base += 4 * CGeo<LH>::NT) {
+      float4 q[4];
+      int hh[4], s0[4], s1[4], kk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int idx = base + j * CGeo<LH>::NT;
+        s0[j] = s1[j] = 255;
+        if (idx < total) {
+          const int half = idx & 1, gi = (idx >> 1) % g_cnt;
+          hh[j] = (idx >> 1) / g_cnt;
+          const int g = g_lo + gi;
+          kk[j] = 4 * p.groups[f * p.ng_all + g] + 2 * half;
+          const uint8_t* gs = p.gslot + ((size_t)f * p.ng_all + g) * 4 + 2 * half;
+          s0[j] = gs[0];
+          s1[j] = gs[1];
+          if (s0[j] != 255 || s1[j] != 255) q[j] = *reinterpret_cast<const float4*>(a.in + (img * LH + hh[j]) * a.W + kk[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float sg0 = sgn(hh[j] + kk[j]);
+        if (s0[j] != 255) xch[(s0[j] - s_lo) * CGeo<LH>::CSTRIDE + hh[j]] = cf32{q[j].x * sg0, q[j].y * sg0};
+        if (s1[j] != 255) xch[(s1[j] - s_lo) * CGeo<LH>::CSTRIDE + hh[j]] = cf32{-q[j].z * sg0, -q[j].w * sg0};
+      }
     }
-    xch[(4 * gi + 2 * half) * P::STRIDE + hh] = cf32{q.x, q.y};
-    xch[(4 * gi + 2 * half + 1) * P::STRIDE + hh] = cf32{q.z, q.w};
   }
   __syncthreads();
   const int cs = tid / G::TPF, t = tid % G::TPF;
-  cf32* sx = xch + cs * P::STRIDE;
-  const bool gvalid = g0 + (cs >> 2) < ng;
-  const int slot = gvalid ? p.gslot[((size_t)f * p.ng_all + g0 + (cs >> 2)) * 4 + (cs & 3)] : 255;
-  Twid<LH, (LH < 512)> tw;
-  tw.init(tws, t);
-  cf32 v[G::E];
+  cf32* sx = xch + cs * CGeo<LH>::CSTRIDE;
+  {
+    Twid<LH, (LH < 512)> tw;
+    tw.init(tws, t);
+    cf32 v[G::E];
 #pragma unroll
-  for (int q = 0; q < G::E; ++q) v[q] = sx[a_pos<LH>(t, q)];
-  __syncwarp();
-  a2b_first<LH, +1>(v, t, sx);
-  __syncwarp();
-  a2b_second<LH, +1>(v, t, sx, tw);
-  if (slot != 255) {
-    cf32* wp = a.ws + (img * LH + t) * p.ns_pad + slot;
+    for (int q = 0; q < G::E; ++q) v[q] = sx[a_pos<LH>(t, q)];
+    __syncwarp();
+    a2b_first<LH, +1>(v, t, sx);
+    __syncwarp();
+    a2b_second<LH, +1>(v, t, sx, tw);
+    __syncwarp();
 #pragma unroll
-    for (int i = 0; i < G::E; ++i) wp[(size_t)b_off<LH>(i) * p.ns_pad] = v[i];
+    for (int i = 0; i < G::E; ++i) sx[b_pos<LH>(t, i)] = v[i];
+  }
+  __syncthreads();
+  {
+    cf32* wp = a.ws + img * LH * p.ns_pad + s_lo;
+    for (int idx = tid; idx < CGeo<LH>::CL * LH; idx += CGeo<LH>::NT) {
+      const int si = idx % CGeo<LH>::CL, hh = idx / CGeo<LH>::CL;
+      if (si < s_cnt) wp[(size_t)hh * p.ns_pad + si] = xch[si * CGeo<LH>::CSTRIDE + hh];
+    }
+  }
+}
+
+// Zero the padded class tables and install the frame's twiddle vectors at their padded positions (sign: ALT as above).
+template <int L, int CMAX, bool ALT>
+__device__ __forceinline__ void fill_padded_tables(cf32* twp, cf32* ysm, int ysm_elems, const PlanView& p, int f, int ns, int tid, int nt) {
+  using P = PR<L>;
+  for (int e = tid; e < 16 * CMAX * P::R1; e += nt) twp[e] = cf32{0.f, 0.f};
+  for (int e = tid; e < ysm_elems; e += nt) ysm[e] = cf32{0.f, 0.f};
+  __syncthreads();
+  for (int e = tid; e < ns * P::R1; e += nt) {
+    const int jj = e / P::R1, tt = e % P::R1;
+    const cf32 w = p.tw[((size_t)f * p.ns_pad + jj) * P::R1 + tt];
+    twp[p.ppos[f * p.ns_pad + jj] * P::R1 + tt] = (ALT && (tt & 1)) ? cf32{-w.x, -w.y} : w;
   }
 }
 
 // ---- adjoint, rows: compact scratch -> pruned inverse transform along W -> conj-coil sum (or SSOS) ---------------
-// grid (batch, H / TPC)
-template <int L, int NOUT, bool CPLX>
-__global__ void __launch_bounds__(128) kp_adj_rows(SenseArgs a, PlanView p) {
+// grid (batch, H / TPC).  Real coil maps (or none / SSOS).
+template <int L, int NOUT, int CMAX>
+__global__ void __launch_bounds__(128, 4) kp_adj_rows(SenseArgs a, PlanView p) {
   using G = PGeo<L>;
   using P = PR<L>;
-  __shared__ __align__(16) cf32 twc[32 * P::R1];
-  __shared__ __align__(16) cf32 ysm[G::TPC * G::YP];
+  __shared__ __align__(16) cf32 twp[16 * CMAX * P::R1];
+  __shared__ __align__(16) cf32 ysm[G::TPC * 16 * CMAX];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t = lane % P::R1, r = warp * G::RPW + lane / P::R1;
   const int b = blockIdx.x, h = blockIdx.y * G::TPC + r;
   const int f = b % p.frames, ns = p.ns[f];
-  for (int e = tid; e < ns * P::R1; e += G::NT) twc[e] = p.tw[(size_t)f * p.ns_pad * P::R1 + e];
-  uint32_t cw[5];
-#pragma unroll
-  for (int i = 0; i < 5; ++i) cw[i] = p.cls[f * 5 + i];
+  fill_padded_tables<L, CMAX, false>(twp, ysm, G::TPC * 16 * CMAX, p, f, ns, tid, G::NT);
+  const uint32_t big2 = p.big[f * 2], big3 = p.big[f * 2 + 1];
   MySlots<L, NOUT> my;
   my.init(p, f, ns, t);
-  cf32* yr = ysm + r * G::YP;
+  cf32* yr = ysm + r * 16 * CMAX;
   const cf32* wsp = a.ws + ((size_t)b * a.H + h) * p.ns_pad;
   const size_t ws_stride = (size_t)a.batch * a.H * p.ns_pad;
   const bool has_maps = a.mre != nullptr && !a.ssos;
   const size_t map_img = (size_t)a.H * L;
   const float* mre = a.mre + (size_t)h * L + t;
-  const float* mim = a.mim + (size_t)h * L + t;
   const float sct = a.scale * sgn(h + t);
   cf32 acc[P::R0], ynext[NOUT];
-  MapVal<CPLX> mnext[P::R0];
+  float mnext[P::R0];
 #pragma unroll
   for (int q = 0; q < P::R0; ++q) acc[q] = cf32{0.f, 0.f};
-  auto prefetch = [&](int c) {
+  auto fetch_y = [&](int c) {
     if (c < a.ncoils) {
 #pragma unroll
       for (int o = 0; o < NOUT; ++o) ynext[o] = my.slot[o] >= 0 ? wsp[my.slot[o]] : cf32{0.f, 0.f};
       wsp += ws_stride;
-      if (has_maps) {
-#pragma unroll
-        for (int q = 0; q < P::R0; ++q) mnext[q].load(mre, mim, P::R1 * q);
-        mre += map_img;
-        mim += map_img;
-      }
     }
   };
-  prefetch(0);
-  __syncthreads();   // twiddle table complete
-  for (int c = 0; c < a.ncoils; ++c) {
-    MapVal<CPLX> m[P::R0];
+  auto fetch_maps = [&](int c) {
+    if (has_maps && c < a.ncoils) {
 #pragma unroll
-    for (int q = 0; q < P::R0; ++q) m[q] = mnext[q];
+      for (int q = 0; q < P::R0; ++q) mnext[q] = mre[P::R1 * q];
+      mre += map_img;
+    }
+  };
+  fetch_y(0);
+  fetch_maps(0);
+  __syncthreads();   // padded tables complete
+  for (int c = 0; c < a.ncoils; ++c) {
     __syncwarp();   // the previous coil's sums have read the spectrum line
 #pragma unroll
     for (int o = 0; o < NOUT; ++o)
-      if (my.slot[o] >= 0) yr[t + P::R1 * o] = ynext[o];
-    prefetch(c + 1);
+      if (my.slot[o] >= 0) yr[my.pp[o]] = ynext[o];
+    fetch_y(c + 1);   // the next coil's spectrum travels during this coil's transform
     __syncwarp();
     cf32 v[P::R0];
-    pr_scatter<L, +1>(v, t, yr, twc, P::R1, cw);
+    pr_scatter<L, +1, CMAX>(v, t, yr, twp, P::R1, big2, big3);
 #pragma unroll
     for (int q = 0; q < P::R0; ++q) {
       if (a.ssos) {
         acc[q].x += v[q].x * v[q].x + v[q].y * v[q].y;
       } else if (has_maps) {
-        acc[q] = cadd(acc[q], m[q].mulc(v[q]));
+        acc[q].x += mnext[q] * v[q].x;
+        acc[q].y += mnext[q] * v[q].y;
       } else {
         acc[q] = cadd(acc[q], v[q]);
       }
     }
+    fetch_maps(c + 1);   // ... and its maps during the next one
   }
   if (a.ssos) {
     float* op = reinterpret_cast<float*>(a.out) + ((size_t)b * a.H + h) * L + t;
@@ -326,14 +385,14 @@ __global__ void __launch_bounds__(128) kp_adj_rows(SenseArgs a, PlanView p) {
 // z = x + step*g + noise_scale*n;  x <- z - kappa*(A^H A z - b).  The H-axis transforms cancel in A^H A (the mask
 // acts on W only) and the (-1)^w factors of the centred transforms turn into the half-period shift k ^ (W/2) of the
 // sampled columns, so per coil: multiply, pruned forward transform (the ns sampled columns), pruned inverse
-// transform, conj multiply-accumulate -- all on the 16 values a thread holds.
-template <int L, int NOUT, bool CPLX>
-__global__ void __launch_bounds__(128) kp_ald_sense(AldArgs a, PlanView p) {
+// transform, conj multiply-accumulate -- all on the 16 values a thread holds.  Real coil maps.
+template <int L, int NOUT, int CMAX>
+__global__ void __launch_bounds__(128, 3) kp_ald_sense(AldArgs a, PlanView p) {
   using G = PGeo<L>;
   using P = PR<L>;
   __shared__ __align__(16) cf32 xch[G::TPC * P::LINE];
-  __shared__ __align__(16) cf32 twc[32 * P::R1];
-  __shared__ __align__(16) cf32 ysm[G::TPC * G::YP];
+  __shared__ __align__(16) cf32 twp[16 * CMAX * P::R1];
+  __shared__ __align__(16) cf32 ysm[G::TPC * 16 * CMAX];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t = lane % P::R1, r = warp * G::RPW + lane / P::R1;
   const int b = blockIdx.x, h = blockIdx.y * G::TPC + r;
@@ -345,31 +404,24 @@ __global__ void __launch_bounds__(128) kp_ald_sense(AldArgs a, PlanView p) {
     sc = a.sched[cur];
     rstep += (uint32_t)cur;
   }
-  for (int e = tid; e < ns * P::R1; e += G::NT) {   // entry e belongs to thread e % R1: (-1)^t' folds the k ^ (W/2) shift in
-    const cf32 w = p.tw[(size_t)f * p.ns_pad * P::R1 + e];
-    twc[e] = (e & 1) ? cf32{-w.x, -w.y} : w;
-  }
-  uint32_t cw[5];
-#pragma unroll
-  for (int i = 0; i < 5; ++i) cw[i] = p.cls[f * 5 + i];
+  fill_padded_tables<L, CMAX, true>(twp, ysm, G::TPC * 16 * CMAX, p, f, ns, tid, G::NT);
+  const uint32_t big2 = p.big[f * 2], big3 = p.big[f * 2 + 1];
   MySlots<L, NOUT> my;
   my.init(p, f, ns, t);
-  cf32 twr[NOUT][P::R1];
-  load_my_twiddles<L, NOUT, true>(twr, p, f, ns, t);
+  cf32 twh[NOUT][P::NTWH];
+  load_my_twiddles<L, NOUT, true>(twh, p, f, ns, t);
   cf32* sx = xch + r * P::LINE;
-  cf32* yr = ysm + r * G::YP;
+  cf32* yr = ysm + r * 16 * CMAX;
   const size_t plane = (size_t)a.batch * a.H * L;
   const size_t rowoff = ((size_t)b * a.H + h) * L + t;
   const size_t map_img = (size_t)a.H * L;
   const float* mre = a.mre + (size_t)h * L + t;
-  const float* mim = a.mim + (size_t)h * L + t;
-  MapVal<CPLX> mnext[P::R0];
+  float mnext[P::R0];
   auto fetch_maps = [&](int c) {
     if (c < a.ncoils) {
 #pragma unroll
-      for (int q = 0; q < P::R0; ++q) mnext[q].load(mre, mim, P::R1 * q);
+      for (int q = 0; q < P::R0; ++q) mnext[q] = mre[P::R1 * q];
       mre += map_img;
-      mim += map_img;
     }
   };
   fetch_maps(0);
@@ -403,14 +455,14 @@ __global__ void __launch_bounds__(128) kp_ald_sense(AldArgs a, PlanView p) {
       }
     }
   }
-  __syncthreads();   // twiddle table complete
+  __syncthreads();   // padded tables complete
   for (int c = 0; c < a.ncoils; ++c) {
-    MapVal<CPLX> m[P::R0];
+    float m[P::R0];
     cf32 u[P::R0];
 #pragma unroll
     for (int q = 0; q < P::R0; ++q) {
       m[q] = mnext[q];
-      u[q] = m[q].mul(z[q]);
+      u[q] = cscale(z[q], m[q]);
     }
     fetch_maps(c + 1);
     __syncwarp();   // line and spectrum of the previous coil are consumed
@@ -418,11 +470,14 @@ __global__ void __launch_bounds__(128) kp_ald_sense(AldArgs a, PlanView p) {
     __syncwarp();
 #pragma unroll
     for (int o = 0; o < NOUT; ++o)
-      if (my.slot[o] >= 0) yr[t + P::R1 * o] = pr_gather<L, -1>(sx, my.k0[o], twr[o]);
+      if (my.slot[o] >= 0) yr[my.pp[o]] = pr_gather<L, -1>(sx, my.k0[o], twh[o]);
     __syncwarp();
-    pr_scatter<L, +1>(u, t, yr, twc, P::R1, cw);
+    pr_scatter<L, +1, CMAX>(u, t, yr, twp, P::R1, big2, big3);
 #pragma unroll
-    for (int q = 0; q < P::R0; ++q) acc[q] = cadd(acc[q], m[q].mulc(u[q]));
+    for (int q = 0; q < P::R0; ++q) {
+      acc[q].x += m[q] * u[q].x;
+      acc[q].y += m[q] * u[q].y;
+    }
   }
   const float ks = sc.kappa / (float)L;
   {

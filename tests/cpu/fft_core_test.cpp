@@ -113,7 +113,13 @@ double check_pruned(int ns_target, unsigned seed) {
     while (n < ns_target - f) { const int k = rand() % L; if (!mask[f * L + k]) { mask[f * L + k] = 1; ++n; } }
   }
   PlanHost pl = build_plan_host(mask.data(), frames, L);
-  if (!pl.pruned || pl.R1 != P::R1) { printf("plan not pruned for L=%d ns=%d\n", L, ns_target); return 1.0; }
+  if (!pl.pruned) {   // legitimate: a residue class with more than 4 columns (the general kernels take over)
+    int cm = 0;
+    for (int f = 0; f < frames; ++f) { int cnt[16] = {0}; for (int k = 0; k < L; ++k) if (mask[f * L + k]) cm = std::max(cm, ++cnt[k & 15]); }
+    printf("plan not pruned for L=%d ns=%d (largest class %d)\n", L, ns_target, cm);
+    return cm > 4 ? 0.0 : 1.0;
+  }
+  if (pl.R1 != P::R1) return 1.0;
   double worst = 0;
   for (int f = 0; f < frames; ++f) {
     const int ns = pl.ns[f], NP = pl.ns_pad;
@@ -127,6 +133,20 @@ double check_pruned(int ns_target, unsigned seed) {
       const int k = pl.kcol[f * NP + pl.nat[f * NP + jj]];
       if ((k & 15) != pl.k0c[f * NP + jj] || jj < cls[k & 15] || jj >= cls[(k & 15) + 1]) return 5.0;
     }
+    {   // column-kernel work items: whole groups, consecutive, <= 16 sampled columns, covering everything once
+      int g_next = 0, s_next = 0;
+      for (int c = 0; c < pl.nchunks[f]; ++c) {
+        const uint8_t* ch = &pl.chunks[(f * (L / 4) + c) * 4];
+        if (ch[0] != g_next || ch[2] != s_next || ch[1] == 0 || ch[3] == 0 || ch[3] > PlanHost::CHUNK_SLOTS) return 11.0;
+        int cnt2 = 0;
+        for (int g = ch[0]; g < ch[0] + ch[1]; ++g)
+          for (int i = 0; i < 4; ++i) cnt2 += pl.gslot[(f * (L / 4) + g) * 4 + i] != 255;
+        if (cnt2 != ch[3]) return 12.0;
+        g_next += ch[1];
+        s_next += ch[3];
+      }
+      if (g_next != pl.ngroups[f] || s_next != ns) return 13.0;
+    }
     for (int g = 0; g < pl.ngroups[f]; ++g) {
       const int q = pl.groups[f * (L / 4) + g];
       if (!((pl.gbitmap[f * 4 + (q >> 5)] >> (q & 31)) & 1u)) return 6.0;
@@ -136,9 +156,14 @@ double check_pruned(int ns_target, unsigned seed) {
         if (s != 255 && pl.kcol[f * NP + s] != 4 * q + i) return 8.0;
       }
     }
-    uint32_t cw[5];
-    memcpy(cw, cls, 20);
     const cf32* tw = reinterpret_cast<const cf32*>(pl.tw.data()) + (size_t)f * NP * P::R1;
+    const cf32* twh = reinterpret_cast<const cf32*>(pl.twh.data()) + (size_t)f * NP * PlanHost::TWH;
+    // padded class positions: inside the class block, distinct
+    std::vector<int> seen(16 * pl.cmax, 0);
+    for (int jj = 0; jj < ns; ++jj) {
+      const int pp = pl.ppos[f * NP + jj];
+      if (pp / pl.cmax != pl.k0c[f * NP + jj] || seen[pp]++) return 9.0;
+    }
     // ---- forward
     std::vector<cf32> x(L), line(P::LINE + 8);
     std::vector<std::complex<double>> xd(L);
@@ -153,7 +178,7 @@ double check_pruned(int ns_target, unsigned seed) {
     }
     double err = 0, nrm = 0;
     for (int jj = 0; jj < ns; ++jj) {
-      const cf32 o = pr_gather<L, -1>(line.data(), pl.k0c[f * NP + jj], tw + jj * P::R1);
+      const cf32 o = pr_gather<L, -1>(line.data(), pl.k0c[f * NP + jj], twh + jj * PlanHost::TWH);
       const int k = pl.kcol[f * NP + pl.nat[f * NP + jj]];
       std::complex<double> s = 0;
       for (int n = 0; n < L; ++n) s += xd[n] * std::polar(1.0, -2.0 * M_PI * k * n / L);
@@ -161,16 +186,21 @@ double check_pruned(int ns_target, unsigned seed) {
       nrm += std::norm(s);
     }
     worst = fmax(worst, sqrt(err / nrm));
-    // ---- adjoint
-    std::vector<cf32> Y(pl.ns_pad), out(L);
+    // ---- adjoint: padded class layout, static indices
+    std::vector<cf32> Y(16 * pl.cmax, cf32{0.f, 0.f}), twp((size_t)16 * pl.cmax * P::R1, cf32{0.f, 0.f}), out(L);
     std::vector<std::complex<double>> Yd(L, 0.0);
     for (int jj = 0; jj < ns; ++jj) {
-      Y[jj] = cf32{(float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f};
-      Yd[pl.kcol[f * NP + pl.nat[f * NP + jj]]] = {Y[jj].x, Y[jj].y};
+      const int pp = pl.ppos[f * NP + jj];
+      Y[pp] = cf32{(float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f};
+      Yd[pl.kcol[f * NP + pl.nat[f * NP + jj]]] = {Y[pp].x, Y[pp].y};
+      for (int t = 0; t < P::R1; ++t) twp[(size_t)pp * P::R1 + t] = tw[jj * P::R1 + t];
     }
     for (int t = 0; t < P::R1; ++t) {
       cf32 v[P::R0];
-      pr_scatter<L, +1>(v, t, Y.data(), tw, P::R1, cw);
+      const uint32_t b2 = pl.big[f * 2], b3 = pl.big[f * 2 + 1];
+      if (pl.cmax == 2) pr_scatter<L, +1, 2>(v, t, Y.data(), twp.data(), P::R1, b2, b3);
+      else if (pl.cmax == 4) pr_scatter<L, +1, 4>(v, t, Y.data(), twp.data(), P::R1, b2, b3);
+      else return 10.0;
       for (int q = 0; q < P::R0; ++q) out[P::R1 * q + t] = v[q];
     }
     err = 0; nrm = 0;

@@ -103,7 +103,9 @@ def _sense_battery(H, W, nc, B, frames, cplx, lines, use_plan):
     m8 = m8h.to(DEV)
     plan = L.SensePlan(m8h.numpy(), H, W) if use_plan else None
     if use_plan and lines is not None:
-        assert plan.pruned and plan.ns_max == lines
+        # pruned unless some residue class (column mod 16) of some frame holds more than 4 sampled columns
+        cmax = max(int(torch.bincount(torch.nonzero(m8h[f])[:, 0] % 16, minlength=16).max()) for f in range(frames))
+        assert plan.ns_max == lines and plan.pruned == (cmax <= 4), (plan.pruned, cmax)
     mask = mask[0] if frames == 1 else mask.repeat(B // frames, 1, 1, 1)     # kernel: frame = b % frames
     x = crandn(H + W, B, 1, H, W)
     mre = maps.real.float().contiguous().to(DEV)

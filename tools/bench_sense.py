@@ -7,6 +7,8 @@ import torch
 import parity_cases as C
 from inverseproblemwithdiffusionmodel_b200 import _lib
 L = _lib.lib()
+if os.environ.get("IPDM_L2_FETCH"):      # experiment: cudaLimitMaxL2FetchGranularity (32 / 64 / 128 bytes)
+    _lib.check(L.ipdm_debug_option(4, int(os.environ["IPDM_L2_FETCH"])))
 dev = torch.device("cuda")
 peak = 6551.7
 try:

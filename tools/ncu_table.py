@@ -1,18 +1,38 @@
-"""Per-kernel key metrics of an .ncu-rep (all kernels):  python tools/ncu_table.py file.ncu-rep"""
-import csv, subprocess, sys, io
-raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(raw)))
-hdr = rows[0]
-cols = [("Kernel Name", "kernel"), ("gpu__time_duration.sum", "us"), ("dram__bytes_read.sum", "rd"), ("dram__bytes_write.sum", "wr"),
-        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"), ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2%"),
-        ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1%"), ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm%"),
-        ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ%"), ("launch__registers_per_thread", "regs"),
-        ("smsp__inst_executed.avg.per_cycle_active", "ipc/smsp"), ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "bankconf"),
-        ("launch__grid_size", "grid"), ("launch__waves_per_multiprocessor", "waves"),
-        ("smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "st_long"), ("smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct", "st_short"),
-        ("smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct", "st_mio"), ("smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct", "st_lg"),
-        ("smsp__warp_issue_stalled_barrier_per_warp_active.pct", "st_bar"), ("smsp__warp_issue_stalled_wait_per_warp_active.pct", "st_wait"),
-        ("smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct", "st_math"), ("smsp__warp_issue_stalled_not_selected_per_warp_active.pct", "st_notsel")]
-idx = [(hdr.index(k), n) for k, n in cols if k in hdr]
-for r in rows[2:]:
-    print("  ".join(f"{n}={r[i][:60]}{rows[1][i] if n in ('rd','wr','us') else ''}" for i, n in idx))
+"""Per-kernel table from an .ncu-rep (ncu -i ... --page raw --csv): time, DRAM bytes, throughputs, occupancy, registers,
+issue activity, top stall reasons.  usage: python tools/ncu_table.py file.ncu-rep [name-filter]"""
+import csv, io, subprocess, sys
+rep = sys.argv[1]
+flt = sys.argv[2] if len(sys.argv) > 2 else ""
+out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(out)))
+hdr, units, data = rows[0], rows[1], rows[2:]
+col = {h: i for i, h in enumerate(hdr)}
+def g(r, name, default=""):
+    i = col.get(name)
+    return r[i] if i is not None and i < len(r) else default
+def f(r, name):
+    try:
+        return float(g(r, name).replace(",", ""))
+    except ValueError:
+        return float("nan")
+stall_cols = [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio") or
+              (h.startswith("smsp__average_warp_latency_issue_stalled_") and h.endswith(".ratio"))]
+stall_cols = [h for h in hdr if "issue_stalled" in h and h.endswith("ratio") and "not_issued" not in h]
+for r in data:
+    name = g(r, "Kernel Name")
+    if flt and flt not in name:
+        continue
+    t_unit = units[col["gpu__time_duration.sum"]]
+    dur = f(r, "gpu__time_duration.sum")
+    dur_us = dur / 1e3 if t_unit in ("nsecond", "ns") else dur * (1e3 if t_unit.startswith("ms") else 1)
+    rd, wr = f(r, "dram__bytes_read.sum"), f(r, "dram__bytes_write.sum")
+    ru, wu = units[col["dram__bytes_read.sum"]], units[col["dram__bytes_write.sum"]]
+    sc = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    rd *= sc.get(ru, 1); wr *= sc.get(wu, 1)
+    stalls = sorted(((f(r, h), h.split("issue_stalled_")[1].split("_per")[0].replace(".ratio", "")) for h in stall_cols), reverse=True)[:4]
+    print(f"{name[:60]:60s} {dur_us:9.1f}us rd {rd/1e6:8.1f}MB wr {wr/1e6:8.1f}MB dram% {f(r,'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):5.1f} "
+          f"sm% {f(r,'sm__throughput.avg.pct_of_peak_sustained_elapsed'):5.1f} l1% {f(r,'l1tex__throughput.avg.pct_of_peak_sustained_active'):5.1f} "
+          f"occ% {f(r,'sm__warps_active.avg.pct_of_peak_sustained_active'):5.1f} regs {g(r,'launch__registers_per_thread')} "
+          f"issue% {f(r,'smsp__issue_active.avg.pct_of_peak_sustained_active'):5.1f} inst {f(r,'smsp__inst_executed.sum'):.3g} "
+          f"bankconf {f(r,'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum'):.3g} grid {g(r,'launch__grid_size')} | " +
+          " ".join(f"{n}={v:.1f}" for v, n in stalls))

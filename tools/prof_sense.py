@@ -6,6 +6,8 @@ import torch
 import parity_cases as C
 from inverseproblemwithdiffusionmodel_b200 import _lib
 L = _lib.lib()
+if os.environ.get("IPDM_L2_FETCH"):      # experiment: cudaLimitMaxL2FetchGranularity (32 / 64 / 128 bytes)
+    _lib.check(L.ipdm_debug_option(4, int(os.environ["IPDM_L2_FETCH"])))
 nc, n, B, R = [int(v) for v in sys.argv[1:5]] if len(sys.argv) > 4 else (4, 256, 64, 40)
 A = C.SENSE("exp", nc, R, 1 / 64, (1, n, n), 0)
 A.random_under_fourier.mask = C.keep_center_mask(n, R, 1 / 64, seed=0)
