@@ -207,6 +207,12 @@ typedef struct {
                              ([P][X][H][W][C]); `stats` rows are then per VOLUME ([N/X][Cout][2])            */
   int slice_shift;        /* output slice x reads input slice x + slice_shift of the same volume (zero outside
                              [0, X)): one kx-plane of a 3x3x3 convolution (layers3d.py:38-60) = one launch   */
+  /* The residual stream in 16 bits (tensor-core kernels only): instead of `residual` / `out_f32`, the residual is read
+   * from and the result f16(acc + bias + residual) written to f16 NHWC tensors -- 8 instead of 12 bytes per output
+   * element for a residual convolution.  InstanceNorm++ sums still come from the fp32 values.  Exclusive with the f32
+   * pair; the flags keep their meaning (IPDM_CONV_POOL2 shapes, IPDM_CONV_RES_ELU, IPDM_CONV_F16_PRE_RES). */
+  const void* residual_f16;
+  void* out_raw_f16;
 } ipdm_conv_desc;
 
 #define IPDM_CONV_F16_ELU 1       /* out_f16 = f16(ELU(v)) instead of f16(v)                               */

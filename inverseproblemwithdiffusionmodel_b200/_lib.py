@@ -22,7 +22,8 @@ class ConvDesc(ctypes.Structure):
     _fields_ = [("in_f16", c_void_p), ("w_f16", c_void_p), ("bias", c_void_p), ("residual", c_void_p),
                 ("out_f32", c_void_p), ("out_f16", c_void_p), ("stats", c_void_p),
                 ("N", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int), ("Cout", c_int),
-                ("taps", c_int), ("dilation", c_int), ("flags", c_int), ("slices", c_int), ("slice_shift", c_int)]
+                ("taps", c_int), ("dilation", c_int), ("flags", c_int), ("slices", c_int), ("slice_shift", c_int),
+                ("residual_f16", c_void_p), ("out_raw_f16", c_void_p)]
 
 
 class Rng(ctypes.Structure):

@@ -12,8 +12,8 @@ constexpr int UMMA_K = 16;
 
 struct IgemmParams {
   const float* bias;
-  const float* residual;
-  float* out_f32;
+  const float* residual;      // f32 residual stream, or (trunk16) the same pointer reinterpreted as f16
+  float* out_f32;             // f32 result, or (trunk16) f16 result ("raw" 16-bit residual stream)
   __half* out_f16;
   double* stats;
   int N, H, W, Cin, Cout, taps, dilation, flags;
@@ -42,7 +42,23 @@ extern int g_conv_variant;       // 0 = auto, 1 = force the per-tap tile kernel 
 //   stage xor 1 swaps c0 <-> p0, stage xor 2 swaps c1 <-> p1
 //   after:  lane = (p0, p1, c2, c3, c4), register = (c0, c1, p2, p3, p4): float4 #i = channels 4*(lane>>2)..+3 of pixel
 //           (lane & 3) + 4*i of the chunk
-// MODE bits: 1 = residual, 2 = fp32 output, 4 = f16 output, 8 = 2x2 mean-pool (pooled before the shuffles: 8 values).
+// MODE bits: 1 = residual, 2 = result output, 4 = f16 operand output, 8 = 2x2 mean-pool (pooled before the shuffles: 8
+// values), 16 = the residual stream is kept in 16 bits: `residual` and the result output (`out_f32`) are f16 tensors.
+// The 16-bit stream takes the residual-variant convolution from 12 to 8 bytes per output element (f16 in, f16 residual,
+// f16 result, f16 operand copy), i.e. from 192 to 288 FLOP/B at 128 channels: over the ridge of the measured peaks.
+template <bool T16> struct ResElem;
+template <> struct ResElem<false> {
+  using type = float4;
+  static __device__ __forceinline__ float4 to_f32(float4 v) { return v; }
+};
+template <> struct ResElem<true> {
+  using type = uint2;   // four f16
+  static __device__ __forceinline__ float4 to_f32(uint2 h) {
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+  }
+};
+
 template <int NV>
 __device__ __forceinline__ void lane_register_swap(float* v, int lane) {
   // NV values; exchanges register bit 0 with lane bit 0, then register bit 1 with lane bit 1
@@ -71,6 +87,7 @@ template <int MODE, int TW, int FAST, class WaitAcc>
 __device__ __forceinline__ void conv_epilogue_chunks(const IgemmParams& p, uint32_t tmem_acc, int quad, int lane, int n, int h0, int w0,
                                                      int m0, int chunk0, int NCHUNK, WaitAcc wait_acc) {
   constexpr bool kRes = (MODE & 1) != 0, kOut32 = (MODE & 2) != 0, kOut16 = (MODE & 4) != 0, pool = (MODE & 8) != 0;
+  constexpr bool T16 = (MODE & 16) != 0;
   constexpr bool LEAN = FAST != 0;
   constexpr int NPX = pool ? 2 : 8;             // float4 groups (pixels) per thread per chunk
   constexpr int OW = pool ? TW / 2 : TW;        // output pixels per chunk row
@@ -95,14 +112,16 @@ __device__ __forceinline__ void conv_epilogue_chunks(const IgemmParams& p, uint3
   const int cols_left = Wo - ox0 - psub;        // pixel i is inside the image iff 4*(i%IPR) < cols_left and its row < Ho
   auto eo = [&](int i) -> uint32_t { return (uint32_t)(i / IPR) * row_stride + (uint32_t)(i % IPR) * col_stride; };
   auto inside = [&](int i, int rows_left) -> bool { return LEAN || (i / IPR < rows_left && 4 * (i % IPR) < cols_left); };
-  float4 rcur[NPX], rnext[NPX];
-  auto issue_res = [&](int chunk, float4* r) {
-    const char* rp = reinterpret_cast<const char*>(p.residual + off0 + (size_t)(chunk * OROWS) * row_stride);
+  // residual tiles: four f32 (float4) or four f16 (uint2) per pixel, software-pipelined one chunk ahead
+  using RT = typename ResElem<T16>::type;
+  RT rcur[NPX], rnext[NPX];
+  auto issue_res = [&](int chunk, RT* r) {
     const int rows_left = Ho - oy0 - chunk * OROWS;
+    const char* rp = reinterpret_cast<const char*>(p.residual) + (off0 + (size_t)(chunk * OROWS) * row_stride) * sizeof(RT) / 4;
 #pragma unroll
     for (int i = 0; i < NPX; ++i) {
-      r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (inside(i, rows_left)) r[i] = *reinterpret_cast<const float4*>(rp + (size_t)eo(i) * 4);
+      r[i] = RT{};
+      if (inside(i, rows_left)) r[i] = *reinterpret_cast<const RT*>(rp + (size_t)eo(i) * (sizeof(RT) / 4));
     }
   };
   if (kRes) issue_res(chunk0, rcur);
@@ -128,7 +147,7 @@ __device__ __forceinline__ void conv_epilogue_chunks(const IgemmParams& p, uint3
     }
     lane_register_swap<4 * NPX>(w, lane);
     const size_t offc = off0 + (size_t)(chunk * OROWS) * row_stride;
-    char* o32 = reinterpret_cast<char*>(p.out_f32 + offc);
+    char* o32 = T16 ? reinterpret_cast<char*>(p.out_f32) + offc * 2 : reinterpret_cast<char*>(p.out_f32 + offc);
     char* o16 = reinterpret_cast<char*>(p.out_f16 + offc);
     const int rows_left = Ho - oy0 - chunk * OROWS;
 #pragma unroll
@@ -138,11 +157,20 @@ __device__ __forceinline__ void conv_epilogue_chunks(const IgemmParams& p, uint3
         if (!LEAN) { a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w; }
         const float4 pre = a;
         if (kRes) {
-          float4 r = rcur[i];
+          float4 r = ResElem<T16>::to_f32(rcur[i]);
           if (res_elu) { r.x = elu_fast(r.x); r.y = elu_fast(r.y); r.z = elu_fast(r.z); r.w = elu_fast(r.w); }
           a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
         }
-        if (kOut32) *reinterpret_cast<float4*>(o32 + (size_t)eo(i) * 4) = a;
+        if (kOut32) {
+          if (T16) {
+            uint2 pk;
+            pk.x = pack_half2_sat(a.x, a.y);
+            pk.y = pack_half2_sat(a.z, a.w);
+            *reinterpret_cast<uint2*>(o32 + (size_t)eo(i) * 2) = pk;
+          } else {
+            *reinterpret_cast<float4*>(o32 + (size_t)eo(i) * 4) = a;
+          }
+        }
         if (kOut16) {
           float4 h = (kRes && f16_pre) ? pre : a;
           if (f16_elu) { h.x = elu_fast(h.x); h.y = elu_fast(h.y); h.z = elu_fast(h.z); h.w = elu_fast(h.w); }

@@ -131,11 +131,12 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
           const int rows = min(pool ? TH / 2 : TH, Ho - oy0), cols = min(pool ? HT_W / 2 : HT_W, Wo - ox0);
           for (int sl = 0; sl < NS; ++sl)
             for (int r = 0; r < rows; ++r) {
-              const float* base = p.residual + (((size_t)(n + sl) * Ho + oy0 + r) * Wo + ox0) * p.Cout + m0;
+              constexpr int EB = (MODE & 16) ? 2 : 4;     // bytes per residual element
+              const char* base = reinterpret_cast<const char*>(p.residual) + ((((size_t)(n + sl) * Ho + oy0 + r) * Wo + ox0) * p.Cout + m0) * EB;
               if (p.Cout == BLOCK_M) {
-                prefetch_l2_bulk(base, cols * BLOCK_M * 4);
+                prefetch_l2_bulk(base, cols * BLOCK_M * EB);
               } else {
-                for (int c = 0; c < cols; ++c) prefetch_l2_bulk(base + (size_t)c * p.Cout, BLOCK_M * 4);
+                for (int c = 0; c < cols; ++c) prefetch_l2_bulk(base + (size_t)c * p.Cout * EB, BLOCK_M * EB);
               }
             }
         }
@@ -296,7 +297,10 @@ int launch_conv_halo(const ipdm_conv_desc& d, cudaStream_t s) {
   if (d.stats) IPDM_CUDA(cudaMemsetAsync(d.stats, 0, (size_t)(d.N / d.slices) * d.Cout * 2 * sizeof(double), s));
   HaloParams hp{};
   IgemmParams& p = hp.g;
-  p.bias = d.bias; p.residual = d.residual; p.out_f32 = d.out_f32; p.out_f16 = reinterpret_cast<__half*>(d.out_f16);
+  const bool t16 = d.residual_f16 != nullptr || d.out_raw_f16 != nullptr;     // 16-bit residual stream
+  p.bias = d.bias; p.out_f16 = reinterpret_cast<__half*>(d.out_f16);
+  p.residual = t16 ? reinterpret_cast<const float*>(d.residual_f16) : d.residual;
+  p.out_f32 = t16 ? reinterpret_cast<float*>(d.out_raw_f16) : d.out_f32;
   p.stats = d.stats;
   p.N = d.N; p.H = d.H; p.W = d.W; p.Cin = d.Cin; p.Cout = d.Cout; p.taps = d.taps; p.dilation = d.dilation; p.flags = d.flags;
   p.slices = d.slices; p.slice_shift = d.slice_shift;
@@ -317,7 +321,7 @@ int launch_conv_halo(const ipdm_conv_desc& d, cudaStream_t s) {
     IPDM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = hp.items < sms ? hp.items : sms;
-  const int mode = (d.residual ? 1 : 0) | (d.out_f32 ? 2 : 0) | (d.out_f16 ? 4 : 0) | (pool ? 8 : 0);
+  const int mode = (p.residual ? 1 : 0) | (p.out_f32 ? 2 : 0) | (d.out_f16 ? 4 : 0) | (pool ? 8 : 0) | (t16 ? 16 : 0);
   int e = 0;
 #define HALO_TH(M, D)                                                                                     \
   (th == 32 ? launch_variant<M, D, 32>(mw, mx, hp, grid, s)                                               \
@@ -334,6 +338,9 @@ int launch_conv_halo(const ipdm_conv_desc& d, cudaStream_t s) {
   switch (mode) {
     HALO_CASE(2) HALO_CASE(3) HALO_CASE(4) HALO_CASE(5) HALO_CASE(6) HALO_CASE(7)
     HALO_CASE_POOL(10) HALO_CASE_POOL(11) HALO_CASE_POOL(12) HALO_CASE_POOL(13) HALO_CASE_POOL(14) HALO_CASE_POOL(15)
+    // 16-bit residual stream: result (+ residual) (+ operand copy)
+    HALO_CASE(18) HALO_CASE(19) HALO_CASE(22) HALO_CASE(23)
+    HALO_CASE_POOL(26) HALO_CASE_POOL(27) HALO_CASE_POOL(30) HALO_CASE_POOL(31)
     default:
       set_error("conv_halo: unsupported output combination %d", mode);
       return IPDM_E_BADARG;

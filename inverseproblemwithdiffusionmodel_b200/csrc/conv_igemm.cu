@@ -218,7 +218,11 @@ extern "C" int ipdm_conv_igemm(const ipdm_conv_desc* dh, void* stream) {
                "conv_igemm: taps must be 9, 1, or 27 (3x3x3 over slice volumes, slices > 1)");
   IPDM_REQUIRE(d.Cin % BLOCK_K == 0 && d.Cin >= BLOCK_K, IPDM_E_UNSUPPORTED, "conv_igemm: Cin=%d must be a multiple of 64", d.Cin);
   IPDM_REQUIRE(d.Cout % BLOCK_M == 0, IPDM_E_UNSUPPORTED, "conv_igemm: Cout=%d must be a multiple of 128", d.Cout);
-  IPDM_REQUIRE(d.out_f32 || d.out_f16, IPDM_E_BADARG, "conv_igemm: no output");
+  const bool t16 = d.residual_f16 != nullptr || d.out_raw_f16 != nullptr;     // 16-bit residual stream
+  IPDM_REQUIRE(!t16 || (d.residual == nullptr && d.out_f32 == nullptr), IPDM_E_BADARG,
+               "conv_igemm: the residual stream is either f32 (residual / out_f32) or f16 (residual_f16 / out_raw_f16)");
+  IPDM_REQUIRE(d.out_f32 || d.out_f16 || d.out_raw_f16, IPDM_E_BADARG, "conv_igemm: no output");
+  IPDM_REQUIRE(!d.stats || d.out_f32 || d.out_raw_f16, IPDM_E_BADARG, "conv_igemm: stats need the result output");
   IPDM_REQUIRE(d.N >= 1 && d.H >= 1 && d.W >= 1 && d.dilation >= 1, IPDM_E_BADARG, "conv_igemm: bad shape");
   const bool pool = (d.flags & IPDM_CONV_POOL2) != 0;
   IPDM_REQUIRE(!pool || (d.H % 2 == 0 && d.W % 2 == 0), IPDM_E_BADARG, "conv_igemm: pooling needs even H, W");
@@ -231,19 +235,22 @@ extern "C" int ipdm_conv_igemm(const ipdm_conv_desc* dh, void* stream) {
   CUtensorMap mw, mx;
   if (int e = get_weight_map(d.w_f16, d.Cout, d.taps * d.Cin, &mw)) return e;
   if (int e = get_act_map(d.in_f16, d.N, d.H, d.W, d.Cin, TILE_W, TILE_H, d.slices, &mx)) return e;
-  const int mode = (d.residual ? 1 : 0) | (d.out_f32 ? 2 : 0) | (d.out_f16 ? 4 : 0) | (pool ? 8 : 0);
+  const int mode = ((d.residual || d.residual_f16) ? 1 : 0) | ((d.out_f32 || d.out_raw_f16) ? 2 : 0) | (d.out_f16 ? 4 : 0) | (pool ? 8 : 0) |
+                   (t16 ? 16 : 0);
   if (d.stats) {
     IPDM_CUDA(cudaMemsetAsync(d.stats, 0, (size_t)(d.N / d.slices) * d.Cout * 2 * sizeof(double), s));
   }
   IgemmParams p{};
   p.slices = d.slices; p.slice_shift = d.slice_shift;
-  p.bias = d.bias; p.residual = d.residual; p.out_f32 = d.out_f32; p.out_f16 = reinterpret_cast<__half*>(d.out_f16);
+  p.bias = d.bias; p.out_f16 = reinterpret_cast<__half*>(d.out_f16);
+  p.residual = t16 ? reinterpret_cast<const float*>(d.residual_f16) : d.residual;
+  p.out_f32 = t16 ? reinterpret_cast<float*>(d.out_raw_f16) : d.out_f32;
   p.stats = d.stats;
   p.N = d.N; p.H = d.H; p.W = d.W; p.Cin = d.Cin; p.Cout = d.Cout; p.taps = d.taps; p.dilation = d.dilation; p.flags = d.flags;
   p.tiles_w = (d.W + TILE_W - 1) / TILE_W;
   p.tiles_h = (d.H + TILE_H - 1) / TILE_H;
   dim3 grid(p.tiles_w * p.tiles_h * d.N, d.Cout / BLOCK_M);
-  static bool attr_set[16] = {};
+  static bool attr_set[32] = {};
 #define IGEMM_CASE(M)                                                                                           \
   case M:                                                                                                       \
     if (!attr_set[M]) {                                                                                         \
@@ -255,6 +262,7 @@ extern "C" int ipdm_conv_igemm(const ipdm_conv_desc* dh, void* stream) {
   switch (mode) {
     IGEMM_CASE(2) IGEMM_CASE(3) IGEMM_CASE(4) IGEMM_CASE(5) IGEMM_CASE(6) IGEMM_CASE(7)
     IGEMM_CASE(10) IGEMM_CASE(11) IGEMM_CASE(12) IGEMM_CASE(13) IGEMM_CASE(14) IGEMM_CASE(15)
+    IGEMM_CASE(18) IGEMM_CASE(19) IGEMM_CASE(22) IGEMM_CASE(23) IGEMM_CASE(26) IGEMM_CASE(27) IGEMM_CASE(30) IGEMM_CASE(31)
     default:
       set_error("conv_igemm: unsupported output combination %d", mode);
       return IPDM_E_BADARG;

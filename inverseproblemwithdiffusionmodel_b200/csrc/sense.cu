@@ -1023,7 +1023,7 @@ extern "C" int ipdm_sense_plan_create(const uint8_t* mask_host, int mask_frames,
     return pieces.size() - 1;
   };
   const size_t i_mask = add(ph.mask.data(), ph.mask.size());
-  size_t i_ns = 0, i_ng = 0, i_nc = 0, i_kcol = 0, i_nat = 0, i_k0c = 0, i_ppos = 0, i_tw = 0, i_twh = 0, i_groups = 0, i_gslot = 0,
+  size_t i_ns = 0, i_ng = 0, i_nc = 0, i_kcol = 0, i_nat = 0, i_k0c = 0, i_ppos = 0, i_tcw = 0, i_tw = 0, i_twh = 0, i_groups = 0, i_gslot = 0,
          i_chunks = 0, i_gbm = 0, i_big = 0, i_tws = 0;
   if (pl->pruned_rows) {
     i_ns = add(ph.ns.data(), ph.ns.size() * sizeof(int));
@@ -1033,6 +1033,7 @@ extern "C" int ipdm_sense_plan_create(const uint8_t* mask_host, int mask_frames,
     i_nat = add(ph.nat.data(), ph.nat.size());
     i_k0c = add(ph.k0c.data(), ph.k0c.size());
     i_ppos = add(ph.ppos.data(), ph.ppos.size());
+    i_tcw = add(ph.tcw.data(), ph.tcw.size());
     i_tw = add(ph.tw.data(), ph.tw.size() * sizeof(float));
     i_twh = add(ph.twh.data(), ph.twh.size() * sizeof(float));
     i_chunks = add(ph.chunks.data(), ph.chunks.size());
@@ -1066,6 +1067,8 @@ extern "C" int ipdm_sense_plan_create(const uint8_t* mask_host, int mask_frames,
     v.nat = at(i_nat);
     v.k0c = at(i_k0c);
     v.ppos = at(i_ppos);
+    v.tcw = at(i_tcw);
+    v.nch_max = ph.nchunks_max;
     v.tw = reinterpret_cast<const cf32*>(at(i_tw));
     v.twh = reinterpret_cast<const cf32*>(at(i_twh));
     v.chunks = at(i_chunks);

@@ -17,6 +17,8 @@
 //                      natural slot of each of its columns (255 = not sampled), and the bitmap over all W/4 groups
 //   nchunks[f], chunks[f][c] = {first group, groups, first slot, slots}
 //                      work items of the column kernels: runs of whole groups holding at most 8 sampled columns
+//   tcw[f][jj]         chunk*8 + position inside the chunk of class entry jj: the compact scratch is laid out
+//                      T[image][chunk][h][8], so that a column-kernel work item is one contiguous block
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -30,7 +32,7 @@ struct PlanHost {
   bool pruned = false;   // every frame keeps <= the limit the pruned kernels are built for and no residue class holds > 4 columns
   std::vector<int> ns, ngroups, nchunks;
   std::vector<uint16_t> kcol;
-  std::vector<uint8_t> nat, k0c, cls, ppos, groups, gslot, chunks, mask;
+  std::vector<uint8_t> nat, k0c, cls, ppos, tcw, groups, gslot, chunks, mask;
   std::vector<uint32_t> gbitmap, big;   // big[f][2]: classes with >= 3 / == 4 entries, one bit per class
   std::vector<float> tw, twh;   // interleaved (re, im)
   static constexpr int CLS_PITCH = 20;   // 17 boundaries padded to five 32-bit words
@@ -77,6 +79,7 @@ inline PlanHost build_plan_host(const uint8_t* mask, int frames, int W) {
   p.k0c.assign((size_t)frames * NP, 0);
   p.cls.assign((size_t)frames * PlanHost::CLS_PITCH, 0);
   p.ppos.assign((size_t)frames * NP, 0);
+  p.tcw.assign((size_t)frames * NP, 0);
   p.tw.assign((size_t)frames * NP * R1 * 2, 0.f);
   p.twh.assign((size_t)frames * NP * PlanHost::TWH * 2, 0.f);
   p.nchunks.assign(frames, 0);
@@ -153,6 +156,13 @@ inline PlanHost build_plan_host(const uint8_t* mask, int frames, int W) {
     }
     p.nchunks[f] = c;
     p.nchunks_max = std::max(p.nchunks_max, c);
+    for (size_t j = 0; j < order.size(); ++j) {      // natural slot -> (chunk, position)
+      const int sl = p.nat[(size_t)f * NP + j];
+      for (int cc = 0; cc < c; ++cc) {
+        const uint8_t* ch = &p.chunks[((size_t)f * ng_all + cc) * 4];
+        if (sl >= ch[2] && sl < ch[2] + ch[3]) p.tcw[(size_t)f * NP + j] = (uint8_t)(cc * PlanHost::CHUNK_SLOTS + (sl - ch[2]));
+      }
+    }
   }
   return p;
 }

@@ -6,9 +6,11 @@
 //   shared memory, and each sampled column is one R1-term sum with a register-resident twiddle vector (forward) or
 //   is spread over its residue class (adjoint).  W = 512 takes R1 = 32: 16 values per thread instead of the 32 of the
 //   full engine, which is what keeps these kernels near 128 registers.
-// * The scratch is compact: T[c][b][h][slot], slot = rank of the column among the sampled ones (ns_pad per row), so a
-//   row kernel reads / writes one contiguous run per row and coil, and the column kernels (full two-pass transforms
-//   along H of the ns sampled columns only) see a few percent of k-space.
+// * The scratch is compact: T[c][b][chunk][h][8] holds the sampled columns only, eight per chunk (a chunk = the work
+//   item of a column kernel: one contiguous block), so a row kernel reads / writes a few 64-byte runs per row and
+//   coil, and the column kernels (full two-pass transforms along H of the ns sampled columns only) see a few percent
+//   of k-space.  (A first layout T[c][b][h][slot] made the column kernels fetch 64-byte pieces at a 192-byte pitch:
+//   2.7x the bytes from DRAM.)
 // * Everything that depends on the mask alone -- column lists, residue classes, twiddle vectors, active 32-byte
 //   sectors, the zero-fill bitmap, the H-transform twiddles -- comes from the plan; no kernel compiles a mask or calls
 //   sincos.
@@ -20,7 +22,7 @@
 namespace ipdm {
 
 struct PlanView {
-  int frames, W, ns_pad, ng_all, cmax;
+  int frames, W, ns_pad, ng_all, cmax, nch_max;
   const int* ns;
   const int* ngroups;
   const int* nchunks;
@@ -28,6 +30,7 @@ struct PlanView {
   const uint8_t* nat;       // [frames][ns_pad]  class position -> natural slot
   const uint8_t* k0c;       // [frames][ns_pad]  class position -> k mod 16
   const uint8_t* ppos;      // [frames][ns_pad]  class position -> position in the padded class layout (k0*cmax + e)
+  const uint8_t* tcw;       // [frames][ns_pad]  class position -> chunk*8 + position inside the chunk (scratch layout)
   const cf32* tw;           // [frames][ns_pad][W/16], class order
   const cf32* twh;          // [frames][ns_pad][10], class order, factored form
   const uint8_t* groups;    // [frames][W/4]
@@ -46,15 +49,17 @@ template <int L> struct PGeo {
 };
 
 // The outputs (forward) / inputs (adjoint) of thread t: class positions jj = t + R1*o, o < NOUT.
+// slot[o] = offset of the column inside the image's scratch block T[chunk][h][8] at h = 0 (-1: no column)
 template <int L, int NOUT> struct MySlots {
   int k0[NOUT], slot[NOUT], pp[NOUT];
-  __device__ __forceinline__ void init(const PlanView& p, int f, int ns, int t) {
+  __device__ __forceinline__ void init(const PlanView& p, int f, int ns, int t, int H) {
 #pragma unroll
     for (int o = 0; o < NOUT; ++o) {
       const int jj = t + PR<L>::R1 * o;
       const bool on = jj < ns;
       k0[o] = on ? p.k0c[f * p.ns_pad + jj] : 0;
-      slot[o] = on ? p.nat[f * p.ns_pad + jj] : -1;
+      const int cw = on ? p.tcw[f * p.ns_pad + jj] : 0;
+      slot[o] = on ? (cw >> 3) * H * 8 + (cw & 7) : -1;
       pp[o] = on ? p.ppos[f * p.ns_pad + jj] : 0;
     }
   }
@@ -91,7 +96,7 @@ __global__ void __launch_bounds__(128, 3) kp_fwd_rows(SenseArgs a, PlanView p) {
   const int f = b % p.frames, ns = p.ns[f];
   cf32* sx = xch + r * P::LINE;
   MySlots<L, NOUT> my;
-  my.init(p, f, ns, t);
+  my.init(p, f, ns, t, a.H);
   cf32 twh[NOUT][P::NTWH];
   load_my_twiddles<L, NOUT, false>(twh, p, f, ns, t);
   cf32 xq[P::R0];
@@ -123,8 +128,9 @@ __global__ void __launch_bounds__(128, 3) kp_fwd_rows(SenseArgs a, PlanView p) {
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const size_t img_stride = (size_t)a.batch * a.H * L;
   float4* zbase = reinterpret_cast<float4*>(a.out + ((size_t)b * a.H + h0) * L);
-  cf32* wsp = a.ws + ((size_t)b * a.H + h) * p.ns_pad;
-  const size_t ws_stride = (size_t)a.batch * a.H * p.ns_pad;
+  const size_t ws_img = (size_t)p.nch_max * a.H * 8;   // scratch of one coil image: [chunk][h][8]
+  cf32* wsp = a.ws + (size_t)b * ws_img + (size_t)h * 8;
+  const size_t ws_stride = (size_t)a.batch * ws_img;
   for (int c = 0; c < a.ncoils; ++c) {
     // (re-reading the row per coil instead of keeping it would free 32 registers for a fourth resident CTA, but this
     // kernel is bound by the L1 / shared-memory data pipe -- ncu: 95 % -- and the re-reads land exactly there)
@@ -148,55 +154,61 @@ __global__ void __launch_bounds__(128, 3) kp_fwd_rows(SenseArgs a, PlanView p) {
 
 // ---- column kernels: full two-pass transforms along H of the sampled columns ------------------------------------
 // grid (ncoils * batch, chunks); a chunk = a run of whole active groups holding at most 8 sampled columns (plan table),
-// one transform per sampled column.  The compact scratch rows of a chunk are contiguous (<= 64 bytes per image row).
+// one transform per sampled column.
+// These kernels move little data and used to wait on its latency (ncu: long-scoreboard stalls, 4 KB in flight per CTA).
+// Now every byte of a chunk is requested at once: the scratch block of a chunk is contiguous ([h][8], 32 KB at H = 512)
+// and 16-byte cp.async copies land it in a row-major staging tile stage[h][slot] (pitch 10) before anybody waits; the
+// adjoint's k-space side issues eight independent 8-byte loads per thread and round.
+// The exchange lines of the transforms alias the staging tile once it has been read into registers.
 template <int LH>
 __device__ __forceinline__ void copy_tws(cf32* tws, const cf32* src, int tid, int nt) {
   for (int e = tid; e < Geo<LH>::NTWS; e += nt) tws[e] = src[e];
 }
-// line pitch of the column kernels: odd, so that the 16 lanes that fill / drain 16 different lines at the same row
-// (the coalesced side of the compact scratch) hit 16 different bank pairs
-// 8 lines (sampled columns) per CTA: half the shared memory of a 16-line CTA, twice the resident CTAs -- these kernels
-// move little data and wait on its latency, so residency is what they need
 template <int LH> struct CGeo {
-  static constexpr int CL = 8;
+  static constexpr int CL = 8;                               // lines (sampled columns) per CTA
   static constexpr int NT = CL * Geo<LH>::TPF;
-  static constexpr int CSTRIDE = P2<LH>::STRIDE | 1;
-  static constexpr size_t SMEM = (size_t)(Geo<LH>::NTWS + CL * CSTRIDE) * sizeof(cf32);
+  static constexpr int SP = CL + 2;                          // staging pitch: rows 16-byte aligned, a column read is 2-way conflicted at worst
+  static constexpr int CSTRIDE = P2<LH>::STRIDE | 1;         // line pitch: odd, the drain loops walk 8 lines at one row
+  static constexpr int TILE = (LH * SP > CL * CSTRIDE ? LH * SP : CL * CSTRIDE);
+  static constexpr size_t SMEM = (size_t)(Geo<LH>::NTWS + TILE) * sizeof(cf32);
 };
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <int LH>
 __global__ void __launch_bounds__(CGeo<LH>::NT) kp_fwd_cols(SenseArgs a, PlanView p) {
   using G = Geo<LH>;
-  using P = P2<LH>;
+  using C = CGeo<LH>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cf32* tws = reinterpret_cast<cf32*>(smem_raw);
-  cf32* xch = tws + G::NTWS;
+  cf32* tile = tws + G::NTWS;       // staging [h][SP] first, then the lines [cs][CSTRIDE]
   const int tid = threadIdx.x;
   const size_t img = blockIdx.x;
   const int b = (int)(img % a.batch), f = b % p.frames;
   if ((int)blockIdx.y >= p.nchunks[f]) return;
   const uchar4 ch = *reinterpret_cast<const uchar4*>(p.chunks + ((size_t)f * p.ng_all + blockIdx.y) * 4);
   const int g_lo = ch.x, g_cnt = ch.y, s_lo = ch.z, s_cnt = ch.w;
-  copy_tws<LH>(tws, p.tws_h, tid, CGeo<LH>::NT);
-  // compact scratch rows -> one line per sampled column (lanes along the slots: contiguous runs of 8*s_cnt bytes)
   {
-    const cf32* wp = a.ws + img * LH * p.ns_pad + s_lo;
-#pragma unroll 4
-    for (int idx = tid; idx < CGeo<LH>::CL * LH; idx += CGeo<LH>::NT) {
-      const int si = idx % CGeo<LH>::CL, hh = idx / CGeo<LH>::CL;
-      if (si < s_cnt) xch[si * CGeo<LH>::CSTRIDE + hh] = wp[(size_t)hh * p.ns_pad + si];
+    const cf32* wp = a.ws + (img * p.nch_max + blockIdx.y) * (size_t)(LH * 8);   // this chunk's block [h][8]
+    for (int idx = tid; idx < 4 * LH; idx += C::NT) {
+      const int pc = idx & 3, hh = idx >> 2;                                    // 16-byte piece pc of row hh
+      cp_async16(tile + hh * C::SP + 2 * pc, wp + hh * 8 + 2 * pc);
     }
   }
+  copy_tws<LH>(tws, p.tws_h, tid, C::NT);
+  cp_async_wait_all();
   __syncthreads();
   const int cs = tid / G::TPF, t = tid % G::TPF;
-  cf32* sx = xch + cs * CGeo<LH>::CSTRIDE;
-  {   // every line is transformed (lines past s_cnt hold stale data nobody reads): no divergence around __syncwarp
+  cf32* sx = tile + cs * C::CSTRIDE;
+  cf32 v[G::E];
+#pragma unroll
+  for (int q = 0; q < G::E; ++q) v[q] = cs < s_cnt ? tile[a_pos<LH>(t, q) * C::SP + cs] : cf32{0.f, 0.f};
+  __syncthreads();   // the staging tile is in registers: the lines may overwrite it
+  {
     Twid<LH, (LH < 512)> tw;
     tw.init(tws, t);
-    cf32 v[G::E];
-#pragma unroll
-    for (int q = 0; q < G::E; ++q) v[q] = sx[a_pos<LH>(t, q)];
-    __syncwarp();
     a2b_first<LH, -1>(v, t, sx);
     __syncwarp();
     a2b_second<LH, -1>(v, t, sx, tw);
@@ -206,14 +218,14 @@ __global__ void __launch_bounds__(CGeo<LH>::NT) kp_fwd_cols(SenseArgs a, PlanVie
   }
   __syncthreads();
   // active sectors, 16-byte pieces: idx = (h * g_cnt + gi) * 2 + half -- consecutive lanes walk the sectors of one image row
-  for (int idx = tid; idx < LH * g_cnt * 2; idx += CGeo<LH>::NT) {
+  for (int idx = tid; idx < LH * g_cnt * 2; idx += C::NT) {
     const int half = idx & 1, gi = (idx >> 1) % g_cnt, hh = (idx >> 1) / g_cnt;
     const int g = g_lo + gi;
     const int kk = 4 * p.groups[f * p.ng_all + g] + 2 * half;
     const uint8_t* gs = p.gslot + ((size_t)f * p.ng_all + g) * 4 + 2 * half;
     const int s0 = gs[0], s1 = gs[1];
-    const cf32 p0 = s0 != 255 ? xch[(s0 - s_lo) * CGeo<LH>::CSTRIDE + hh] : cf32{0.f, 0.f};
-    const cf32 p1 = s1 != 255 ? xch[(s1 - s_lo) * CGeo<LH>::CSTRIDE + hh] : cf32{0.f, 0.f};
+    const cf32 p0 = s0 != 255 ? tile[(s0 - s_lo) * C::CSTRIDE + hh] : cf32{0.f, 0.f};
+    const cf32 p1 = s1 != 255 ? tile[(s1 - s_lo) * C::CSTRIDE + hh] : cf32{0.f, 0.f};
     const float sc0 = a.scale * sgn(hh + kk);
     *reinterpret_cast<float4*>(a.out + (img * LH + hh) * a.W + kk) = make_float4(p0.x * sc0, p0.y * sc0, -p1.x * sc0, -p1.y * sc0);
   }
@@ -223,69 +235,60 @@ __global__ void __launch_bounds__(CGeo<LH>::NT) kp_fwd_cols(SenseArgs a, PlanVie
 template <int LH>
 __global__ void __launch_bounds__(CGeo<LH>::NT) kp_adj_cols(SenseArgs a, PlanView p) {
   using G = Geo<LH>;
-  using P = P2<LH>;
+  using C = CGeo<LH>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cf32* tws = reinterpret_cast<cf32*>(smem_raw);
-  cf32* xch = tws + G::NTWS;
+  cf32* tile = tws + G::NTWS;
   const int tid = threadIdx.x;
   const size_t img = blockIdx.x;
   const int b = (int)(img % a.batch), f = b % p.frames;
   if ((int)blockIdx.y >= p.nchunks[f]) return;
   const uchar4 ch = *reinterpret_cast<const uchar4*>(p.chunks + ((size_t)f * p.ng_all + blockIdx.y) * 4);
-  const int g_lo = ch.x, g_cnt = ch.y, s_lo = ch.z, s_cnt = ch.w;
-  copy_tws<LH>(tws, p.tws_h, tid, CGeo<LH>::NT);
-  // active sectors of this chunk -> lines of the sampled columns; four independent 16-byte loads in flight per thread
+  const int s_lo = ch.z, s_cnt = ch.w;
   {
-    const int total = LH * g_cnt * 2;
-    for (int base = tid; base < total; base += 4 * CGeo<LH>::NT) {
-      float4 q[4];
-      int hh[4], s0[4], s1[4], kk[4];
+    // the sampled columns themselves (8 bytes each; the memory system fetches their sectors either way): eight independent
+    // loads per thread in flight, then eight stores into the staging tile
+    const int si = tid % C::CL;
+    const int kcol = si < s_cnt ? p.kcol[f * p.ns_pad + s_lo + si] : 0;
+    const cf32* sp = a.in + img * LH * a.W + kcol;
+    constexpr int RS = C::NT / C::CL;      // rows per round
+    for (int h0 = tid / C::CL; h0 < LH; h0 += 8 * RS) {
+      cf32 q[8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int idx = base + j * CGeo<LH>::NT;
-        s0[j] = s1[j] = 255;
-        if (idx < total) {
-          const int half = idx & 1, gi = (idx >> 1) % g_cnt;
-          hh[j] = (idx >> 1) / g_cnt;
-          const int g = g_lo + gi;
-          kk[j] = 4 * p.groups[f * p.ng_all + g] + 2 * half;
-          const uint8_t* gs = p.gslot + ((size_t)f * p.ng_all + g) * 4 + 2 * half;
-          s0[j] = gs[0];
-          s1[j] = gs[1];
-          if (s0[j] != 255 || s1[j] != 255) q[j] = *reinterpret_cast<const float4*>(a.in + (img * LH + hh[j]) * a.W + kk[j]);
-        }
-      }
+      for (int j = 0; j < 8; ++j) q[j] = (si < s_cnt && h0 + j * RS < LH) ? sp[(size_t)(h0 + j * RS) * a.W] : cf32{0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float sg0 = sgn(hh[j] + kk[j]);
-        if (s0[j] != 255) xch[(s0[j] - s_lo) * CGeo<LH>::CSTRIDE + hh[j]] = cf32{q[j].x * sg0, q[j].y * sg0};
-        if (s1[j] != 255) xch[(s1[j] - s_lo) * CGeo<LH>::CSTRIDE + hh[j]] = cf32{-q[j].z * sg0, -q[j].w * sg0};
-      }
+      for (int j = 0; j < 8; ++j)
+        if (h0 + j * RS < LH) tile[(h0 + j * RS) * C::SP + si] = q[j];
     }
   }
+  copy_tws<LH>(tws, p.tws_h, tid, C::NT);
   __syncthreads();
   const int cs = tid / G::TPF, t = tid % G::TPF;
-  cf32* sx = xch + cs * CGeo<LH>::CSTRIDE;
+  cf32* sx = tile + cs * C::CSTRIDE;
+  const int kc = cs < s_cnt ? p.kcol[f * p.ns_pad + s_lo + cs] : 0;
+  cf32 v[G::E];
+  {
+    const float sg = sgn(t + kc);   // a_off is even: (-1)^(h + k) is one sign per thread
+#pragma unroll
+    for (int q = 0; q < G::E; ++q) v[q] = cs < s_cnt ? cscale(tile[a_pos<LH>(t, q) * C::SP + cs], sg) : cf32{0.f, 0.f};
+  }
+  __syncthreads();   // the staging tile is in registers: the lines may overwrite it
   {
     Twid<LH, (LH < 512)> tw;
     tw.init(tws, t);
-    cf32 v[G::E];
-#pragma unroll
-    for (int q = 0; q < G::E; ++q) v[q] = sx[a_pos<LH>(t, q)];
-    __syncwarp();
     a2b_first<LH, +1>(v, t, sx);
     __syncwarp();
     a2b_second<LH, +1>(v, t, sx, tw);
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < G::E; ++i) sx[b_pos<LH>(t, i)] = v[i];
   }
+  __syncthreads();   // every exchange is finished: the tile becomes the row-major staging of the results
+#pragma unroll
+  for (int i = 0; i < G::E; ++i) tile[b_pos<LH>(t, i) * C::SP + cs] = v[i];
   __syncthreads();
   {
-    cf32* wp = a.ws + img * LH * p.ns_pad + s_lo;
-    for (int idx = tid; idx < CGeo<LH>::CL * LH; idx += CGeo<LH>::NT) {
-      const int si = idx % CGeo<LH>::CL, hh = idx / CGeo<LH>::CL;
-      if (si < s_cnt) wp[(size_t)hh * p.ns_pad + si] = xch[si * CGeo<LH>::CSTRIDE + hh];
+    cf32* wp = a.ws + (img * p.nch_max + blockIdx.y) * (size_t)(LH * 8);   // this chunk's block [h][8], 16-byte pieces
+    for (int idx = tid; idx < 4 * LH; idx += C::NT) {
+      const int pc = idx & 3, hh = idx >> 2;
+      *reinterpret_cast<float4*>(wp + hh * 8 + 2 * pc) = *reinterpret_cast<const float4*>(tile + hh * C::SP + 2 * pc);
     }
   }
 }
@@ -319,10 +322,11 @@ __global__ void __launch_bounds__(128, 4) kp_adj_rows(SenseArgs a, PlanView p) {
   fill_padded_tables<L, CMAX, false>(twp, ysm, G::TPC * 16 * CMAX, p, f, ns, tid, G::NT);
   const uint32_t big2 = p.big[f * 2], big3 = p.big[f * 2 + 1];
   MySlots<L, NOUT> my;
-  my.init(p, f, ns, t);
+  my.init(p, f, ns, t, a.H);
   cf32* yr = ysm + r * 16 * CMAX;
-  const cf32* wsp = a.ws + ((size_t)b * a.H + h) * p.ns_pad;
-  const size_t ws_stride = (size_t)a.batch * a.H * p.ns_pad;
+  const size_t ws_img = (size_t)p.nch_max * a.H * 8;   // scratch of one coil image: [chunk][h][8]
+  const cf32* wsp = a.ws + (size_t)b * ws_img + (size_t)h * 8;
+  const size_t ws_stride = (size_t)a.batch * ws_img;
   const bool has_maps = a.mre != nullptr && !a.ssos;
   const size_t map_img = (size_t)a.H * L;
   const float* mre = a.mre + (size_t)h * L + t;
@@ -407,7 +411,7 @@ __global__ void __launch_bounds__(128, 3) kp_ald_sense(AldArgs a, PlanView p) {
   fill_padded_tables<L, CMAX, true>(twp, ysm, G::TPC * 16 * CMAX, p, f, ns, tid, G::NT);
   const uint32_t big2 = p.big[f * 2], big3 = p.big[f * 2 + 1];
   MySlots<L, NOUT> my;
-  my.init(p, f, ns, t);
+  my.init(p, f, ns, t, a.H);
   cf32 twh[NOUT][P::NTWH];
   load_my_twiddles<L, NOUT, true>(twh, p, f, ns, t);
   cf32* sx = xch + r * P::LINE;

@@ -146,6 +146,12 @@ double check_pruned(int ns_target, unsigned seed) {
         s_next += ch[3];
       }
       if (g_next != pl.ngroups[f] || s_next != ns) return 13.0;
+      for (int jj = 0; jj < ns; ++jj) {      // scratch position of every class entry: (chunk, position) of its natural slot
+        const int cw = pl.tcw[f * NP + jj], cc = cw >> 3, within = cw & 7;
+        if (cc >= pl.nchunks[f]) return 14.0;
+        const uint8_t* ch = &pl.chunks[(f * (L / 4) + cc) * 4];
+        if (within >= ch[3] || ch[2] + within != pl.nat[f * NP + jj]) return 15.0;
+      }
     }
     for (int g = 0; g < pl.ngroups[f]; ++g) {
       const int q = pl.groups[f * (L / 4) + g];
