@@ -81,14 +81,22 @@ IPDM_HD void pr_scatter(cf32* v, int t, const cf32* Y, const cf32* twp, int pitc
   for (int k0 = 0; k0 < P::R0; ++k0) {
     const cf32x2 y01 = reinterpret_cast<const cf32x2*>(Y + k0 * CMAX)[0];   // class rows are 16-byte aligned
     cf32 acc = twmul<DIR>(y01.a, twp[(k0 * CMAX) * pitch + t]);
-    acc = cadd(acc, twmul<DIR>(y01.b, twp[(k0 * CMAX + 1) * pitch + t]));
-    if (CMAX == 4) {
-      if ((big2 >> k0) & 1u) {
-        acc = cadd(acc, twmul<DIR>(Y[k0 * CMAX + 2], twp[(k0 * CMAX + 2) * pitch + t]));
-        if ((big3 >> k0) & 1u) acc = cadd(acc, twmul<DIR>(Y[k0 * CMAX + 3], twp[(k0 * CMAX + 3) * pitch + t]));
+    v[k0] = cadd(acc, twmul<DIR>(y01.b, twp[(k0 * CMAX + 1) * pitch + t]));
+  }
+  if (CMAX == 4) {
+    // third and fourth entries: one test per four classes skips the common case outright
+#pragma unroll
+    for (int g = 0; g < P::R0 / 4; ++g) {
+      if ((big2 >> (4 * g)) & 0xFu) {
+#pragma unroll
+        for (int k0 = 4 * g; k0 < 4 * g + 4; ++k0) {
+          if ((big2 >> k0) & 1u) {
+            v[k0] = cadd(v[k0], twmul<DIR>(Y[k0 * CMAX + 2], twp[(k0 * CMAX + 2) * pitch + t]));
+            if ((big3 >> k0) & 1u) v[k0] = cadd(v[k0], twmul<DIR>(Y[k0 * CMAX + 3], twp[(k0 * CMAX + 3) * pitch + t]));
+          }
+        }
       }
     }
-    v[k0] = acc;
   }
   dft_n<P::R0, DIR>(v);
 }

@@ -198,6 +198,19 @@ __global__ void __launch_bounds__(CGeo<LH>::NT) kp_fwd_cols(SenseArgs a, PlanVie
     }
   }
   copy_tws<LH>(tws, p.tws_h, tid, C::NT);
+  // this chunk's groups (first column, line of each of the four columns or -1) in shared memory: the drain loop below
+  // must not chase three dependent global loads per 16-byte store
+  __shared__ int g_col[C::CL];
+  __shared__ int g_line[C::CL][4];
+  if (tid < g_cnt) {
+    const int g = g_lo + tid;
+    g_col[tid] = 4 * p.groups[f * p.ng_all + g];
+    const uchar4 gs = *reinterpret_cast<const uchar4*>(p.gslot + ((size_t)f * p.ng_all + g) * 4);
+    g_line[tid][0] = gs.x != 255 ? gs.x - s_lo : -1;
+    g_line[tid][1] = gs.y != 255 ? gs.y - s_lo : -1;
+    g_line[tid][2] = gs.z != 255 ? gs.z - s_lo : -1;
+    g_line[tid][3] = gs.w != 255 ? gs.w - s_lo : -1;
+  }
   cp_async_wait_all();
   __syncthreads();
   const int cs = tid / G::TPF, t = tid % G::TPF;
@@ -220,12 +233,10 @@ __global__ void __launch_bounds__(CGeo<LH>::NT) kp_fwd_cols(SenseArgs a, PlanVie
   // active sectors, 16-byte pieces: idx = (h * g_cnt + gi) * 2 + half -- consecutive lanes walk the sectors of one image row
   for (int idx = tid; idx < LH * g_cnt * 2; idx += C::NT) {
     const int half = idx & 1, gi = (idx >> 1) % g_cnt, hh = (idx >> 1) / g_cnt;
-    const int g = g_lo + gi;
-    const int kk = 4 * p.groups[f * p.ng_all + g] + 2 * half;
-    const uint8_t* gs = p.gslot + ((size_t)f * p.ng_all + g) * 4 + 2 * half;
-    const int s0 = gs[0], s1 = gs[1];
-    const cf32 p0 = s0 != 255 ? tile[(s0 - s_lo) * C::CSTRIDE + hh] : cf32{0.f, 0.f};
-    const cf32 p1 = s1 != 255 ? tile[(s1 - s_lo) * C::CSTRIDE + hh] : cf32{0.f, 0.f};
+    const int kk = g_col[gi] + 2 * half;
+    const int l0 = g_line[gi][2 * half], l1 = g_line[gi][2 * half + 1];
+    const cf32 p0 = l0 >= 0 ? tile[l0 * C::CSTRIDE + hh] : cf32{0.f, 0.f};
+    const cf32 p1 = l1 >= 0 ? tile[l1 * C::CSTRIDE + hh] : cf32{0.f, 0.f};
     const float sc0 = a.scale * sgn(hh + kk);
     *reinterpret_cast<float4*>(a.out + (img * LH + hh) * a.W + kk) = make_float4(p0.x * sc0, p0.y * sc0, -p1.x * sc0, -p1.y * sc0);
   }

@@ -304,6 +304,62 @@ def test_conv_halo_output_modes(N, H, W, Cin, Cout, dil, flags, bias, residual, 
         assert rel_l2(ast.float().cpu(), bst.float().cpu()) < 1e-5
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("N,H,W,Cin,Cout,taps,dil,flags,bias,residual,want16,stats", [
+    (2, 64, 64, 128, 128, 9, 1, 1, False, True, True, False),        # RCU second convolution: residual + result + ELU copy
+    (2, 64, 64, 128, 128, 9, 1, 0, True, True, False, True),         # last refine block: residual + result + sums
+    (1, 40, 24, 128, 256, 9, 2, 0, True, False, False, True),        # encoder conv1: result + sums, ragged tiles
+    (2, 32, 32, 256, 256, 9, 1, 4 | 2, False, True, True, False),    # CRP entry: ELU'd residual, pre-residual f16 copy
+    (2, 64, 64, 128, 256, 9, 1, 8 | 1, True, True, True, True),      # pooled conv2 of a down block
+    (1, 64, 64, 128, 256, 1, 1, 8, True, False, False, False),       # pooled 1x1 shortcut (per-tap kernel either way)
+    (3, 24, 8, 128, 128, 9, 2, 1, False, True, True, False),         # 24-row tile
+    (4, 12, 16, 128, 128, 9, 1, 1, True, True, True, False),         # 12-row tile, two images per work item
+    (4, 256, 256, 128, 128, 9, 1, 1, False, True, True, False),      # the dominant launch of the benchmark
+    (2, 32, 32, 256, 512, 9, 4, 0, True, True, False, False)])       # dilation 4 (per-tap kernel)
+def test_conv_16bit_residual_stream(N, H, W, Cin, Cout, taps, dil, flags, bias, residual, want16, stats, variant):
+    """ipdm_conv_desc.residual_f16 / out_raw_f16: the residual stream kept in 16 bits.  Same operands through the f32-stream
+    path with the f16 residual widened: the result must be that path's result rounded to f16 (fp32 arithmetic in between is
+    identical), the f16 operand copy and the InstanceNorm++ sums (taken from the fp32 values) must agree."""
+    L = _lib()
+    g = torch.Generator().manual_seed(H * 11 + Cin + Cout + taps + dil + flags)
+    x16 = torch.randn(N, H, W, Cin, generator=g).half().to(DEV)
+    w16 = (torch.randn(Cout, taps, Cin, generator=g) / (taps * Cin) ** 0.5).half().to(DEV)
+    b = torch.randn(Cout, generator=g).to(DEV) if bias else None
+    pool = bool(flags & 8)
+    Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+    res16 = (3 * torch.randn(N, Ho, Wo, Cout, generator=g)).half().to(DEV) if residual else None
+    res32 = res16.float() if residual else None
+    L.check(L.lib().ipdm_debug_option(1, variant))
+    try:
+        outs = []
+        for t16 in (False, True):
+            o_res = torch.full((N, Ho, Wo, Cout), float("nan"), device=DEV, dtype=torch.float16 if t16 else torch.float32)
+            o16 = torch.full((N, Ho, Wo, Cout), float("nan"), device=DEV, dtype=torch.float16) if want16 else None
+            st = torch.zeros(N, Cout, 2, device=DEV, dtype=torch.float64) if stats else None
+            if t16:
+                d = L.ConvDesc(x16.data_ptr(), w16.data_ptr(), L.ptr(b), None, None, L.ptr(o16), L.ptr(st), N, H, W, Cin, Cout, taps, dil, flags,
+                               0, 0, L.ptr(res16), o_res.data_ptr())
+            else:
+                d = L.ConvDesc(x16.data_ptr(), w16.data_ptr(), L.ptr(b), L.ptr(res32), o_res.data_ptr(), L.ptr(o16), L.ptr(st), N, H, W, Cin, Cout,
+                               taps, dil, flags)
+            L.check(L.lib().ipdm_conv_igemm(ctypes.byref(d), L.stream()), "conv")
+            torch.cuda.synchronize()
+            outs.append((o_res, o16, st))
+    finally:
+        L.check(L.lib().ipdm_debug_option(1, 0))
+    (a32, a16, ast), (t_raw, t16c, tst) = outs
+    assert not torch.isnan(t_raw.float()).any()
+    assert torch.equal(t_raw, a32.half())                      # the 16-bit stream is the fp32 result, rounded once
+    if want16:
+        assert torch.equal(t16c, a16)
+    if stats:
+        assert rel_l2(tst.cpu(), ast.cpu()) < 1e-12
+    # mixing the two streams is refused
+    bad = L.ConvDesc(x16.data_ptr(), w16.data_ptr(), None, L.ptr(res32), None, None, None, N, H, W, Cin, Cout, taps, dil, flags, 0, 0, None, t_raw.data_ptr())
+    if residual:
+        assert L.lib().ipdm_conv_igemm(ctypes.byref(bad), L.stream()) != 0
+
+
 @pytest.mark.parametrize("N,H,W,C", [(2, 14, 14, 256), (1, 28, 28, 128), (3, 40, 24, 64), (2, 256, 256, 128), (5, 32, 32, 512), (1, 7, 5, 8)])
 def test_maxpool5_bit_exact(N, H, W, C):
     """5x5 / stride 1 / pad 2 max-pool of the CRP blocks (layers.py:69-80): exact against torch on the same f16 values."""
