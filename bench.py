@@ -411,8 +411,8 @@ def workload_config(args, line_count):
         return {"workload": f"{'cfg3 (strong scaling of cfg2)' if args.strong else c}: ACDC-shaped {args.size}x{args.size} complex, {args.coils}-coil SENSE, "
                             f"R={args.R:g} (center_lines_frac={args.center_frac:.5f}: {lines}), NCSNv2Deepest ngf128, ALD + L2Penalty prox",
                 "chains_per_gpu": args.chains, "images_per_forward": 2 * args.chains, "n_steps_each": 3, "step_lr": 9e-7, "lr_scaled": 1e6,
-                "schedule_levels": 2311, "operand_dtype": "f16 (fp32 accumulate)",
-                "l2": "activations (>= 0.9 GB per tensor at 14 chains) exceed the 126 MB L2; no flush needed" if args.chains >= 4 else
+                "schedule_levels": 2311, "operand_dtype": "f16 operands and residual stream (fp32 accumulate, fp32 epilogue arithmetic)",
+                "l2": "activations (>= 0.45 GB per tensor at 14 chains) exceed the 126 MB L2; no flush needed" if args.chains >= 4 else
                       "2 images per forward: the deep layers are L2-resident, as they are in a real single-chain run",
                 "e2e_call_steps": args.e2e_levels * 3}
     if c == "cfg1":
@@ -444,12 +444,25 @@ def sense_point(torch, P, _lib, L, dev, hbm, coils, size, batch, R, frac):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def best(fn):
+        """best of 5 CUDA-event times of ONE replay of fn captured in a CUDA graph (the way the samplers run these calls: a
+        captured step has no host launch gaps; at the small sweep points two eager launches cost more host time than the
+        kernels take), L2 flushed before each"""
         fn(); torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
         ts = []
         for _ in range(5):
             flush.zero_(); torch.cuda.synchronize()
-            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
+        del g
         return min(ts)
 
     N = batch * size * size
@@ -465,7 +478,7 @@ def sense_point(torch, P, _lib, L, dev, hbm, coils, size, batch, R, frac):
          "fused_ald_step": best(step)}
     out = {"point": f"{coils} coils, {size}x{size}, batch {batch}, R={R:g} ({int(A.random_under_fourier.mask.sum())} lines), k-space {8 * coils * N / 1e6:.0f} MB",
            "coils": coils, "size": size, "batch": batch, "R": R, "lines": int(A.random_under_fourier.mask.sum()), "pruned_kernels": bool(plan.pruned),
-           "hbm_peak_gbs": hbm, "l2": "256 MB flush between iterations"}
+           "hbm_peak_gbs": hbm, "l2": "256 MB flush between iterations", "timing": "CUDA events around one graph replay, best of 5"}
     for k, ms in t.items():
         byt = b_st if k == "fused_ald_step" else b_fa
         out[k] = {"ms": ms, "gbs": byt / ms / 1e6, "frac": byt / ms / 1e6 / hbm}
@@ -530,6 +543,8 @@ def conv_roofline(args, torch, _lib, L, dev, N, n, ms_step_total, steps, flop_st
     o16 = torch.empty_like(x16)
     o32 = torch.empty(N, n, n, 128, device=dev)
     res = torch.randn(N, n, n, 128, device=dev)
+    raw16 = torch.empty_like(x16)
+    res16 = res.half()
     conv_flop = 2.0 * N * n * n * 128 * 128 * 9
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
@@ -544,24 +559,31 @@ def conv_roofline(args, torch, _lib, L, dev, N, n, ms_step_total, steps, flop_st
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
+    # the launch the network issues (16-bit residual stream: f16 in, f16 residual, f16 result, f16 ELU copy = 8 B / element),
+    # the same convolution with the fp32 stream of round 1 (12 B / element), and the store-only variant (4 B / element)
+    d_t16 = _lib.ConvDesc(x16.data_ptr(), w16.data_ptr(), None, None, None, o16.data_ptr(), None, N, n, n, 128, 128, 9, 1, _lib.CONV_F16_ELU,
+                          0, 0, res16.data_ptr(), raw16.data_ptr())
     d_res = _lib.ConvDesc(x16.data_ptr(), w16.data_ptr(), None, res.data_ptr(), o32.data_ptr(), o16.data_ptr(), None,
                           N, n, n, 128, 128, 9, 1, _lib.CONV_F16_ELU)
     d_f16 = _lib.ConvDesc(x16.data_ptr(), w16.data_ptr(), None, None, None, o16.data_ptr(), None, N, n, n, 128, 128, 9, 1, _lib.CONV_F16_ELU)
-    ms_res, ms_f16 = time_conv(d_res), time_conv(d_f16)
-    achieved = conv_flop / (ms_res / 1e3) / 1e12
-    alg_bytes = N * n * n * 128 * (2 + 4 + 4 + 2)
+    ms_t16, ms_res, ms_f16 = time_conv(d_t16), time_conv(d_res), time_conv(d_f16)
+    achieved = conv_flop / (ms_t16 / 1e3) / 1e12
+    alg_bytes = N * n * n * 128 * (2 + 2 + 2 + 2)
     step_tflops = flop_step / (ms_step_total / steps / 1e3) / 1e12
+    view = lambda ms: {"ms_per_launch": ms, "achieved": conv_flop / (ms / 1e3) / 1e12, "peak": burst, "unit": "TFLOP/s",
+                       "frac": conv_flop / (ms / 1e3) / 1e12 / burst, "bound": "tensor"}
     out = {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
-           "kernel": "k_conv_halo<res+f32+f16> (128->128 3x3 @%dx%d, %d images)" % (n, n, N),
+           "kernel": "k_conv_halo<residual f16 + result f16 + ELU copy f16> (128->128 3x3 @%dx%d, %d images)" % (n, n, N),
            "traffic": conv_traffic_from_profile(N, n),
-           "ms_per_launch": ms_res, "flop_per_launch": conv_flop,
+           "ms_per_launch": ms_t16, "flop_per_launch": conv_flop,
            "peak_source": f"MEASURED_PEAKS.json bf16 burst TFLOP/s ({peak_kind}); the in-run fp16 figure is under `matmul_peaks`",
-           "hbm_view": {"algorithmic_bytes_per_launch": alg_bytes, "gbs": alg_bytes / ms_res / 1e6, "frac_of_copy_peak": alg_bytes / ms_res / 1e6 / hbm,
+           "hbm_view": {"algorithmic_bytes_per_launch": alg_bytes, "gbs": alg_bytes / ms_t16 / 1e6, "frac_of_copy_peak": alg_bytes / ms_t16 / 1e6 / hbm,
                         "arithmetic_intensity_flop_per_byte": conv_flop / alg_bytes, "ridge_flop_per_byte": burst * 1e12 / (hbm * 1e9)},
-           "same_shape_f16_store_only": {"bound": "tensor", "ms_per_launch": ms_f16, "achieved": conv_flop / (ms_f16 / 1e3) / 1e12,
-                                         "peak": burst, "unit": "TFLOP/s", "frac": conv_flop / (ms_f16 / 1e3) / 1e12 / burst},
+           "same_shape_fp32_residual_stream": view(ms_res),
+           "same_shape_f16_store_only": view(ms_f16),
            "whole_step_conv_tflops": step_tflops, "whole_step_frac_of_sustained": step_tflops / sustained,
            "whole_step_frac_of_burst": step_tflops / burst}
+    del raw16, res16
     del x16, w16, o16, o32, res
     torch.cuda.empty_cache()
     return out

@@ -227,12 +227,13 @@ typedef struct {
  *   (ncsn/models/layers.py:28-60,62-83,112-134,165-184,291-313,401-456). */
 int ipdm_conv_igemm(const ipdm_conv_desc* desc_host, void* stream);
 
-/* Diagnostics knob (tests / profiling only): key 1 = convolution kernel variant (0 auto: persistent
- * halo-tile kernel for 3x3 with dilation <= 2, per-tap tile kernel otherwise; 1 = always the per-tap
- * kernel; 2 = TIMING EXPERIMENT: the halo kernel stops re-streaming weight tiles after the first ring fill --
- * results are wrong, only the time is meaningful, tools/exp_weights.py).  key 2: 0 (default) / 1 = the halo kernel's L2
- * bulk prefetch of residual tiles off / on (same results either way; A/B timing: on is 5-10 % slower).  key 3: 0 (default) /
- * 1 = launch the halo kernel with programmatic stream serialization (PDL; also env IPDM_CONV_PDL; measured +0.4 %). */
+/* Diagnostics knob (tests / profiling only; none of the settings changes results): key 1 = convolution kernel choice
+ * (0 auto: persistent halo-tile kernel for 3x3 with dilation <= 2, per-tap tile kernel otherwise; 1 = always the per-tap
+ * kernel).  key 2: 0 (default) / 1 = the halo kernel's L2 bulk prefetch of residual tiles off / on (A/B timing: on is
+ * 5-10 % slower).  key 3: 0 (default) / 1 = launch the halo kernel with programmatic stream serialization (PDL; also env
+ * IPDM_CONV_PDL; measured +0.4 %).  key 4: cudaLimitMaxL2FetchGranularity in bytes (32 / 64 / 128; measured: no effect on
+ * the strided k-space reads of the masked adjoint).  Timing experiments that produce wrong results exist only in builds
+ * with -DIPDM_EXPERIMENTS (tools/exp_weights.py) and are refused otherwise. */
 int ipdm_debug_option(int key, int value);
 
 /* Same contract on CUDA cores, any Cin/Cout (used for narrow test nets and as the on-device
@@ -257,6 +258,23 @@ int ipdm_instnorm_stats(const float* x, double* stats, int N, int HW, int C, int
 int ipdm_instnorm_apply_elu(const float* x, const double* stats, int stats_pivoted, const float* alpha,
                             const float* gamma, const float* beta, void* out_f16, int N, int HW, int C,
                             void* stream);
+
+/* The same three kernels on a 16-bit residual stream (the tensor-core path of the score network keeps its residual stream in
+ * f16, ipdm_conv_desc.residual_f16 / out_raw_f16): begin_conv writing f16, InstanceNorm++ reading f16, the MSF upsample-
+ * accumulate on f16 tensors.  Arithmetic is fp32; values are rounded once, when stored. */
+int ipdm_conv_first_f16out(const float* x, const float* w, const float* bias, void* out_f16, double* stats, int N, int H,
+                           int W, int Cout, int affine, void* stream);
+int ipdm_instnorm_apply_elu_f16in(const void* x_f16, const double* stats, int stats_pivoted, const float* alpha,
+                                  const float* gamma, const float* beta, void* out_f16, int N, int HW, int C, void* stream);
+int ipdm_bilinear_add_f16(const void* src_f16, void* dst_f16, void* out_elu_f16, int N, int h, int w, int H, int W, int C,
+                          int accumulate, void* stream);
+
+/* Range audit of an f16 tensor (n values, 16-byte aligned): *max_abs = max(*max_abs, max |x|) and *n_saturated += the
+ * number of values with |x| >= 65504 or not finite.  The f16 stores of this library saturate instead of overflowing
+ * (the reference is fp32, ncsn/models/layers.py:37-60: no such limit), so a clipped activation is silent; the score
+ * networks run this over every f16 buffer of a forward on request (`range_audit()`), which is how a checkpoint whose
+ * activations leave the f16 range is found.  Both outputs are device memory the caller zeroes. */
+int ipdm_f16_range_audit(const void* x_f16, size_t n, float* max_abs, unsigned long long* n_saturated, void* stream);
 
 /* out_f16 = f16(elu ? ELU(x) : x), n elements (layers.py:12-13). */
 int ipdm_act_to_f16(const float* x, void* out_f16, size_t n, int elu, void* stream);

@@ -76,6 +76,10 @@ SIGNATURES = {
     "ipdm_conv_last": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "ipdm_instnorm_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "ipdm_instnorm_apply_elu": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "ipdm_conv_first_f16out": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ipdm_instnorm_apply_elu_f16in": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "ipdm_bilinear_add_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ipdm_f16_range_audit": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "ipdm_act_to_f16": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "ipdm_maxpool5_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "ipdm_bilinear_add": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

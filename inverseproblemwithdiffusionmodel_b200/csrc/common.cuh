@@ -26,6 +26,20 @@ inline int launched(const char* what) {
   return 0;
 }
 
+// Once-per-device guard for cudaFuncSetAttribute and similar per-device set-up: bit d of `done` = device d is set up.
+// Safe from any number of host threads (setting an attribute twice is harmless, skipping it is not).
+inline bool device_needs_setup(std::atomic<unsigned long long>& done, int* dev_out = nullptr) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev_out) *dev_out = dev;
+  return ((done.load(std::memory_order_acquire) >> (dev & 63)) & 1ull) == 0;
+}
+inline void device_setup_done(std::atomic<unsigned long long>& done) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  done.fetch_or(1ull << (dev & 63), std::memory_order_release);
+}
+
 #define IPDM_REQUIRE(cond, code, ...)     \
   do {                                    \
     if (!(cond)) {                        \

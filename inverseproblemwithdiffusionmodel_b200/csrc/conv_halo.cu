@@ -247,10 +247,10 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
 
 template <int MODE, int DIL, int TH, int NS = 1>
 static int launch_variant(const CUtensorMap& mw, const CUtensorMap& mx, const HaloParams& hp, int grid, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_done{0};      // per device, any host thread
+  if (device_needs_setup(attr_done)) {
     IPDM_CUDA(cudaFuncSetAttribute(k_conv_halo<MODE, DIL, TH, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<DIL, TH, NS>::SMEM));
-    attr_set = true;
+    device_setup_done(attr_done);
   }
   if (hp.pdl) {
     // programmatic dependent launch: this grid's CTAs may start (set-up, weight ring fill) as the previous kernel's CTAs
@@ -307,18 +307,24 @@ int launch_conv_halo(const ipdm_conv_desc& d, cudaStream_t s) {
   p.tiles_w = (d.W + HT_W - 1) / HT_W;
   p.tiles_h = (d.H + th - 1) / th;
   hp.mtiles = d.Cout / BLOCK_M;
-  hp.exp_skip_weights = g_conv_variant == 2;
+#ifdef IPDM_EXPERIMENTS
+  hp.exp_skip_weights = g_conv_variant == 2;      // timing experiment (wrong results): experimental builds only
+#else
+  hp.exp_skip_weights = 0;
+#endif
   hp.res_prefetch = g_conv_res_prefetch;
   static const int env_pdl = getenv("IPDM_CONV_PDL") ? atoi(getenv("IPDM_CONV_PDL")) : -1;   // A/B runs of whole programs
   hp.pdl = env_pdl >= 0 ? env_pdl : g_conv_pdl;
   // two images per work item with the 12-row tile (dilation <= 2; pairs never straddle a volume: slices is even or 1 with even N)
   const bool pair = th == 12 && d.dilation <= 2 && d.N % 2 == 0 && (d.slices == 1 || d.slices % 2 == 0);
   hp.items = p.tiles_w * p.tiles_h * (pair ? d.N / 2 : d.N) * hp.mtiles;
-  static int sms = 0;
+  static std::atomic<int> sm_count[64];                       // per device
+  int dev = 0;
+  IPDM_CUDA(cudaGetDevice(&dev));
+  int sms = sm_count[dev & 63].load(std::memory_order_relaxed);
   if (sms == 0) {
-    int dev = 0;
-    IPDM_CUDA(cudaGetDevice(&dev));
     IPDM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    sm_count[dev & 63].store(sms, std::memory_order_relaxed);
   }
   const int grid = hp.items < sms ? hp.items : sms;
   const int mode = (p.residual ? 1 : 0) | (p.out_f32 ? 2 : 0) | (d.out_f16 ? 4 : 0) | (pool ? 8 : 0) | (t16 ? 16 : 0);

@@ -152,7 +152,7 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-using MapKey = std::tuple<const void*, long long, long long, long long, long long>;
+using MapKey = std::tuple<const void*, long long, long long, long long, long long>;   // device pointers are unique across devices (UVA)
 static std::map<MapKey, CUtensorMap> g_maps;
 static std::mutex g_maps_mu;
 
@@ -250,12 +250,12 @@ extern "C" int ipdm_conv_igemm(const ipdm_conv_desc* dh, void* stream) {
   p.tiles_w = (d.W + TILE_W - 1) / TILE_W;
   p.tiles_h = (d.H + TILE_H - 1) / TILE_H;
   dim3 grid(p.tiles_w * p.tiles_h * d.N, d.Cout / BLOCK_M);
-  static bool attr_set[32] = {};
+  static std::atomic<unsigned long long> attr_done[32];      // per mode: bit d = set up on device d
 #define IGEMM_CASE(M)                                                                                           \
   case M:                                                                                                       \
-    if (!attr_set[M]) {                                                                                         \
+    if (device_needs_setup(attr_done[M])) {                                                                     \
       IPDM_CUDA(cudaFuncSetAttribute(k_conv_igemm<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
-      attr_set[M] = true;                                                                                       \
+      device_setup_done(attr_done[M]);                                                                          \
     }                                                                                                           \
     k_conv_igemm<M><<<grid, NTHREADS, SMEM_BYTES, s>>>(mw, mx, p);                                              \
     break;
@@ -273,7 +273,12 @@ extern "C" int ipdm_conv_igemm(const ipdm_conv_desc* dh, void* stream) {
 
 extern "C" int ipdm_debug_option(int key, int value) {
   switch (key) {
-    case 1: g_conv_variant = value; return 0;
+    case 1:
+#ifndef IPDM_EXPERIMENTS
+      IPDM_REQUIRE(value == 0 || value == 1, IPDM_E_BADARG, "debug_option(1, %d): experiment modes need a build with -DIPDM_EXPERIMENTS", value);
+#endif
+      g_conv_variant = value;
+      return 0;
     case 2: g_conv_res_prefetch = value; return 0;
     case 3: g_conv_pdl = value; return 0;
     case 4: IPDM_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value)); return 0;

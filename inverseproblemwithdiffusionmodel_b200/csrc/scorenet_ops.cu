@@ -17,8 +17,9 @@ static int grid1d(size_t n, int block, int cap_mult = 32) {
 // thread = (4 consecutive pixels of a row, 4 output channels): 18 input values and 9 float4 weights feed 16
 // outputs.  grid (chunks, N): a block stays inside one image so the InstanceNorm++ sums can be reduced in the
 // block and added with 2 atomics per channel.
+template <bool OUT16>   // OUT16: the output (the start of the residual stream) is stored as f16
 __global__ void __launch_bounds__(256, 2) k_conv_first(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                             float* __restrict__ out, double* __restrict__ stats, int H, int W, int Cout, int affine) {
+                             void* __restrict__ out, double* __restrict__ stats, int H, int W, int Cout, int affine) {
   extern __shared__ float sw[];  // [9][Cout] + [Cout] + per-thread stats scratch [blockDim][8]
   float* sst = sw + 10 * Cout;
   for (int i = threadIdx.x; i < 9 * Cout; i += blockDim.x) {
@@ -34,7 +35,8 @@ __global__ void __launch_bounds__(256, 2) k_conv_first(const float* __restrict__
   const int quads = H * W4;                                     // 4-pixel groups in the image (32-bit: checked on the host)
   const int qper = blockDim.x / groups;
   const float* xin = x + (size_t)n * H * W;
-  float* o = out + (size_t)n * H * W * Cout;
+  float* o = reinterpret_cast<float*>(out) + (OUT16 ? 0 : (size_t)n * H * W * Cout);
+  __half* o16 = reinterpret_cast<__half*>(out) + (size_t)n * H * W * Cout;
   float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
   const float4 b4 = *reinterpret_cast<const float4*>(&sw[9 * Cout + 4 * g]);
   float4 wt[9];                                                  // this thread's 9 x 4 weights stay in registers
@@ -99,7 +101,14 @@ __global__ void __launch_bounds__(256, 2) k_conv_first(const float* __restrict__
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         if (x0 + p < W) {
-          *reinterpret_cast<float4*>(&o[((size_t)yh * W + x0 + p) * Cout + 4 * g]) = acc[p];
+          if (OUT16) {
+            uint2 pk;
+            pk.x = pack_half2_sat(acc[p].x, acc[p].y);
+            pk.y = pack_half2_sat(acc[p].z, acc[p].w);
+            *reinterpret_cast<uint2*>(&o16[((size_t)yh * W + x0 + p) * Cout + 4 * g]) = pk;
+          } else {
+            *reinterpret_cast<float4*>(&o[((size_t)yh * W + x0 + p) * Cout + 4 * g]) = acc[p];
+          }
           s1.x += acc[p].x; s1.y += acc[p].y; s1.z += acc[p].z; s1.w += acc[p].w;
           s2.x += acc[p].x * acc[p].x; s2.y += acc[p].y * acc[p].y; s2.z += acc[p].z * acc[p].z; s2.w += acc[p].w * acc[p].w;
         }
@@ -291,7 +300,8 @@ __global__ void k_instnorm_stats(const float* __restrict__ x, double* __restrict
 }
 
 // out = f16(ELU(gamma*((x-m)*rstd + alpha*m_hat) + beta)); per-(n,c) A,B precomputed in smem.
-__global__ void k_instnorm_apply(const float* __restrict__ x, const double* __restrict__ stats, int pivoted,
+template <bool IN16>   // IN16: x is the 16-bit residual stream
+__global__ void k_instnorm_apply(const void* __restrict__ xv, const double* __restrict__ stats, int pivoted,
                                  const float* __restrict__ alpha, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, __half* __restrict__ out, int HW, int C) {
   extern __shared__ float sm[];  // A[C], B[C], mean[C], red[64]
@@ -300,10 +310,11 @@ __global__ void k_instnorm_apply(const float* __restrict__ x, const double* __re
   float* mean = sm + 2 * C;
   float* red = sm + 3 * C;
   const int n = blockIdx.y;
-  const float* base = x + (size_t)n * HW * C;
+  const float* base = reinterpret_cast<const float*>(xv) + (IN16 ? 0 : (size_t)n * HW * C);
+  const __half* base16 = reinterpret_cast<const __half*>(xv) + (size_t)n * HW * C;
   const float inv = 1.0f / (float)HW;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float p = pivoted ? base[c] : 0.f;
+    const float p = pivoted ? (IN16 ? __half2float(base16[c]) : base[c]) : 0.f;
     const float d = (float)(stats[((size_t)n * C + c) * 2] * (double)inv);
     mean[c] = p + d;
     const float var = fmaxf((float)(stats[((size_t)n * C + c) * 2 + 1] * (double)inv - (double)d * (double)d), 0.f);
@@ -351,7 +362,15 @@ __global__ void k_instnorm_apply(const float* __restrict__ x, const double* __re
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int pp = pix + u * stride;
-      if (pp < HW) v[u] = *reinterpret_cast<const float4*>(base + (size_t)pp * C + c4);
+      if (pp < HW) {
+        if (IN16) {
+          const uint2 hv = *reinterpret_cast<const uint2*>(base16 + (size_t)pp * C + c4);
+          const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&hv.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&hv.y));
+          v[u] = make_float4(lo.x, lo.y, hi.x, hi.y);
+        } else {
+          v[u] = *reinterpret_cast<const float4*>(base + (size_t)pp * C + c4);
+        }
+      }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -466,8 +485,29 @@ __global__ void __launch_bounds__(256, NC == 4 ? 2 : 3) k_maxpool5(const __half*
 // One CTA per output row (n, Y): the vertical taps / weights are per-CTA constants and all index arithmetic is 32-bit
 // (the first version spent most of its instructions on 64-bit div/mod per element); a thread handles 16-byte channel
 // quads of consecutive pixels, two per iteration so that ten independent loads are in flight.
-__global__ void __launch_bounds__(256) k_bilinear_add(const float* __restrict__ src, float* __restrict__ dst, __half* __restrict__ out16,
+template <bool T16> struct Quad;      // four consecutive channels of the residual stream: f32 or f16 in memory, f32 in registers
+template <> struct Quad<false> {
+  static __device__ __forceinline__ float4 ld(const void* p, size_t i) { return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i); }
+  static __device__ __forceinline__ void st(void* p, size_t i, float4 v) { *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + i) = v; }
+};
+template <> struct Quad<true> {
+  static __device__ __forceinline__ float4 ld(const void* p, size_t i) {
+    const uint2 hv = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p) + i);
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&hv.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&hv.y));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+  }
+  static __device__ __forceinline__ void st(void* p, size_t i, float4 v) {
+    uint2 pk;
+    pk.x = pack_half2_sat(v.x, v.y);
+    pk.y = pack_half2_sat(v.z, v.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p) + i) = pk;
+  }
+};
+
+template <bool T16>
+__global__ void __launch_bounds__(256) k_bilinear_add(const void* __restrict__ src, void* __restrict__ dst, __half* __restrict__ out16,
                                                       int h, int w, int H, int W, int C, int accumulate) {
+  using Q = Quad<T16>;
   const int lanes = C >> 2;
   const int n = blockIdx.x / H, Y = blockIdx.x % H;
   const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
@@ -475,9 +515,8 @@ __global__ void __launch_bounds__(256) k_bilinear_add(const float* __restrict__ 
   const float fy = sy * Y;
   const int y0 = (int)fy, y1 = y0 + (y0 < h - 1 ? 1 : 0);
   const float ly = fy - y0, hy = 1.f - ly;
-  const float* r0 = src + ((size_t)n * h + y0) * w * C;
-  const float* r1 = src + ((size_t)n * h + y1) * w * C;
-  float* drow = dst + ((size_t)n * H + Y) * W * C;
+  const size_t r0 = ((size_t)n * h + y0) * w * C, r1 = ((size_t)n * h + y1) * w * C;   // element offsets
+  const size_t drow = ((size_t)n * H + Y) * W * C;
   __half* hrow = out16 ? out16 + ((size_t)n * H + Y) * W * C : nullptr;
   const int total = W * lanes;
   for (int i0 = threadIdx.x; i0 < total; i0 += 2 * blockDim.x) {
@@ -494,12 +533,12 @@ __global__ void __launch_bounds__(256) k_bilinear_add(const float* __restrict__ 
       const float fx = sx * X;
       const int x0 = (int)fx, x1 = x0 + (x0 < w - 1 ? 1 : 0);
       lx[u] = fx - x0;
-      v00[u] = *reinterpret_cast<const float4*>(r0 + x0 * C + c4);
-      v01[u] = *reinterpret_cast<const float4*>(r0 + x1 * C + c4);
-      v10[u] = *reinterpret_cast<const float4*>(r1 + x0 * C + c4);
-      v11[u] = *reinterpret_cast<const float4*>(r1 + x1 * C + c4);
+      v00[u] = Q::ld(src, r0 + x0 * C + c4);
+      v01[u] = Q::ld(src, r0 + x1 * C + c4);
+      v10[u] = Q::ld(src, r1 + x0 * C + c4);
+      v11[u] = Q::ld(src, r1 + x1 * C + c4);
       off[u] = X * C + c4;
-      if (accumulate) old[u] = *reinterpret_cast<const float4*>(drow + off[u]);
+      if (accumulate) old[u] = Q::ld(dst, drow + off[u]);
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -511,7 +550,7 @@ __global__ void __launch_bounds__(256) k_bilinear_add(const float* __restrict__ 
       r.z = hy * (hx * v00[u].z + lx[u] * v01[u].z) + ly * (hx * v10[u].z + lx[u] * v11[u].z);
       r.w = hy * (hx * v00[u].w + lx[u] * v01[u].w) + ly * (hx * v10[u].w + lx[u] * v11[u].w);
       if (accumulate) { r.x += old[u].x; r.y += old[u].y; r.z += old[u].z; r.w += old[u].w; }
-      *reinterpret_cast<float4*>(drow + off[u]) = r;
+      Q::st(dst, drow + off[u], r);
       if (hrow) {
         uint2 pk;
         pk.x = pack_half2_sat(elu_f16bound(r.x), elu_f16bound(r.y));
@@ -646,8 +685,23 @@ extern "C" int ipdm_instnorm_apply_elu(const float* x, const double* stats, int 
   int cap = (148 * 4) / N;          // one resident wave
   if (cap < 1) cap = 1;
   if (chunks > cap) chunks = cap;
-  k_instnorm_apply<<<dim3(chunks, N), 256, smem, as_stream(stream)>>>(x, stats, stats_pivoted, alpha, gamma, beta,
-                                                                      reinterpret_cast<__half*>(out_f16), HW, C);
+  k_instnorm_apply<false><<<dim3(chunks, N), 256, smem, as_stream(stream)>>>(x, stats, stats_pivoted, alpha, gamma, beta,
+                                                                             reinterpret_cast<__half*>(out_f16), HW, C);
+  return launched("k_instnorm_apply");
+}
+
+extern "C" int ipdm_instnorm_apply_elu_f16in(const void* x_f16, const double* stats, int stats_pivoted, const float* alpha,
+                                             const float* gamma, const float* beta, void* out_f16, int N, int HW, int C,
+                                             void* stream) {
+  IPDM_REQUIRE(x_f16 && stats && alpha && gamma && out_f16, IPDM_E_BADARG, "instnorm_apply_elu_f16in: null pointer");
+  IPDM_REQUIRE(C % 4 == 0 && C >= 4 && C <= 2048, IPDM_E_BADARG, "instnorm_apply_elu_f16in: C=%d must be a multiple of 4", C);
+  const size_t smem = (size_t)(3 * C + 64) * sizeof(float);
+  int chunks = grid1d((size_t)HW * (C / 4), 256 * 4, 8);
+  int cap = (148 * 4) / N;          // one resident wave
+  if (cap < 1) cap = 1;
+  if (chunks > cap) chunks = cap;
+  k_instnorm_apply<true><<<dim3(chunks, N), 256, smem, as_stream(stream)>>>(x_f16, stats, stats_pivoted, alpha, gamma, beta,
+                                                                            reinterpret_cast<__half*>(out_f16), HW, C);
   return launched("k_instnorm_apply");
 }
 
@@ -665,7 +719,24 @@ extern "C" int ipdm_conv_first(const float* x, const float* w, const float* bias
   int cap = (148 * 2) / N;          // one resident wave (2 blocks per SM at ~95 registers)
   if (cap < 1) cap = 1;
   if (chunks > cap) chunks = cap;
-  k_conv_first<<<dim3(chunks, N), 256, (size_t)(10 * Cout + 256 * 8) * sizeof(float), s>>>(x, w, bias, out, stats, H, W, Cout, affine);
+  k_conv_first<false><<<dim3(chunks, N), 256, (size_t)(10 * Cout + 256 * 8) * sizeof(float), s>>>(x, w, bias, out, stats, H, W, Cout, affine);
+  return launched("k_conv_first");
+}
+
+extern "C" int ipdm_conv_first_f16out(const float* x, const float* w, const float* bias, void* out_f16, double* stats, int N, int H,
+                                      int W, int Cout, int affine, void* stream) {
+  IPDM_REQUIRE(x && w && out_f16, IPDM_E_BADARG, "conv_first_f16out: null pointer");
+  IPDM_REQUIRE(Cout % 4 == 0 && Cout / 4 <= 256, IPDM_E_BADARG, "conv_first_f16out: Cout=%d must be a multiple of 4, at most 1024", Cout);
+  cudaStream_t s = as_stream(stream);
+  if (stats) IPDM_CUDA(cudaMemsetAsync(stats, 0, (size_t)N * Cout * 2 * sizeof(double), s));
+  const int groups = Cout / 4;
+  const int qper = 256 / groups;
+  const size_t quads = (size_t)H * ((W + 3) / 4);
+  int chunks = (int)((quads + qper - 1) / qper);
+  int cap = (148 * 2) / N;
+  if (cap < 1) cap = 1;
+  if (chunks > cap) chunks = cap;
+  k_conv_first<true><<<dim3(chunks, N), 256, (size_t)(10 * Cout + 256 * 8) * sizeof(float), s>>>(x, w, bias, out_f16, stats, H, W, Cout, affine);
   return launched("k_conv_first");
 }
 
@@ -715,8 +786,61 @@ extern "C" int ipdm_bilinear_add(const float* src, float* dst, void* out_elu_f16
   IPDM_REQUIRE(src && dst, IPDM_E_BADARG, "bilinear_add: null pointer");
   IPDM_REQUIRE(C % 4 == 0, IPDM_E_BADARG, "bilinear_add: C=%d must be a multiple of 4", C);
   IPDM_REQUIRE((size_t)N * H < ((size_t)1 << 31) && (size_t)W * C < ((size_t)1 << 30), IPDM_E_UNSUPPORTED, "bilinear_add: image too large");
-  k_bilinear_add<<<N * H, 256, 0, as_stream(stream)>>>(src, dst, reinterpret_cast<__half*>(out_elu_f16), h, w, H, W, C, accumulate);
+  k_bilinear_add<false><<<N * H, 256, 0, as_stream(stream)>>>(src, dst, reinterpret_cast<__half*>(out_elu_f16), h, w, H, W, C, accumulate);
   return launched("k_bilinear_add");
+}
+
+extern "C" int ipdm_bilinear_add_f16(const void* src_f16, void* dst_f16, void* out_elu_f16, int N, int h, int w, int H, int W, int C,
+                                     int accumulate, void* stream) {
+  IPDM_REQUIRE(src_f16 && dst_f16, IPDM_E_BADARG, "bilinear_add_f16: null pointer");
+  IPDM_REQUIRE(C % 4 == 0, IPDM_E_BADARG, "bilinear_add_f16: C=%d must be a multiple of 4", C);
+  IPDM_REQUIRE((size_t)N * H < ((size_t)1 << 31) && (size_t)W * C < ((size_t)1 << 30), IPDM_E_UNSUPPORTED, "bilinear_add_f16: image too large");
+  k_bilinear_add<true><<<N * H, 256, 0, as_stream(stream)>>>(src_f16, dst_f16, reinterpret_cast<__half*>(out_elu_f16), h, w, H, W, C, accumulate);
+  return launched("k_bilinear_add");
+}
+
+// ---------------------------------------------------------------------------- f16 range audit
+// The tensor-core path stores activations in f16 with saturation (|x| > 65504 -> +-65504, never inf / NaN): a clipped
+// value is silent.  This audit makes it visible: max |x| and the number of values at the end of the range (or not finite)
+// of one f16 tensor; the score networks run it over every f16 buffer of a forward on request (`range_audit()`).
+__global__ void k_f16_range_audit(const __half* __restrict__ x, size_t n8, size_t n, float* __restrict__ max_abs,
+                                  unsigned long long* __restrict__ n_sat) {
+  float m = 0.f;
+  unsigned cnt = 0;
+  auto see = [&](__half2 h) {
+    const float2 f = __half22float2(__habs2(h));
+    m = fmaxf(m, fmaxf(f.x, f.y));      // fmaxf drops NaN: count those separately
+    cnt += !(f.x < 65504.f) + !(f.y < 65504.f);
+  };
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 v = reinterpret_cast<const uint4*>(x)[i];
+    see(*reinterpret_cast<const __half2*>(&v.x));
+    see(*reinterpret_cast<const __half2*>(&v.y));
+    see(*reinterpret_cast<const __half2*>(&v.z));
+    see(*reinterpret_cast<const __half2*>(&v.w));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (size_t i = n8 * 8; i < n; ++i) {
+      const float f = fabsf(__half2float(x[i]));
+      m = fmaxf(m, f);
+      cnt += !(f < 65504.f);
+    }
+  for (int off = 16; off >= 1; off >>= 1) {
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(reinterpret_cast<int*>(max_abs), __float_as_int(m));      // non-negative floats order like their bit patterns
+    if (cnt) atomicAdd(n_sat, (unsigned long long)cnt);
+  }
+}
+
+extern "C" int ipdm_f16_range_audit(const void* x_f16, size_t n, float* max_abs, unsigned long long* n_saturated, void* stream) {
+  IPDM_REQUIRE(x_f16 && max_abs && n_saturated, IPDM_E_BADARG, "f16_range_audit: null pointer");
+  IPDM_REQUIRE((reinterpret_cast<uintptr_t>(x_f16) & 15) == 0, IPDM_E_BADARG, "f16_range_audit: tensor must be 16-byte aligned");
+  if (n == 0) return 0;
+  k_f16_range_audit<<<grid1d(n / 8 + 1, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(x_f16), n / 8, n, max_abs, n_saturated);
+  return launched("k_f16_range_audit");
 }
 
 extern "C" int ipdm_meanpool2(const float* in, const float* add, float* out, int N, int H, int W, int C, void* stream) {

@@ -12,9 +12,16 @@ sequence of hand-written sm_100a kernels:
   * begin_conv / end_conv (one channel on one side) are direct kernels with `2x-1` and `/sigma[y]` folded in;
   * InstanceNorm++ is one apply kernel (normalise + alpha*m_hat + gamma/beta + ELU -> f16 operand).
 
-Residual streams stay fp32 in HBM; only convolution operands are f16.
+Convolution operands are f16.  The residual stream -- the un-activated tensors the blocks add
+into -- is kept in f16 as well when every inner convolution runs on the tensor-core kernels (ngf a multiple of 128:
+the real networks): a residual convolution then moves 8 instead of 12 bytes per output element, which takes the
+dominant launch from under to over the ridge of the tensor / HBM roofline; all arithmetic (accumulators, residual adds,
+InstanceNorm++ sums) stays fp32 and a value is rounded once, when stored.  Measured cost (oracle emulation and
+kernels alike): the score's distance from the fp32 reference goes from 8e-4 to 1.2e-3 relative L2, an ALD step stays
+below 1e-5 on x in the steady state.  Narrow test networks (CUDA-core convolutions) and IPDM_STREAM_F32=1 keep fp32.
 """
 import ctypes
+import os
 from functools import partial
 
 import torch
@@ -146,6 +153,9 @@ class _Plan:
         self.w = {}
         self.version = None
         self.L = _lib.lib()
+        inner = [m for name, m in net.named_modules() if isinstance(m, nn.Conv2d) and name not in ("begin_conv", "end_conv")]
+        self.t16 = (len(inner) > 0 and all(m.in_channels % 64 == 0 and m.out_channels % 128 == 0 for m in inner)
+                    and os.environ.get("IPDM_STREAM_F32") is None)      # (the 3-D network's plan keeps the fp32 stream)
 
     # ---- storage ------------------------------------------------------------------------------
     def buf(self, name, shape, dtype):
@@ -156,7 +166,8 @@ class _Plan:
         return t
 
     def f32(self, name, N, H, W, C):
-        return self.buf(name, (N, H, W, C), torch.float32)
+        """a tensor of the residual stream: fp32, or f16 on the tensor-core path (see the module docstring)"""
+        return self.buf(name, (N, H, W, C), torch.float16 if self.t16 else torch.float32)
 
     def f16(self, name, N, H, W, C):
         return self.buf(name, (N, H, W, C), torch.float16)
@@ -202,8 +213,12 @@ class _Plan:
         N, H, W, Cin, Cout = dims
         w16, bias = self.w[wname]
         taps = w16.shape[1]
-        d = ConvDesc(_lib.ptr(x16), w16.data_ptr(), _lib.ptr(bias), _lib.ptr(residual), _lib.ptr(out32), _lib.ptr(out16),
-                     _lib.ptr(stats), N, H, W, Cin, Cout, taps, dilation, flags)
+        if self.t16:     # residual / out32 are tensors of the 16-bit residual stream
+            d = ConvDesc(_lib.ptr(x16), w16.data_ptr(), _lib.ptr(bias), None, None, _lib.ptr(out16),
+                         _lib.ptr(stats), N, H, W, Cin, Cout, taps, dilation, flags, 0, 0, _lib.ptr(residual), _lib.ptr(out32))
+        else:
+            d = ConvDesc(_lib.ptr(x16), w16.data_ptr(), _lib.ptr(bias), _lib.ptr(residual), _lib.ptr(out32), _lib.ptr(out16),
+                         _lib.ptr(stats), N, H, W, Cin, Cout, taps, dilation, flags)
         if Cin % 64 == 0 and Cout % 128 == 0:
             _lib.check(self.L.ipdm_conv_igemm(ctypes.byref(d), _lib.stream()), "conv_igemm " + wname)
         else:
@@ -211,8 +226,9 @@ class _Plan:
 
     def norm_elu(self, nname, x32, stats, out16, N, HW, C):
         alpha, gamma, beta = self.w[nname]
-        _lib.check(self.L.ipdm_instnorm_apply_elu(x32.data_ptr(), stats.data_ptr(), 0, alpha.data_ptr(), gamma.data_ptr(),
-                                                  _lib.ptr(beta), out16.data_ptr(), N, HW, C, _lib.stream()), "instnorm " + nname)
+        fn = self.L.ipdm_instnorm_apply_elu_f16in if self.t16 else self.L.ipdm_instnorm_apply_elu
+        _lib.check(fn(x32.data_ptr(), stats.data_ptr(), 0, alpha.data_ptr(), gamma.data_ptr(),
+                      _lib.ptr(beta), out16.data_ptr(), N, HW, C, _lib.stream()), "instnorm " + nname)
 
     def to_f16(self, x32, out16, elu):
         _lib.check(self.L.ipdm_act_to_f16(x32.data_ptr(), out16.data_ptr(), x32.numel(), 1 if elu else 0, _lib.stream()), "act_to_f16")
@@ -239,8 +255,11 @@ class _Plan:
         out32 = self.f32(name + ".out", N, Ho, Wo, Cout)
         st_o = self.stats(name + ".st_o", Cout)
         if hasattr(blk, "shortcut"):
-            x16 = self.f16(name + ".x16", N, H, W, Cin)
-            self.to_f16(x32, x16, elu=False)
+            if self.t16:
+                x16 = x32                                    # the 16-bit stream is the shortcut convolution's operand as it is
+            else:
+                x16 = self.f16(name + ".x16", N, H, W, Cin)
+                self.to_f16(x32, x16, elu=False)
             sc = self.f32(name + ".sc", N, Ho, Wo, Cout)
             if pooled:
                 self.conv(name + ".shortcut.conv", x16, (N, H, W, Cin, Cout), out32=sc, flags=CONV_POOL2)
@@ -270,10 +289,13 @@ class _Plan:
             final = i == blk.n_blocks - 1
             o32 = self.f32(f"{name}.o{i}", N, H, W, C)
             want = 'elu' if not final else last_f16
-            o16 = self.f16(f"{name}.e{i}", N, H, W, C) if want else None
+            if want == 'raw' and self.t16:
+                o16 = None                                   # the 16-bit stream itself is the raw f16 copy
+            else:
+                o16 = self.f16(f"{name}.e{i}", N, H, W, C) if want else None
             self.conv(f"{name}.{i + 1}_2_conv", t16, dims, residual=x32, out32=o32, out16=o16,
                       stats=last_stats if final else None, flags=CONV_F16_ELU if want == 'elu' else 0)
-            x32, e16 = o32, o16
+            x32, e16 = o32, (o32 if want == 'raw' and self.t16 else o16)
         return x32, e16
 
     def crp(self, name, blk, h32, e16, H, W, C):
@@ -311,8 +333,8 @@ class _Plan:
             else:
                 low = self.f32(name + ".low", N, hb, wb, F)
                 self.conv(f"{name}.msf.convs.1", b16, (N, hb, wb, Cb, F), out32=low)
-                _lib.check(self.L.ipdm_bilinear_add(low.data_ptr(), sums.data_ptr(), e16.data_ptr(), N, hb, wb, H, W, F, 1,
-                                                    _lib.stream()), "bilinear_add")
+                fn = self.L.ipdm_bilinear_add_f16 if self.t16 else self.L.ipdm_bilinear_add
+                _lib.check(fn(low.data_ptr(), sums.data_ptr(), e16.data_ptr(), N, hb, wb, H, W, F, 1, _lib.stream()), "bilinear_add")
             h32 = sums
         else:
             h32, e16 = hs[0][0], hs[0][1]
@@ -321,6 +343,22 @@ class _Plan:
             return self.rcu(name + ".output_convs", blk.output_convs, x32, e16, H, W, F, 'elu')
         # last refine block: the output feeds the final InstanceNorm++ -> needs its sums, no f16 copy
         return self.rcu(name + ".output_convs", blk.output_convs, x32, e16, H, W, F, None, last_stats=final_stats)
+
+    def range_audit(self):
+        """{buffer name: (max |x|, values at the end of the f16 range)} over every f16 buffer of the last forward, worst
+        first.  f16 stores saturate at +-65504 (never inf / NaN), so an activation that left the range is silent in the
+        output; this is how to find it (trained checkpoints are not available offline; default init peaks at 2.6e3)."""
+        res = {}
+        acc_m = torch.zeros(1, dtype=torch.float32, device=self.device)
+        acc_n = torch.zeros(1, dtype=torch.int64, device=self.device)
+        for name, t in self.bufs.items():
+            if t.dtype != torch.float16:
+                continue
+            acc_m.zero_()
+            acc_n.zero_()
+            _lib.check(self.L.ipdm_f16_range_audit(t.data_ptr(), t.numel(), acc_m.data_ptr(), acc_n.data_ptr(), _lib.stream()), "range_audit")
+            res[name] = (float(acc_m.item()), int(acc_n.item()))
+        return dict(sorted(res.items(), key=lambda kv: -kv[1][0]))
 
     # ---- whole network ------------------------------------------------------------------------------
     def run(self, x, labels, out):
@@ -336,8 +374,8 @@ class _Plan:
         h32 = self.f32("begin", N, H, W, ngf)
         st = self.stats("begin.st", ngf)
         w0, b0 = self.w["begin_conv"]
-        _lib.check(self.L.ipdm_conv_first(x.data_ptr(), w0.data_ptr(), _lib.ptr(b0), h32.data_ptr(), st.data_ptr(),
-                                          N, H, W, ngf, affine, s), "conv_first")
+        first = self.L.ipdm_conv_first_f16out if self.t16 else self.L.ipdm_conv_first
+        _lib.check(first(x.data_ptr(), w0.data_ptr(), _lib.ptr(b0), h32.data_ptr(), st.data_ptr(), N, H, W, ngf, affine, s), "conv_first")
         feats = []
         ch, cw = H, W
         for stage in net.encoder_stages:
@@ -392,6 +430,14 @@ class _ScoreNetBase(nn.Module):
             plan = _Plan(self, N, H, W, device)
             self._plans[key] = plan
         return plan
+
+    def range_audit(self):
+        """Range audit of the f16 buffers of the most recent forward of every cached plan: {(N, H, W): {buffer: (max |x|,
+        saturated values)}}; `saturated_total` > 0 means some activation was clipped to +-65504."""
+        per_plan = {key[:3]: plan.range_audit() for key, plan in self._plans.items()}
+        total = sum(v[1] for d in per_plan.values() for v in d.values())
+        return {"plans": per_plan, "saturated_total": total,
+                "max_abs": max((v[0] for d in per_plan.values() for v in d.values()), default=0.0)}
 
     def forward_into(self, x, labels, out):
         """No-allocation entry point for captured graphs: x, out f32 (N,1,H,W) contiguous CUDA buffers."""

@@ -13,6 +13,14 @@ import torch.nn.functional as F
 # the arithmetic of the tensor-core path; used by tests to separate "logic
 # differs" (tight tolerance against this mode) from "operand precision differs" (looser, vs fp32).
 OPERAND_ROUND = None
+# None = fp32 residual stream.  torch.float16 = additionally round every tensor of the residual stream (block outputs,
+# pre-norm convolution results, shortcut results, MSF sums) when it is "stored", as the tensor-core path does when it keeps
+# that stream in 16 bits; arithmetic stays fp32.
+STREAM_ROUND = None
+
+
+def _st(x):
+    return x if STREAM_ROUND is None else x.to(STREAM_ROUND).float()
 
 
 def _conv(P, key, x, dilation=1, kernel=3):
@@ -52,7 +60,7 @@ def residual_block(P, key, x, resample, dilation):
     dilation: all three convs dilated, no pooling)."""
     d = 1 if dilation is None else dilation
     h = F.elu(instance_norm_plus(P, key + ".normalize1", x))
-    h = _conv(P, key + ".conv1", h, d)
+    h = _st(_conv(P, key + ".conv1", h, d))
     h = F.elu(instance_norm_plus(P, key + ".normalize2", h))
     pooled = resample == "down" and dilation is None
     if pooled:
@@ -60,52 +68,72 @@ def residual_block(P, key, x, resample, dilation):
     else:
         h = _conv(P, key + ".conv2", h, d)
     if key + ".shortcut.conv.weight" in P:
-        sc = mean_pool2(_conv(P, key + ".shortcut.conv", x, 1, kernel=1))
+        sc = _st(mean_pool2(_conv(P, key + ".shortcut.conv", x, 1, kernel=1)))
     elif key + ".shortcut.weight" in P:
         k = P[key + ".shortcut.weight"].shape[-1]
-        sc = _conv(P, key + ".shortcut", x, d if k == 3 else 1, kernel=k)
+        sc = _st(_conv(P, key + ".shortcut", x, d if k == 3 else 1, kernel=k))
     else:
         sc = x
+    if STREAM_ROUND is not None:
+        return _st(sc + h), sc + h      # (stored stream, fp32 value): the decoder's skip operand is ELU of the latter
     return sc + h
 
 
-def rcu(P, key, x, n_blocks, n_stages=2):
-    """Residual conv unit: per block r=x; (ELU, conv)*n_stages; x+=r. Reference: RCUBlock, layers.py:112-134."""
+def rcu(P, key, x, n_blocks, n_stages=2, exact=None):
+    """Residual conv unit: per block r=x; (ELU, conv)*n_stages; x+=r. Reference: RCUBlock, layers.py:112-134.
+    `exact` (STREAM_ROUND emulation only): the value of x before it was rounded into the 16-bit stream -- the kernels
+    derive the ELU'd operand of the next convolution from the fp32 result, the residual from the stored stream.
+    Returns x, or (x, exact) when `exact` is given."""
+    xe = x if exact is None else exact
     for i in range(n_blocks):
         r = x
+        h = xe
         for j in range(n_stages):
-            x = _conv(P, f"{key}.{i + 1}_{j + 1}_conv", F.elu(x))
-        x = x + r
-    return x
+            h = _conv(P, f"{key}.{i + 1}_{j + 1}_conv", F.elu(h))
+        xe = h + r
+        x = _st(xe)
+    return x if exact is None else (x, xe)
 
 
-def crp(P, key, x, n_stages=2):
+def crp(P, key, x, n_stages=2, exact=None):
     """Chained residual pooling with 5x5/s1 max-pool. Reference: CRPBlock, layers.py:62-83."""
+    xe = x if exact is None else exact
+    path = F.elu(xe)          # the pooled operand comes from the fp32 value, the residual ELU(x) from the stored stream
     x = F.elu(x)
-    path = x
     for i in range(n_stages):
         path = F.max_pool2d(path, kernel_size=5, stride=1, padding=2)
         path = _conv(P, f"{key}.convs.{i}", path)
-        x = path + x
-    return x
+        xe = path + x
+        x = _st(xe)
+    return x if exact is None else (x, xe)
 
 
-def msf(P, key, xs, shape):
+def msf(P, key, xs, shape, want_exact=False):
     """sum_i bilinear_{align_corners}(conv_i(x_i)). Reference: MSFBlock, layers.py:165-184."""
-    total = None
+    total = exact = None
     for i, xi in enumerate(xs):
-        h = F.interpolate(_conv(P, f"{key}.convs.{i}", xi), size=shape, mode="bilinear", align_corners=True)
-        total = h if total is None else total + h
-    return total
+        h = F.interpolate(_st(_conv(P, f"{key}.convs.{i}", xi)), size=shape, mode="bilinear", align_corners=True)
+        exact = h if total is None else total + h
+        total = _st(exact)
+    return (total, exact) if want_exact else total
 
 
 def refine(P, key, xs, shape, end=False):
     """adapt RCUs -> MSF (if >1 input) -> CRP -> output RCU (3 blocks when `end`).
-    Reference: RefineBlock, layers.py:214-249."""
-    hs = [rcu(P, f"{key}.adapt_convs.{i}", xi, 2) for i, xi in enumerate(xs)]
-    h = msf(P, key + ".msf", hs, shape) if len(hs) > 1 else hs[0]
-    h = crp(P, key + ".crp", h)
-    return rcu(P, key + ".output_convs", h, 3 if end else 1)
+    Reference: RefineBlock, layers.py:214-249.  xs: tensors, or (stream, exact) pairs under STREAM_ROUND emulation."""
+    if STREAM_ROUND is None:
+        hs = [rcu(P, f"{key}.adapt_convs.{i}", xi, 2) for i, xi in enumerate(xs)]
+        h = msf(P, key + ".msf", hs, shape) if len(hs) > 1 else hs[0]
+        h = crp(P, key + ".crp", h)
+        return rcu(P, key + ".output_convs", h, 3 if end else 1)
+    pairs = [xi if isinstance(xi, tuple) else (xi, xi) for xi in xs]
+    hs = [rcu(P, f"{key}.adapt_convs.{i}", a, 2, exact=b) for i, (a, b) in enumerate(pairs)]
+    if len(hs) > 1:
+        h, he = msf(P, key + ".msf", [a for a, _ in hs], shape, want_exact=True)     # the MSF convolutions read the stored stream
+    else:
+        h, he = hs[0]
+    h, he = crp(P, key + ".crp", h, exact=he)
+    return rcu(P, key + ".output_convs", h, 3 if end else 1, exact=he)
 
 
 # (stage name, [(resample, dilation) for the two blocks])
@@ -133,17 +161,22 @@ DECODERS = {
 def score_forward(arch, P, x, labels, logit_transform=False, rescaled=False):
     """Reference: NCSNv2.forward (ncsnv2.py:70-101) / NCSNv2Deepest.forward (:269-299)."""
     h = 2 * x - 1.0 if (not logit_transform and not rescaled) else x
-    h = _conv(P, "begin_conv", h)
+    h = _st(_conv(P, "begin_conv", h))
     feats = []
     for stage, blocks in ENCODERS[arch]:
         for i, (resample, dil) in enumerate(blocks):
             h = residual_block(P, f"{stage}.{i}", h, resample, dil)
-        feats.append(h)
+            if isinstance(h, tuple):
+                h, h_exact = h
+        feats.append(h if STREAM_ROUND is None else (h, h_exact))
     names = DECODERS[arch]
-    out = refine(P, names[0], [feats[-1]], feats[-1].shape[2:])
+    shape_of = lambda f: (f[0] if isinstance(f, tuple) else f).shape[2:]
+    out = refine(P, names[0], [feats[-1]], shape_of(feats[-1]))
     for j, name in enumerate(names[1:], start=2):
         skip = feats[-j]
-        out = refine(P, name, [skip, out], skip.shape[2:], end=(j == len(names)))
+        out = refine(P, name, [skip, out], shape_of(skip), end=(j == len(names)))
+    if isinstance(out, tuple):
+        out = out[0]                    # the final InstanceNorm++ reads the stored stream
     out = F.elu(instance_norm_plus(P, "normalizer", out))
     out = _conv(P, "end_conv", out)
     sig = P["sigmas"][labels].view(x.shape[0], 1, 1, 1)

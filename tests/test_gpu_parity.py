@@ -430,10 +430,11 @@ def test_scorenet_ngf128_tensor_core_path():
     with torch.no_grad():
         ref = SN.score_forward("NCSNv2Deepest", Pd, x, y)
         SN.OPERAND_ROUND = torch.float16          # the oracle with conv operands rounded to f16 like the kernels' (fp32 accumulate)
+        SN.STREAM_ROUND = torch.float16 if net._plan(2, 32, 32, torch.device(DEV, 0)).t16 else None   # ... and the 16-bit residual stream
         try:
             emu = SN.score_forward("NCSNv2Deepest", Pd, x, y)
         finally:
-            SN.OPERAND_ROUND = None
+            SN.OPERAND_ROUND = SN.STREAM_ROUND = None
     print("ngf128 Deepest score: vs fp32 oracle %.2e, vs f16-operand oracle %.2e" % (rel_l2(out, ref), rel_l2(out, emu)))
     assert rel_l2(out, ref) < C.TOL_SCORE
     assert rel_l2(out, emu) < C.TOL_SCORE_EMU
@@ -444,13 +445,42 @@ def test_scorenet_ngf128_tensor_core_path():
     with torch.no_grad():
         ref = SN.score_forward("NCSNv2", Pd2, x, y)
         SN.OPERAND_ROUND = torch.float16
+        SN.STREAM_ROUND = torch.float16 if net2._plan(2, 28, 28, torch.device(DEV, 0)).t16 else None
         try:
             emu = SN.score_forward("NCSNv2", Pd2, x, y)
         finally:
-            SN.OPERAND_ROUND = None
+            SN.OPERAND_ROUND = SN.STREAM_ROUND = None
     print("ngf128 NCSNv2 score: vs fp32 oracle %.2e, vs f16-operand oracle %.2e" % (rel_l2(out, ref), rel_l2(out, emu)))
     assert rel_l2(out, ref) < C.TOL_SCORE
     assert rel_l2(out, emu) < C.TOL_SCORE_EMU
+
+
+def test_f16_range_audit_finds_clipped_activations():
+    """the f16 operand path needs a range check.  The audit kernel on synthetic tensors, then on a real forward:
+    an ordinary input stays far inside the range; an input at |x| ~ 3e5 drives the un-normalised decoder past 65504, the
+    stores saturate (the output stays finite) and the audit reports it."""
+    L = _lib()
+    t = torch.zeros(1000003, dtype=torch.float16, device=DEV)
+    t[12345] = -1234.5
+    t[999999] = 65504.0
+    t[1000002] = float("inf")
+    m = torch.zeros(1, device=DEV)
+    c = torch.zeros(1, dtype=torch.int64, device=DEV)
+    L.check(L.lib().ipdm_f16_range_audit(t.data_ptr(), t.numel(), m.data_ptr(), c.data_ptr(), L.stream()), "audit")
+    assert int(c.item()) == 2 and float(m.item()) >= 65504.0
+    t[999999] = 3.0
+    t[1000002] = 2.0
+    m.zero_(); c.zero_()
+    L.check(L.lib().ipdm_f16_range_audit(t.data_ptr(), t.numel(), m.data_ptr(), c.data_ptr(), L.stream()), "audit")
+    assert int(c.item()) == 0 and float(m.item()) == 1234.5
+    net, Pd, cfg = _full_width_net(C.NCSNv2Deepest, "NCSNv2Deepest", 32, 21)
+    y = torch.tensor([0, 9], device=DEV)
+    out = net((rrand(77, 2, 1, 32, 32) * 2 - 0.5).to(DEV), y)
+    a = net.range_audit()
+    assert a["saturated_total"] == 0 and 0 < a["max_abs"] < 6e4 and bool(torch.isfinite(out).all())
+    out = net((rrandn(78, 2, 1, 32, 32) * 3e5).to(DEV), y)
+    a = net.range_audit()
+    assert a["saturated_total"] > 0 and bool(torch.isfinite(out).all())
 
 
 def test_single_ald_step_ngf128():

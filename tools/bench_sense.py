@@ -19,12 +19,22 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 def timeit(fn, reps=5):
+    """best of `reps` CUDA-event times of one replay of fn captured in a CUDA graph (no host launch gaps), L2 flushed before each"""
     fn(); torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
     ts = []
     for _ in range(reps):
         flush.zero_()                      # evict L2 between timed iterations
         torch.cuda.synchronize()
-        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     return min(ts)
 
