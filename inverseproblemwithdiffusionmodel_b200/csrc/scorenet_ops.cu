@@ -347,6 +347,42 @@ __global__ void k_instnorm_apply(const void* __restrict__ xv, const double* __re
     Bv[c] = g * (alpha[c] * mhat - mean[c] * rstd) + (beta ? beta[c] : 0.f);
   }
   __syncthreads();
+  if (IN16 && (C & 7) == 0) {
+    // 16-bit stream: thread = 8 channels (16-byte loads and stores), 4 pixels in flight per thread
+    const int lanes = C / 8;
+    const int c8 = (int)(threadIdx.x % lanes) * 8;
+    const int rows = blockDim.x / lanes;
+    const int row = threadIdx.x / lanes;
+    if (row >= rows) return;
+    float a[8], bb[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a[k] = A[c8 + k]; bb[k] = Bv[c8 + k]; }
+    __half* obase = out + (size_t)n * HW * C;
+    const int stride = gridDim.x * rows;
+    for (int pix = blockIdx.x * rows + row; pix < HW; pix += 4 * stride) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int pp = pix + u * stride;
+        if (pp < HW) v[u] = *reinterpret_cast<const uint4*>(base16 + (size_t)pp * C + c8);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int pp = pix + u * stride;
+        if (pp < HW) {
+          const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+          uint32_t o[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+            o[k] = pack_half2_sat(elu_f16bound(f.x * a[2 * k] + bb[2 * k]), elu_f16bound(f.y * a[2 * k + 1] + bb[2 * k + 1]));
+          }
+          *reinterpret_cast<uint4*>(obase + (size_t)pp * C + c8) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+    return;
+  }
   // main pass: thread = 4 channels; 4 pixels in flight per thread (independent 16-byte loads)
   const int lanes = C / 4;
   const int c4 = (int)(threadIdx.x % lanes) * 4;

@@ -1059,7 +1059,7 @@ extern "C" int ipdm_sense_plan_create(const uint8_t* mask_host, int mask_frames,
   pl->mask_dev = at(i_mask);
   if (pl->pruned_rows) {
     PlanView& v = pl->view;
-    v.frames = mask_frames; v.W = W; v.ns_pad = ph.ns_pad; v.ng_all = W / 4; v.cmax = ph.cmax;
+    v.frames = mask_frames; v.W = W; v.ns_pad = ph.ns_pad; v.ng_all = W / PlanHost::GW; v.cmax = ph.cmax;
     v.ns = reinterpret_cast<const int*>(at(i_ns));
     v.ngroups = reinterpret_cast<const int*>(at(i_ng));
     v.nchunks = reinterpret_cast<const int*>(at(i_nc));

@@ -12,9 +12,9 @@
 //                      frame): the inverse transforms read their classes with static indices, pads hold zeros
 //   twh[f][jj][10]     the twiddle vector in factored form, w^(t*k) = w^((t&3)*k) * w^(4*(t>>2)*k): entries
 //                      w^k, w^2k, w^3k, then w^(4m*k) for m = 1 .. W/64-1 (20 registers instead of 2*W/16)
-//   ngroups[f], groups[f][g], gslot[f][g][0..3], gbitmap[f][4]
-//                      the active 4-column groups (one 32-byte sector of a k-space row each), for every group the
-//                      natural slot of each of its columns (255 = not sampled), and the bitmap over all W/4 groups
+//   ngroups[f], groups[f][g], gslot[f][g][0..GW-1], gbitmap[f][4]
+//                      the active GW-column groups (GW = 8: 64 aligned bytes of a k-space row each), for every group the
+//                      natural slot of each of its columns (255 = not sampled), and the bitmap over all W/GW groups
 //   nchunks[f], chunks[f][c] = {first group, groups, first slot, slots}
 //                      work items of the column kernels: runs of whole groups holding at most 8 sampled columns
 //   tcw[f][jj]         chunk*8 + position inside the chunk of class entry jj: the compact scratch is laid out
@@ -37,7 +37,15 @@ struct PlanHost {
   std::vector<float> tw, twh;   // interleaved (re, im)
   static constexpr int CLS_PITCH = 20;   // 17 boundaries padded to five 32-bit words
   static constexpr int TWH = 10;         // factored twiddle entries per column
-  static constexpr int CHUNK_SLOTS = 8;  // sampled columns per work item of the column kernels
+  // Output columns are handled in groups of GW: the forward column kernel writes whole groups (GW * 8 bytes, aligned), the
+  // forward row kernel zero-fills every group without a sampled column, so no GW*8-byte unit of the output is written by
+  // both.  With 32-byte groups (GW = 4) every 128-byte line that holds a sample was written twice, partially, by two
+  // kernels: the scattered sector writes of the column kernel ran at 1.3 TB/s.
+#ifndef IPDM_PLAN_GW
+#define IPDM_PLAN_GW 8
+#endif
+  static constexpr int GW = IPDM_PLAN_GW;
+  static constexpr int CHUNK_SLOTS = GW > 8 ? GW : 8;  // sampled columns per work item of the column kernels (>= GW)
 };
 
 // Largest ns the pruned row kernels take for a row length W (0: W not served).  One register-resident twiddle vector
@@ -52,13 +60,16 @@ inline PlanHost build_plan_host(const uint8_t* mask, int frames, int W) {
   p.mask.assign(mask, mask + (size_t)frames * W);
   p.ns.resize(frames);
   p.ngroups.resize(frames);
-  const int ng_all = W / 4;
+  const int ng_all = W / PlanHost::GW;
+  constexpr int GW = PlanHost::GW;
   for (int f = 0; f < frames; ++f) {
     int n = 0, g = 0;
     for (int k = 0; k < W; ++k) n += mask[(size_t)f * W + k] != 0;
     for (int q = 0; q < ng_all; ++q) {
-      const uint8_t* m = mask + (size_t)f * W + 4 * q;
-      g += (m[0] | m[1] | m[2] | m[3]) != 0;
+      const uint8_t* m = mask + (size_t)f * W + GW * q;
+      int any = 0;
+      for (int i = 0; i < GW; ++i) any |= m[i];
+      g += any != 0;
     }
     p.ns[f] = n;
     p.ngroups[f] = g;
@@ -85,7 +96,7 @@ inline PlanHost build_plan_host(const uint8_t* mask, int frames, int W) {
   p.nchunks.assign(frames, 0);
   p.chunks.assign((size_t)frames * ng_all * 4, 0);
   p.groups.assign((size_t)frames * ng_all, 0);
-  p.gslot.assign((size_t)frames * ng_all * 4, 255);
+  p.gslot.assign((size_t)frames * ng_all * GW, 255);
   p.gbitmap.assign((size_t)frames * 4, 0u);
   p.big.assign((size_t)frames * 2, 0u);
   for (int f = 0; f < frames; ++f) {
@@ -127,13 +138,15 @@ inline PlanHost build_plan_host(const uint8_t* mask, int frames, int W) {
     }
     int g = 0;
     for (int q = 0; q < ng_all; ++q) {
-      if (!(m[4 * q] | m[4 * q + 1] | m[4 * q + 2] | m[4 * q + 3])) continue;
+      int any = 0;
+      for (int i = 0; i < GW; ++i) any |= m[GW * q + i];
+      if (!any) continue;
       p.groups[(size_t)f * ng_all + g] = (uint8_t)q;
       p.gbitmap[(size_t)f * 4 + (q >> 5)] |= 1u << (q & 31);
-      for (int i = 0; i < 4; ++i) {
-        if (!m[4 * q + i]) continue;
-        const int s = (int)(std::lower_bound(cols.begin(), cols.end(), 4 * q + i) - cols.begin());
-        p.gslot[((size_t)f * ng_all + g) * 4 + i] = (uint8_t)s;
+      for (int i = 0; i < GW; ++i) {
+        if (!m[GW * q + i]) continue;
+        const int s = (int)(std::lower_bound(cols.begin(), cols.end(), GW * q + i) - cols.begin());
+        p.gslot[((size_t)f * ng_all + g) * GW + i] = (uint8_t)s;
       }
       ++g;
     }
@@ -143,7 +156,7 @@ inline PlanHost build_plan_host(const uint8_t* mask, int frames, int W) {
       int g_hi = g_lo, s_hi = s_lo;
       while (g_hi < g) {
         int in_group = 0;
-        for (int i = 0; i < 4; ++i) in_group += p.gslot[((size_t)f * ng_all + g_hi) * 4 + i] != 255;
+        for (int i = 0; i < GW; ++i) in_group += p.gslot[((size_t)f * ng_all + g_hi) * GW + i] != 255;
         if (s_hi - s_lo + in_group > PlanHost::CHUNK_SLOTS) break;
         s_hi += in_group;
         ++g_hi;

@@ -18,6 +18,7 @@
 //   the arithmetic); the forward column kernel writes the active sectors whole.
 #pragma once
 #include "fftpr.cuh"
+#include "sense_plan.h"
 
 namespace ipdm {
 
@@ -33,14 +34,15 @@ struct PlanView {
   const uint8_t* tcw;       // [frames][ns_pad]  class position -> chunk*8 + position inside the chunk (scratch layout)
   const cf32* tw;           // [frames][ns_pad][W/16], class order
   const cf32* twh;          // [frames][ns_pad][10], class order, factored form
-  const uint8_t* groups;    // [frames][W/4]
-  const uint8_t* gslot;     // [frames][W/4][4]
-  const uint8_t* chunks;    // [frames][W/4][4] = {first group, groups, first slot, slots}
+  const uint8_t* groups;    // [frames][W/GW]
+  const uint8_t* gslot;     // [frames][W/GW][GW]
+  const uint8_t* chunks;    // [frames][W/GW][4] = {first group, groups, first slot, slots}
   const uint32_t* gbitmap;  // [frames][4]
   const uint32_t* big;      // [frames][2]  classes with >= 3 / 4 sampled columns
   const cf32* tws_h;        // layout-B twiddles of the H transform (Geo<H>::NTWS entries)
 };
 constexpr int PLAN_TWH = 10;
+constexpr int PLAN_GW = PlanHost::GW;      // columns per output group (see sense_plan.h)
 
 template <int L> struct PGeo {
   using P = PR<L>;
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(128, 3) kp_fwd_rows(SenseArgs a, PlanView p) {
   uint32_t zmask = 0;
 #pragma unroll
   for (int z = 0; z < G::ZP; ++z) {
-    const int grp = ((tid + z * G::NT) % (L / 2)) >> 1;
+    const int grp = ((tid + z * G::NT) % (L / 2)) / (PLAN_GW / 2);      // 16-byte piece -> group
     if (((p.gbitmap[f * 4 + (grp >> 5)] >> (grp & 31)) & 1u) == 0u) zmask |= 1u << z;
   }
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -165,7 +167,7 @@ __device__ __forceinline__ void copy_tws(cf32* tws, const cf32* src, int tid, in
   for (int e = tid; e < Geo<LH>::NTWS; e += nt) tws[e] = src[e];
 }
 template <int LH> struct CGeo {
-  static constexpr int CL = 8;                               // lines (sampled columns) per CTA
+  static constexpr int CL = PlanHost::CHUNK_SLOTS;            // lines (sampled columns) per CTA
   static constexpr int NT = CL * Geo<LH>::TPF;
   static constexpr int SP = CL + 2;                          // staging pitch: rows 16-byte aligned, a column read is 2-way conflicted at worst
   static constexpr int CSTRIDE = P2<LH>::STRIDE | 1;         // line pitch: odd, the drain loops walk 8 lines at one row
@@ -201,15 +203,13 @@ __global__ void __launch_bounds__(CGeo<LH>::NT) kp_fwd_cols(SenseArgs a, PlanVie
   // this chunk's groups (first column, line of each of the four columns or -1) in shared memory: the drain loop below
   // must not chase three dependent global loads per 16-byte store
   __shared__ int g_col[C::CL];
-  __shared__ int g_line[C::CL][4];
+  __shared__ int g_line[C::CL][PLAN_GW];
   if (tid < g_cnt) {
     const int g = g_lo + tid;
-    g_col[tid] = 4 * p.groups[f * p.ng_all + g];
-    const uchar4 gs = *reinterpret_cast<const uchar4*>(p.gslot + ((size_t)f * p.ng_all + g) * 4);
-    g_line[tid][0] = gs.x != 255 ? gs.x - s_lo : -1;
-    g_line[tid][1] = gs.y != 255 ? gs.y - s_lo : -1;
-    g_line[tid][2] = gs.z != 255 ? gs.z - s_lo : -1;
-    g_line[tid][3] = gs.w != 255 ? gs.w - s_lo : -1;
+    g_col[tid] = PLAN_GW * p.groups[f * p.ng_all + g];
+    const uint8_t* gs = p.gslot + ((size_t)f * p.ng_all + g) * PLAN_GW;
+#pragma unroll
+    for (int i = 0; i < PLAN_GW; ++i) g_line[tid][i] = gs[i] != 255 ? gs[i] - s_lo : -1;
   }
   cp_async_wait_all();
   __syncthreads();
@@ -230,11 +230,12 @@ __global__ void __launch_bounds__(CGeo<LH>::NT) kp_fwd_cols(SenseArgs a, PlanVie
     for (int i = 0; i < G::E; ++i) sx[b_pos<LH>(t, i)] = v[i];   // the exchange line doubles as the column's tile line
   }
   __syncthreads();
-  // active sectors, 16-byte pieces: idx = (h * g_cnt + gi) * 2 + half -- consecutive lanes walk the sectors of one image row
-  for (int idx = tid; idx < LH * g_cnt * 2; idx += C::NT) {
-    const int half = idx & 1, gi = (idx >> 1) % g_cnt, hh = (idx >> 1) / g_cnt;
-    const int kk = g_col[gi] + 2 * half;
-    const int l0 = g_line[gi][2 * half], l1 = g_line[gi][2 * half + 1];
+  // active groups, 16-byte pieces: idx = (h * g_cnt + gi) * PG + piece -- consecutive lanes walk the groups of one image row
+  constexpr int PG = PLAN_GW / 2;
+  for (int idx = tid; idx < LH * g_cnt * PG; idx += C::NT) {
+    const int pc = idx % PG, gi = (idx / PG) % g_cnt, hh = (idx / PG) / g_cnt;
+    const int kk = g_col[gi] + 2 * pc;
+    const int l0 = g_line[gi][2 * pc], l1 = g_line[gi][2 * pc + 1];
     const cf32 p0 = l0 >= 0 ? tile[l0 * C::CSTRIDE + hh] : cf32{0.f, 0.f};
     const cf32 p1 = l1 >= 0 ? tile[l1 * C::CSTRIDE + hh] : cf32{0.f, 0.f};
     const float sc0 = a.scale * sgn(hh + kk);

@@ -102,7 +102,7 @@ def sense_forward(x, maps, mask):
 
 def sense_adjoint(S, maps):
     """sum_c conj(s_c) * k2i(S[c]) -- no mask (quirk Q3). Reference: SENSE.conj_op, :152-160."""
-    out = torch.zeros(S.shape[1:], dtype=S.dtype)
+    out = torch.zeros(S.shape[1:], dtype=S.dtype, device=S.device)
     for c in range(S.shape[0]):
         out += maps[c].conj() * k2i(S[c])
     return out
@@ -110,7 +110,7 @@ def sense_adjoint(S, maps):
 
 def sense_ssos(S):
     """sqrt(sum_c |k2i(S[c])|^2), float32. Reference: SENSE.SSOS, :162-170."""
-    acc = torch.zeros(S.shape[1:], dtype=torch.float32)
+    acc = torch.zeros(S.shape[1:], dtype=torch.float32, device=S.device)
     for c in range(S.shape[0]):
         acc += k2i(S[c]).abs() ** 2
     return acc.sqrt()

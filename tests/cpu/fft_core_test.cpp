@@ -136,11 +136,11 @@ double check_pruned(int ns_target, unsigned seed) {
     {   // column-kernel work items: whole groups, consecutive, <= 16 sampled columns, covering everything once
       int g_next = 0, s_next = 0;
       for (int c = 0; c < pl.nchunks[f]; ++c) {
-        const uint8_t* ch = &pl.chunks[(f * (L / 4) + c) * 4];
+        const uint8_t* ch = &pl.chunks[(f * (L / PlanHost::GW) + c) * 4];
         if (ch[0] != g_next || ch[2] != s_next || ch[1] == 0 || ch[3] == 0 || ch[3] > PlanHost::CHUNK_SLOTS) return 11.0;
         int cnt2 = 0;
         for (int g = ch[0]; g < ch[0] + ch[1]; ++g)
-          for (int i = 0; i < 4; ++i) cnt2 += pl.gslot[(f * (L / 4) + g) * 4 + i] != 255;
+          for (int i = 0; i < PlanHost::GW; ++i) cnt2 += pl.gslot[(f * (L / PlanHost::GW) + g) * PlanHost::GW + i] != 255;
         if (cnt2 != ch[3]) return 12.0;
         g_next += ch[1];
         s_next += ch[3];
@@ -149,17 +149,17 @@ double check_pruned(int ns_target, unsigned seed) {
       for (int jj = 0; jj < ns; ++jj) {      // scratch position of every class entry: (chunk, position) of its natural slot
         const int cw = pl.tcw[f * NP + jj], cc = cw >> 3, within = cw & 7;
         if (cc >= pl.nchunks[f]) return 14.0;
-        const uint8_t* ch = &pl.chunks[(f * (L / 4) + cc) * 4];
+        const uint8_t* ch = &pl.chunks[(f * (L / PlanHost::GW) + cc) * 4];
         if (within >= ch[3] || ch[2] + within != pl.nat[f * NP + jj]) return 15.0;
       }
     }
     for (int g = 0; g < pl.ngroups[f]; ++g) {
-      const int q = pl.groups[f * (L / 4) + g];
+      const int q = pl.groups[f * (L / PlanHost::GW) + g];
       if (!((pl.gbitmap[f * 4 + (q >> 5)] >> (q & 31)) & 1u)) return 6.0;
-      for (int i = 0; i < 4; ++i) {
-        const int s = pl.gslot[(f * (L / 4) + g) * 4 + i];
-        if ((s != 255) != (mask[f * L + 4 * q + i] != 0)) return 7.0;
-        if (s != 255 && pl.kcol[f * NP + s] != 4 * q + i) return 8.0;
+      for (int i = 0; i < PlanHost::GW; ++i) {
+        const int s = pl.gslot[(f * (L / PlanHost::GW) + g) * PlanHost::GW + i];
+        if ((s != 255) != (mask[f * L + PlanHost::GW * q + i] != 0)) return 7.0;
+        if (s != 255 && pl.kcol[f * NP + s] != PlanHost::GW * q + i) return 8.0;
       }
     }
     const cf32* tw = reinterpret_cast<const cf32*>(pl.tw.data()) + (size_t)f * NP * P::R1;

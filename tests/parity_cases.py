@@ -32,8 +32,15 @@ from inverseproblemwithdiffusionmodel_b200.sde.sampling import AnnealedLangevinD
 from inverseproblemwithdiffusionmodel_b200.ncsn.models import MAP_optimizers as MAP
 
 TOL32 = 1e-5
-TOL_SCORE = 2e-3        # score vs the fp32 oracle / reference: f16 conv operands cost ~8e-4
-TOL_SCORE_EMU = 1.5e-3   # score vs the oracle with f16-rounded conv operands (same arithmetic as the kernels up to summation order)
+# Score of a whole network vs the fp32 oracle / reference.  f16 convolution operands cost ~8e-4 relative L2, the 16-bit
+# residual stream of the tensor-core path takes it to ~1.3e-3 (measured on the GPU: 1.37e-3 Deepest, 32^2; oracle emulation
+# on the CPU: 1.25e-3).  NB an emulation of the kernels' rounding points cannot be matched more tightly than that: in an
+# f16-operand network a 1e-7 relative perturbation of the convolution results (summation order) flips roundings, the
+# flips perturb the next layer by more, and after a few layers two runs differ by the full rounding-noise level (measured
+# with the oracle: 1e-7 in -> 7.6e-4 out; in fp32 arithmetic the same perturbation gives 1e-6).  So the emulation bound is the
+# noise level times ~sqrt(2), and regressions of the epilogues are caught by the per-kernel tests, which are bit-level.
+TOL_SCORE = 2e-3
+TOL_SCORE_EMU = 2.2e-3   # vs the oracle with f16-rounded operands (+ 16-bit stream): two realisations of the same rounding noise
 TOL_X = 1e-4
 
 

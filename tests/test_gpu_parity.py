@@ -461,7 +461,7 @@ def test_f16_range_audit_finds_clipped_activations():
     stores saturate (the output stays finite) and the audit reports it."""
     L = _lib()
     t = torch.zeros(1000003, dtype=torch.float16, device=DEV)
-    t[12345] = -1234.5
+    t[12345] = -1234.0
     t[999999] = 65504.0
     t[1000002] = float("inf")
     m = torch.zeros(1, device=DEV)
@@ -472,7 +472,7 @@ def test_f16_range_audit_finds_clipped_activations():
     t[1000002] = 2.0
     m.zero_(); c.zero_()
     L.check(L.lib().ipdm_f16_range_audit(t.data_ptr(), t.numel(), m.data_ptr(), c.data_ptr(), L.stream()), "audit")
-    assert int(c.item()) == 0 and float(m.item()) == 1234.5
+    assert int(c.item()) == 0 and float(m.item()) == 1234.0
     net, Pd, cfg = _full_width_net(C.NCSNv2Deepest, "NCSNv2Deepest", 32, 21)
     y = torch.tensor([0, 9], device=DEV)
     out = net((rrand(77, 2, 1, 32, 32) * 2 - 0.5).to(DEV), y)
