@@ -232,7 +232,9 @@ int ipdm_conv_igemm(const ipdm_conv_desc* desc_host, void* stream);
  * kernel).  key 2: 0 (default) / 1 = the halo kernel's L2 bulk prefetch of residual tiles off / on (A/B timing: on is
  * 5-10 % slower).  key 3: 0 (default) / 1 = launch the halo kernel with programmatic stream serialization (PDL; also env
  * IPDM_CONV_PDL; measured +0.4 %).  key 4: cudaLimitMaxL2FetchGranularity in bytes (32 / 64 / 128; measured: no effect on
- * the strided k-space reads of the masked adjoint).  Timing experiments that produce wrong results exist only in builds
+ * the strided k-space reads of the masked adjoint).  key 5: 0 (default) / 1 = the pruned SENSE plan entry points split a
+ * batch whose k-space is >= 512 MB into image sub-ranges and run row and column kernels of neighbouring sub-ranges side by
+ * side on the plan's high-priority side stream (also env IPDM_SENSE_SPLIT; measured 2-7 % slower).  Timing experiments that produce wrong results exist only in builds
  * with -DIPDM_EXPERIMENTS (tools/exp_weights.py) and are refused otherwise. */
 int ipdm_debug_option(int key, int value);
 

@@ -5,8 +5,10 @@ The reference has no multi-GPU code; its "mean of 105 recons
 mean/std over a stack of results (helpers/visualizations.py:93-95,117-142).  Here every rank owns the
 chains `i % world == rank`, accumulates sum|x|, sum|x|^2, sum(angle x), sum(angle x)^2 with
 `ipdm_chain_stats_accumulate` (float64), and a single all-reduce (NCCL on GPUs, gloo in CPU tests)
-merges them.  Chains are keyed by their GLOBAL index (Philox seed), so results do not depend on the
-number of GPUs.
+merges them.  A rank passes its global chain indices to the sampler (`chain_ids=chain_partition(...)`, one seed on
+every rank): the in-kernel noise of chain i is Philox(seed, counter = (pixel, i, step)), so chain i is the same chain
+on any rank of any world size and at any slot of the rank's batch (tests: test_chain_noise_is_keyed_by_global_chain_id).
+A rank that owns no chain (more ranks than chains) skips sampling but must still call `all_reduce`.
 """
 import os
 

@@ -159,6 +159,7 @@ static std::mutex g_maps_mu;
 int g_conv_variant = 0;
 int g_conv_res_prefetch = 0;
 int g_conv_pdl = 0;
+extern int g_sense_split;   // sense.cu
 
 int get_weight_map(const void* w, int Cout, int K, CUtensorMap* out) {
   MapKey key{w, 2, Cout, K, 0};
@@ -281,6 +282,7 @@ extern "C" int ipdm_debug_option(int key, int value) {
       return 0;
     case 2: g_conv_res_prefetch = value; return 0;
     case 3: g_conv_pdl = value; return 0;
+    case 5: g_sense_split = value; return 0;
     case 4: IPDM_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value)); return 0;
     default: set_error("debug_option: unknown key %d", key); return IPDM_E_BADARG;
   }

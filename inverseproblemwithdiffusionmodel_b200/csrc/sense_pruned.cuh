@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(128, 3) kp_fwd_rows(SenseArgs a, PlanView p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t = lane % P::R1, r = warp * G::RPW + lane / P::R1;
   // batch index fastest: CTAs that run together share the same rows of the coil maps (L2 hits instead of DRAM re-reads)
-  const int b = blockIdx.x, h0 = blockIdx.y * G::TPC, h = h0 + r;
+  const int b = a.b0 + blockIdx.x, h0 = blockIdx.y * G::TPC, h = h0 + r;   // images [b0, b0 + nb) of the batch in this launch
   const int f = b % p.frames, ns = p.ns[f];
   cf32* sx = xch + r * P::LINE;
   MySlots<L, NOUT> my;
@@ -187,8 +187,8 @@ __global__ void __launch_bounds__(CGeo<LH>::NT) kp_fwd_cols(SenseArgs a, PlanVie
   cf32* tws = reinterpret_cast<cf32*>(smem_raw);
   cf32* tile = tws + G::NTWS;       // staging [h][SP] first, then the lines [cs][CSTRIDE]
   const int tid = threadIdx.x;
-  const size_t img = blockIdx.x;
-  const int b = (int)(img % a.batch), f = b % p.frames;
+  const int b = a.b0 + (int)(blockIdx.x % a.nb), f = b % p.frames;      // grid.x = ncoils * nb: images [b0, b0 + nb) of every coil
+  const size_t img = (size_t)(blockIdx.x / a.nb) * a.batch + b;
   if ((int)blockIdx.y >= p.nchunks[f]) return;
   const uchar4 ch = *reinterpret_cast<const uchar4*>(p.chunks + ((size_t)f * p.ng_all + blockIdx.y) * 4);
   const int g_lo = ch.x, g_cnt = ch.y, s_lo = ch.z, s_cnt = ch.w;
@@ -252,8 +252,8 @@ __global__ void __launch_bounds__(CGeo<LH>::NT) kp_adj_cols(SenseArgs a, PlanVie
   cf32* tws = reinterpret_cast<cf32*>(smem_raw);
   cf32* tile = tws + G::NTWS;
   const int tid = threadIdx.x;
-  const size_t img = blockIdx.x;
-  const int b = (int)(img % a.batch), f = b % p.frames;
+  const int b = a.b0 + (int)(blockIdx.x % a.nb), f = b % p.frames;      // grid.x = ncoils * nb: images [b0, b0 + nb) of every coil
+  const size_t img = (size_t)(blockIdx.x / a.nb) * a.batch + b;
   if ((int)blockIdx.y >= p.nchunks[f]) return;
   const uchar4 ch = *reinterpret_cast<const uchar4*>(p.chunks + ((size_t)f * p.ng_all + blockIdx.y) * 4);
   const int s_lo = ch.z, s_cnt = ch.w;
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(128, 4) kp_adj_rows(SenseArgs a, PlanView p) {
   __shared__ __align__(16) cf32 ysm[G::TPC * 16 * CMAX];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t = lane % P::R1, r = warp * G::RPW + lane / P::R1;
-  const int b = blockIdx.x, h = blockIdx.y * G::TPC + r;
+  const int b = a.b0 + blockIdx.x, h = blockIdx.y * G::TPC + r;
   const int f = b % p.frames, ns = p.ns[f];
   fill_padded_tables<L, CMAX, false>(twp, ysm, G::TPC * 16 * CMAX, p, f, ns, tid, G::NT);
   const uint32_t big2 = p.big[f * 2], big3 = p.big[f * 2 + 1];

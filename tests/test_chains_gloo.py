@@ -33,7 +33,8 @@ def _worker(rank, world, port, n_chains, outdir):
     mine = CH.chain_partition(n_chains, world, rank)
     allx = crandn(99, n_chains, 1, 8, 8)            # chain i is the same tensor on every rank (keyed by global index)
     st = CH.PosteriorStats(64, torch.device("cpu"))
-    st.add_sums(_sums(allx[mine]), len(mine))
+    if mine:                                         # a rank that owns no chain adds nothing but still joins the collective
+        st.add_sums(_sums(allx[mine]), len(mine))
     st.all_reduce()
     out = st.finalize((8, 8))
     torch.save({"mine": mine, "out": out}, os.path.join(outdir, f"r{rank}.pt"))
@@ -48,8 +49,12 @@ def test_partition():
     assert CH.chain_partition(3, 8, 5) == []
 
 
-def test_posterior_allreduce_gloo(tmp_path):
-    world, n_chains = 2, 7
+import pytest
+
+
+@pytest.mark.parametrize("n_chains", [7, 1])        # 1 chain over 2 ranks: rank 1 owns nothing (more ranks than chains)
+def test_posterior_allreduce_gloo(tmp_path, n_chains):
+    world = 2
     mp.spawn(_worker, args=(world, _free_port(), n_chains, str(tmp_path)), nprocs=world, join=True)
     ref = OALD.posterior_stats(crandn(99, n_chains, 1, 8, 8))
     seen = []

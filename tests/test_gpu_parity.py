@@ -203,6 +203,63 @@ def test_sense_pruned_plan_variants(H, W, nc, B, frames, cplx, lines):
     _sense_battery(H, W, nc, B, frames, cplx, lines, use_plan=True)
 
 
+def test_sense_pruned_big_batch_overlaps_on_a_side_stream():
+    """k-space >= 512 MB with >= 16 images and ipdm_debug_option(5, 1) (off by default: measured slower): the plan entry
+    points split the batch into four image sub-ranges and run the column kernel of each on the plan's side stream (fork /
+    join by events).  Same numbers as the general kernels, also when the call is captured into a CUDA graph and replayed."""
+    L = _lib()
+    lib = L.lib()
+    L.check(lib.ipdm_debug_option(5, 1), "split on")
+    try:
+        _split_stream_body(L, lib)
+    finally:
+        L.check(lib.ipdm_debug_option(5, 0), "split off")
+
+
+def _split_stream_body(L, lib):
+    nc, B, n = 16, 16, 512
+    A = C.SENSE("exp", nc, 40, 1 / 64, (1, n, n), 0)
+    A.random_under_fourier.mask = C.keep_center_mask(n, 40, 1 / 64, seed=0)
+    dev = torch.device(DEV, 0)
+    plan = A.device_plan(dev, n)
+    assert plan.pruned
+    m8, frames = A.device_mask(dev)
+    mre, _ = A.device_maps(dev)
+    g = torch.Generator(device=DEV).manual_seed(12)
+    x = torch.randn(B, 1, n, n, generator=g, device=DEV, dtype=torch.complex64)
+    ws = torch.empty(lib.ipdm_sense_workspace_bytes(nc, B, n, n), dtype=torch.uint8, device=DEV)
+    S_plan = torch.full((nc, B, 1, n, n), float("nan"), dtype=torch.complex64, device=DEV)
+    S_gen = torch.empty_like(S_plan)
+    L.check(lib.ipdm_sense_forward_plan(plan.handle, x.data_ptr(), mre.data_ptr(), None, S_plan.data_ptr(), nc, B, ws.data_ptr(), L.stream()), "fwd")
+    L.check(lib.ipdm_sense_forward(x.data_ptr(), mre.data_ptr(), None, m8.data_ptr(), frames, S_gen.data_ptr(), nc, B, n, n, ws.data_ptr(), L.stream()), "fwd")
+    torch.cuda.synchronize()
+    assert rel_l2(S_plan.cpu(), S_gen.cpu()) < 2e-6
+    ref = M.sense_forward(x[[0, B - 1]].cpu(), A.sens_maps, A.random_under_fourier.mask)
+    assert rel_l2(S_plan[:, [0, B - 1]].cpu(), ref) < 1e-5
+    o_plan = torch.full((B, 1, n, n), float("nan"), dtype=torch.complex64, device=DEV)
+    o_gen = torch.empty_like(o_plan)
+    L.check(lib.ipdm_sense_adjoint_plan(plan.handle, S_gen.data_ptr(), mre.data_ptr(), None, o_plan.data_ptr(), nc, B, 0, ws.data_ptr(), L.stream()), "adj")
+    L.check(lib.ipdm_sense_adjoint(S_gen.data_ptr(), mre.data_ptr(), None, m8.data_ptr(), frames, o_gen.data_ptr(), nc, B, n, n, 0, ws.data_ptr(), L.stream()), "adj")
+    torch.cuda.synchronize()
+    assert rel_l2(o_plan.cpu(), o_gen.cpu()) < 2e-6
+    L.check(lib.ipdm_sense_adjoint_plan(plan.handle, S_plan.data_ptr(), mre.data_ptr(), None, o_plan.data_ptr(), nc, B, 0, ws.data_ptr(), L.stream()), "adj")
+    torch.cuda.synchronize()
+    # captured: the side stream joins the capture through the fork event and leaves it through the join event
+    S_cap = torch.zeros_like(S_plan)
+    o_cap = torch.zeros_like(o_plan)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        L.check(lib.ipdm_sense_forward_plan(plan.handle, x.data_ptr(), mre.data_ptr(), None, S_cap.data_ptr(), nc, B, ws.data_ptr(), L.stream()), "fwd")
+        L.check(lib.ipdm_sense_adjoint_plan(plan.handle, S_cap.data_ptr(), mre.data_ptr(), None, o_cap.data_ptr(), nc, B, 0, ws.data_ptr(), L.stream()), "adj")
+    for _ in range(2):
+        S_cap.fill_(float("nan")); o_cap.fill_(float("nan"))
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(S_cap, S_plan) and torch.equal(o_cap, o_plan)
+
+
 def test_sense_plan_falls_back_to_the_general_kernels():
     """A mask that keeps too many columns for the pruned kernels (141 of 512 at R = 4) still works through a plan."""
     _sense_battery(128, 512, 2, 2, 1, False, None, use_plan=True)

@@ -19,6 +19,7 @@ ap.add_argument("--chains", type=int, default=105)
 ap.add_argument("--levels", type=int, default=2311, help="noise levels of the geometric 348 -> 0.01 schedule (acdc.yml: 2311)")
 ap.add_argument("--size", type=int, default=256)
 ap.add_argument("--out", default="gpurun_out/posterior")
+ap.add_argument("--seed", type=int, default=1234, help="one seed for every rank: the chains differ by their global ids")
 args = ap.parse_args()
 rank, local, world = CH.init_distributed()
 dev = torch.device("cuda", local)
@@ -32,18 +33,22 @@ A.random_under_fourier.mask = C.keep_center_mask(n, 40, 1 / 64, seed=0)
 truth = C.phantom(1, 1, 1, n, n).to(dev)
 y1 = A(truth)
 sig = C.get_sigmas(cfg, mode="recons")
-mine = CH.chain_partition(args.chains, world, rank)
+mine = CH.chain_partition(args.chains, world, rank)      # GLOBAL chain ids of this rank: chain i draws Philox(seed, chain i) on any rank
 B = len(mine)
 params = {"n_steps_each": 3, "step_lr": 9e-7, "denoise": True, "final_only": True}
-sampler = C.ALD.ALDInvSegProximalRealImag(C.L2Penalty(A), 1.0, "linear", (B, 1, n, n), net, sig, params, cfg,
-                                          measurement=y1.repeat(1, B, 1, 1, 1), linear_tfm=A, seg=None, device=dev)
 if world > 1:
     dist.barrier()
 torch.cuda.synchronize(); t0 = time.perf_counter()
-recon = sampler(label=None, lamda=1.0, save_dir="/tmp", lr_scaled=1e6, seg_mode="full", seed=1234 + 7919 * rank)[0]   # (B,1,H,W) on the host
-x = sampler.final_state                                                                                              # same, on the device
 stats = CH.PosteriorStats(n * n, dev)
-stats.add(x.reshape(B, n, n))
+if B > 0:                                                # a rank without chains (more ranks than chains) still joins the all-reduce
+    sampler = C.ALD.ALDInvSegProximalRealImag(C.L2Penalty(A), 1.0, "linear", (B, 1, n, n), net, sig, params, cfg,
+                                              measurement=y1.repeat(1, B, 1, 1, 1), linear_tfm=A, seg=None, device=dev)
+    recon = sampler(label=None, lamda=1.0, save_dir="/tmp", lr_scaled=1e6, seg_mode="full", seed=args.seed, chain_ids=mine)[0]   # (B,1,H,W) on the host
+    x = sampler.final_state                                                                                                          # same, on the device
+    stats.add(x.reshape(B, n, n))
+else:
+    recon = torch.zeros(0, 1, n, n, dtype=torch.complex64)
+    x = torch.zeros(0, 1, n, n, dtype=torch.complex64, device=dev)
 post = stats.all_reduce().finalize((n, n))
 torch.cuda.synchronize(); wall = time.perf_counter() - t0
 t_all = torch.tensor([wall], dtype=torch.float64, device=dev)
