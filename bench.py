@@ -397,9 +397,15 @@ def run_reference_gpu(args):
     torch.cuda.set_device(dev)
     lib = library_leg(args, torch, dev, args.chains)
     best = max((v["value"] for v in lib.values() if isinstance(v, dict) and "value" in v), default=None)
-    out = {"impl": "reference-gpu", "metric": METRIC, "value": lib.get("tf32", {}).get("value", best), "unit": UNIT, "n_gpus": 1,
-           "steps": 3, "warmup": 2, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
-           "data": "synthetic", "config": workload_config(args, None), "library_baseline": lib, "gpu_launches": None}
+    head = lib.get("tf32") or {}
+    out = {"impl": "reference-gpu", "metric": METRIC, "value": head.get("value", best), "unit": UNIT, "n_gpus": 1,
+           "steps": 3, "warmup": 2, "ms_per_step": head.get("ms_per_step"), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "tf32", "data": "synthetic", "config": workload_config(args, None),
+           "e2e": {"value": head.get("value", best), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                   "note": "state resident on the device (eager torch ops); no host copies in the timed region"},
+           "library_baseline": lib, "gpu_launches": None,
+           "note": "library arm: none of this repo's kernels; the headline value is the TF32 leg (torch's default conv precision "
+                   "is TF32-off = 'fp32' leg; the fp16 channels-last leg is the fastest library setting tried)"}
     print(json.dumps(out), flush=True)
 
 

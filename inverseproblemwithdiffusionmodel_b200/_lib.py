@@ -9,7 +9,7 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint32, c_uint64, c_ulonglong, c_void_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libipdm_b200.so")
+LIB_PATH = os.environ.get("IPDM_B200_LIB") or os.path.join(_HERE, "libipdm_b200.so")   # override: A/B builds of the same ABI
 
 
 class AldScalars(ctypes.Structure):

@@ -16,7 +16,10 @@
 #include "sense_plan.h"
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
+#include <map>
 #include <mutex>
+#include <utility>
 
 namespace ipdm {
 
@@ -622,15 +625,44 @@ static int launch_pruned_rows_any(bool fwd, const SenseArgs& a, const SensePlan*
   return launched(fwd ? "kp_fwd_rows" : "kp_adj_rows");
 }
 
+// Persistent column kernels: as many CTAs as fit on the device at once (occupancy query, cached per kernel and device), or
+// fewer so that every CTA walks the same number of work items.
+template <typename K>
+static int cols_grid(K kernel, int threads, size_t smem, int n_items, int* grid) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> slots_of;
+  int dev = 0;
+  IPDM_CUDA(cudaGetDevice(&dev));
+  int slots = 0;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_pair((const void*)kernel, dev);
+    auto it = slots_of.find(key);
+    if (it == slots_of.end()) {
+      int per_sm = 0, sms = 0;
+      IPDM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+      IPDM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      it = slots_of.emplace(key, std::max(1, per_sm * sms)).first;
+    }
+    slots = it->second;
+  }
+  const int rounds = (n_items + slots - 1) / slots;
+  *grid = (n_items + rounds - 1) / rounds;
+  return 0;
+}
+
 static int launch_pruned_cols(bool fwd, const SenseArgs& a, const SensePlan* pl, cudaStream_t s) {
+  const int n_items = a.ncoils * a.nb * pl->nchunks_max;
+  int grid = 0;
 #define PCOLS_CASE(LL)                                                                   \
   {                                                                                      \
-    dim3 grid(a.ncoils * a.nb, pl->nchunks_max);                                         \
     if (fwd) {                                                                           \
       if (int e = set_smem(kp_fwd_cols<LL>, CGeo<LL>::SMEM)) return e;                   \
+      if (int e = cols_grid(kp_fwd_cols<LL>, CGeo<LL>::NT, CGeo<LL>::SMEM, n_items, &grid)) return e; \
       kp_fwd_cols<LL><<<grid, CGeo<LL>::NT, CGeo<LL>::SMEM, s>>>(a, pl->view);           \
     } else {                                                                             \
       if (int e = set_smem(kp_adj_cols<LL>, CGeo<LL>::SMEM)) return e;                   \
+      if (int e = cols_grid(kp_adj_cols<LL>, CGeo<LL>::NT, CGeo<LL>::SMEM, n_items, &grid)) return e; \
       kp_adj_cols<LL><<<grid, CGeo<LL>::NT, CGeo<LL>::SMEM, s>>>(a, pl->view);           \
     }                                                                                    \
   }

@@ -155,13 +155,14 @@ __global__ void __launch_bounds__(128, 3) kp_fwd_rows(SenseArgs a, PlanView p) {
 }
 
 // ---- column kernels: full two-pass transforms along H of the sampled columns ------------------------------------
-// grid (ncoils * batch, chunks); a chunk = a run of whole active groups holding at most 8 sampled columns (plan table),
-// one transform per sampled column.
+// Work item = (coil image, chunk); a chunk = a run of whole active groups holding at most 8 sampled columns (plan table),
+// one transform per sampled column, one warp-slice per line.
 // These kernels move little data and used to wait on its latency (ncu: long-scoreboard stalls, 4 KB in flight per CTA).
-// Now every byte of a chunk is requested at once: the scratch block of a chunk is contiguous ([h][8], 32 KB at H = 512)
-// and 16-byte cp.async copies land it in a row-major staging tile stage[h][slot] (pitch 10) before anybody waits; the
-// adjoint's k-space side issues eight independent 8-byte loads per thread and round.
-// The exchange lines of the transforms alias the staging tile once it has been read into registers.
+// Every byte of an item is requested at once by asynchronous copies into a row-major staging tile stage[h][slot]
+// (pitch 10): the scratch block of a chunk is contiguous ([h][8], 32 KB at H = 512, 16-byte copies), the adjoint's k-space
+// side is 8-byte copies of the sampled columns.  The exchange lines of the transforms alias the staging tile once it has
+// been read into registers.  The kernels are persistent with two tiles: the copies of the next item fly during the
+// transform and the drain of the current one (masked adjoint at 32 coils x 512^2 x 64: 1.11 -> 0.98 ms).
 template <int LH>
 __device__ __forceinline__ void copy_tws(cf32* tws, const cf32* src, int tid, int nt) {
   for (int e = tid; e < Geo<LH>::NTWS; e += nt) tws[e] = src[e];
@@ -171,13 +172,35 @@ template <int LH> struct CGeo {
   static constexpr int NT = CL * Geo<LH>::TPF;
   static constexpr int SP = CL + 2;                          // staging pitch: rows 16-byte aligned, a column read is 2-way conflicted at worst
   static constexpr int CSTRIDE = P2<LH>::STRIDE | 1;         // line pitch: odd, the drain loops walk 8 lines at one row
-  static constexpr int TILE = (LH * SP > CL * CSTRIDE ? LH * SP : CL * CSTRIDE);
-  static constexpr size_t SMEM = (size_t)(Geo<LH>::NTWS + TILE) * sizeof(cf32);
+  static constexpr int TILE = ((LH * SP > CL * CSTRIDE ? LH * SP : CL * CSTRIDE) + 1) & ~1;   // even: both tiles 16-byte aligned
+  static constexpr size_t SMEM = (size_t)(Geo<LH>::NTWS + 2 * TILE) * sizeof(cf32);           // twiddles + two tiles
 };
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// One work item of the column kernels = (coil image, chunk of <= 8 sampled columns).  The kernels are PERSISTENT: CTA i takes
+// items i, i + gridDim.x, ... and keeps two tiles, so the (latency-bound) loads of the next item are in flight while the
+// current one is transformed and drained.  Items are numbered (coil * nb + image) * nch_max + chunk = scratch order.
+struct ColItem {
+  int f, chunk;
+  size_t img;
+  bool valid;
+};
+__device__ __forceinline__ ColItem col_item(const SenseArgs& a, const PlanView& p, int item, int n_items) {
+  ColItem it;
+  const int bx = item / p.nch_max;
+  it.chunk = item - bx * p.nch_max;
+  const int b = a.b0 + bx % a.nb;
+  it.f = b % p.frames;
+  it.img = (size_t)(bx / a.nb) * a.batch + b;
+  it.valid = item < n_items && it.chunk < p.nchunks[it.f];
+  return it;
+}
 
 template <int LH>
 __global__ void __launch_bounds__(CGeo<LH>::NT) kp_fwd_cols(SenseArgs a, PlanView p) {
@@ -185,62 +208,87 @@ __global__ void __launch_bounds__(CGeo<LH>::NT) kp_fwd_cols(SenseArgs a, PlanVie
   using C = CGeo<LH>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cf32* tws = reinterpret_cast<cf32*>(smem_raw);
-  cf32* tile = tws + G::NTWS;       // staging [h][SP] first, then the lines [cs][CSTRIDE]
-  const int tid = threadIdx.x;
-  const int b = a.b0 + (int)(blockIdx.x % a.nb), f = b % p.frames;      // grid.x = ncoils * nb: images [b0, b0 + nb) of every coil
-  const size_t img = (size_t)(blockIdx.x / a.nb) * a.batch + b;
-  if ((int)blockIdx.y >= p.nchunks[f]) return;
-  const uchar4 ch = *reinterpret_cast<const uchar4*>(p.chunks + ((size_t)f * p.ng_all + blockIdx.y) * 4);
-  const int g_lo = ch.x, g_cnt = ch.y, s_lo = ch.z, s_cnt = ch.w;
-  {
-    const cf32* wp = a.ws + (img * p.nch_max + blockIdx.y) * (size_t)(LH * 8);   // this chunk's block [h][8]
-    for (int idx = tid; idx < 4 * LH; idx += C::NT) {
-      const int pc = idx & 3, hh = idx >> 2;                                    // 16-byte piece pc of row hh
-      cp_async16(tile + hh * C::SP + 2 * pc, wp + hh * 8 + 2 * pc);
-    }
-  }
-  copy_tws<LH>(tws, p.tws_h, tid, C::NT);
-  // this chunk's groups (first column, line of each of the four columns or -1) in shared memory: the drain loop below
+  cf32* tiles = tws + G::NTWS;       // per tile: staging [h][SP] first, then the lines [cs][CSTRIDE]
+  // this item's groups (first column, line of each of the GW columns or -1) in shared memory: the drain loop below
   // must not chase three dependent global loads per 16-byte store
   __shared__ int g_col[C::CL];
   __shared__ int g_line[C::CL][PLAN_GW];
-  if (tid < g_cnt) {
-    const int g = g_lo + tid;
-    g_col[tid] = PLAN_GW * p.groups[f * p.ng_all + g];
-    const uint8_t* gs = p.gslot + ((size_t)f * p.ng_all + g) * PLAN_GW;
-#pragma unroll
-    for (int i = 0; i < PLAN_GW; ++i) g_line[tid][i] = gs[i] != 255 ? gs[i] - s_lo : -1;
-  }
-  cp_async_wait_all();
-  __syncthreads();
+  const int tid = threadIdx.x;
+  const int n_items = a.ncoils * a.nb * p.nch_max;
+  auto issue = [&](int item, cf32* tile) {
+    const ColItem it = col_item(a, p, item, n_items);
+    if (!it.valid) return;
+    const cf32* wp = a.ws + (it.img * p.nch_max + it.chunk) * (size_t)(LH * 8);   // this chunk's block [h][8]
+    for (int idx = tid; idx < 4 * LH; idx += C::NT) {
+      const int pc = idx & 3, hh = idx >> 2;                                      // 16-byte piece pc of row hh
+      cp_async16(tile + hh * C::SP + 2 * pc, wp + hh * 8 + 2 * pc);
+    }
+  };
+  issue(blockIdx.x, tiles);
+  copy_tws<LH>(tws, p.tws_h, tid, C::NT);
   const int cs = tid / G::TPF, t = tid % G::TPF;
-  cf32* sx = tile + cs * C::CSTRIDE;
-  cf32 v[G::E];
+  __syncthreads();
+  Twid<LH, (LH < 512)> tw;
+  tw.init(tws, t);
+  int par = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, par ^= 1) {
+    cf32* tile = tiles + par * C::TILE;
+    const ColItem it = col_item(a, p, item, n_items);     // CTA-uniform
+    cp_async_wait_all();
+    __syncthreads();      // this item's tile has landed; every thread is done with the other tile (previous drain)
+    if (!it.valid) {
+      issue(item + gridDim.x, tiles + (par ^ 1) * C::TILE);
+      continue;
+    }
+    const uchar4 ch = *reinterpret_cast<const uchar4*>(p.chunks + ((size_t)it.f * p.ng_all + it.chunk) * 4);
+    const int g_lo = ch.x, g_cnt = ch.y, s_lo = ch.z, s_cnt = ch.w;
+    cf32* sx = tile + cs * C::CSTRIDE;
+    cf32 v[G::E];
 #pragma unroll
-  for (int q = 0; q < G::E; ++q) v[q] = cs < s_cnt ? tile[a_pos<LH>(t, q) * C::SP + cs] : cf32{0.f, 0.f};
-  __syncthreads();   // the staging tile is in registers: the lines may overwrite it
-  {
-    Twid<LH, (LH < 512)> tw;
-    tw.init(tws, t);
+    for (int q = 0; q < G::E; ++q) v[q] = cs < s_cnt ? tile[a_pos<LH>(t, q) * C::SP + cs] : cf32{0.f, 0.f};
+    if (tid < g_cnt) {
+      const int g = g_lo + tid;
+      g_col[tid] = PLAN_GW * p.groups[it.f * p.ng_all + g];
+      const uint8_t* gs = p.gslot + ((size_t)it.f * p.ng_all + g) * PLAN_GW;
+#pragma unroll
+      for (int i = 0; i < PLAN_GW; ++i) g_line[tid][i] = gs[i] != 255 ? gs[i] - s_lo : -1;
+    }
+    __syncthreads();   // the staging tile is in registers: the lines may overwrite it
+    issue(item + gridDim.x, tiles + (par ^ 1) * C::TILE);
     a2b_first<LH, -1>(v, t, sx);
     __syncwarp();
     a2b_second<LH, -1>(v, t, sx, tw);
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < G::E; ++i) sx[b_pos<LH>(t, i)] = v[i];   // the exchange line doubles as the column's tile line
+    __syncthreads();
+    // Drain: 16-byte pieces of the active groups.  A warp writes RPI image rows per round, lane = (row in round, group,
+    // piece); everything that does not depend on the row -- the two source lines, the column -- is fixed per lane up front,
+    // so one piece costs two shared loads, four multiplies and the store (the first version divided by g_cnt per piece:
+    // 70 % of the kernel's instructions).  Group columns are even, so (-1)^(h + k) is (-1)^h for a piece's first column.
+    {
+      constexpr int PG = PLAN_GW / 2, NW = C::NT / 32;
+      const int lane = tid & 31, warp = tid >> 5;
+      const int npc = g_cnt * PG, rpi = 32 / npc;        // g_cnt <= CL = 8 groups -> npc <= 32
+      const int rsub = lane / npc, pcs = lane - rsub * npc;
+      const int gi = pcs / PG, pc = pcs - gi * PG;
+      const bool on = rsub < rpi;
+      const int kk = on ? g_col[gi] + 2 * pc : 0;
+      const int l0 = on ? g_line[gi][2 * pc] : -1, l1 = on ? g_line[gi][2 * pc + 1] : -1;
+      const cf32* s0 = tile + (l0 >= 0 ? l0 : 0) * C::CSTRIDE;
+      const cf32* s1 = tile + (l1 >= 0 ? l1 : 0) * C::CSTRIDE;
+      const float m0 = l0 >= 0 ? a.scale : 0.f, m1 = l1 >= 0 ? -a.scale : 0.f;
+      cf32* op = a.out + it.img * LH * a.W + kk;
+      if (on)
+        for (int hh = warp * rpi + rsub; hh < LH; hh += NW * rpi) {
+          const cf32 p0 = s0[hh], p1 = s1[hh];
+          const float sg = (hh & 1) ? -1.f : 1.f;
+          const float c0 = m0 * sg, c1 = m1 * sg;
+          *reinterpret_cast<float4*>(op + (size_t)hh * a.W) = make_float4(p0.x * c0, p0.y * c0, p1.x * c1, p1.y * c1);
+        }
+    }
   }
-  __syncthreads();
-  // active groups, 16-byte pieces: idx = (h * g_cnt + gi) * PG + piece -- consecutive lanes walk the groups of one image row
-  constexpr int PG = PLAN_GW / 2;
-  for (int idx = tid; idx < LH * g_cnt * PG; idx += C::NT) {
-    const int pc = idx % PG, gi = (idx / PG) % g_cnt, hh = (idx / PG) / g_cnt;
-    const int kk = g_col[gi] + 2 * pc;
-    const int l0 = g_line[gi][2 * pc], l1 = g_line[gi][2 * pc + 1];
-    const cf32 p0 = l0 >= 0 ? tile[l0 * C::CSTRIDE + hh] : cf32{0.f, 0.f};
-    const cf32 p1 = l1 >= 0 ? tile[l1 * C::CSTRIDE + hh] : cf32{0.f, 0.f};
-    const float sc0 = a.scale * sgn(hh + kk);
-    *reinterpret_cast<float4*>(a.out + (img * LH + hh) * a.W + kk) = make_float4(p0.x * sc0, p0.y * sc0, -p1.x * sc0, -p1.y * sc0);
-  }
+  cp_async_wait_all();
 }
 
 // adjoint, columns: inverse transform of the sampled columns along H into the compact scratch
@@ -250,59 +298,67 @@ __global__ void __launch_bounds__(CGeo<LH>::NT) kp_adj_cols(SenseArgs a, PlanVie
   using C = CGeo<LH>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cf32* tws = reinterpret_cast<cf32*>(smem_raw);
-  cf32* tile = tws + G::NTWS;
+  cf32* tiles = tws + G::NTWS;
   const int tid = threadIdx.x;
-  const int b = a.b0 + (int)(blockIdx.x % a.nb), f = b % p.frames;      // grid.x = ncoils * nb: images [b0, b0 + nb) of every coil
-  const size_t img = (size_t)(blockIdx.x / a.nb) * a.batch + b;
-  if ((int)blockIdx.y >= p.nchunks[f]) return;
-  const uchar4 ch = *reinterpret_cast<const uchar4*>(p.chunks + ((size_t)f * p.ng_all + blockIdx.y) * 4);
-  const int s_lo = ch.z, s_cnt = ch.w;
-  {
-    // the sampled columns themselves (8 bytes each; the memory system fetches their sectors either way): eight independent
-    // loads per thread in flight, then eight stores into the staging tile
+  const int n_items = a.ncoils * a.nb * p.nch_max;
+  // the sampled columns themselves, 8 bytes each (the memory system fetches their sectors either way), as asynchronous
+  // copies straight into the staging tile: LH * CL / NT of them per thread in flight, none of them holding a register
+  auto issue = [&](int item, cf32* tile) {
+    const ColItem it = col_item(a, p, item, n_items);
+    if (!it.valid) return;
+    const uchar4 ch = *reinterpret_cast<const uchar4*>(p.chunks + ((size_t)it.f * p.ng_all + it.chunk) * 4);
+    const int s_lo = ch.z, s_cnt = ch.w;
     const int si = tid % C::CL;
-    const int kcol = si < s_cnt ? p.kcol[f * p.ns_pad + s_lo + si] : 0;
-    const cf32* sp = a.in + img * LH * a.W + kcol;
+    if (si >= s_cnt) return;
+    const int kcol = p.kcol[it.f * p.ns_pad + s_lo + si];
+    const cf32* sp = a.in + it.img * LH * a.W + kcol;
     constexpr int RS = C::NT / C::CL;      // rows per round
-    for (int h0 = tid / C::CL; h0 < LH; h0 += 8 * RS) {
-      cf32 q[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) q[j] = (si < s_cnt && h0 + j * RS < LH) ? sp[(size_t)(h0 + j * RS) * a.W] : cf32{0.f, 0.f};
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (h0 + j * RS < LH) tile[(h0 + j * RS) * C::SP + si] = q[j];
-    }
-  }
+    for (int h = tid / C::CL; h < LH; h += RS) cp_async8(tile + h * C::SP + si, sp + (size_t)h * a.W);
+  };
+  issue(blockIdx.x, tiles);
   copy_tws<LH>(tws, p.tws_h, tid, C::NT);
-  __syncthreads();
   const int cs = tid / G::TPF, t = tid % G::TPF;
-  cf32* sx = tile + cs * C::CSTRIDE;
-  const int kc = cs < s_cnt ? p.kcol[f * p.ns_pad + s_lo + cs] : 0;
-  cf32 v[G::E];
-  {
-    const float sg = sgn(t + kc);   // a_off is even: (-1)^(h + k) is one sign per thread
+  __syncthreads();
+  Twid<LH, (LH < 512)> tw;
+  tw.init(tws, t);
+  int par = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, par ^= 1) {
+    cf32* tile = tiles + par * C::TILE;
+    const ColItem it = col_item(a, p, item, n_items);     // CTA-uniform
+    cp_async_wait_all();
+    __syncthreads();      // this item's columns have landed; every thread is done with the other tile (previous drain)
+    if (!it.valid) {
+      issue(item + gridDim.x, tiles + (par ^ 1) * C::TILE);
+      continue;
+    }
+    const uchar4 ch = *reinterpret_cast<const uchar4*>(p.chunks + ((size_t)it.f * p.ng_all + it.chunk) * 4);
+    const int s_lo = ch.z, s_cnt = ch.w;
+    cf32* sx = tile + cs * C::CSTRIDE;
+    const int kc = cs < s_cnt ? p.kcol[it.f * p.ns_pad + s_lo + cs] : 0;
+    cf32 v[G::E];
+    {
+      const float sg = sgn(t + kc);   // a_off is even: (-1)^(h + k) is one sign per thread
 #pragma unroll
-    for (int q = 0; q < G::E; ++q) v[q] = cs < s_cnt ? cscale(tile[a_pos<LH>(t, q) * C::SP + cs], sg) : cf32{0.f, 0.f};
-  }
-  __syncthreads();   // the staging tile is in registers: the lines may overwrite it
-  {
-    Twid<LH, (LH < 512)> tw;
-    tw.init(tws, t);
+      for (int q = 0; q < G::E; ++q) v[q] = cs < s_cnt ? cscale(tile[a_pos<LH>(t, q) * C::SP + cs], sg) : cf32{0.f, 0.f};
+    }
+    __syncthreads();   // the staging tile is in registers: the lines may overwrite it
+    issue(item + gridDim.x, tiles + (par ^ 1) * C::TILE);
     a2b_first<LH, +1>(v, t, sx);
     __syncwarp();
     a2b_second<LH, +1>(v, t, sx, tw);
-  }
-  __syncthreads();   // every exchange is finished: the tile becomes the row-major staging of the results
+    __syncthreads();   // every exchange is finished: the tile becomes the row-major staging of the results
 #pragma unroll
-  for (int i = 0; i < G::E; ++i) tile[b_pos<LH>(t, i) * C::SP + cs] = v[i];
-  __syncthreads();
-  {
-    cf32* wp = a.ws + (img * p.nch_max + blockIdx.y) * (size_t)(LH * 8);   // this chunk's block [h][8], 16-byte pieces
-    for (int idx = tid; idx < 4 * LH; idx += C::NT) {
-      const int pc = idx & 3, hh = idx >> 2;
-      *reinterpret_cast<float4*>(wp + hh * 8 + 2 * pc) = *reinterpret_cast<const float4*>(tile + hh * C::SP + 2 * pc);
+    for (int i = 0; i < G::E; ++i) tile[b_pos<LH>(t, i) * C::SP + cs] = v[i];
+    __syncthreads();
+    {
+      cf32* wp = a.ws + (it.img * p.nch_max + it.chunk) * (size_t)(LH * 8);   // this chunk's block [h][8], 16-byte pieces
+      for (int idx = tid; idx < 4 * LH; idx += C::NT) {
+        const int pc = idx & 3, hh = idx >> 2;
+        *reinterpret_cast<float4*>(wp + hh * 8 + 2 * pc) = *reinterpret_cast<const float4*>(tile + hh * C::SP + 2 * pc);
+      }
     }
   }
+  cp_async_wait_all();
 }
 
 // Zero the padded class tables and install the frame's twiddle vectors at their padded positions (sign: ALT as above).

@@ -12,7 +12,14 @@ w16 = (torch.randn(Cout, 9, Cin, device=dev) / (9 * Cin) ** 0.5).half()
 o32 = torch.empty(N, H, H, Cout, device=dev) if mode in ("res", "f32") else None
 o16 = torch.empty(N, H, H, Cout, device=dev, dtype=torch.float16) if mode in ("res", "f16") else None
 res = torch.randn(N, H, H, Cout, device=dev) if mode == "res" else None
-d = _lib.ConvDesc(x16.data_ptr(), w16.data_ptr(), None, _lib.ptr(res), _lib.ptr(o32), _lib.ptr(o16), None, N, H, H, Cin, Cout, 9, 1, 1)
+if mode == "t16":      # the launch the network issues on the 16-bit residual stream: f16 residual in, f16 result + f16 ELU copy out
+    o16 = torch.empty(N, H, H, Cout, device=dev, dtype=torch.float16)
+    raw16 = torch.empty_like(o16)
+    res16 = torch.randn(N, H, H, Cout, device=dev).half()
+    d = _lib.ConvDesc(x16.data_ptr(), w16.data_ptr(), None, None, None, o16.data_ptr(), None, N, H, H, Cin, Cout, 9, 1, 1,
+                      0, 0, res16.data_ptr(), raw16.data_ptr())
+else:
+    d = _lib.ConvDesc(x16.data_ptr(), w16.data_ptr(), None, _lib.ptr(res), _lib.ptr(o32), _lib.ptr(o16), None, N, H, H, Cin, Cout, 9, 1, 1)
 for _ in range(4):
     _lib.check(L.ipdm_conv_igemm(ctypes.byref(d), _lib.stream()))
 torch.cuda.synchronize()
