@@ -39,10 +39,10 @@ struct PlanHost {
   static constexpr int TWH = 10;         // factored twiddle entries per column
   // Output columns are handled in groups of GW: the forward column kernel writes whole groups (GW * 8 bytes, aligned), the
   // forward row kernel zero-fills every group without a sampled column, so no GW*8-byte unit of the output is written by
-  // both.  With 32-byte groups (GW = 4) every 128-byte line that holds a sample was written twice, partially, by two
-  // kernels: the scattered sector writes of the column kernel ran at 1.3 TB/s.
+  // both.  GW = 4 (one 32-byte sector) or 8 (64 bytes): measured the same within 2 % at every sweep point, GW = 4 slightly
+  // ahead on the forward (1.200 vs 1.226 ms at 32 coils x 512^2 x 64; 51.5 vs 54 us at 4 x 256^2 x 64).
 #ifndef IPDM_PLAN_GW
-#define IPDM_PLAN_GW 8
+#define IPDM_PLAN_GW 4
 #endif
   static constexpr int GW = IPDM_PLAN_GW;
   static constexpr int CHUNK_SLOTS = GW > 8 ? GW : 8;  // sampled columns per work item of the column kernels (>= GW)

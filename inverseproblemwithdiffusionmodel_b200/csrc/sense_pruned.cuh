@@ -54,15 +54,19 @@ template <int L> struct PGeo {
 // slot[o] = offset of the column inside the image's scratch block T[chunk][h][8] at h = 0 (-1: no column)
 template <int L, int NOUT> struct MySlots {
   int k0[NOUT], slot[NOUT], pp[NOUT];
+  // The table reads do not wait for `ns`: the index is clamped into the frame's padded row instead of predicated, so that a
+  // CTA's start-up is ONE round of independent loads (it was a chain of two L2 latencies before any x row was requested:
+  // 10 % of kp_fwd_rows' samples sat on the first branch that needs loaded data).
   __device__ __forceinline__ void init(const PlanView& p, int f, int ns, int t, int H) {
 #pragma unroll
     for (int o = 0; o < NOUT; ++o) {
       const int jj = t + PR<L>::R1 * o;
+      const int jc = f * p.ns_pad + (jj < p.ns_pad ? jj : p.ns_pad - 1);
+      const int k0v = p.k0c[jc], cw = p.tcw[jc], ppv = p.ppos[jc];
       const bool on = jj < ns;
-      k0[o] = on ? p.k0c[f * p.ns_pad + jj] : 0;
-      const int cw = on ? p.tcw[f * p.ns_pad + jj] : 0;
+      k0[o] = on ? k0v : 0;
       slot[o] = on ? (cw >> 3) * H * 8 + (cw & 7) : -1;
-      pp[o] = on ? p.ppos[f * p.ns_pad + jj] : 0;
+      pp[o] = on ? ppv : 0;
     }
   }
 };
@@ -75,7 +79,7 @@ __device__ __forceinline__ void load_my_twiddles(cf32 (&twh)[NOUT][PR<L>::NTWH],
 #pragma unroll
   for (int o = 0; o < NOUT; ++o) {
     const int jj = t + P::R1 * o;
-    const cf32* src = p.twh + ((size_t)f * p.ns_pad + (jj < ns ? jj : 0)) * PLAN_TWH;
+    const cf32* src = p.twh + ((size_t)f * p.ns_pad + (jj < p.ns_pad ? jj : 0)) * PLAN_TWH;   // unused when jj >= ns (slot < 0)
 #pragma unroll
     for (int i = 0; i < P::NTWH; ++i) {
       const cf32 w = src[i];
@@ -87,7 +91,7 @@ __device__ __forceinline__ void load_my_twiddles(cf32 (&twh)[NOUT][PR<L>::NTWH],
 // ---- forward, rows: coil multiply, pruned transform along W, compact scratch, zero-fill -------------------------
 // grid (batch, H / TPC).  Real coil maps (or none).
 template <int L, int NOUT>
-__global__ void __launch_bounds__(128, 3) kp_fwd_rows(SenseArgs a, PlanView p) {
+__global__ void __launch_bounds__(128, 4) kp_fwd_rows(SenseArgs a, PlanView p) {
   using G = PGeo<L>;
   using P = PR<L>;
   __shared__ __align__(16) cf32 xch[G::TPC * P::LINE];
@@ -97,17 +101,16 @@ __global__ void __launch_bounds__(128, 3) kp_fwd_rows(SenseArgs a, PlanView p) {
   const int b = a.b0 + blockIdx.x, h0 = blockIdx.y * G::TPC, h = h0 + r;   // images [b0, b0 + nb) of the batch in this launch
   const int f = b % p.frames, ns = p.ns[f];
   cf32* sx = xch + r * P::LINE;
+  cf32 xq[P::R0];          // the row first: it comes from DRAM, the plan tables below from L2
+  {
+    const cf32* xp = a.in + ((size_t)b * a.H + h) * L + t;
+#pragma unroll
+    for (int q = 0; q < P::R0; ++q) xq[q] = xp[P::R1 * q];
+  }
   MySlots<L, NOUT> my;
   my.init(p, f, ns, t, a.H);
   cf32 twh[NOUT][P::NTWH];
   load_my_twiddles<L, NOUT, false>(twh, p, f, ns, t);
-  cf32 xq[P::R0];
-  {
-    const cf32* xp = a.in + ((size_t)b * a.H + h) * L + t;
-    const float sg = sgn(h + t);   // R1 is even: the (-1)^(h+w) factor is one sign per thread
-#pragma unroll
-    for (int q = 0; q < P::R0; ++q) xq[q] = cscale(xp[P::R1 * q], sg);
-  }
   const bool has_maps = a.mre != nullptr;
   const size_t map_img = (size_t)a.H * L;
   const float* mre = a.mre + (size_t)h * L + t;
@@ -120,6 +123,11 @@ __global__ void __launch_bounds__(128, 3) kp_fwd_rows(SenseArgs a, PlanView p) {
     }
   };
   fetch_maps(0);
+  {
+    const float sg = sgn(h + t);   // R1 is even: the (-1)^(h+w) factor is one sign per thread
+#pragma unroll
+    for (int q = 0; q < P::R0; ++q) xq[q] = cscale(xq[q], sg);
+  }
   // this thread's zero-fill pieces are the same for every coil: which of them lie in inactive sectors
   uint32_t zmask = 0;
 #pragma unroll
@@ -173,7 +181,8 @@ template <int LH> struct CGeo {
   static constexpr int SP = CL + 2;                          // staging pitch: rows 16-byte aligned, a column read is 2-way conflicted at worst
   static constexpr int CSTRIDE = P2<LH>::STRIDE | 1;         // line pitch: odd, the drain loops walk 8 lines at one row
   static constexpr int TILE = ((LH * SP > CL * CSTRIDE ? LH * SP : CL * CSTRIDE) + 1) & ~1;   // even: both tiles 16-byte aligned
-  static constexpr size_t SMEM = (size_t)(Geo<LH>::NTWS + 2 * TILE) * sizeof(cf32);           // twiddles + two tiles
+  static constexpr size_t SMEM = (size_t)(Geo<LH>::NTWS + 2 * TILE) * sizeof(cf32);           // twiddles + two tiles (persistent CTAs)
+  static constexpr size_t SMEM1 = (size_t)(Geo<LH>::NTWS + TILE) * sizeof(cf32);              // one item per CTA: one tile
 };
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
