@@ -651,11 +651,12 @@ static int cols_slots(K kernel, int threads, size_t smem, int* slots) {
   return 0;
 }
 template <typename K>
-static int cols_grid(K kernel, int threads, size_t smem1, size_t smem2, int n_items, int* grid, size_t* smem) {
+static int cols_grid(K kernel, int threads, size_t smem1, size_t smem2, int n_items, int* grid, size_t* smem, int which) {
   if (int e = set_smem(kernel, smem2)) return e;
   int slots = 0;
   if (int e = cols_slots(kernel, threads, smem1, &slots)) return e;
-  if (n_items <= slots) {
+  static const int force_one = getenv("IPDM_COLS_ONE") ? atoi(getenv("IPDM_COLS_ONE")) : 0;   // A/B: 1 = fwd, 2 = adj, 3 = both
+  if (n_items <= slots || (force_one & which)) {
     *grid = n_items;
     *smem = smem1;
     return 0;
@@ -674,10 +675,10 @@ static int launch_pruned_cols(bool fwd, const SenseArgs& a, const SensePlan* pl,
 #define PCOLS_CASE(LL)                                                                                                   \
   {                                                                                                                      \
     if (fwd) {                                                                                                           \
-      if (int e = cols_grid(kp_fwd_cols<LL>, CGeo<LL>::NT, CGeo<LL>::SMEM1, CGeo<LL>::SMEM, n_items, &grid, &smem)) return e; \
+      if (int e = cols_grid(kp_fwd_cols<LL>, CGeo<LL>::NT, CGeo<LL>::SMEM1, CGeo<LL>::SMEM, n_items, &grid, &smem, 1)) return e; \
       kp_fwd_cols<LL><<<grid, CGeo<LL>::NT, smem, s>>>(a, pl->view);                                                     \
     } else {                                                                                                             \
-      if (int e = cols_grid(kp_adj_cols<LL>, CGeo<LL>::NT, CGeo<LL>::SMEM1, CGeo<LL>::SMEM, n_items, &grid, &smem)) return e; \
+      if (int e = cols_grid(kp_adj_cols<LL>, CGeo<LL>::NT, CGeo<LL>::SMEM1, CGeo<LL>::SMEM, n_items, &grid, &smem, 2)) return e; \
       kp_adj_cols<LL><<<grid, CGeo<LL>::NT, smem, s>>>(a, pl->view);                                                     \
     }                                                                                                                    \
   }
@@ -1082,7 +1083,7 @@ extern "C" int ipdm_sense_plan_create(const uint8_t* mask_host, int mask_frames,
   };
   const size_t i_mask = add(ph.mask.data(), ph.mask.size());
   size_t i_ns = 0, i_ng = 0, i_nc = 0, i_kcol = 0, i_nat = 0, i_k0c = 0, i_ppos = 0, i_tcw = 0, i_tw = 0, i_twh = 0, i_groups = 0, i_gslot = 0,
-         i_chunks = 0, i_gbm = 0, i_big = 0, i_tws = 0;
+         i_chunks = 0, i_gbm = 0, i_big = 0, i_tws = 0, i_crec = 0;
   if (pl->pruned_rows) {
     i_ns = add(ph.ns.data(), ph.ns.size() * sizeof(int));
     i_ng = add(ph.ngroups.data(), ph.ngroups.size() * sizeof(int));
@@ -1099,6 +1100,7 @@ extern "C" int ipdm_sense_plan_create(const uint8_t* mask_host, int mask_frames,
     i_gslot = add(ph.gslot.data(), ph.gslot.size());
     i_gbm = add(ph.gbitmap.data(), ph.gbitmap.size() * sizeof(uint32_t));
     i_big = add(ph.big.data(), ph.big.size() * sizeof(uint32_t));
+    i_crec = add(ph.crec.data(), ph.crec.size() * sizeof(ChunkRec));
     if (!tws.empty()) i_tws = add(tws.data(), tws.size() * sizeof(float));
   }
   pl->mu = new std::mutex();
@@ -1147,6 +1149,7 @@ extern "C" int ipdm_sense_plan_create(const uint8_t* mask_host, int mask_frames,
     v.gbitmap = reinterpret_cast<const uint32_t*>(at(i_gbm));
     v.big = reinterpret_cast<const uint32_t*>(at(i_big));
     v.tws_h = tws.empty() ? nullptr : reinterpret_cast<const cf32*>(at(i_tws));
+    v.crec = reinterpret_cast<const ChunkRec*>(at(i_crec));
   }
   *plan_out = pl;
   return 0;

@@ -27,6 +27,19 @@
 
 namespace ipdm {
 
+#ifndef IPDM_PLAN_GW
+#define IPDM_PLAN_GW 4
+#endif
+
+// Everything a column-kernel work item needs to know about its chunk, in ONE record (one 16-byte-aligned read instead of
+// the chain nchunks -> chunks -> groups -> gslot -> kcol of dependent table reads: half of kp_fwd_cols' stall samples).
+struct alignas(16) ChunkRec {
+  uint8_t g_cnt, s_cnt, s_lo, valid;     // active groups, sampled columns, first natural slot; valid = chunk exists in this frame
+  uint16_t kcol[8];                      // the sampled columns (natural order)
+  uint16_t gcol[8];                      // first column of each active group
+  int8_t gline[8][IPDM_PLAN_GW];         // per group and column: line (= slot - s_lo) or -1
+};
+
 struct PlanHost {
   int frames = 0, W = 0, R1 = 0, ns_max = 0, ns_pad = 0, ng_max = 0, cmax = 0, nchunks_max = 0;
   bool pruned = false;   // every frame keeps <= the limit the pruned kernels are built for and no residue class holds > 4 columns
@@ -35,15 +48,13 @@ struct PlanHost {
   std::vector<uint8_t> nat, k0c, cls, ppos, tcw, groups, gslot, chunks, mask;
   std::vector<uint32_t> gbitmap, big;   // big[f][2]: classes with >= 3 / == 4 entries, one bit per class
   std::vector<float> tw, twh;   // interleaved (re, im)
+  std::vector<ChunkRec> crec;   // [frames][W/GW] (chunk index), zero (valid = 0) past nchunks[f]
   static constexpr int CLS_PITCH = 20;   // 17 boundaries padded to five 32-bit words
   static constexpr int TWH = 10;         // factored twiddle entries per column
   // Output columns are handled in groups of GW: the forward column kernel writes whole groups (GW * 8 bytes, aligned), the
   // forward row kernel zero-fills every group without a sampled column, so no GW*8-byte unit of the output is written by
   // both.  GW = 4 (one 32-byte sector) or 8 (64 bytes): measured the same within 2 % at every sweep point, GW = 4 slightly
   // ahead on the forward (1.200 vs 1.226 ms at 32 coils x 512^2 x 64; 51.5 vs 54 us at 4 x 256^2 x 64).
-#ifndef IPDM_PLAN_GW
-#define IPDM_PLAN_GW 4
-#endif
   static constexpr int GW = IPDM_PLAN_GW;
   static constexpr int CHUNK_SLOTS = GW > 8 ? GW : 8;  // sampled columns per work item of the column kernels (>= GW)
 };
@@ -99,6 +110,7 @@ inline PlanHost build_plan_host(const uint8_t* mask, int frames, int W) {
   p.gslot.assign((size_t)frames * ng_all * GW, 255);
   p.gbitmap.assign((size_t)frames * 4, 0u);
   p.big.assign((size_t)frames * 2, 0u);
+  p.crec.assign((size_t)frames * ng_all, ChunkRec{});
   for (int f = 0; f < frames; ++f) {
     const uint8_t* m = mask + (size_t)f * W;
     std::vector<int> cols;
@@ -163,6 +175,16 @@ inline PlanHost build_plan_host(const uint8_t* mask, int frames, int W) {
       }
       uint8_t* ch = &p.chunks[((size_t)f * ng_all + c) * 4];
       ch[0] = (uint8_t)g_lo; ch[1] = (uint8_t)(g_hi - g_lo); ch[2] = (uint8_t)s_lo; ch[3] = (uint8_t)(s_hi - s_lo);
+      ChunkRec& rec = p.crec[(size_t)f * ng_all + c];
+      rec.g_cnt = ch[1]; rec.s_cnt = ch[3]; rec.s_lo = ch[2]; rec.valid = 1;
+      for (int i = 0; i < s_hi - s_lo; ++i) rec.kcol[i] = (uint16_t)cols[s_lo + i];
+      for (int gi = 0; gi < g_hi - g_lo; ++gi) {
+        rec.gcol[gi] = (uint16_t)(GW * p.groups[(size_t)f * ng_all + g_lo + gi]);
+        for (int i = 0; i < GW; ++i) {
+          const uint8_t sl = p.gslot[((size_t)f * ng_all + g_lo + gi) * GW + i];
+          rec.gline[gi][i] = sl != 255 ? (int8_t)(sl - s_lo) : (int8_t)-1;
+        }
+      }
       g_lo = g_hi;
       s_lo = s_hi;
       ++c;

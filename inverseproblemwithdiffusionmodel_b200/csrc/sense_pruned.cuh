@@ -40,6 +40,7 @@ struct PlanView {
   const uint32_t* gbitmap;  // [frames][4]
   const uint32_t* big;      // [frames][2]  classes with >= 3 / 4 sampled columns
   const cf32* tws_h;        // layout-B twiddles of the H transform (Geo<H>::NTWS entries)
+  const ChunkRec* crec;     // [frames][W/GW] one record per (frame, chunk)
 };
 constexpr int PLAN_TWH = 10;
 constexpr int PLAN_GW = PlanHost::GW;      // columns per output group (see sense_plan.h)
@@ -54,19 +55,15 @@ template <int L> struct PGeo {
 // slot[o] = offset of the column inside the image's scratch block T[chunk][h][8] at h = 0 (-1: no column)
 template <int L, int NOUT> struct MySlots {
   int k0[NOUT], slot[NOUT], pp[NOUT];
-  // The table reads do not wait for `ns`: the index is clamped into the frame's padded row instead of predicated, so that a
-  // CTA's start-up is ONE round of independent loads (it was a chain of two L2 latencies before any x row was requested:
-  // 10 % of kp_fwd_rows' samples sat on the first branch that needs loaded data).
   __device__ __forceinline__ void init(const PlanView& p, int f, int ns, int t, int H) {
 #pragma unroll
     for (int o = 0; o < NOUT; ++o) {
       const int jj = t + PR<L>::R1 * o;
-      const int jc = f * p.ns_pad + (jj < p.ns_pad ? jj : p.ns_pad - 1);
-      const int k0v = p.k0c[jc], cw = p.tcw[jc], ppv = p.ppos[jc];
       const bool on = jj < ns;
-      k0[o] = on ? k0v : 0;
+      k0[o] = on ? p.k0c[f * p.ns_pad + jj] : 0;
+      const int cw = on ? p.tcw[f * p.ns_pad + jj] : 0;
       slot[o] = on ? (cw >> 3) * H * 8 + (cw & 7) : -1;
-      pp[o] = on ? ppv : 0;
+      pp[o] = on ? p.ppos[f * p.ns_pad + jj] : 0;
     }
   }
 };
@@ -79,7 +76,7 @@ __device__ __forceinline__ void load_my_twiddles(cf32 (&twh)[NOUT][PR<L>::NTWH],
 #pragma unroll
   for (int o = 0; o < NOUT; ++o) {
     const int jj = t + P::R1 * o;
-    const cf32* src = p.twh + ((size_t)f * p.ns_pad + (jj < p.ns_pad ? jj : 0)) * PLAN_TWH;   // unused when jj >= ns (slot < 0)
+    const cf32* src = p.twh + ((size_t)f * p.ns_pad + (jj < ns ? jj : 0)) * PLAN_TWH;
 #pragma unroll
     for (int i = 0; i < P::NTWH; ++i) {
       const cf32 w = src[i];
@@ -91,7 +88,7 @@ __device__ __forceinline__ void load_my_twiddles(cf32 (&twh)[NOUT][PR<L>::NTWH],
 // ---- forward, rows: coil multiply, pruned transform along W, compact scratch, zero-fill -------------------------
 // grid (batch, H / TPC).  Real coil maps (or none).
 template <int L, int NOUT>
-__global__ void __launch_bounds__(128, 4) kp_fwd_rows(SenseArgs a, PlanView p) {
+__global__ void __launch_bounds__(128, 3) kp_fwd_rows(SenseArgs a, PlanView p) {
   using G = PGeo<L>;
   using P = PR<L>;
   __shared__ __align__(16) cf32 xch[G::TPC * P::LINE];
@@ -101,16 +98,17 @@ __global__ void __launch_bounds__(128, 4) kp_fwd_rows(SenseArgs a, PlanView p) {
   const int b = a.b0 + blockIdx.x, h0 = blockIdx.y * G::TPC, h = h0 + r;   // images [b0, b0 + nb) of the batch in this launch
   const int f = b % p.frames, ns = p.ns[f];
   cf32* sx = xch + r * P::LINE;
-  cf32 xq[P::R0];          // the row first: it comes from DRAM, the plan tables below from L2
-  {
-    const cf32* xp = a.in + ((size_t)b * a.H + h) * L + t;
-#pragma unroll
-    for (int q = 0; q < P::R0; ++q) xq[q] = xp[P::R1 * q];
-  }
   MySlots<L, NOUT> my;
   my.init(p, f, ns, t, a.H);
   cf32 twh[NOUT][P::NTWH];
   load_my_twiddles<L, NOUT, false>(twh, p, f, ns, t);
+  cf32 xq[P::R0];
+  {
+    const cf32* xp = a.in + ((size_t)b * a.H + h) * L + t;
+    const float sg = sgn(h + t);   // R1 is even: the (-1)^(h+w) factor is one sign per thread
+#pragma unroll
+    for (int q = 0; q < P::R0; ++q) xq[q] = cscale(xp[P::R1 * q], sg);
+  }
   const bool has_maps = a.mre != nullptr;
   const size_t map_img = (size_t)a.H * L;
   const float* mre = a.mre + (size_t)h * L + t;
@@ -123,11 +121,6 @@ __global__ void __launch_bounds__(128, 4) kp_fwd_rows(SenseArgs a, PlanView p) {
     }
   };
   fetch_maps(0);
-  {
-    const float sg = sgn(h + t);   // R1 is even: the (-1)^(h+w) factor is one sign per thread
-#pragma unroll
-    for (int q = 0; q < P::R0; ++q) xq[q] = cscale(xq[q], sg);
-  }
   // this thread's zero-fill pieces are the same for every coil: which of them lie in inactive sectors
   uint32_t zmask = 0;
 #pragma unroll
@@ -195,10 +188,13 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // One work item of the column kernels = (coil image, chunk of <= 8 sampled columns).  The kernels are PERSISTENT: CTA i takes
 // items i, i + gridDim.x, ... and keeps two tiles, so the (latency-bound) loads of the next item are in flight while the
 // current one is transformed and drained.  Items are numbered (coil * nb + image) * nch_max + chunk = scratch order.
+// What an item needs to know about its chunk is ONE ChunkRec (sense_plan.h); the records travel two items ahead through a
+// ring of three in shared memory (the record of item k+1 addresses the copies issued during item k), so no thread ever
+// waits on a table read: the first version chased nchunks -> chunks -> groups -> gslot / kcol per item, 50 % of its samples.
 struct ColItem {
   int f, chunk;
   size_t img;
-  bool valid;
+  bool in_range;
 };
 __device__ __forceinline__ ColItem col_item(const SenseArgs& a, const PlanView& p, int item, int n_items) {
   ColItem it;
@@ -207,8 +203,19 @@ __device__ __forceinline__ ColItem col_item(const SenseArgs& a, const PlanView& 
   const int b = a.b0 + bx % a.nb;
   it.f = b % p.frames;
   it.img = (size_t)(bx / a.nb) * a.batch + b;
-  it.valid = item < n_items && it.chunk < p.nchunks[it.f];
+  it.in_range = item < n_items;
   return it;
+}
+constexpr int REC_PIECES = (int)(sizeof(ChunkRec) / 16);
+// asynchronous: the record lands with the next cp.async wait + barrier
+__device__ __forceinline__ void fetch_rec(const SenseArgs& a, const PlanView& p, int item, int n_items, ChunkRec* dst, int tid) {
+  const ColItem it = col_item(a, p, item, n_items);
+  if (it.in_range) {
+    if (tid < REC_PIECES)
+      cp_async16(reinterpret_cast<char*>(dst) + 16 * tid, reinterpret_cast<const char*>(p.crec + (size_t)it.f * p.ng_all + it.chunk) + 16 * tid);
+  } else if (tid == 0) {
+    dst->valid = 0;
+  }
 }
 
 template <int LH>
@@ -218,52 +225,47 @@ __global__ void __launch_bounds__(CGeo<LH>::NT) kp_fwd_cols(SenseArgs a, PlanVie
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cf32* tws = reinterpret_cast<cf32*>(smem_raw);
   cf32* tiles = tws + G::NTWS;       // per tile: staging [h][SP] first, then the lines [cs][CSTRIDE]
-  // this item's groups (first column, line of each of the GW columns or -1) in shared memory: the drain loop below
-  // must not chase three dependent global loads per 16-byte store
-  __shared__ int g_col[C::CL];
-  __shared__ int g_line[C::CL][PLAN_GW];
+  __shared__ ChunkRec recs[3];
   const int tid = threadIdx.x;
   const int n_items = a.ncoils * a.nb * p.nch_max;
-  auto issue = [&](int item, cf32* tile) {
+  auto issue = [&](int item, cf32* tile, const ChunkRec& rec) {
+    if (item >= n_items || !rec.valid) return;
     const ColItem it = col_item(a, p, item, n_items);
-    if (!it.valid) return;
     const cf32* wp = a.ws + (it.img * p.nch_max + it.chunk) * (size_t)(LH * 8);   // this chunk's block [h][8]
     for (int idx = tid; idx < 4 * LH; idx += C::NT) {
       const int pc = idx & 3, hh = idx >> 2;                                      // 16-byte piece pc of row hh
       cp_async16(tile + hh * C::SP + 2 * pc, wp + hh * 8 + 2 * pc);
     }
   };
-  issue(blockIdx.x, tiles);
+  fetch_rec(a, p, blockIdx.x, n_items, &recs[0], tid);
+  fetch_rec(a, p, blockIdx.x + gridDim.x, n_items, &recs[1], tid);
   copy_tws<LH>(tws, p.tws_h, tid, C::NT);
-  const int cs = tid / G::TPF, t = tid % G::TPF;
+  cp_async_wait_all();
   __syncthreads();
+  issue(blockIdx.x, tiles, recs[0]);
+  const int cs = tid / G::TPF, t = tid % G::TPF;
   Twid<LH, (LH < 512)> tw;
   tw.init(tws, t);
-  int par = 0;
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x, par ^= 1) {
+  int par = 0, slot = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, par ^= 1, slot = slot == 2 ? 0 : slot + 1) {
     cf32* tile = tiles + par * C::TILE;
-    const ColItem it = col_item(a, p, item, n_items);     // CTA-uniform
+    const ChunkRec& rec = recs[slot];
+    const ChunkRec& rec_next = recs[slot == 2 ? 0 : slot + 1];
     cp_async_wait_all();
-    __syncthreads();      // this item's tile has landed; every thread is done with the other tile (previous drain)
-    if (!it.valid) {
-      issue(item + gridDim.x, tiles + (par ^ 1) * C::TILE);
+    __syncthreads();      // this item's tile and the next item's record have landed; every thread is done with the previous item
+    fetch_rec(a, p, item + 2 * gridDim.x, n_items, &recs[slot == 0 ? 2 : slot - 1], tid);
+    if (!rec.valid) {     // CTA-uniform
+      issue(item + gridDim.x, tiles + (par ^ 1) * C::TILE, rec_next);
       continue;
     }
-    const uchar4 ch = *reinterpret_cast<const uchar4*>(p.chunks + ((size_t)it.f * p.ng_all + it.chunk) * 4);
-    const int g_lo = ch.x, g_cnt = ch.y, s_lo = ch.z, s_cnt = ch.w;
+    const ColItem it = col_item(a, p, item, n_items);
+    const int g_cnt = rec.g_cnt, s_cnt = rec.s_cnt;
     cf32* sx = tile + cs * C::CSTRIDE;
     cf32 v[G::E];
 #pragma unroll
     for (int q = 0; q < G::E; ++q) v[q] = cs < s_cnt ? tile[a_pos<LH>(t, q) * C::SP + cs] : cf32{0.f, 0.f};
-    if (tid < g_cnt) {
-      const int g = g_lo + tid;
-      g_col[tid] = PLAN_GW * p.groups[it.f * p.ng_all + g];
-      const uint8_t* gs = p.gslot + ((size_t)it.f * p.ng_all + g) * PLAN_GW;
-#pragma unroll
-      for (int i = 0; i < PLAN_GW; ++i) g_line[tid][i] = gs[i] != 255 ? gs[i] - s_lo : -1;
-    }
     __syncthreads();   // the staging tile is in registers: the lines may overwrite it
-    issue(item + gridDim.x, tiles + (par ^ 1) * C::TILE);
+    issue(item + gridDim.x, tiles + (par ^ 1) * C::TILE, rec_next);
     a2b_first<LH, -1>(v, t, sx);
     __syncwarp();
     a2b_second<LH, -1>(v, t, sx, tw);
@@ -273,8 +275,8 @@ __global__ void __launch_bounds__(CGeo<LH>::NT) kp_fwd_cols(SenseArgs a, PlanVie
     __syncthreads();
     // Drain: 16-byte pieces of the active groups.  A warp writes RPI image rows per round, lane = (row in round, group,
     // piece); everything that does not depend on the row -- the two source lines, the column -- is fixed per lane up front,
-    // so one piece costs two shared loads, four multiplies and the store (the first version divided by g_cnt per piece:
-    // 70 % of the kernel's instructions).  Group columns are even, so (-1)^(h + k) is (-1)^h for a piece's first column.
+    // so one piece costs two shared loads, four multiplies and the store (the first version divided by g_cnt per piece).
+    // Group columns are even, so (-1)^(h + k) is (-1)^h for a piece's first column.
     {
       constexpr int PG = PLAN_GW / 2, NW = C::NT / 32;
       const int lane = tid & 31, warp = tid >> 5;
@@ -282,8 +284,8 @@ __global__ void __launch_bounds__(CGeo<LH>::NT) kp_fwd_cols(SenseArgs a, PlanVie
       const int rsub = lane / npc, pcs = lane - rsub * npc;
       const int gi = pcs / PG, pc = pcs - gi * PG;
       const bool on = rsub < rpi;
-      const int kk = on ? g_col[gi] + 2 * pc : 0;
-      const int l0 = on ? g_line[gi][2 * pc] : -1, l1 = on ? g_line[gi][2 * pc + 1] : -1;
+      const int kk = on ? rec.gcol[gi] + 2 * pc : 0;
+      const int l0 = on ? rec.gline[gi][2 * pc] : -1, l1 = on ? rec.gline[gi][2 * pc + 1] : -1;
       const cf32* s0 = tile + (l0 >= 0 ? l0 : 0) * C::CSTRIDE;
       const cf32* s1 = tile + (l1 >= 0 ? l1 : 0) * C::CSTRIDE;
       const float m0 = l0 >= 0 ? a.scale : 0.f, m1 = l1 >= 0 ? -a.scale : 0.f;
@@ -308,42 +310,45 @@ __global__ void __launch_bounds__(CGeo<LH>::NT) kp_adj_cols(SenseArgs a, PlanVie
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cf32* tws = reinterpret_cast<cf32*>(smem_raw);
   cf32* tiles = tws + G::NTWS;
+  __shared__ ChunkRec recs[3];
   const int tid = threadIdx.x;
   const int n_items = a.ncoils * a.nb * p.nch_max;
   // the sampled columns themselves, 8 bytes each (the memory system fetches their sectors either way), as asynchronous
   // copies straight into the staging tile: LH * CL / NT of them per thread in flight, none of them holding a register
-  auto issue = [&](int item, cf32* tile) {
-    const ColItem it = col_item(a, p, item, n_items);
-    if (!it.valid) return;
-    const uchar4 ch = *reinterpret_cast<const uchar4*>(p.chunks + ((size_t)it.f * p.ng_all + it.chunk) * 4);
-    const int s_lo = ch.z, s_cnt = ch.w;
+  auto issue = [&](int item, cf32* tile, const ChunkRec& rec) {
+    if (item >= n_items || !rec.valid) return;
     const int si = tid % C::CL;
-    if (si >= s_cnt) return;
-    const int kcol = p.kcol[it.f * p.ns_pad + s_lo + si];
-    const cf32* sp = a.in + it.img * LH * a.W + kcol;
+    if (si >= rec.s_cnt) return;
+    const ColItem it = col_item(a, p, item, n_items);
+    const cf32* sp = a.in + it.img * LH * a.W + rec.kcol[si];
     constexpr int RS = C::NT / C::CL;      // rows per round
     for (int h = tid / C::CL; h < LH; h += RS) cp_async8(tile + h * C::SP + si, sp + (size_t)h * a.W);
   };
-  issue(blockIdx.x, tiles);
+  fetch_rec(a, p, blockIdx.x, n_items, &recs[0], tid);
+  fetch_rec(a, p, blockIdx.x + gridDim.x, n_items, &recs[1], tid);
   copy_tws<LH>(tws, p.tws_h, tid, C::NT);
-  const int cs = tid / G::TPF, t = tid % G::TPF;
+  cp_async_wait_all();
   __syncthreads();
+  issue(blockIdx.x, tiles, recs[0]);
+  const int cs = tid / G::TPF, t = tid % G::TPF;
   Twid<LH, (LH < 512)> tw;
   tw.init(tws, t);
-  int par = 0;
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x, par ^= 1) {
+  int par = 0, slot = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, par ^= 1, slot = slot == 2 ? 0 : slot + 1) {
     cf32* tile = tiles + par * C::TILE;
-    const ColItem it = col_item(a, p, item, n_items);     // CTA-uniform
+    const ChunkRec& rec = recs[slot];
+    const ChunkRec& rec_next = recs[slot == 2 ? 0 : slot + 1];
     cp_async_wait_all();
-    __syncthreads();      // this item's columns have landed; every thread is done with the other tile (previous drain)
-    if (!it.valid) {
-      issue(item + gridDim.x, tiles + (par ^ 1) * C::TILE);
+    __syncthreads();      // this item's columns and the next item's record have landed; every thread is done with the previous item
+    fetch_rec(a, p, item + 2 * gridDim.x, n_items, &recs[slot == 0 ? 2 : slot - 1], tid);
+    if (!rec.valid) {     // CTA-uniform
+      issue(item + gridDim.x, tiles + (par ^ 1) * C::TILE, rec_next);
       continue;
     }
-    const uchar4 ch = *reinterpret_cast<const uchar4*>(p.chunks + ((size_t)it.f * p.ng_all + it.chunk) * 4);
-    const int s_lo = ch.z, s_cnt = ch.w;
+    const ColItem it = col_item(a, p, item, n_items);
+    const int s_cnt = rec.s_cnt;
     cf32* sx = tile + cs * C::CSTRIDE;
-    const int kc = cs < s_cnt ? p.kcol[it.f * p.ns_pad + s_lo + cs] : 0;
+    const int kc = cs < s_cnt ? rec.kcol[cs] : 0;
     cf32 v[G::E];
     {
       const float sg = sgn(t + kc);   // a_off is even: (-1)^(h + k) is one sign per thread
@@ -351,7 +356,7 @@ __global__ void __launch_bounds__(CGeo<LH>::NT) kp_adj_cols(SenseArgs a, PlanVie
       for (int q = 0; q < G::E; ++q) v[q] = cs < s_cnt ? cscale(tile[a_pos<LH>(t, q) * C::SP + cs], sg) : cf32{0.f, 0.f};
     }
     __syncthreads();   // the staging tile is in registers: the lines may overwrite it
-    issue(item + gridDim.x, tiles + (par ^ 1) * C::TILE);
+    issue(item + gridDim.x, tiles + (par ^ 1) * C::TILE, rec_next);
     a2b_first<LH, +1>(v, t, sx);
     __syncwarp();
     a2b_second<LH, +1>(v, t, sx, tw);

@@ -146,6 +146,25 @@ double check_pruned(int ns_target, unsigned seed) {
         s_next += ch[3];
       }
       if (g_next != pl.ngroups[f] || s_next != ns) return 13.0;
+      // the one-read chunk records of the column kernels say the same as the tables they were built from
+      for (int c = 0; c < L / PlanHost::GW; ++c) {
+        const ipdm::ChunkRec& rec = pl.crec[f * (L / PlanHost::GW) + c];
+        if ((rec.valid != 0) != (c < pl.nchunks[f])) return 16.0;
+        if (!rec.valid) continue;
+        const uint8_t* ch = &pl.chunks[(f * (L / PlanHost::GW) + c) * 4];
+        if (rec.g_cnt != ch[1] || rec.s_lo != ch[2] || rec.s_cnt != ch[3]) return 17.0;
+        for (int i = 0; i < rec.s_cnt; ++i)
+          if (rec.kcol[i] != pl.kcol[f * NP + rec.s_lo + i]) return 18.0;
+        for (int gi = 0; gi < rec.g_cnt; ++gi) {
+          const int g = ch[0] + gi;
+          if (rec.gcol[gi] != PlanHost::GW * pl.groups[f * (L / PlanHost::GW) + g]) return 19.0;
+          for (int i = 0; i < PlanHost::GW; ++i) {
+            const int sl = pl.gslot[(f * (L / PlanHost::GW) + g) * PlanHost::GW + i];
+            if (rec.gline[gi][i] != (sl != 255 ? sl - rec.s_lo : -1)) return 20.0;
+            if (sl != 255 && rec.kcol[rec.gline[gi][i]] != rec.gcol[gi] + i) return 21.0;
+          }
+        }
+      }
       for (int jj = 0; jj < ns; ++jj) {      // scratch position of every class entry: (chunk, position) of its natural slot
         const int cw = pl.tcw[f * NP + jj], cc = cw >> 3, within = cw & 7;
         if (cc >= pl.nchunks[f]) return 14.0;
