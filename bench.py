@@ -89,16 +89,20 @@ def phantom(seed, *shape):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms.  start() BEFORE the warm-up steps (nvidia-smi needs a few
+    hundred ms to produce its first line -- longer than a 10-step timed region when eight ranks start one each), mark() when
+    the timed region begins, stop() when it ends: the reported numbers are the samples received inside [mark, stop]; if the
+    region was shorter than one period, the samples of the warm-up (the same steps, the same load) are used and the
+    window says so."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.lines, self.proc, self.index = [], None, index
+        self.lines, self.proc, self.index, self.t_mark = [], None, index, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -107,16 +111,33 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def wait_first(self, timeout=3.0):
+        """block (bounded) until nvidia-smi has produced its first line, so that the timed region is covered"""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+        return self
+
+    def mark(self):
+        self.t_mark = time.perf_counter()
+        return self
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        t_end = time.perf_counter()
         self.proc.terminate()
+        t_mark = self.t_mark if self.t_mark is not None else 0.0
+        inside = [ln for (t, ln) in self.lines if t_mark <= t <= t_end]
+        window = "timed region"
+        if not inside:
+            inside = [ln for (t, ln) in self.lines if t <= t_end]
+            window = "warm-up + timed region (timed region shorter than one sampling period)"
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in inside:
             f = [t.strip() for t in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -129,7 +150,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def measured_peaks():
@@ -329,6 +350,53 @@ def cpu_leg(args, warm, timed):
                         f"), scaled to the whole volume (per-frame / per-patch cost is uniform), torch CPU {cores} threads, after {warm} warm-up")
 
 
+def cpu_side_legs(args):
+    """SURVEY 8(d) CPU legs beside the step: (i) SENSE forward + adjoint of the oracle port at a cfg-5 point, (ii) one
+    NCSNv2Deepest forward of 2 images at the benchmark size.  Bounded: a few seconds on 16 cores."""
+    import torch
+    from oracle import mri_ops as M, scorenet as SN
+    from inverseproblemwithdiffusionmodel_b200.ncsn.models.ncsnv2 import NCSNv2Deepest
+    torch.set_num_threads(os.cpu_count())
+    n, coils, batch = args.size, args.coils, 16
+    maps = M.exp_coil_maps(coils, n, n, 0)
+    mask = M.keep_center_mask(n, args.R, args.center_frac, seed=0)
+    g = torch.Generator().manual_seed(5)
+    x = torch.complex(torch.randn(batch, 1, n, n, generator=g), torch.randn(batch, 1, n, n, generator=g))
+    S = M.sense_forward(x, maps, mask)
+    sec_f = time_host(lambda: M.sense_forward(x, maps, mask), 1, 3)
+    sec_a = time_host(lambda: M.sense_adjoint(S, maps), 1, 3)
+    alg = 8.0 * batch * n * n * (1 + coils) + 4.0 * coils * n * n
+    cfg = make_config("ACDC", 128, n, 2311, 348.0, device="cpu")
+    torch.manual_seed(0)
+    net = NCSNv2Deepest(cfg)
+    Pd = {k: v.detach() for k, v in net.state_dict().items()}
+    Pd["sigmas"] = Pd["sigmas"].float()
+    xin = torch.rand(2, 1, n, n, generator=g)
+    labels = torch.zeros(2, dtype=torch.long)
+    with torch.no_grad():
+        sec_n = time_host(lambda: SN.score_forward("NCSNv2Deepest", Pd, xin, labels), 1, 2)
+    return {"sense_fwd_adj": {"point": f"{coils} coils, {n}x{n}, batch {batch}, R={args.R:g}", "forward_ms": sec_f * 1e3, "adjoint_ms": sec_a * 1e3,
+                              "forward_gbs": alg / sec_f / 1e9, "adjoint_gbs": alg / sec_a / 1e9},
+            "ncsnv2deepest_forward_2_images": {"size": n, "ms": sec_n * 1e3, "tflops": 2 * 838.36e9 * (n / 256) ** 2 / sec_n / 1e12}}
+
+
+def cpu_sense_forward(warm, timed):
+    """The sweep's headline point on the host cores: two of its 64 images per timed step (per-image cost is uniform)."""
+    import torch
+    from oracle import mri_ops as M
+    torch.set_num_threads(os.cpu_count())
+    coils, n, batch, R = 32, 512, 2, 40.0
+    maps = M.exp_coil_maps(coils, n, n, 0)
+    mask = M.keep_center_mask(n, R, 1 / 64, seed=0)
+    g = torch.Generator().manual_seed(5)
+    x = torch.complex(torch.randn(batch, 1, n, n, generator=g), torch.randn(batch, 1, n, n, generator=g))
+    sec = time_host(lambda: M.sense_forward(x, maps, mask), warm, timed)
+    alg = 8.0 * batch * n * n * (1 + coils) + 4.0 * coils * n * n
+    sample = (f"{timed} timed SENSE forwards of 2 of the 64 images at 32 coils x 512x512, R=40 (oracle port: torch FFT + coil multiply "
+              f"+ mask, {os.cpu_count()} threads), after {warm} warm-up")
+    return alg / sec / 1e9, sec, sample
+
+
 def run_reference(args):
     """`--impl reference`: the path's CPU implementation (the oracle port; the reference itself cannot travel to the box) on the
     host cores with every thread, on the native arm's config / metric / unit; every one of the K timed steps is a bounded
@@ -337,7 +405,12 @@ def run_reference(args):
     if rank != 0:
         return
     if args.config == "cfg5-sweep":
-        print(json.dumps({"impl": "reference", "unavailable": "the CPU arm times ALD steps; use --config cfg2 / cfg1 / cfg4-*"}), flush=True)
+        val, sec, sample = cpu_sense_forward(args.warmup, args.steps)
+        print(json.dumps({"impl": "reference", "metric": "SENSE forward algorithmic GB/s", "value": val, "unit": "GB/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, None),
+                          "cpu_baseline": {"value": val, "unit": "GB/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+                          "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
         return
     val, sec, sample = cpu_leg(args, args.warmup, args.steps)
     cfg = workload_config(args, None)
@@ -514,23 +587,24 @@ def build_cfg2(args, P, torch, dev, B):
 
 
 def time_replays(torch, dist, world, step, warmup, steps, local):
+    clocks = ClockSampler(local).start().wait_first()
     for _ in range(warmup):
         step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clocks = ClockSampler(local).start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    clocks.mark()
     e0.record()
     for _ in range(steps):
         step()
     e1.record()
     torch.cuda.synchronize()
+    info = clocks.stop()
     if world > 1:
         dist.barrier()
     ms = e0.elapsed_time(e1)
-    info = clocks.stop()
     t = torch.tensor([ms], dtype=torch.float64, device=torch.device("cuda", local))
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -643,35 +717,39 @@ def run_cfg2(args, torch, dist, P, _lib, CH, L, dev, rank, local, world):
     run_step = step if B > 0 else (lambda: None)                   # a rank without chains idles but joins every collective
     stats = CH.PosteriorStats(n * n, dev)
 
-    def posterior_tail():
+    def posterior_tail(st=None):
         """what cfg 3 does after the chains: statistics of this rank's chains, ONE all-reduce, per-pixel mean / std"""
+        st = stats if st is None else st
         if B > 0:
-            stats.add(torch.complex(chain["state"][0], chain["state"][1]).reshape(B, 1, n, n))
-        stats.all_reduce()
-        return stats.finalize((n, n))
+            st.add(torch.complex(chain["state"][0], chain["state"][1]).reshape(B, 1, n, n))
+        st.all_reduce()
+        return st.finalize((n, n))
 
     if args.strong:
         # the collective and the reduction are INSIDE the timed region: K steps of every chain + posterior statistics
+        clocks = ClockSampler(local).start().wait_first()
         for _ in range(args.warmup):
             run_step()
+        posterior_tail(CH.PosteriorStats(n * n, dev))              # warm-up of the tail too (first all-reduce of this size: 90 ms of NCCL set-up)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        clocks = ClockSampler(local).start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
+        clocks.mark()
         e0.record()
         for _ in range(args.steps):
             run_step()
         post = posterior_tail()
         e1.record()
         torch.cuda.synchronize()
+        clock_info = clocks.stop()
         if world > 1:
             dist.barrier()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, clock_info = float(t.item()), clocks.stop()
+        ms_total = float(t.item())
     else:
         ms_total, clock_info = time_replays(torch, dist, world, run_step, args.warmup, args.steps, local)
         post = posterior_tail()
@@ -725,6 +803,10 @@ def run_cfg2(args, torch, dist, P, _lib, CH, L, dev, rank, local, world):
     if world == 1 and not args.no_cpu_baseline:
         v, _, sample = cpu_leg(args, 1, 2)
         cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample}
+        try:
+            cpu["legs"] = cpu_side_legs(args)
+        except Exception as e:      # the legs are side information: never lose the bench line over them
+            cpu["legs"] = {"error": repr(e)[:200]}
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
            "dtype": "f16", "data": "synthetic", "config": workload_config(args, W.lines),
@@ -852,6 +934,9 @@ def run_sweep(args, torch, P, _lib, L, dev, hbm, rank, world, dist):
            "roofline": {"bound": "hbm", "achieved": big["forward"]["gbs"], "peak": hbm, "unit": "GB/s", "frac": big["forward"]["frac"], "traffic": None,
                         "kernel": "kp_fwd_rows + kp_fwd_cols at " + big["point"]},
            "e2e": None, "gpu_launches": int(L.ipdm_launch_count() - before), "sweep": pts}
+    if not args.no_cpu_baseline:
+        v, _, sample = cpu_sense_forward(1, 3)
+        out["cpu_baseline"] = {"value": v, "unit": "GB/s", "cores": os.cpu_count(), "kind": "port", "sample": sample}
     print(json.dumps(out), flush=True)
 
 
