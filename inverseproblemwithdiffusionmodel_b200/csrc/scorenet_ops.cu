@@ -597,6 +597,76 @@ __global__ void __launch_bounds__(256) k_bilinear_add(const void* __restrict__ s
   }
 }
 
+// The same on the 16-bit stream with EIGHT channels per thread (16-byte accesses; C % 8 == 0): the 4-channel version above moved
+// 1.5 GB in 0.46 ms at 256^2 x 128 channels (3.3 TB/s, 8-byte requests).
+struct H8 {
+  float v[8];
+  static __device__ __forceinline__ H8 ld(const __half* p) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    H8 r;
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&q.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&q.z)), d = __half22float2(*reinterpret_cast<const __half2*>(&q.w));
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; r.v[4] = c.x; r.v[5] = c.y; r.v[6] = d.x; r.v[7] = d.y;
+    return r;
+  }
+};
+__global__ void __launch_bounds__(256) k_bilinear_add_h8(const __half* __restrict__ src, __half* __restrict__ dst, __half* __restrict__ out16,
+                                                         int h, int w, int H, int W, int C, int accumulate) {
+  const int lanes = C >> 3;
+  const int n = blockIdx.x / H, Y = blockIdx.x % H;
+  const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
+  const float sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  const float fy = sy * Y;
+  const int y0 = (int)fy, y1 = y0 + (y0 < h - 1 ? 1 : 0);
+  const float ly = fy - y0, hy = 1.f - ly;
+  const __half* s0 = src + ((size_t)n * h + y0) * w * C;
+  const __half* s1 = src + ((size_t)n * h + y1) * w * C;
+  __half* drow = dst + ((size_t)n * H + Y) * W * C;
+  __half* hrow = out16 ? out16 + ((size_t)n * H + Y) * W * C : nullptr;
+  const int total = W * lanes;
+  for (int i0 = threadIdx.x; i0 < total; i0 += 2 * blockDim.x) {
+    H8 v00[2], v01[2], v10[2], v11[2], old[2];
+    float lx[2];
+    int off[2];
+    bool live[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = i0 + u * blockDim.x;
+      live[u] = i < total;
+      if (!live[u]) continue;
+      const int X = i / lanes, c8 = (i - X * lanes) * 8;
+      const float fx = sx * X;
+      const int x0 = (int)fx, x1 = x0 + (x0 < w - 1 ? 1 : 0);
+      lx[u] = fx - x0;
+      v00[u] = H8::ld(s0 + x0 * C + c8);
+      v01[u] = H8::ld(s0 + x1 * C + c8);
+      v10[u] = H8::ld(s1 + x0 * C + c8);
+      v11[u] = H8::ld(s1 + x1 * C + c8);
+      off[u] = X * C + c8;
+      if (accumulate) old[u] = H8::ld(drow + off[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!live[u]) continue;
+      const float hx = 1.f - lx[u];
+      float r[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        r[k] = hy * (hx * v00[u].v[k] + lx[u] * v01[u].v[k]) + ly * (hx * v10[u].v[k] + lx[u] * v11[u].v[k]);
+        if (accumulate) r[k] += old[u].v[k];
+      }
+      uint4 pk;
+      pk.x = pack_half2_sat(r[0], r[1]); pk.y = pack_half2_sat(r[2], r[3]); pk.z = pack_half2_sat(r[4], r[5]); pk.w = pack_half2_sat(r[6], r[7]);
+      *reinterpret_cast<uint4*>(drow + off[u]) = pk;
+      if (hrow) {
+        pk.x = pack_half2_sat(elu_f16bound(r[0]), elu_f16bound(r[1])); pk.y = pack_half2_sat(elu_f16bound(r[2]), elu_f16bound(r[3]));
+        pk.z = pack_half2_sat(elu_f16bound(r[4]), elu_f16bound(r[5])); pk.w = pack_half2_sat(elu_f16bound(r[6]), elu_f16bound(r[7]));
+        *reinterpret_cast<uint4*>(hrow + off[u]) = pk;
+      }
+    }
+  }
+}
+
 __global__ void k_meanpool2(const float* __restrict__ in, const float* __restrict__ add, float* __restrict__ out, int N,
                             int H, int W, int C) {
   const int lanes = C / 4, Ho = H / 2, Wo = W / 2;
@@ -831,7 +901,11 @@ extern "C" int ipdm_bilinear_add_f16(const void* src_f16, void* dst_f16, void* o
   IPDM_REQUIRE(src_f16 && dst_f16, IPDM_E_BADARG, "bilinear_add_f16: null pointer");
   IPDM_REQUIRE(C % 4 == 0, IPDM_E_BADARG, "bilinear_add_f16: C=%d must be a multiple of 4", C);
   IPDM_REQUIRE((size_t)N * H < ((size_t)1 << 31) && (size_t)W * C < ((size_t)1 << 30), IPDM_E_UNSUPPORTED, "bilinear_add_f16: image too large");
-  k_bilinear_add<true><<<N * H, 256, 0, as_stream(stream)>>>(src_f16, dst_f16, reinterpret_cast<__half*>(out_elu_f16), h, w, H, W, C, accumulate);
+  if (C % 8 == 0)
+    k_bilinear_add_h8<<<N * H, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(src_f16), reinterpret_cast<__half*>(dst_f16),
+                                                            reinterpret_cast<__half*>(out_elu_f16), h, w, H, W, C, accumulate);
+  else
+    k_bilinear_add<true><<<N * H, 256, 0, as_stream(stream)>>>(src_f16, dst_f16, reinterpret_cast<__half*>(out_elu_f16), h, w, H, W, C, accumulate);
   return launched("k_bilinear_add");
 }
 

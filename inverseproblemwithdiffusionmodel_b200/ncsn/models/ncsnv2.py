@@ -152,6 +152,7 @@ class _Plan:
         self.bufs = {}
         self.w = {}
         self.version = None
+        self._audited = None
         self.L = _lib.lib()
         inner = [m for name, m in net.named_modules() if isinstance(m, nn.Conv2d) and name not in ("begin_conv", "end_conv")]
         self.t16 = (len(inner) > 0 and all(m.in_channels % 64 == 0 and m.out_channels % 128 == 0 for m in inner)
@@ -161,7 +162,7 @@ class _Plan:
     def buf(self, name, shape, dtype):
         t = self.bufs.get(name)
         if t is None:
-            t = torch.empty(shape, dtype=dtype, device=self.device)
+            t = torch.zeros(shape, dtype=dtype, device=self.device)   # zeros, once: the range audit reads every f16 buffer whole
             self.bufs[name] = t
         return t
 
@@ -404,6 +405,25 @@ class _Plan:
         dots = self.buf("final.dots", (N, H, W, 9), torch.float32)
         _lib.check(self.L.ipdm_conv_last(a16.data_ptr(), we.data_ptr(), _lib.ptr(be), self.sigmas.data_ptr(), labels.data_ptr(),
                                          out.data_ptr(), dots.data_ptr(), N, H, W, ngf, s), "conv_last")
+        self._auto_audit()
+
+    def _auto_audit(self):
+        """Once per set of weights (the first forward after they changed -- in the samplers that is the largest noise level,
+        the largest activations): refuse to go on when an activation was clipped to the end of the f16 range.  There is no
+        wider operand path to fall back to, so a silent clip would be a silent wrong score.  Skipped inside a
+        stream capture (the samplers run one eager step first) and with IPDM_ALLOW_F16_SATURATION=1."""
+        if self._audited == self.version or (torch.device(self.device).type == 'cuda' and torch.cuda.is_current_stream_capturing()):
+            return
+        self._audited = self.version
+        if os.environ.get("IPDM_ALLOW_F16_SATURATION"):
+            return
+        worst = [(name, m, k) for name, (m, k) in self.range_audit().items() if k > 0]
+        if worst:
+            name, m, k = worst[0]
+            raise _lib.IpdmError(f"f16 range: {sum(w[2] for w in worst)} activation values were clipped at +-65504 in the first forward with "
+                                 f"these weights (worst buffer '{name}': max |x| = {m:.3g}, {k} values).  The tensor-core path keeps "
+                                 "convolution operands in f16; this checkpoint needs a wider operand type than this library has.  "
+                                 "Set IPDM_ALLOW_F16_SATURATION=1 to run anyway (clipped values, never inf / NaN).")
 
 
 class _ScoreNetBase(nn.Module):

@@ -449,6 +449,16 @@ class EmuLib:
     def ipdm_debug_option(self, key, value):
         return 0
 
+    def ipdm_f16_range_audit(self, x16, n, max_abs, n_sat, stream):
+        self.launches += 1
+        a = _t(x16, (n,), np.float16).float().abs()
+        m = _t(max_abs, (1,), np.float32)
+        finite_max = float(torch.nan_to_num(a, nan=0.0, posinf=65504.0).max()) if n else 0.0
+        m.copy_(torch.maximum(m, torch.tensor([finite_max])))
+        c = _t(n_sat, (1,), np.int64)
+        c.add_(int((~(a < 65504.0)).sum()))
+        return 0
+
     def ipdm_maxpool5_f16(self, in16, out16, N, H, W, C, stream):
         self.launches += 1
         X = _t(in16, (N, H, W, C), np.float16).float().permute(0, 3, 1, 2)

@@ -445,6 +445,26 @@ def test_bilinear_add_vs_torch(N, h, w, H, W, C, acc):
     assert rel_l2(h16.float().cpu(), torch.nn.functional.elu(ref).half().float().cpu()) < 1e-3
 
 
+@pytest.mark.parametrize("N,h,w,H,W,C,acc", [(2, 16, 16, 32, 32, 128, 1), (1, 7, 5, 14, 10, 64, 0), (3, 64, 64, 128, 128, 128, 1), (2, 8, 8, 8, 8, 256, 1),
+                                             (2, 9, 6, 18, 12, 12, 1), (1, 128, 128, 256, 256, 128, 1)])
+def test_bilinear_add_f16_stream_vs_torch(N, h, w, H, W, C, acc):
+    """The same on the 16-bit residual stream (ipdm_bilinear_add_f16; 8 channels per thread when C % 8 == 0, else 4): f16 in,
+    fp32 interpolation and add, f16 result + f16(ELU) copy -- against torch on the same f16 inputs, one f16 rounding."""
+    L = _lib()
+    g = torch.Generator().manual_seed(h * 19 + W)
+    src = torch.randn(N, h, w, C, generator=g).half().to(DEV)
+    dst0 = torch.randn(N, H, W, C, generator=g).half().to(DEV)
+    dst = dst0.clone()
+    h16 = torch.full((N, H, W, C), float("nan"), device=DEV, dtype=torch.float16)
+    L.check(L.lib().ipdm_bilinear_add_f16(src.data_ptr(), dst.data_ptr(), h16.data_ptr(), N, h, w, H, W, C, acc, L.stream()), "bilinear_add_f16")
+    up = torch.nn.functional.interpolate(src.float().permute(0, 3, 1, 2), size=(H, W), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+    ref = up + dst0.float() if acc else up
+    assert torch.isfinite(dst.float()).all() and torch.isfinite(h16.float()).all()
+    assert (dst.float() - ref).abs().max() <= 1e-3 * ref.abs().max() + 1e-6          # half an f16 ulp at the largest value
+    assert rel_l2(dst.float().cpu(), ref.cpu()) < 5e-4
+    assert rel_l2(h16.float().cpu(), torch.nn.functional.elu(ref).cpu()) < 1e-3
+
+
 def test_conv_direct_vs_torch():
     """Anchor of the chain igemm -> direct -> torch: the CUDA-core kernel against F.conv2d on the same f16 operands."""
     import torch.nn.functional as F
@@ -538,6 +558,21 @@ def test_f16_range_audit_finds_clipped_activations():
     out = net((rrandn(78, 2, 1, 32, 32) * 3e5).to(DEV), y)
     a = net.range_audit()
     assert a["saturated_total"] > 0 and bool(torch.isfinite(out).all())
+
+
+def test_first_forward_refuses_clipped_activations(monkeypatch):
+    """Range safety by default: the first forward with a set of weights audits its f16 buffers and raises when anything was
+    clipped (there is no wider operand path to fall back to); IPDM_ALLOW_F16_SATURATION=1 lets it run (finite, clipped)."""
+    from inverseproblemwithdiffusionmodel_b200._lib import IpdmError
+    y = torch.tensor([0, 9], device=DEV)
+    big = (rrandn(78, 2, 1, 32, 32) * 3e5).to(DEV)
+    net, Pd, cfg = _full_width_net(C.NCSNv2Deepest, "NCSNv2Deepest", 32, 21)
+    with pytest.raises(IpdmError, match="f16 range"):
+        net(big, y)
+    assert bool(torch.isfinite(net((rrand(77, 2, 1, 32, 32) * 2 - 0.5).to(DEV), y)).all())     # the same net stays usable
+    net2, _, _ = _full_width_net(C.NCSNv2Deepest, "NCSNv2Deepest", 32, 21)
+    monkeypatch.setenv("IPDM_ALLOW_F16_SATURATION", "1")
+    assert bool(torch.isfinite(net2(big, y)).all())
 
 
 def test_single_ald_step_ngf128():
