@@ -560,6 +560,86 @@ def test_f16_range_audit_finds_clipped_activations():
     assert a["saturated_total"] > 0 and bool(torch.isfinite(out).all())
 
 
+class _Guarded:
+    """A device buffer with guard bands: the kernel gets the middle, the bands must come back untouched (compute-sanitizer is
+    closed on the GPU pool, so out-of-bounds WRITES are caught this way; unwritten outputs by the NaN pre-fills of the parity
+    tests)."""
+    GUARD = 4096     # bytes on either side
+
+    def __init__(self, nbytes, fill=0xA5):
+        self.n = nbytes
+        self.raw = torch.full((nbytes + 2 * self.GUARD,), fill, dtype=torch.uint8, device=DEV)
+        self.fill = fill
+
+    def view(self, dtype, shape):
+        return self.raw[self.GUARD:self.GUARD + self.n].view(dtype).view(shape)
+
+    def intact(self):
+        lo, hi = self.raw[:self.GUARD], self.raw[self.GUARD + self.n:]
+        return bool((lo == self.fill).all()) and bool((hi == self.fill).all())
+
+
+@pytest.mark.parametrize("n,nc,B,lines", [(256, 4, 5, 11), (512, 3, 3, 21), (128, 4, 6, 9), (64, 2, 3, 5)])
+def test_no_kernel_writes_outside_its_buffers_sense(n, nc, B, lines):
+    """Plan (pruned) SENSE kernels and the fused step: output, scratch and state sit between guard bands."""
+    L = _lib()
+    lib = L.lib()
+    g = torch.Generator().manual_seed(n + lines)
+    m8h = _sparse_mask(g, 1, n, lines).reshape(1, n).to(torch.uint8).contiguous()
+    plan = L.SensePlan(m8h.numpy(), n, n)
+    maps = (torch.rand(nc, n, n, generator=g) + 0.2).to(DEV)
+    x = crandn(n, B, 1, n, n).to(DEV)
+    ws_bytes = lib.ipdm_sense_workspace_bytes(nc, B, n, n)
+    gws, gS, gout, gx = _Guarded(ws_bytes), _Guarded(nc * B * n * n * 8), _Guarded(B * n * n * 8), _Guarded(2 * B * n * n * 4)
+    ws, S = gws.view(torch.uint8, (ws_bytes,)), gS.view(torch.complex64, (nc, B, 1, n, n))
+    out, st = gout.view(torch.complex64, (B, 1, n, n)), gx.view(torch.float32, (2, B, n, n))
+    L.check(lib.ipdm_sense_forward_plan(plan.handle, x.data_ptr(), maps.data_ptr(), None, S.data_ptr(), nc, B, ws.data_ptr(), L.stream()), "fwd")
+    L.check(lib.ipdm_sense_adjoint_plan(plan.handle, S.data_ptr(), maps.data_ptr(), None, out.data_ptr(), nc, B, 0, ws.data_ptr(), L.stream()), "adj")
+    L.check(lib.ipdm_sense_adjoint_plan(plan.handle, S.data_ptr(), None, None, out.data_ptr(), nc, B, 1, ws.data_ptr(), L.stream()), "ssos")
+    st.copy_(torch.randn(2, B, n, n, generator=g))
+    grad, bvec = torch.randn(2, B, n, n, generator=g).to(DEV), torch.randn(2, B, n, n, generator=g).to(DEV)
+    sc = L.AldScalars(0.1, 0.4, 0.01, 1.0)
+    L.check(lib.ipdm_ald_sense_step_plan(plan.handle, st.data_ptr(), grad.data_ptr(), None, bvec.data_ptr(), maps.data_ptr(), None, nc, B, n,
+                                         sc, None, None, L.rng(7, 0), L.stream()), "step")
+    torch.cuda.synchronize()
+    assert plan.pruned == (n >= 128) and bool(torch.isfinite(st).all())      # W = 64: general kernels behind the same entry points
+    for name, gb in (("workspace", gws), ("k-space", gS), ("image", gout), ("state", gx)):
+        assert gb.intact(), f"{name}: guard band overwritten"
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,pool", [(2, 40, 24, 128, 128, 0), (1, 64, 64, 128, 256, 1), (3, 32, 32, 256, 128, 0), (2, 24, 40, 128, 128, 0)])
+def test_no_kernel_writes_outside_its_buffers_stream(N, H, W, Cin, Cout, pool):
+    """16-bit-stream convolution (f16 residual in, f16 result + f16 ELU copy out, optionally 2x2-pooled), norm-apply and
+    bilinear kernels: every output between guard bands, images that do not fill whole pixel tiles included."""
+    import ctypes
+    L = _lib()
+    lib = L.lib()
+    g = torch.Generator().manual_seed(H * 7 + W + Cout)
+    x16 = torch.randn(N, H, W, Cin, generator=g).half().to(DEV)
+    w16 = (torch.randn(Cout, 9, Cin, generator=g) / (9 * Cin) ** 0.5).half().to(DEV)
+    Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+    nout = N * Ho * Wo * Cout
+    res16 = torch.randn(N, Ho, Wo, Cout, generator=g).half().to(DEV)
+    graw, gelu, gst = _Guarded(nout * 2), _Guarded(nout * 2), _Guarded(N * Cout * 2 * 8, fill=0)
+    raw, elu = graw.view(torch.float16, (N, Ho, Wo, Cout)), gelu.view(torch.float16, (N, Ho, Wo, Cout))
+    stats = gst.view(torch.float64, (N, Cout, 2))
+    d = L.ConvDesc(x16.data_ptr(), w16.data_ptr(), None, None, None, elu.data_ptr(), stats.data_ptr(), N, H, W, Cin, Cout, 9, 1,
+                   L.CONV_F16_ELU | (L.CONV_POOL2 if pool else 0), 0, 0, res16.data_ptr(), raw.data_ptr())
+    L.check(lib.ipdm_conv_igemm(ctypes.byref(d), L.stream()), "igemm t16")
+    # norm-apply on the f16 stream and the f16 bilinear accumulate, into guarded outputs as well
+    gop = _Guarded(nout * 2)
+    op = gop.view(torch.float16, (N, Ho, Wo, Cout))
+    alpha, gamma, beta = (torch.randn(Cout, generator=g).to(DEV) for _ in range(3))
+    L.check(lib.ipdm_instnorm_apply_elu_f16in(raw.data_ptr(), stats.data_ptr(), 0, alpha.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                              op.data_ptr(), N, Ho * Wo, Cout, L.stream()), "norm f16in")
+    src = torch.randn(N, max(Ho // 2, 1), max(Wo // 2, 1), Cout, generator=g).half().to(DEV)
+    L.check(lib.ipdm_bilinear_add_f16(src.data_ptr(), raw.data_ptr(), elu.data_ptr(), N, src.shape[1], src.shape[2], Ho, Wo, Cout, 1, L.stream()), "bilinear f16")
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(raw.float()).all()) and bool(torch.isfinite(op.float()).all())
+    for name, gb in (("raw stream", graw), ("ELU copy", gelu), ("norm sums", gst), ("operand", gop)):
+        assert gb.intact(), f"{name}: guard band overwritten"
+
+
 def test_first_forward_refuses_clipped_activations(monkeypatch):
     """Range safety by default: the first forward with a set of weights audits its f16 buffers and raises when anything was
     clipped (there is no wider operand path to fall back to); IPDM_ALLOW_F16_SATURATION=1 lets it run (finite, clipped)."""
