@@ -213,6 +213,13 @@ typedef struct {
    * pair; the flags keep their meaning (IPDM_CONV_POOL2 shapes, IPDM_CONV_RES_ELU, IPDM_CONV_F16_PRE_RES). */
   const void* residual_f16;
   void* out_raw_f16;
+  /* Operand exponent shift (block floating point per tensor; 0 is read as 1): the accumulator is multiplied by acc_scale
+   * before bias / residual (= 1 / scale of the input operand), the f16 operand output by out_f16_scale after its ELU.
+   * With power-of-two scales this is exact; the score network uses it to keep the operands of its un-normalised decoder
+   * inside the f16 range when an activation would otherwise be clipped.  Scales of 1 cost nothing: the
+   * straight-line epilogue paths are taken as before. */
+  float acc_scale;
+  float out_f16_scale;
 } ipdm_conv_desc;
 
 #define IPDM_CONV_F16_ELU 1       /* out_f16 = f16(ELU(v)) instead of f16(v)                               */
@@ -268,6 +275,8 @@ int ipdm_conv_first_f16out(const float* x, const float* w, const float* bias, vo
                            int W, int Cout, int affine, void* stream);
 int ipdm_instnorm_apply_elu_f16in(const void* x_f16, const double* stats, int stats_pivoted, const float* alpha,
                                   const float* gamma, const float* beta, void* out_f16, int N, int HW, int C, void* stream);
+/* out_f16[i] = f16(scale * (elu ? ELU(x[i]) : x[i])): the cast of ipdm_act_to_f16 with an operand exponent shift. */
+int ipdm_act_to_f16_scaled(const float* x, void* out_f16, size_t n, int elu, float scale, void* stream);
 int ipdm_bilinear_add_f16(const void* src_f16, void* dst_f16, void* out_elu_f16, int N, int h, int w, int H, int W, int C,
                           int accumulate, void* stream);
 

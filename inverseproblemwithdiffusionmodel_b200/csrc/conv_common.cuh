@@ -19,6 +19,7 @@ struct IgemmParams {
   int N, H, W, Cin, Cout, taps, dilation, flags;
   int tiles_w, tiles_h;
   int slices, slice_shift;   // volumes of `slices` consecutive images; input slice = output slice + slice_shift
+  float acc_scale, out16_scale;   // operand exponent shift (1 = off): accumulator * acc_scale, f16 operand output * out16_scale
 };
 
 int get_weight_map(const void* w, int Cout, int K, CUtensorMap* out);
@@ -154,7 +155,9 @@ __device__ __forceinline__ void conv_epilogue_chunks(const IgemmParams& p, uint3
     for (int i = 0; i < NPX; ++i) {
       if (inside(i, rows_left)) {
         float4 a = make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
-        if (!LEAN) { a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w; }
+        if (!LEAN) {
+          a.x = a.x * p.acc_scale + bias4.x; a.y = a.y * p.acc_scale + bias4.y; a.z = a.z * p.acc_scale + bias4.z; a.w = a.w * p.acc_scale + bias4.w;
+        }
         const float4 pre = a;
         if (kRes) {
           float4 r = ResElem<T16>::to_f32(rcur[i]);
@@ -174,6 +177,7 @@ __device__ __forceinline__ void conv_epilogue_chunks(const IgemmParams& p, uint3
         if (kOut16) {
           float4 h = (kRes && f16_pre) ? pre : a;
           if (f16_elu) { h.x = elu_fast(h.x); h.y = elu_fast(h.y); h.z = elu_fast(h.z); h.w = elu_fast(h.w); }
+          if (!LEAN) { h.x *= p.out16_scale; h.y *= p.out16_scale; h.z *= p.out16_scale; h.w *= p.out16_scale; }
           uint2 pk;
           pk.x = pack_half2_sat(h.x, h.y);
           pk.y = pack_half2_sat(h.z, h.w);
@@ -217,7 +221,7 @@ __device__ __forceinline__ void conv_epilogue_shfl(const IgemmParams& p, uint32_
   const int Ho = pool ? p.H / 2 : p.H, Wo = pool ? p.W / 2 : p.W;
   const int oy0 = pool ? h0 / 2 : h0, ox0 = pool ? w0 / 2 : w0;
   // warp-uniform: the chunks [chunk0, chunk0 + NCHUNK) of this item lie inside the image and nothing optional is asked for
-  const bool lean = p.bias == nullptr && p.stats == nullptr && (p.flags & IPDM_CONV_RES_ELU) == 0 &&
+  const bool lean = p.bias == nullptr && p.stats == nullptr && (p.flags & IPDM_CONV_RES_ELU) == 0 && p.acc_scale == 1.f && p.out16_scale == 1.f &&
                     oy0 + (chunk0 + NCHUNK) * OROWS <= Ho && ox0 + OW <= Wo;
   const bool elu = (p.flags & IPDM_CONV_F16_ELU) != 0, pre = kRes && (p.flags & IPDM_CONV_F16_PRE_RES) != 0;
   if (lean && (!kOut16 || (elu && !pre)))

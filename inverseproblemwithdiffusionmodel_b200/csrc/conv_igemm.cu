@@ -246,6 +246,8 @@ extern "C" int ipdm_conv_igemm(const ipdm_conv_desc* dh, void* stream) {
   p.bias = d.bias; p.out_f16 = reinterpret_cast<__half*>(d.out_f16);
   p.residual = t16 ? reinterpret_cast<const float*>(d.residual_f16) : d.residual;
   p.out_f32 = t16 ? reinterpret_cast<float*>(d.out_raw_f16) : d.out_f32;
+  p.acc_scale = d.acc_scale != 0.f ? d.acc_scale : 1.f;
+  p.out16_scale = d.out_f16_scale != 0.f ? d.out_f16_scale : 1.f;
   p.stats = d.stats;
   p.N = d.N; p.H = d.H; p.W = d.W; p.Cin = d.Cin; p.Cout = d.Cout; p.taps = d.taps; p.dilation = d.dilation; p.flags = d.flags;
   p.tiles_w = (d.W + TILE_W - 1) / TILE_W;

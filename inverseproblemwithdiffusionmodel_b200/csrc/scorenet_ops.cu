@@ -433,6 +433,17 @@ __global__ void k_act_to_f16(const float* __restrict__ x, __half* __restrict__ o
   }
 }
 
+__global__ void k_act_to_f16_scaled(const float* __restrict__ x, __half* __restrict__ out, size_t n4, int elu, float scale) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(x)[i];
+    if (elu) { v.x = elu_f16bound(v.x); v.y = elu_f16bound(v.y); v.z = elu_f16bound(v.z); v.w = elu_f16bound(v.w); }
+    uint2 pk;
+    pk.x = pack_half2_sat(v.x * scale, v.y * scale);
+    pk.y = pack_half2_sat(v.z * scale, v.w * scale);
+    reinterpret_cast<uint2*>(out)[i] = pk;
+  }
+}
+
 #ifndef IPDM_MAXPOOL_NC
 #define IPDM_MAXPOOL_NC 2
 #endif
@@ -733,7 +744,7 @@ __global__ void k_conv_direct(ipdm_conv_desc d) {
     } else {
       acc = conv_at(d, n, y, x, co);
     }
-    float v = acc + (d.bias ? d.bias[co] : 0.f);
+    float v = acc * (d.acc_scale != 0.f ? d.acc_scale : 1.f) + (d.bias ? d.bias[co] : 0.f);
     const float pre = v;
     if (d.residual) {
       float r = d.residual[i];
@@ -744,6 +755,7 @@ __global__ void k_conv_direct(ipdm_conv_desc d) {
     if (d.out_f16) {
       float s = (d.flags & IPDM_CONV_F16_PRE_RES) ? pre : v;
       if (d.flags & IPDM_CONV_F16_ELU) s = elu1(s);
+      s *= d.out_f16_scale != 0.f ? d.out_f16_scale : 1.f;
       reinterpret_cast<__half*>(d.out_f16)[i] = __float2half_rn(fminf(fmaxf(s, -65504.f), 65504.f));
     }
   }
@@ -867,6 +879,14 @@ extern "C" int ipdm_act_to_f16(const float* x, void* out_f16, size_t n, int elu,
   IPDM_REQUIRE(n % 4 == 0, IPDM_E_BADARG, "act_to_f16: n must be a multiple of 4");
   k_act_to_f16<<<grid1d(n / 4, 256), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<__half*>(out_f16), n / 4, elu);
   return launched("k_act_to_f16");
+}
+
+extern "C" int ipdm_act_to_f16_scaled(const float* x, void* out_f16, size_t n, int elu, float scale, void* stream) {
+  IPDM_REQUIRE(x && out_f16, IPDM_E_BADARG, "act_to_f16_scaled: null pointer");
+  IPDM_REQUIRE(n % 4 == 0, IPDM_E_BADARG, "act_to_f16_scaled: n must be a multiple of 4");
+  IPDM_REQUIRE(scale > 0.f, IPDM_E_BADARG, "act_to_f16_scaled: scale must be positive");
+  k_act_to_f16_scaled<<<grid1d(n / 4, 256), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<__half*>(out_f16), n / 4, elu, scale);
+  return launched("k_act_to_f16_scaled");
 }
 
 extern "C" int ipdm_maxpool5_f16(const void* in_f16, void* out_f16, int N, int H, int W, int C, void* stream) {

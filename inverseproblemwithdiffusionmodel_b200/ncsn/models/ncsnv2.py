@@ -157,6 +157,25 @@ class _Plan:
         inner = [m for name, m in net.named_modules() if isinstance(m, nn.Conv2d) and name not in ("begin_conv", "end_conv")]
         self.t16 = (len(inner) > 0 and all(m.in_channels % 64 == 0 and m.out_channels % 128 == 0 for m in inner)
                     and os.environ.get("IPDM_STREAM_F32") is None)      # (the 3-D network's plan keeps the fp32 stream)
+        # Operand exponent shift (block floating point per tensor): f16 operands that do not come out of an InstanceNorm++
+        # are stored as 2^-shift * value and the consuming convolution multiplies its accumulator by 2^shift -- exact, and
+        # it moves the end of the f16 range from 6.5e4 to 6.5e4 * 2^shift.  0 unless the first-forward audit finds clipped
+        # activations (`_auto_audit`), or IPDM_OPERAND_SHIFT says so; a shift > 0 also keeps the residual stream in fp32.
+        self.shift = 0
+        self.scale_of = {}       # data_ptr of an f16 operand tensor -> its scale (absent: 1)
+        if os.environ.get("IPDM_OPERAND_SHIFT"):
+            self.set_shift(int(os.environ["IPDM_OPERAND_SHIFT"]))
+
+    def set_shift(self, shift):
+        self.shift = int(shift)
+        if self.shift > 0:
+            self.t16 = False
+        self.bufs.clear()
+        self.scale_of.clear()
+
+    @property
+    def oscale(self):
+        return 2.0 ** (-self.shift)
 
     # ---- storage ------------------------------------------------------------------------------
     def buf(self, name, shape, dtype):
@@ -220,6 +239,11 @@ class _Plan:
         else:
             d = ConvDesc(_lib.ptr(x16), w16.data_ptr(), _lib.ptr(bias), _lib.ptr(residual), _lib.ptr(out32), _lib.ptr(out16),
                          _lib.ptr(stats), N, H, W, Cin, Cout, taps, dilation, flags)
+        if self.shift:   # operand exponent shift: undo the input operand's scale on the accumulator, scale the operand output
+            d.acc_scale = 1.0 / self.scale_of.get(x16.data_ptr(), 1.0)
+            if out16 is not None:
+                d.out_f16_scale = self.oscale
+                self.scale_of[out16.data_ptr()] = self.oscale
         if Cin % 64 == 0 and Cout % 128 == 0:
             _lib.check(self.L.ipdm_conv_igemm(ctypes.byref(d), _lib.stream()), "conv_igemm " + wname)
         else:
@@ -232,10 +256,17 @@ class _Plan:
                       _lib.ptr(beta), out16.data_ptr(), N, HW, C, _lib.stream()), "instnorm " + nname)
 
     def to_f16(self, x32, out16, elu):
+        if self.shift:
+            _lib.check(self.L.ipdm_act_to_f16_scaled(x32.data_ptr(), out16.data_ptr(), x32.numel(), 1 if elu else 0, self.oscale, _lib.stream()),
+                       "act_to_f16_scaled")
+            self.scale_of[out16.data_ptr()] = self.oscale
+            return
         _lib.check(self.L.ipdm_act_to_f16(x32.data_ptr(), out16.data_ptr(), x32.numel(), 1 if elu else 0, _lib.stream()), "act_to_f16")
 
     def maxpool(self, x16, out16, N, H, W, C):
         _lib.check(self.L.ipdm_maxpool5_f16(x16.data_ptr(), out16.data_ptr(), N, H, W, C, _lib.stream()), "maxpool5")
+        if self.shift:   # max commutes with a positive scale
+            self.scale_of[out16.data_ptr()] = self.scale_of.get(x16.data_ptr(), 1.0)
 
     # ---- blocks -------------------------------------------------------------------------------------
     def residual_block(self, name, blk, x32, stats_x, H, W, elu16=None):
@@ -335,7 +366,11 @@ class _Plan:
                 low = self.f32(name + ".low", N, hb, wb, F)
                 self.conv(f"{name}.msf.convs.1", b16, (N, hb, wb, Cb, F), out32=low)
                 fn = self.L.ipdm_bilinear_add_f16 if self.t16 else self.L.ipdm_bilinear_add
-                _lib.check(fn(low.data_ptr(), sums.data_ptr(), e16.data_ptr(), N, hb, wb, H, W, F, 1, _lib.stream()), "bilinear_add")
+                if self.shift:   # the kernel's own f16(ELU) copy is unscaled: make the operand with the scaled cast instead
+                    _lib.check(fn(low.data_ptr(), sums.data_ptr(), None, N, hb, wb, H, W, F, 1, _lib.stream()), "bilinear_add")
+                    self.to_f16(sums, e16, elu=True)
+                else:
+                    _lib.check(fn(low.data_ptr(), sums.data_ptr(), e16.data_ptr(), N, hb, wb, H, W, F, 1, _lib.stream()), "bilinear_add")
             h32 = sums
         else:
             h32, e16 = hs[0][0], hs[0][1]
@@ -405,25 +440,35 @@ class _Plan:
         dots = self.buf("final.dots", (N, H, W, 9), torch.float32)
         _lib.check(self.L.ipdm_conv_last(a16.data_ptr(), we.data_ptr(), _lib.ptr(be), self.sigmas.data_ptr(), labels.data_ptr(),
                                          out.data_ptr(), dots.data_ptr(), N, H, W, ngf, s), "conv_last")
-        self._auto_audit()
+        self._auto_audit(x, labels, out)
 
-    def _auto_audit(self):
+    MAX_SHIFT = 18
+
+    def _auto_audit(self, x, labels, out):
         """Once per set of weights (the first forward after they changed -- in the samplers that is the largest noise level,
-        the largest activations): refuse to go on when an activation was clipped to the end of the f16 range.  There is no
-        wider operand path to fall back to, so a silent clip would be a silent wrong score.  Skipped inside a
-        stream capture (the samplers run one eager step first) and with IPDM_ALLOW_F16_SATURATION=1."""
+        the largest activations): if an activation was clipped at the end of the f16 range, raise the operand exponent
+        shift by 6 (x64 range; the residual stream goes to fp32), run the forward again and look again; give up with an
+        error at 2^18.  Skipped inside a stream capture (the samplers run one eager step first);
+        IPDM_ALLOW_F16_SATURATION=1 keeps the clipped result instead."""
         if self._audited == self.version or (torch.device(self.device).type == 'cuda' and torch.cuda.is_current_stream_capturing()):
             return
         self._audited = self.version
         if os.environ.get("IPDM_ALLOW_F16_SATURATION"):
             return
         worst = [(name, m, k) for name, (m, k) in self.range_audit().items() if k > 0]
-        if worst:
-            name, m, k = worst[0]
-            raise _lib.IpdmError(f"f16 range: {sum(w[2] for w in worst)} activation values were clipped at +-65504 in the first forward with "
-                                 f"these weights (worst buffer '{name}': max |x| = {m:.3g}, {k} values).  The tensor-core path keeps "
-                                 "convolution operands in f16; this checkpoint needs a wider operand type than this library has.  "
-                                 "Set IPDM_ALLOW_F16_SATURATION=1 to run anyway (clipped values, never inf / NaN).")
+        if not worst:
+            return
+        name, m, k = worst[0]
+        what = (f"{sum(w[2] for w in worst)} activation values were clipped at +-65504 in the first forward with these weights "
+                f"(worst buffer '{name}', {k} values, operand shift {self.shift})")
+        if self.shift >= self.MAX_SHIFT:
+            raise _lib.IpdmError("f16 range: " + what + f"; still clipped at the largest operand shift (2^{self.MAX_SHIFT})")
+        import warnings
+        warnings.warn("f16 range: " + what + f": re-running with operand exponent shift {self.shift + 6} and an fp32 residual stream "
+                      "(DESIGN 2; slower: the straight-line epilogue paths need unscaled operands)")
+        self.set_shift(self.shift + 6)
+        self._audited = None
+        self.run(x, labels, out)
 
 
 class _ScoreNetBase(nn.Module):

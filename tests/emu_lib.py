@@ -284,6 +284,8 @@ class EmuLib:
             v = (((v[:, :, ::2, ::2] + v[:, :, 1::2, ::2]) + v[:, :, ::2, 1::2]) + v[:, :, 1::2, 1::2]) * 0.25
         Ho, Wo = v.shape[2:]
         v = v.permute(0, 2, 3, 1)
+        if getattr(d, "acc_scale", 0.0):
+            v = v * d.acc_scale
         if d.bias:
             v = v + _t(d.bias, (Cout,), np.float32)
         pre = v
@@ -298,7 +300,9 @@ class EmuLib:
             s = pre if d.flags & 2 else v
             if d.flags & 1:
                 s = F.elu(s)
-            _t(d.out_f16, (N, Ho, Wo, Cout), np.float16).copy_(s.half())
+            if getattr(d, "out_f16_scale", 0.0):
+                s = s * d.out_f16_scale
+            _t(d.out_f16, (N, Ho, Wo, Cout), np.float16).copy_(s.clamp(-65504.0, 65504.0).half())
         if d.stats:
             st = _t(d.stats, (N // X, Cout, 2), np.float64)
             flat = v.reshape(N // X, -1, Cout)
@@ -444,6 +448,12 @@ class EmuLib:
         self.launches += 1
         X = _t(x, (n,), np.float32)
         _t(out16, (n,), np.float16).copy_((F.elu(X) if elu else X).half())
+        return 0
+
+    def ipdm_act_to_f16_scaled(self, x, out16, n, elu, scale, stream):
+        self.launches += 1
+        X = _t(x, (n,), np.float32)
+        _t(out16, (n,), np.float16).copy_(((F.elu(X) if elu else X) * scale).clamp(-65504.0, 65504.0).half())
         return 0
 
     def ipdm_debug_option(self, key, value):

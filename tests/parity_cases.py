@@ -184,6 +184,48 @@ def case_scorenet_small(dev):
     assert torch.equal(a, b)
 
 
+def case_operand_shift(dev):
+    """Operand exponent shift: (a) forced by IPDM_OPERAND_SHIFT it changes nothing beyond f16 rounding of shifted
+    values -- same golden score; (b) an input whose activations leave the f16 range makes the first forward escalate by itself
+    (warning), and the result then agrees with the fp32 oracle, while the clipped run (IPDM_ALLOW_F16_SATURATION) does not."""
+    import os, warnings
+    g = G("scorenet")
+    cfg = make_config("ACDC", 8, 32, 12, 30.0)
+    x, y = (rrand(1301, 2, 1, 32, 32) * 3 - 1).to(dev), torch.tensor([0, 7]).to(dev)
+    os.environ["IPDM_OPERAND_SHIFT"] = "6"
+    try:
+        net, _ = build_net(NCSNv2Deepest, "NCSNv2Deepest_ngf8", 1, cfg, dev)
+        out = net(x, y)
+        plan = next(iter(net._plans.values()))
+        assert plan.shift == 6 and not plan.t16
+    finally:
+        del os.environ["IPDM_OPERAND_SHIFT"]
+    assert rel_l2(out.cpu(), g["deepest_out"]) < TOL_SCORE
+    # (b) |x| ~ 3e5: the un-normalised decoder leaves the f16 range
+    big = (rrandn(78, 2, 1, 32, 32) * 3e5)
+    net, Pd = build_net(NCSNv2Deepest, "NCSNv2Deepest_ngf8", 1, cfg, dev)
+    with torch.no_grad():
+        ref = SN.score_forward("NCSNv2Deepest", Pd, big, y.cpu())
+    with warnings.catch_warnings(record=True) as wlist:
+        warnings.simplefilter("always")
+        out = net(big.to(dev), y)
+    plan = next(iter(net._plans.values()))
+    assert plan.shift >= 6 and any("operand exponent shift" in str(w.message) for w in wlist), plan.shift
+    e_shift = rel_l2(out.cpu(), ref)
+    os.environ["IPDM_ALLOW_F16_SATURATION"] = "1"
+    try:
+        net2, _ = build_net(NCSNv2Deepest, "NCSNv2Deepest_ngf8", 1, cfg, dev)
+        clipped = net2(big.to(dev), y)
+    finally:
+        del os.environ["IPDM_ALLOW_F16_SATURATION"]
+    e_clip = rel_l2(clipped.cpu(), ref)
+    print(f"operand shift {plan.shift}: rel-L2 vs fp32 oracle {e_shift:.2e}; clipped run {e_clip:.2e}")
+    assert bool(torch.isfinite(out).all())
+    if str(dev) != "cpu":      # the kernels saturate (finite); the CPU emulator's casts go to inf
+        assert bool(torch.isfinite(clipped).all())
+    assert e_shift < 5e-3 and not (e_clip <= 10 * e_shift), (e_shift, e_clip)
+
+
 def case_ncsn3d_shallow(dev):
     """NCSN3DShallow (the learned temporal prior) at full width against the reference's output:
     5-D and flattened inputs, state-dict layout, and the f16-operand emulation of the oracle for the tight bound."""

@@ -640,19 +640,43 @@ def test_no_kernel_writes_outside_its_buffers_stream(N, H, W, Cin, Cout, pool):
         assert gb.intact(), f"{name}: guard band overwritten"
 
 
-def test_first_forward_refuses_clipped_activations(monkeypatch):
-    """Range safety by default: the first forward with a set of weights audits its f16 buffers and raises when anything was
-    clipped (there is no wider operand path to fall back to); IPDM_ALLOW_F16_SATURATION=1 lets it run (finite, clipped)."""
-    from inverseproblemwithdiffusionmodel_b200._lib import IpdmError
+def test_operand_shift_narrow_net():
+    """Range safety: forced shift == golden score; clipped activations make the first forward escalate by itself (CUDA-core convs)."""
+    C.case_operand_shift(DEV)
+
+
+def test_operand_shift_tensor_core_path(monkeypatch):
+    """The same on the tensor-core kernels (ngf 128): an input at |x| ~ 3e5 drives the un-normalised decoder past 65504; the first
+    forward notices, moves to operand shift >= 6 + fp32 stream and then agrees with the fp32 oracle at the usual f16-operand
+    level, while the clipped run (IPDM_ALLOW_F16_SATURATION=1) is finite but far off.  A forced shift on an ordinary input
+    gives the unshifted score up to rounding."""
+    import warnings
     y = torch.tensor([0, 9], device=DEV)
-    big = (rrandn(78, 2, 1, 32, 32) * 3e5).to(DEV)
+    big = rrandn(78, 2, 1, 32, 32) * 3e5
     net, Pd, cfg = _full_width_net(C.NCSNv2Deepest, "NCSNv2Deepest", 32, 21)
-    with pytest.raises(IpdmError, match="f16 range"):
-        net(big, y)
-    assert bool(torch.isfinite(net((rrand(77, 2, 1, 32, 32) * 2 - 0.5).to(DEV), y)).all())     # the same net stays usable
-    net2, _, _ = _full_width_net(C.NCSNv2Deepest, "NCSNv2Deepest", 32, 21)
+    with torch.no_grad():
+        ref = SN.score_forward("NCSNv2Deepest", Pd, big, y.cpu())
+    with warnings.catch_warnings(record=True) as wlist:
+        warnings.simplefilter("always")
+        out = net(big.to(DEV), y)
+    plan = next(iter(net._plans.values()))
+    assert plan.shift >= 6 and not plan.t16 and any("operand exponent shift" in str(w.message) for w in wlist)
+    assert net.range_audit()["saturated_total"] == 0
+    e_shift = rel_l2(out.cpu(), ref)
+    ordinary = (rrand(77, 2, 1, 32, 32) * 2 - 0.5)
+    with torch.no_grad():
+        ref_o = SN.score_forward("NCSNv2Deepest", Pd, ordinary, y.cpu())
+    e_ord_shifted = rel_l2(net(ordinary.to(DEV), y).cpu(), ref_o)          # the plan stays shifted: still the right score
+    net0, _, _ = _full_width_net(C.NCSNv2Deepest, "NCSNv2Deepest", 32, 21)
+    e_ord = rel_l2(net0(ordinary.to(DEV), y).cpu(), ref_o)
     monkeypatch.setenv("IPDM_ALLOW_F16_SATURATION", "1")
-    assert bool(torch.isfinite(net2(big, y)).all())
+    net2, _, _ = _full_width_net(C.NCSNv2Deepest, "NCSNv2Deepest", 32, 21)
+    clipped = net2(big.to(DEV), y)
+    e_clip = rel_l2(clipped.cpu(), ref)
+    print(f"shift {plan.shift}: big input {e_shift:.2e} (clipped run {e_clip:.2e}); ordinary input {e_ord_shifted:.2e} shifted vs {e_ord:.2e} unshifted")
+    assert bool(torch.isfinite(out).all()) and bool(torch.isfinite(clipped).all())
+    assert e_shift < 5e-3 and e_clip > 10 * e_shift
+    assert e_ord < C.TOL_SCORE and e_ord_shifted < 2 * C.TOL_SCORE
 
 
 def test_single_ald_step_ngf128():

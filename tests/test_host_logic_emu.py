@@ -33,6 +33,11 @@ def test_scorenet_small(emu):
     C.case_scorenet_small("cpu")
 
 
+def test_operand_shift_host_logic(emu):
+    """the plan's scale bookkeeping (which operand carries which power of two) and the self-escalating first forward"""
+    C.case_operand_shift("cpu")
+
+
 def test_ncsn3d_shallow_host_logic(emu):
     """kernel sequence of the 3-D temporal prior (slice-shifted conv launches, gathers, pools) against the reference output"""
     C.case_ncsn3d_shallow("cpu")
