@@ -1,7 +1,9 @@
 #!/bin/bash
-# ncu --set full of every SENSE kernel at one sweep point (second repetition = warm)
-mkdir -p gpurun_out
-ARGS="${POINT:-4 256 64 40}"
-python tools/prof_sense.py $ARGS > gpurun_out/ps.log 2>&1 || { cat gpurun_out/ps.log; exit 1; }
-ncu --set full --clock-control none --import-source on -k regex:'k2_|k_fwd|k_adj|k_ald' --launch-skip 7 -c 7 -f -o gpurun_out/prof_sense python tools/prof_sense.py $ARGS > gpurun_out/ncu_ps.log 2>&1
-echo "ncu rc=$?"; tail -3 gpurun_out/ncu_ps.log
+# ncu --set full of the plan (pruned) SENSE kernels at two sweep points, second repetition
+O=gpurun_out; mkdir -p $O
+for P in "32 512 64 40:big" "4 256 64 40:small"; do
+  ARGS=${P%%:*}; TAG=${P##*:}
+  python tools/prof_sense.py $ARGS > $O/ps.log 2>&1 || { cat $O/ps.log; exit 1; }
+  ncu --set full --clock-control none --import-source on -k regex:'kp_' --launch-skip 5 -c 5 -f -o $O/r2_sense_${TAG}_k python tools/prof_sense.py $ARGS > $O/ncu_ps_$TAG.log 2>&1
+  echo "$TAG ncu rc=$?"
+done

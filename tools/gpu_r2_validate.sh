@@ -20,7 +20,7 @@ ncu --set full --clock-control none --import-source on -k regex:k_conv_halo -s 2
 python tools/ncu_summary.py $O/r2_conv_t16.ncu-rep > $O/r02_ncu_conv_halo_t16_mode.txt 2>&1
 python tools/ncu_table.py $O/r2_conv_t16.ncu-rep "" --json $O/r02_ncu_conv_dominant.json 28 256 > /dev/null 2>&1
 rm -f $O/r2_conv_t16.ncu-rep
-bash tools/gpu_prof_sense2.sh
+bash tools/gpu_prof_sense.sh
 for t in big small; do
   { python tools/ncu_table.py $O/r2_sense_${t}_k.ncu-rep; for i in 0 1 2 3 4; do echo; python tools/ncu_stalls.py $O/r2_sense_${t}_k.ncu-rep $i 12; done; } > $O/r02_ncu_sense_$t.txt 2>&1
   rm -f $O/r2_sense_${t}_k.ncu-rep
