@@ -9,6 +9,7 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint32, c_uint64, c_ulonglong, c_void_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+ABI_VERSION = 3     # what this binding was written against (include/ipdm_b200.h); lib() refuses another library
 LIB_PATH = os.environ.get("IPDM_B200_LIB") or os.path.join(_HERE, "libipdm_b200.so")   # override: A/B builds of the same ABI
 
 
@@ -114,6 +115,9 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
+        got = handle.ipdm_abi_version()
+        if got != ABI_VERSION:
+            raise IpdmError(f"{LIB_PATH} has ABI version {got}, this binding needs {ABI_VERSION}: rebuild the library (csrc/build.sh)")
         _lib = handle
     return _lib
 

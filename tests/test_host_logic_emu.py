@@ -92,8 +92,19 @@ def test_library_exports_every_declared_symbol():
     handle = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(handle, name), name
-    assert _lib.lib().ipdm_abi_version() == 3
+    import re
+    header = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "ipdm_b200.h")).read()
+    declared_version = int(re.search(r"ipdm_abi_version\(void\);\s*/\*\s*(\d+)\s*\*/", header).group(1))
+    assert _lib.lib().ipdm_abi_version() == _lib.ABI_VERSION == declared_version == 3     # header, binding and library agree
     assert _lib.lib().ipdm_sense_workspace_bytes(4, 2, 256, 256) == 4 * 2 * 256 * 256 * 8
+
+
+def test_graft_entry_build_check_agrees_with_the_binding():
+    """__graft_entry__.build() ends with an ABI check: it must compare against the binding's version, not a literal."""
+    import inspect
+    import __graft_entry__
+    src = inspect.getsource(__graft_entry__.build)
+    assert "_lib.ABI_VERSION" in src
 
 
 def test_noise_uniform_conversion_stays_inside_the_open_interval():
