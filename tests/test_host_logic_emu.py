@@ -92,7 +92,6 @@ def test_library_exports_every_declared_symbol():
     handle = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(handle, name), name
-    import re
     header = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "ipdm_b200.h")).read()
     declared_version = int(re.search(r"ipdm_abi_version\(void\);\s*/\*\s*(\d+)\s*\*/", header).group(1))
     assert _lib.lib().ipdm_abi_version() == _lib.ABI_VERSION == declared_version == 3     # header, binding and library agree
