@@ -1046,6 +1046,20 @@ extern "C" int ipdm_chain_stats_accumulate(const void* x, double* acc, int chain
 }
 
 // ---- plans ------------------------------------------------------------------------------------------------------
+// Releases whatever a (possibly half-built) plan owns; every member is zero until it has been created.
+static void plan_release(SensePlan* pl) {
+  if (pl == nullptr) return;
+  pl->magic = 0;
+  if (pl->buf) cudaFree(pl->buf);
+  if (pl->side) cudaStreamDestroy(pl->side);
+  if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
+  if (pl->ev_join) cudaEventDestroy(pl->ev_join);
+  for (int i = 0; i < PLAN_SPLIT_MAX; ++i)
+    if (pl->ev_part[i]) cudaEventDestroy(pl->ev_part[i]);
+  delete pl->mu;
+  delete pl;
+}
+
 extern "C" int ipdm_sense_plan_create(const uint8_t* mask_host, int mask_frames, int H, int W, void** plan_out) {
   IPDM_REQUIRE(mask_host && plan_out && mask_frames >= 1, IPDM_E_BADARG, "sense_plan_create: bad argument");
   IPDM_REQUIRE(pow2_ok(W) && H >= 1, IPDM_E_UNSUPPORTED, "sense_plan_create: W=%d must be a power of two in [8,512]", W);
@@ -1062,7 +1076,7 @@ extern "C" int ipdm_sense_plan_create(const uint8_t* mask_host, int mask_frames,
   pl->nchunks_max = ph.nchunks_max;
   if (pl->nout > 2) { pl->pruned_rows = pl->pruned_2d = false; }
   cudaError_t ce = cudaGetDevice(&pl->device);
-  if (ce != cudaSuccess) { delete pl; set_error("sense_plan_create: %s", cudaGetErrorString(ce)); return (int)ce; }
+  if (ce != cudaSuccess) { plan_release(pl); set_error("sense_plan_create: %s", cudaGetErrorString(ce)); return (int)ce; }
   std::vector<float> tws;
   if (pl->pruned_2d) {
     switch (H) {
@@ -1114,15 +1128,14 @@ extern "C" int ipdm_sense_plan_create(const uint8_t* mask_host, int mask_frames,
   if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming);
   if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming);
   for (int i = 0; i < PLAN_SPLIT_MAX && ce == cudaSuccess; ++i) ce = cudaEventCreateWithFlags(&pl->ev_part[i], cudaEventDisableTiming);
-  if (ce != cudaSuccess) { delete pl->mu; delete pl; set_error("sense_plan_create: stream / events: %s", cudaGetErrorString(ce)); return (int)ce; }
+  if (ce != cudaSuccess) { plan_release(pl); set_error("sense_plan_create: stream / events: %s", cudaGetErrorString(ce)); return (int)ce; }
   ce = cudaMalloc(reinterpret_cast<void**>(&pl->buf), total);
-  if (ce != cudaSuccess) { delete pl; set_error("sense_plan_create: cudaMalloc: %s", cudaGetErrorString(ce)); return (int)ce; }
+  if (ce != cudaSuccess) { pl->buf = nullptr; plan_release(pl); set_error("sense_plan_create: cudaMalloc: %s", cudaGetErrorString(ce)); return (int)ce; }
   for (const Piece& pc : pieces) {
     if (pc.bytes == 0) continue;
     ce = cudaMemcpy(pl->buf + pc.off, pc.src, pc.bytes, cudaMemcpyHostToDevice);
     if (ce != cudaSuccess) {
-      cudaFree(pl->buf);
-      delete pl;
+      plan_release(pl);
       set_error("sense_plan_create: cudaMemcpy: %s", cudaGetErrorString(ce));
       return (int)ce;
     }
@@ -1158,14 +1171,7 @@ extern "C" int ipdm_sense_plan_create(const uint8_t* mask_host, int mask_frames,
 extern "C" int ipdm_sense_plan_destroy(void* plan) {
   SensePlan* pl = const_cast<SensePlan*>(as_plan(plan));
   IPDM_REQUIRE(pl, IPDM_E_BADARG, "sense_plan_destroy: not a plan");
-  pl->magic = 0;
-  cudaFree(pl->buf);
-  cudaStreamDestroy(pl->side);
-  cudaEventDestroy(pl->ev_fork);
-  cudaEventDestroy(pl->ev_join);
-  for (int i = 0; i < PLAN_SPLIT_MAX; ++i) cudaEventDestroy(pl->ev_part[i]);
-  delete pl->mu;
-  delete pl;
+  plan_release(pl);
   return 0;
 }
 
