@@ -168,6 +168,12 @@ class ALDOptimizer(abc.ABC):
         cls = type(self)
         return (cls.adjust_grad is not ALDOptimizer.adjust_grad or cls.init_estimation is not ALDOptimizer.init_estimation)
 
+    def _range_check_on(self, x, labels, out):
+        """Before a step graph is primed (its warm-up runs on dummy zeros): one eager score forward on the REAL initial state
+        at the first -- largest -- noise level, so that the score network's first-forward range audit (operand exponent shift,
+        DESIGN 2) looks at real activations and has settled before anything is captured."""
+        self._score_into(x, labels, out)
+
     def _score_into(self, x, labels, out):
         if hasattr(self.scorenet, "forward_into"):
             return self.scorenet.forward_into(x, labels, out)
@@ -203,6 +209,7 @@ class ALDOptimizer(abc.ABC):
             key = ("uncond", tuple(x_mod.shape), n_total, n_steps_each, x_mod.device)
             fc = self._fast_cache.get(key)
             if fc is None:
+                self._range_check_on(x_mod, labels, torch.empty_like(x_mod))
                 fc = {"x": torch.zeros_like(x_mod), "grad": torch.zeros_like(x_mod), "labels": torch.zeros_like(labels),
                       "sched": torch.zeros_like(sched_host, device=x_mod.device),
                       "cursor": torch.zeros(1, dtype=torch.int32, device=x_mod.device),
@@ -362,6 +369,7 @@ class ALDInvSegProximalRealImag(_SenseChainMixin, ALDOptimizer):
             key = ("sense", B, H, W, n_total, n_steps_each, state.device)
             fc = self._fast_cache.get(key)
             if fc is None:
+                self._range_check_on(x_flat, labels, g_flat)
                 fc = {"state": torch.zeros_like(state), "grad": torch.zeros_like(state), "bvec": torch.zeros_like(state),
                       "labels": torch.zeros_like(labels), "sched": torch.zeros_like(sched_host, device=state.device),
                       "cursor": torch.zeros(1, dtype=torch.int32, device=state.device),
@@ -579,6 +587,7 @@ class ALD2DTime(_SenseChainMixin, ALDOptimizer):
             fc = self._fast_cache.get(key)
             real = (state, bvec)
             if fc is None:
+                self._range_check_on(x_flat, labels, g_flat)      # the spatial prior on the real initial frames
                 fc = {"state": torch.zeros_like(state), "grad": torch.zeros_like(state), "bvec": torch.zeros_like(state),
                       "labels": torch.zeros_like(labels_all), "sched": torch.zeros_like(sched_host, device=state.device),
                       "cursor": torch.zeros(1, dtype=torch.int32, device=state.device),

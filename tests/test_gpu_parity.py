@@ -713,6 +713,32 @@ def test_single_ald_step_ngf128():
         assert rel_l2(got, ref) < 1e-4, float(levels[0])
 
 
+def test_sampler_range_check_sees_the_real_state():
+    """The captured-graph fast path primes its step graph on dummy zeros, so the sampler first runs one eager score forward on the
+    REAL initial state: with a measurement 3e5 times too large the plan must have moved to an operand shift before the graph
+    was captured (finite chain), with an ordinary one it must not."""
+    import warnings
+    n, B = 32, 2
+    A = C.SENSE("exp", 4, 8, 1 / 8, (1, n, n), 0)
+    A.random_under_fourier.mask = C.keep_center_mask(n, 8, 1 / 8, seed=0)
+    params = {"n_steps_each": 2, "step_lr": 9e-7, "denoise": False, "final_only": True}
+    for scale, want_shift in ((1.0, False), (3e5, True)):
+        net, Pd, cfg = _full_width_net(C.NCSNv2Deepest, "NCSNv2Deepest", n, 21, num_classes=4, sigma_begin=30.0)
+        sig = C.get_sigmas(cfg, mode="recons")
+        meas = A(phantom(14, 1, 1, n, n).to(DEV)).repeat(1, B, 1, 1, 1) * scale
+        sampler = C.ALD.ALDInvSegProximalRealImag(C.L2Penalty(A), 1.0, "linear", (B, 1, n, n), net, sig.to(DEV), params, cfg,
+                                                  measurement=meas, linear_tfm=A, seg=None, device=torch.device(DEV))
+        with warnings.catch_warnings(record=True) as wlist:
+            warnings.simplefilter("always")
+            out = sampler(label=None, lamda=1.0, save_dir="/tmp", lr_scaled=1.0, seg_mode="full", seed=3)[0]
+        torch.set_grad_enabled(True)
+        plan = next(iter(net._plans.values()))
+        assert bool(torch.isfinite(out).all())
+        assert (plan.shift >= 6) == want_shift, (scale, plan.shift)
+        assert any("operand exponent shift" in str(w.message) for w in wlist) == want_shift
+        assert net.range_audit()["saturated_total"] == 0      # the last replayed step left nothing clipped either
+
+
 def test_single_ald_step_ngf128_bench_config():
     """The benchmarked configuration itself: 256x256, 14 chains (28 images per forward: work items >> SMs), 4 coils, R = 40,
     ngf 128 on the tensor-core path.  One ALD step (2 score forwards + update + prox) with injected noise at the first
