@@ -13,10 +13,12 @@
 //   twh[f][jj][10]     the twiddle vector in factored form, w^(t*k) = w^((t&3)*k) * w^(4*(t>>2)*k): entries
 //                      w^k, w^2k, w^3k, then w^(4m*k) for m = 1 .. W/64-1 (20 registers instead of 2*W/16)
 //   ngroups[f], groups[f][g], gslot[f][g][0..GW-1], gbitmap[f][4]
-//                      the active GW-column groups (GW = 8: 64 aligned bytes of a k-space row each), for every group the
+//                      the active GW-column groups (GW = 4: one aligned 32-byte sector of a k-space row each), for every group the
 //                      natural slot of each of its columns (255 = not sampled), and the bitmap over all W/GW groups
 //   nchunks[f], chunks[f][c] = {first group, groups, first slot, slots}
 //                      work items of the column kernels: runs of whole groups holding at most 8 sampled columns
+//   crec[f][c]         ChunkRec: everything a column-kernel work item needs about chunk c in one 80-byte record (sampled
+//                      columns, first column of each group, line of every group column)
 //   tcw[f][jj]         chunk*8 + position inside the chunk of class entry jj: the compact scratch is laid out
 //                      T[image][chunk][h][8], so that a column-kernel work item is one contiguous block
 #pragma once
