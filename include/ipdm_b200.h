@@ -297,6 +297,9 @@ int ipdm_bilinear_add(const float* src, float* dst, void* out_elu_f16, int N, in
                       int accumulate, void* stream);
 /* out f32 [N][H/2][W/2][C] = mean of the four stride-2 phases of in (+ add if non-NULL). */
 int ipdm_meanpool2(const float* in, const float* add, float* out, int N, int H, int W, int C, void* stream);
+/* 2x2 mean-pool of an f16 NHWC tensor (fp32 arithmetic): the operand of a pooled 1x1 shortcut, which the score network
+ * evaluates as conv1x1(meanpool(x)) instead of meanpool(conv1x1(x)) (ConvMeanPool with kernel 1, layers.py:291-313). */
+int ipdm_meanpool2_f16(const void* in_f16, void* out_f16, int N, int H, int W, int C, void* stream);
 /* f32 [Cout][Cin][kh][kw] (PyTorch OIHW) -> f16 [Cout][kh*kw][Cin] weight repack for the igemm. */
 int ipdm_pack_weights_f16(const float* w_oihw, void* w_f16, int Cout, int Cin, int taps, void* stream);
 

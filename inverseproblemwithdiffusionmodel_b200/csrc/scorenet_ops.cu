@@ -981,6 +981,34 @@ extern "C" int ipdm_meanpool2(const float* in, const float* add, float* out, int
   return launched("k_meanpool2");
 }
 
+// 2x2 mean-pool of an f16 NHWC tensor, fp32 arithmetic, one rounding: the operand of a pooled 1x1 shortcut convolution
+// (mean-pool and a 1x1 convolution commute: pooling first is 4x fewer FLOPs and bytes for the convolution).
+__global__ void k_meanpool2_f16(const __half* __restrict__ in, __half* __restrict__ out, int N, int H, int W, int C) {
+  const int lanes = C / 8, Ho = H / 2, Wo = W / 2;
+  const size_t total = (size_t)N * Ho * Wo * lanes;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % lanes) * 8;
+    const size_t pix = i / lanes;
+    const int X = (int)(pix % Wo), Y = (int)((pix / Wo) % Ho), n = (int)(pix / ((size_t)Wo * Ho));
+    const __half* b = in + (((size_t)n * H + 2 * Y) * W + 2 * X) * C + c8;
+    const H8 a00 = H8::ld(b), a01 = H8::ld(b + C), a10 = H8::ld(b + (size_t)W * C), a11 = H8::ld(b + (size_t)W * C + C);
+    float r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = (((a00.v[k] + a10.v[k]) + a01.v[k]) + a11.v[k]) * 0.25f;
+    uint4 pk;
+    pk.x = pack_half2_sat(r[0], r[1]); pk.y = pack_half2_sat(r[2], r[3]); pk.z = pack_half2_sat(r[4], r[5]); pk.w = pack_half2_sat(r[6], r[7]);
+    *reinterpret_cast<uint4*>(out + pix * C + c8) = pk;
+  }
+}
+
+extern "C" int ipdm_meanpool2_f16(const void* in_f16, void* out_f16, int N, int H, int W, int C, void* stream) {
+  IPDM_REQUIRE(in_f16 && out_f16, IPDM_E_BADARG, "meanpool2_f16: null pointer");
+  IPDM_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0 && N >= 1, IPDM_E_BADARG, "meanpool2_f16: C=%d must be a multiple of 8, H and W even", C);
+  const size_t total = (size_t)N * (H / 2) * (W / 2) * (C / 8);
+  k_meanpool2_f16<<<grid1d(total, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(in_f16), reinterpret_cast<__half*>(out_f16), N, H, W, C);
+  return launched("k_meanpool2_f16");
+}
+
 extern "C" int ipdm_pack_weights_f16(const float* w_oihw, void* w_f16, int Cout, int Cin, int taps, void* stream) {
   IPDM_REQUIRE(w_oihw && w_f16 && taps >= 1 && Cout >= 1 && Cin >= 1, IPDM_E_BADARG, "pack_weights: bad argument");
   const size_t total = (size_t)Cout * taps * Cin;

@@ -293,7 +293,14 @@ class _Plan:
                 x16 = self.f16(name + ".x16", N, H, W, Cin)
                 self.to_f16(x32, x16, elu=False)
             sc = self.f32(name + ".sc", N, Ho, Wo, Cout)
-            if pooled:
+            if pooled and Cin % 8 == 0 and self.w[name + ".shortcut.conv"][0].shape[1] == 1 and os.environ.get("IPDM_POOL_AFTER_SHORTCUT") is None:
+                # mean-pool and the 1x1 shortcut convolution commute (the bias too): pool the operand, convolve a quarter of the pixels
+                xp = self.f16(name + ".xp16", N, Ho, Wo, Cin)
+                _lib.check(self.L.ipdm_meanpool2_f16(x16.data_ptr(), xp.data_ptr(), N, H, W, Cin, _lib.stream()), "meanpool2_f16")
+                if self.shift:
+                    self.scale_of[xp.data_ptr()] = self.scale_of.get(x16.data_ptr(), 1.0)
+                self.conv(name + ".shortcut.conv", xp, (N, Ho, Wo, Cin, Cout), out32=sc)
+            elif pooled:
                 self.conv(name + ".shortcut.conv", x16, (N, H, W, Cin, Cout), out32=sc, flags=CONV_POOL2)
             else:
                 k = blk.shortcut.kernel_size[0]

@@ -486,6 +486,13 @@ class EmuLib:
             _t(out16, (N, H, W, C), np.float16).copy_(F.elu(D).half())
         return 0
 
+    def ipdm_meanpool2_f16(self, inp, out, N, H, W, C, stream):
+        self.launches += 1
+        v = _t(inp, (N, H, W, C), np.float16).float()
+        r = (((v[:, ::2, ::2] + v[:, 1::2, ::2]) + v[:, ::2, 1::2]) + v[:, 1::2, 1::2]) * 0.25
+        _t(out, (N, H // 2, W // 2, C), np.float16).copy_(r.clamp(-65504.0, 65504.0).half())
+        return 0
+
     def ipdm_meanpool2(self, inp, add, out, N, H, W, C, stream):
         self.launches += 1
         v = _t(inp, (N, H, W, C), np.float32)

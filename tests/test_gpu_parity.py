@@ -465,6 +465,19 @@ def test_bilinear_add_f16_stream_vs_torch(N, h, w, H, W, C, acc):
     assert rel_l2(h16.float().cpu(), torch.nn.functional.elu(ref).cpu()) < 1e-3
 
 
+@pytest.mark.parametrize("N,H,W,C", [(2, 16, 24, 128), (1, 256, 256, 128), (3, 6, 10, 8)])
+def test_meanpool2_f16_vs_torch(N, H, W, C):
+    """Operand of the pooled 1x1 shortcut: 2x2 mean of f16 values in fp32, one rounding."""
+    L = _lib()
+    g = torch.Generator().manual_seed(H + W + C)
+    x = (torch.randn(N, H, W, C, generator=g) * 50).half().to(DEV)
+    out = torch.full((N, H // 2, W // 2, C), float("nan"), dtype=torch.float16, device=DEV)
+    L.check(L.lib().ipdm_meanpool2_f16(x.data_ptr(), out.data_ptr(), N, H, W, C, L.stream()), "meanpool2_f16")
+    v = x.float()
+    ref = ((((v[:, ::2, ::2] + v[:, 1::2, ::2]) + v[:, ::2, 1::2]) + v[:, 1::2, 1::2]) * 0.25).half()
+    assert torch.equal(out, ref)
+
+
 def test_conv_direct_vs_torch():
     """Anchor of the chain igemm -> direct -> torch: the CUDA-core kernel against F.conv2d on the same f16 operands."""
     import torch.nn.functional as F
