@@ -670,6 +670,10 @@ def conv_roofline(args, torch, _lib, L, dev, N, n, ms_step_total, steps, flop_st
            "same_shape_fp32_residual_stream": view(ms_res),
            "same_shape_f16_store_only": view(ms_f16),
            "whole_step_conv_tflops": step_tflops, "whole_step_frac_of_sustained": step_tflops / sustained,
+           "whole_step_note": ("algorithmic FLOPs of the reference's layers (SURVEY A.1: 838.36 GFLOP per 256x256 forward) over the step time.  "
+                               "The kernels EXECUTE 0.952 of them: the three ConvMeanPool layers run as 4x4 stride-2 convolutions (16/36 of "
+                               "their tap evaluations) and the three pooled 1x1 shortcuts on pooled operands (1/4), DESIGN 4.1"),
+           "executed_flop_fraction": 0.952,
            "whole_step_frac_of_burst": step_tflops / burst}
     del raw16, res16
     del x16, w16, o16, o32, res

@@ -220,6 +220,12 @@ typedef struct {
    * straight-line epilogue paths are taken as before. */
   float acc_scale;
   float out_f16_scale;
+  /* Optional sparsity hint for 3x3 convolutions, per 64-channel chunk of Cin (chunk i = channels [64 i, 64 i + 64), Cin <=
+   * 1024): bit ky*3+kx set = the weight block (tap, chunk) may be non-zero; every block whose bit is clear MUST be zero in
+   * w_f16.  0 = all nine taps.  The persistent halo kernel skips the cleared blocks (no weight traffic, no MMAs); the other
+   * kernels ignore the hint (same result).  Used for ConvMeanPool in its 4x4 stride-2 form on space-to-depth operands:
+   * 16 of 36 (tap, parity) blocks. */
+  uint16_t tap_mask[16];
 } ipdm_conv_desc;
 
 #define IPDM_CONV_F16_ELU 1       /* out_f16 = f16(ELU(v)) instead of f16(v)                               */
@@ -277,6 +283,11 @@ int ipdm_instnorm_apply_elu_f16in(const void* x_f16, const double* stats, int st
                                   const float* gamma, const float* beta, void* out_f16, int N, int HW, int C, void* stream);
 /* out_f16[i] = f16(scale * (elu ? ELU(x[i]) : x[i])): the cast of ipdm_act_to_f16 with an operand exponent shift. */
 int ipdm_act_to_f16_scaled(const float* x, void* out_f16, size_t n, int elu, float scale, void* stream);
+/* InstanceNorm++ + ELU with the f16 result written in space-to-depth layout [N][H/2][W/2][(y&1)*2 + (x&1)][C] (x: f32, or the
+ * 16-bit stream when x_is_f16): the operand of ConvMeanPool evaluated as one 4x4 stride-2 convolution = a 3x3 convolution over
+ * the space-to-depth tensor with 16 of its 36 (tap, parity) weight blocks non-zero (ipdm_conv_desc.tap_mask). */
+int ipdm_instnorm_apply_elu_s2d(const void* x, int x_is_f16, const double* stats, int stats_pivoted, const float* alpha,
+                                const float* gamma, const float* beta, void* out_f16, int N, int H, int W, int C, void* stream);
 int ipdm_bilinear_add_f16(const void* src_f16, void* dst_f16, void* out_elu_f16, int N, int h, int w, int H, int W, int C,
                           int accumulate, void* stream);
 

@@ -24,7 +24,7 @@ class ConvDesc(ctypes.Structure):
                 ("out_f32", c_void_p), ("out_f16", c_void_p), ("stats", c_void_p),
                 ("N", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int), ("Cout", c_int),
                 ("taps", c_int), ("dilation", c_int), ("flags", c_int), ("slices", c_int), ("slice_shift", c_int),
-                ("residual_f16", c_void_p), ("out_raw_f16", c_void_p), ("acc_scale", ctypes.c_float), ("out_f16_scale", ctypes.c_float)]
+                ("residual_f16", c_void_p), ("out_raw_f16", c_void_p), ("acc_scale", ctypes.c_float), ("out_f16_scale", ctypes.c_float), ("tap_mask", ctypes.c_uint16 * 16)]
 
 
 class Rng(ctypes.Structure):
@@ -81,6 +81,7 @@ SIGNATURES = {
     "ipdm_instnorm_apply_elu_f16in": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "ipdm_bilinear_add_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ipdm_f16_range_audit": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "ipdm_instnorm_apply_elu_s2d": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "ipdm_act_to_f16": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "ipdm_act_to_f16_scaled": (c_int, [c_void_p, c_void_p, c_size_t, c_int, ctypes.c_float, c_void_p]),
     "ipdm_maxpool5_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

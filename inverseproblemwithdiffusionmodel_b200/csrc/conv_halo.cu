@@ -55,6 +55,10 @@ struct HaloParams {
   int exp_skip_weights;
   int res_prefetch;
   int pdl;
+  // Per 64-channel chunk of Cin, the taps that are evaluated (bit ky*3+kx; 0x1FF = all nine).  A convolution whose weight
+  // blocks are structurally zero -- the 4x4 stride-2 form of ConvMeanPool on space-to-depth operands keeps 16 of its 36
+  // (tap, parity) blocks -- neither streams those weight tiles nor issues their MMAs.  2-D convolutions only.
+  uint16_t tap_mask[16];
 };
 
 template <int MODE, int DIL, int TH, int NS>
@@ -161,10 +165,13 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
         int n, h0, w0, m0;
         decode(item, n, h0, w0, m0);
         for (int kc = 0; kc < kchunks; ++kc) {
-          for (int tap = 0; tap < 9 * planes; ++tap, ++cnt) {     // weights [Cout][(kx,) ky, kx taps][Cin]
-            const int s = cnt % NW;
-            mbar_wait(&w_empty[s], ((cnt / NW) & 1) ^ 1);
-            if (hp.exp_skip_weights && cnt >= (uint32_t)NW) {      // TIMING EXPERIMENT ONLY: stale weights, no L2 traffic
+          const uint32_t tmask = planes == 1 ? hp.tap_mask[kc & 15] : 0x7FFFFFFu;
+          for (int tap = 0; tap < 9 * planes; ++tap) {     // weights [Cout][(kx,) ky, kx taps][Cin]
+            if (!((tmask >> tap) & 1u)) continue;
+            const uint32_t cnt_now = cnt++;
+            const int s = cnt_now % NW;
+            mbar_wait(&w_empty[s], ((cnt_now / NW) & 1) ^ 1);
+            if (hp.exp_skip_weights && cnt_now >= (uint32_t)NW) {      // TIMING EXPERIMENT ONLY: stale weights, no L2 traffic
               asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&w_full[s])) : "memory");
               continue;
             }
@@ -184,14 +191,18 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
         mbar_wait(&acc_empty[as], ((acnt >> 1) & 1) ^ 1);
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + as * BLOCK_N;
+        bool fresh = true;       // the item's first MMA overwrites the accumulator
         for (int kc = 0; kc < kchunks; ++kc) {
+          const uint32_t tmask = planes == 1 ? hp.tap_mask[kc & 15] : 0x1FFu;
           for (int pl = 0; pl < planes; ++pl, ++hcnt) {
             const int hs = hcnt % NH;
             mbar_wait(&halo_full[hs], (hcnt / NH) & 1);
             const uint32_t hbase = smem_u32(halo + hs * CFG::HALO_BYTES);
-            for (int tap = 0; tap < 9; ++tap, ++wcnt) {
+            for (int tap = 0; tap < 9; ++tap) {
+              if (!((tmask >> tap) & 1u)) continue;
               const int ws = wcnt % NW;
               mbar_wait(&w_full[ws], (wcnt / NW) & 1);
+              ++wcnt;
               tcgen05_fence_after();
               const int dy = (tap / 3) * DIL, dx = (tap % 3) * DIL;
               const uint64_t adesc = make_smem_desc(smem_u32(wts + ws * W_BYTES));
@@ -200,8 +211,9 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
                 const uint64_t bdesc = make_smem_desc(hbase + sl * CFG::TILE_BYTES + dy * CFG::PITCH + dx * 128, CFG::PITCH);
 #pragma unroll
                 for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                  umma_f16(tacc + sl * BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | pl | tap | k) != 0);
+                  umma_f16(tacc + sl * BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, !(fresh && k == 0));
               }
+              fresh = false;
               umma_commit(&w_empty[ws]);
             }
             umma_commit(&halo_empty[hs]);
@@ -301,6 +313,12 @@ int launch_conv_halo(const ipdm_conv_desc& d, cudaStream_t s) {
   p.bias = d.bias; p.out_f16 = reinterpret_cast<__half*>(d.out_f16);
   p.residual = t16 ? reinterpret_cast<const float*>(d.residual_f16) : d.residual;
   p.out_f32 = t16 ? reinterpret_cast<float*>(d.out_raw_f16) : d.out_f32;
+  for (int i = 0; i < 16; ++i) hp.tap_mask[i] = (d.taps == 9 && d.tap_mask[i] != 0) ? (uint16_t)(d.tap_mask[i] & 0x1FF) : (uint16_t)0x1FF;
+  if (d.taps == 9) {
+    for (int i = 0; i < 16 && i < d.Cin / 64; ++i)
+      IPDM_REQUIRE(hp.tap_mask[i] != 0, IPDM_E_BADARG, "conv: tap_mask[%d] selects no tap", i);
+    IPDM_REQUIRE(d.Cin <= 1024 || d.tap_mask[0] == 0, IPDM_E_UNSUPPORTED, "conv: tap masks need Cin <= 1024");
+  }
   p.acc_scale = d.acc_scale != 0.f ? d.acc_scale : 1.f;
   p.out16_scale = d.out_f16_scale != 0.f ? d.out_f16_scale : 1.f;
   p.stats = d.stats;

@@ -303,7 +303,9 @@ __global__ void k_instnorm_stats(const float* __restrict__ x, double* __restrict
 template <bool IN16>   // IN16: x is the 16-bit residual stream
 __global__ void k_instnorm_apply(const void* __restrict__ xv, const double* __restrict__ stats, int pivoted,
                                  const float* __restrict__ alpha, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, __half* __restrict__ out, int HW, int C) {
+                                 const float* __restrict__ beta, __half* __restrict__ out, int HW, int C, int s2d_w) {
+  // s2d_w != 0: the image is s2d_w pixels wide and the output is written in space-to-depth layout
+  // [N][H/2][W/2][(y&1)*2 + (x&1)][C] -- the operand of ConvMeanPool in its 4x4 stride-2 form
   extern __shared__ float sm[];  // A[C], B[C], mean[C], red[64]
   float* A = sm;
   float* Bv = sm + C;
@@ -347,6 +349,11 @@ __global__ void k_instnorm_apply(const void* __restrict__ xv, const double* __re
     Bv[c] = g * (alpha[c] * mhat - mean[c] * rstd) + (beta ? beta[c] : 0.f);
   }
   __syncthreads();
+  auto out_pix = [&](int pp) -> size_t {      // element offset of pixel pp's channel 0 inside the image's output
+    if (s2d_w == 0) return (size_t)pp * C;
+    const int y = pp / s2d_w, x = pp - y * s2d_w;
+    return ((size_t)((y >> 1) * (s2d_w >> 1) + (x >> 1)) * 4 + (size_t)((y & 1) * 2 + (x & 1))) * C;
+  };
   if (IN16 && (C & 7) == 0) {
     // 16-bit stream: thread = 8 channels (16-byte loads and stores), 4 pixels in flight per thread
     const int lanes = C / 8;
@@ -377,7 +384,7 @@ __global__ void k_instnorm_apply(const void* __restrict__ xv, const double* __re
             const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
             o[k] = pack_half2_sat(elu_f16bound(f.x * a[2 * k] + bb[2 * k]), elu_f16bound(f.y * a[2 * k + 1] + bb[2 * k + 1]));
           }
-          *reinterpret_cast<uint4*>(obase + (size_t)pp * C + c8) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(obase + out_pix(pp) + c8) = make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
     }
@@ -415,7 +422,7 @@ __global__ void k_instnorm_apply(const void* __restrict__ xv, const double* __re
         uint2 pk;
         pk.x = pack_half2_sat(elu_f16bound(v[u].x * a0 + b0), elu_f16bound(v[u].y * a1 + b1));
         pk.y = pack_half2_sat(elu_f16bound(v[u].z * a2 + b2), elu_f16bound(v[u].w * a3 + b3));
-        *reinterpret_cast<uint2*>(obase + (size_t)pp * C + c4) = pk;
+        *reinterpret_cast<uint2*>(obase + out_pix(pp) + c4) = pk;
       }
     }
   }
@@ -804,7 +811,7 @@ extern "C" int ipdm_instnorm_apply_elu(const float* x, const double* stats, int 
   if (cap < 1) cap = 1;
   if (chunks > cap) chunks = cap;
   k_instnorm_apply<false><<<dim3(chunks, N), 256, smem, as_stream(stream)>>>(x, stats, stats_pivoted, alpha, gamma, beta,
-                                                                             reinterpret_cast<__half*>(out_f16), HW, C);
+                                                                             reinterpret_cast<__half*>(out_f16), HW, C, 0);
   return launched("k_instnorm_apply");
 }
 
@@ -819,7 +826,28 @@ extern "C" int ipdm_instnorm_apply_elu_f16in(const void* x_f16, const double* st
   if (cap < 1) cap = 1;
   if (chunks > cap) chunks = cap;
   k_instnorm_apply<true><<<dim3(chunks, N), 256, smem, as_stream(stream)>>>(x_f16, stats, stats_pivoted, alpha, gamma, beta,
-                                                                            reinterpret_cast<__half*>(out_f16), HW, C);
+                                                                            reinterpret_cast<__half*>(out_f16), HW, C, 0);
+  return launched("k_instnorm_apply");
+}
+
+extern "C" int ipdm_instnorm_apply_elu_s2d(const void* x, int x_is_f16, const double* stats, int stats_pivoted, const float* alpha,
+                                           const float* gamma, const float* beta, void* out_f16, int N, int H, int W, int C,
+                                           void* stream) {
+  IPDM_REQUIRE(x && stats && alpha && gamma && out_f16, IPDM_E_BADARG, "instnorm_apply_elu_s2d: null pointer");
+  IPDM_REQUIRE(C % 4 == 0 && C >= 4 && C <= 2048, IPDM_E_BADARG, "instnorm_apply_elu_s2d: C=%d must be a multiple of 4", C);
+  IPDM_REQUIRE(H % 2 == 0 && W % 2 == 0 && H >= 2 && W >= 2, IPDM_E_BADARG, "instnorm_apply_elu_s2d: H=%d, W=%d must be even", H, W);
+  const int HW = H * W;
+  const size_t smem = (size_t)(3 * C + 64) * sizeof(float);
+  int chunks = grid1d((size_t)HW * (C / 4), 256 * 4, 8);
+  int cap = (148 * 4) / N;          // one resident wave
+  if (cap < 1) cap = 1;
+  if (chunks > cap) chunks = cap;
+  if (x_is_f16)
+    k_instnorm_apply<true><<<dim3(chunks, N), 256, smem, as_stream(stream)>>>(x, stats, stats_pivoted, alpha, gamma, beta,
+                                                                              reinterpret_cast<__half*>(out_f16), HW, C, W);
+  else
+    k_instnorm_apply<false><<<dim3(chunks, N), 256, smem, as_stream(stream)>>>(x, stats, stats_pivoted, alpha, gamma, beta,
+                                                                               reinterpret_cast<__half*>(out_f16), HW, C, W);
   return launched("k_instnorm_apply");
 }
 

@@ -220,6 +220,26 @@ class _Plan:
                 w16 = torch.empty((cout, kh * kw, cin), dtype=torch.float16, device=self.device)
                 _lib.check(self.L.ipdm_pack_weights_f16(w.data_ptr(), w16.data_ptr(), cout, cin, kh * kw, s), "pack_weights")
                 self.w[name] = (w16, bias)
+                if name.endswith(".conv2.conv") and kh == 3 and 4 * cin <= 1024:
+                    # ConvMeanPool (3x3 convolution, then 2x2 mean) = ONE 4x4 stride-2 convolution = a 3x3 convolution over the
+                    # space-to-depth input [.., (y&1)*2 + (x&1), C] in which parity (pr, pc) meets only 2 x 2 of the 9 taps:
+                    #   row offset dy of the s2d tensor, row parity pr  <-  original row taps oy:   (0,0): {0,-1}  (0,+1): {+1}
+                    #                                                                                (1,0): {+1,0}  (1,-1): {-1}
+                    R = torch.zeros(2, 3, 3, device=self.device)            # R[parity][dy + 1][o + 1]
+                    R[0, 1, 1] = R[0, 1, 0] = R[0, 2, 2] = 1.0
+                    R[1, 1, 2] = R[1, 1, 1] = R[1, 0, 0] = 1.0
+                    w2 = 0.25 * torch.einsum("pyo,qxu,kcou->kpqcyx", R, R, w)   # [Cout][pr][pc][Cin][dy][dx]
+                    w2 = w2.reshape(cout, 4 * cin, 3, 3).contiguous()
+                    w16s = torch.empty((cout, 9, 4 * cin), dtype=torch.float16, device=self.device)
+                    _lib.check(self.L.ipdm_pack_weights_f16(w2.data_ptr(), w16s.data_ptr(), cout, 4 * cin, 9, s), "pack_weights s2d")
+                    mask = []
+                    for kc in range(4 * cin // 64 if cin % 64 == 0 else 0):   # (narrow nets: no hint, the zero blocks are multiplied)
+                        par = (kc * 64) // cin
+                        pr, pc = par >> 1, par & 1
+                        rows = (1, 2) if pr == 0 else (0, 1)                # dy + 1
+                        cols = (1, 2) if pc == 0 else (0, 1)
+                        mask.append(sum(1 << (3 * r + c) for r in rows for c in cols))
+                    self.w[name + ".s2d"] = (w16s, bias, mask or None)
         for name, mod in net.named_modules():
             if isinstance(mod, InstanceNorm2dPlus):
                 self.w[name] = tuple(None if t is None else t.detach().to(self.device, torch.float32).contiguous()
@@ -231,7 +251,8 @@ class _Plan:
     # ---- primitive launches ----------------------------------------------------------------------
     def conv(self, wname, x16, dims, residual=None, out32=None, out16=None, stats=None, flags=0, dilation=1):
         N, H, W, Cin, Cout = dims
-        w16, bias = self.w[wname]
+        w16, bias = self.w[wname][:2]
+        tap_mask = self.w[wname][2] if len(self.w[wname]) > 2 else None
         taps = w16.shape[1]
         if self.t16:     # residual / out32 are tensors of the 16-bit residual stream
             d = ConvDesc(_lib.ptr(x16), w16.data_ptr(), _lib.ptr(bias), None, None, _lib.ptr(out16),
@@ -239,6 +260,9 @@ class _Plan:
         else:
             d = ConvDesc(_lib.ptr(x16), w16.data_ptr(), _lib.ptr(bias), _lib.ptr(residual), _lib.ptr(out32), _lib.ptr(out16),
                          _lib.ptr(stats), N, H, W, Cin, Cout, taps, dilation, flags)
+        if tap_mask is not None:
+            for i, m in enumerate(tap_mask):
+                d.tap_mask[i] = m
         if self.shift:   # operand exponent shift: undo the input operand's scale on the accumulator, scale the operand output
             d.acc_scale = 1.0 / self.scale_of.get(x16.data_ptr(), 1.0)
             if out16 is not None:
@@ -254,6 +278,11 @@ class _Plan:
         fn = self.L.ipdm_instnorm_apply_elu_f16in if self.t16 else self.L.ipdm_instnorm_apply_elu
         _lib.check(fn(x32.data_ptr(), stats.data_ptr(), 0, alpha.data_ptr(), gamma.data_ptr(),
                       _lib.ptr(beta), out16.data_ptr(), N, HW, C, _lib.stream()), "instnorm " + nname)
+
+    def norm_elu_s2d(self, nname, x32, stats, out16, N, H, W, C):
+        alpha, gamma, beta = self.w[nname]
+        _lib.check(self.L.ipdm_instnorm_apply_elu_s2d(x32.data_ptr(), 1 if self.t16 else 0, stats.data_ptr(), 0, alpha.data_ptr(), gamma.data_ptr(),
+                                                      _lib.ptr(beta), out16.data_ptr(), N, H, W, C, _lib.stream()), "instnorm s2d " + nname)
 
     def to_f16(self, x32, out16, elu):
         if self.shift:
@@ -281,8 +310,12 @@ class _Plan:
         h32 = self.f32(name + ".h", N, H, W, Cmid)
         st_h = self.stats(name + ".st_h", Cmid)
         self.conv(name + ".conv1", a1, (N, H, W, Cin, Cmid), out32=h32, stats=st_h, dilation=d)
+        s2d = pooled and (name + ".conv2.conv.s2d") in self.w and os.environ.get("IPDM_POOL_AFTER_CONV") is None
         a2 = self.f16(name + ".a2", N, H, W, Cmid)
-        self.norm_elu(name + ".normalize2", h32, st_h, a2, N, H * W, Cmid)
+        if s2d:     # the same values in space-to-depth order: (N, H/2, W/2, 4*Cmid) in the same buffer
+            self.norm_elu_s2d(name + ".normalize2", h32, st_h, a2, N, H, W, Cmid)
+        else:
+            self.norm_elu(name + ".normalize2", h32, st_h, a2, N, H * W, Cmid)
         Ho, Wo = (H // 2, W // 2) if pooled else (H, W)
         out32 = self.f32(name + ".out", N, Ho, Wo, Cout)
         st_o = self.stats(name + ".st_o", Cout)
@@ -308,7 +341,10 @@ class _Plan:
             res = sc
         else:
             res = x32
-        if pooled:
+        if s2d:
+            self.conv(name + ".conv2.conv.s2d", a2, (N, Ho, Wo, 4 * Cmid, Cout), residual=res, out32=out32, out16=elu16, stats=st_o,
+                      flags=CONV_F16_ELU)
+        elif pooled:
             self.conv(name + ".conv2.conv", a2, (N, H, W, Cmid, Cout), residual=res, out32=out32, out16=elu16, stats=st_o,
                       flags=CONV_POOL2 | CONV_F16_ELU)
         else:

@@ -444,6 +444,14 @@ class EmuLib:
         _t(out16, (N, HW, C), np.float16).copy_(F.elu(o).half())
         return 0
 
+    def ipdm_instnorm_apply_elu_s2d(self, x, x_is_f16, stats, pivoted, alpha, gamma, beta, out16, N, H, W, C, stream):
+        assert not x_is_f16          # the emulated plans keep the fp32 stream
+        tmp = torch.zeros(N, H * W, C, dtype=torch.float16)
+        self.ipdm_instnorm_apply_elu(x, stats, pivoted, alpha, gamma, beta, tmp.data_ptr(), N, H * W, C, stream)
+        v = tmp.reshape(N, H // 2, 2, W // 2, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(N, H // 2, W // 2, 4 * C)   # [(y&1)*2 + (x&1)][C]
+        _t(out16, (N, H // 2, W // 2, 4 * C), np.float16).copy_(v)
+        return 0
+
     def ipdm_act_to_f16(self, x, out16, n, elu, stream):
         self.launches += 1
         X = _t(x, (n,), np.float32)

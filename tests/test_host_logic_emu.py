@@ -38,6 +38,24 @@ def test_operand_shift_host_logic(emu):
     C.case_operand_shift("cpu")
 
 
+def test_pooled_convs_in_their_strided_forms(emu, monkeypatch):
+    """ConvMeanPool as one 4x4 stride-2 convolution on space-to-depth operands (weights combined on the host, 16 of 36 blocks
+    non-zero) and the pooled 1x1 shortcut on pooled operands: the plan takes these paths and gives the score of the
+    conv-then-pool order (IPDM_POOL_AFTER_CONV / IPDM_POOL_AFTER_SHORTCUT) up to operand rounding."""
+    cfg = C.make_config("ACDC", 8, 32, 12, 30.0)
+    x, y = (C.rrand(1301, 2, 1, 32, 32) * 3 - 1), torch.tensor([0, 7])
+    net, _ = C.build_net(C.NCSNv2Deepest, "NCSNv2Deepest_ngf8", 1, cfg, "cpu")
+    out = net(x, y)
+    plan = next(iter(net._plans.values()))
+    assert any(k.endswith(".conv2.conv.s2d") for k in plan.w) and any(k.endswith(".xp16") for k in plan.bufs)
+    monkeypatch.setenv("IPDM_POOL_AFTER_CONV", "1")
+    monkeypatch.setenv("IPDM_POOL_AFTER_SHORTCUT", "1")
+    net2, _ = C.build_net(C.NCSNv2Deepest, "NCSNv2Deepest_ngf8", 1, cfg, "cpu")
+    ref = net2(x, y)
+    assert not any(k.endswith(".xp16") for k in next(iter(net2._plans.values())).bufs)
+    assert C.rel_l2(out, ref) < 1e-3, C.rel_l2(out, ref)
+
+
 def test_ncsn3d_shallow_host_logic(emu):
     """kernel sequence of the 3-D temporal prior (slice-shifted conv launches, gathers, pools) against the reference output"""
     C.case_ncsn3d_shallow("cpu")
