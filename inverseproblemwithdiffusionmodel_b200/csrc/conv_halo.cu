@@ -59,9 +59,12 @@ struct HaloParams {
   // blocks are structurally zero -- the 4x4 stride-2 form of ConvMeanPool on space-to-depth operands keeps 16 of its 36
   // (tap, parity) blocks -- neither streams those weight tiles nor issues their MMAs.  2-D convolutions only.
   uint16_t tap_mask[16];
+  int masked;      // some chunk skips taps (host-computed): the dense loops stay exactly as they were otherwise
 };
 
-template <int MODE, int DIL, int TH, int NS>
+// MASKED: the sparse-3x3 instantiation (tap masks).  A template parameter rather than a run-time branch: the dense kernels
+// stay textually what they were (a run-time branch in the single-thread producer / issuer loops cost the dominant launch 2.4 %).
+template <int MODE, int DIL, int TH, int NS, bool MASKED = false>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, HaloParams hp) {
   using CFG = HaloCfg<DIL, TH, NS>;
@@ -165,18 +168,27 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
         int n, h0, w0, m0;
         decode(item, n, h0, w0, m0);
         for (int kc = 0; kc < kchunks; ++kc) {
-          const uint32_t tmask = planes == 1 ? hp.tap_mask[kc & 15] : 0x7FFFFFFu;
-          for (int tap = 0; tap < 9 * planes; ++tap) {     // weights [Cout][(kx,) ky, kx taps][Cin]
-            if (!((tmask >> tap) & 1u)) continue;
-            const uint32_t cnt_now = cnt++;
-            const int s = cnt_now % NW;
-            mbar_wait(&w_empty[s], ((cnt_now / NW) & 1) ^ 1);
-            if (hp.exp_skip_weights && cnt_now >= (uint32_t)NW) {      // TIMING EXPERIMENT ONLY: stale weights, no L2 traffic
-              asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&w_full[s])) : "memory");
-              continue;
+          if constexpr (!MASKED) {
+            for (int tap = 0; tap < 9 * planes; ++tap, ++cnt) {     // weights [Cout][(kx,) ky, kx taps][Cin]
+              const int s = cnt % NW;
+              mbar_wait(&w_empty[s], ((cnt / NW) & 1) ^ 1);
+              if (hp.exp_skip_weights && cnt >= (uint32_t)NW) {      // TIMING EXPERIMENT ONLY: stale weights, no L2 traffic
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&w_full[s])) : "memory");
+                continue;
+              }
+              mbar_expect_tx(&w_full[s], W_BYTES);
+              tma_load_2d(wts + s * W_BYTES, &tmap_w, &w_full[s], tap * p.Cin + kc * BLOCK_K, m0);
             }
-            mbar_expect_tx(&w_full[s], W_BYTES);
-            tma_load_2d(wts + s * W_BYTES, &tmap_w, &w_full[s], tap * p.Cin + kc * BLOCK_K, m0);
+          } else {                                                  // sparse 3x3: only the chunk's listed taps
+            const uint32_t tmask = hp.tap_mask[kc & 15];
+            for (int tap = 0; tap < 9; ++tap) {
+              if (!((tmask >> tap) & 1u)) continue;
+              const int s = cnt % NW;
+              mbar_wait(&w_empty[s], ((cnt / NW) & 1) ^ 1);
+              ++cnt;
+              mbar_expect_tx(&w_full[s], W_BYTES);
+              tma_load_2d(wts + s * W_BYTES, &tmap_w, &w_full[s], tap * p.Cin + kc * BLOCK_K, m0);
+            }
           }
         }
       }
@@ -191,30 +203,44 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
         mbar_wait(&acc_empty[as], ((acnt >> 1) & 1) ^ 1);
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + as * BLOCK_N;
-        bool fresh = true;       // the item's first MMA overwrites the accumulator
-        for (int kc = 0; kc < kchunks; ++kc) {
-          const uint32_t tmask = planes == 1 ? hp.tap_mask[kc & 15] : 0x1FFu;
-          for (int pl = 0; pl < planes; ++pl, ++hcnt) {
+        // one tap = BLOCK_K / UMMA_K MMAs per slice on the halo tile `hbase` with the next weight tile of the ring
+        auto issue_tap = [&](uint32_t hbase, int tap, bool accumulate_first) {
+          const int ws = wcnt % NW;
+          mbar_wait(&w_full[ws], (wcnt / NW) & 1);
+          ++wcnt;
+          tcgen05_fence_after();
+          const int dy = (tap / 3) * DIL, dx = (tap % 3) * DIL;
+          const uint64_t adesc = make_smem_desc(smem_u32(wts + ws * W_BYTES));
+#pragma unroll
+          for (int sl = 0; sl < NS; ++sl) {
+            const uint64_t bdesc = make_smem_desc(hbase + sl * CFG::TILE_BYTES + dy * CFG::PITCH + dx * 128, CFG::PITCH);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_f16(tacc + sl * BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accumulate_first || k != 0);
+          }
+          umma_commit(&w_empty[ws]);
+        };
+        if constexpr (!MASKED) {
+          for (int kc = 0; kc < kchunks; ++kc) {
+            for (int pl = 0; pl < planes; ++pl, ++hcnt) {
+              const int hs = hcnt % NH;
+              mbar_wait(&halo_full[hs], (hcnt / NH) & 1);
+              const uint32_t hbase = smem_u32(halo + hs * CFG::HALO_BYTES);
+              for (int tap = 0; tap < 9; ++tap) issue_tap(hbase, tap, (kc | pl | tap) != 0);
+              umma_commit(&halo_empty[hs]);
+            }
+          }
+        } else {           // sparse 3x3 (2-D): the chunk's listed taps only; the item's first MMA overwrites the accumulator
+          bool fresh = true;
+          for (int kc = 0; kc < kchunks; ++kc, ++hcnt) {
+            const uint32_t tmask = hp.tap_mask[kc & 15];
             const int hs = hcnt % NH;
             mbar_wait(&halo_full[hs], (hcnt / NH) & 1);
             const uint32_t hbase = smem_u32(halo + hs * CFG::HALO_BYTES);
             for (int tap = 0; tap < 9; ++tap) {
               if (!((tmask >> tap) & 1u)) continue;
-              const int ws = wcnt % NW;
-              mbar_wait(&w_full[ws], (wcnt / NW) & 1);
-              ++wcnt;
-              tcgen05_fence_after();
-              const int dy = (tap / 3) * DIL, dx = (tap % 3) * DIL;
-              const uint64_t adesc = make_smem_desc(smem_u32(wts + ws * W_BYTES));
-#pragma unroll
-              for (int sl = 0; sl < NS; ++sl) {
-                const uint64_t bdesc = make_smem_desc(hbase + sl * CFG::TILE_BYTES + dy * CFG::PITCH + dx * 128, CFG::PITCH);
-#pragma unroll
-                for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                  umma_f16(tacc + sl * BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, !(fresh && k == 0));
-              }
+              issue_tap(hbase, tap, !fresh);
               fresh = false;
-              umma_commit(&w_empty[ws]);
             }
             umma_commit(&halo_empty[hs]);
           }
@@ -257,11 +283,11 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ 
   }
 }
 
-template <int MODE, int DIL, int TH, int NS = 1>
+template <int MODE, int DIL, int TH, int NS = 1, bool MASKED = false>
 static int launch_variant(const CUtensorMap& mw, const CUtensorMap& mx, const HaloParams& hp, int grid, cudaStream_t s) {
   static std::atomic<unsigned long long> attr_done{0};      // per device, any host thread
   if (device_needs_setup(attr_done)) {
-    IPDM_CUDA(cudaFuncSetAttribute(k_conv_halo<MODE, DIL, TH, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<DIL, TH, NS>::SMEM));
+    IPDM_CUDA(cudaFuncSetAttribute(k_conv_halo<MODE, DIL, TH, NS, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<DIL, TH, NS>::SMEM));
     device_setup_done(attr_done);
   }
   if (hp.pdl) {
@@ -273,10 +299,10 @@ static int launch_variant(const CUtensorMap& mw, const CUtensorMap& mx, const Ha
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    IPDM_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<MODE, DIL, TH, NS>, mw, mx, hp));
+    IPDM_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<MODE, DIL, TH, NS, MASKED>, mw, mx, hp));
     return 0;
   }
-  k_conv_halo<MODE, DIL, TH, NS><<<grid, HALO_THREADS, HaloCfg<DIL, TH, NS>::SMEM, s>>>(mw, mx, hp);
+  k_conv_halo<MODE, DIL, TH, NS, MASKED><<<grid, HALO_THREADS, HaloCfg<DIL, TH, NS>::SMEM, s>>>(mw, mx, hp);
   return 0;
 }
 
@@ -314,6 +340,8 @@ int launch_conv_halo(const ipdm_conv_desc& d, cudaStream_t s) {
   p.residual = t16 ? reinterpret_cast<const float*>(d.residual_f16) : d.residual;
   p.out_f32 = t16 ? reinterpret_cast<float*>(d.out_raw_f16) : d.out_f32;
   for (int i = 0; i < 16; ++i) hp.tap_mask[i] = (d.taps == 9 && d.tap_mask[i] != 0) ? (uint16_t)(d.tap_mask[i] & 0x1FF) : (uint16_t)0x1FF;
+  hp.masked = 0;
+  for (int i = 0; i < 16 && i < d.Cin / 64; ++i) hp.masked |= hp.tap_mask[i] != 0x1FF;
   if (d.taps == 9) {
     for (int i = 0; i < 16 && i < d.Cin / 64; ++i)
       IPDM_REQUIRE(hp.tap_mask[i] != 0, IPDM_E_BADARG, "conv: tap_mask[%d] selects no tap", i);
@@ -361,6 +389,14 @@ int launch_conv_halo(const ipdm_conv_desc& d, cudaStream_t s) {
   case M:                                                                            \
     e = d.dilation == 1 ? launch_variant<M, 1, 32>(mw, mx, hp, grid, s) : launch_variant<M, 2, 32>(mw, mx, hp, grid, s); \
     break;
+  // sparse 3x3 (ConvMeanPool on space-to-depth operands): its own instantiations for the output modes the score network
+  // uses there; anything else runs the dense kernel, which multiplies the zero blocks (same result)
+  const bool sparse = hp.masked && d.dilation == 1 && (mode == 3 || mode == 7 || mode == 19 || mode == 23) && (th == 32 || th == 24);
+  if (!sparse) hp.masked = 0;
+#define HALO_SPARSE(M) (th == 32 ? launch_variant<M, 1, 32, 1, true>(mw, mx, hp, grid, s) : launch_variant<M, 1, 24, 1, true>(mw, mx, hp, grid, s))
+  if (sparse) {      // residual + result, with or without the f16 operand copy, on either stream
+    e = mode == 23 ? HALO_SPARSE(23) : mode == 19 ? HALO_SPARSE(19) : mode == 7 ? HALO_SPARSE(7) : HALO_SPARSE(3);
+  } else
   switch (mode) {
     HALO_CASE(2) HALO_CASE(3) HALO_CASE(4) HALO_CASE(5) HALO_CASE(6) HALO_CASE(7)
     HALO_CASE_POOL(10) HALO_CASE_POOL(11) HALO_CASE_POOL(12) HALO_CASE_POOL(13) HALO_CASE_POOL(14) HALO_CASE_POOL(15)
@@ -371,6 +407,7 @@ int launch_conv_halo(const ipdm_conv_desc& d, cudaStream_t s) {
       set_error("conv_halo: unsupported output combination %d", mode);
       return IPDM_E_BADARG;
   }
+#undef HALO_SPARSE
 #undef HALO_TH
 #undef HALO_CASE_POOL
 #undef HALO_CASE

@@ -310,7 +310,11 @@ class _Plan:
         h32 = self.f32(name + ".h", N, H, W, Cmid)
         st_h = self.stats(name + ".st_h", Cmid)
         self.conv(name + ".conv1", a1, (N, H, W, Cin, Cmid), out32=h32, stats=st_h, dilation=d)
-        s2d = pooled and (name + ".conv2.conv.s2d") in self.w and os.environ.get("IPDM_POOL_AFTER_CONV") is None
+        # the strided forms of the pooled convolutions pay off when the POOLED image still fills the machine with pixel tiles
+        # (tools/bench_pooled_conv.py: 28 x 256^2 0.83 -> 0.46 ms, 2 x 64^2 0.024 -> 0.040 ms): at least one wave of work items
+        items = N * -(-(H // 2) // 32) * -(-(W // 2) // 8) * max(1, Cout // 128)
+        big = (H // 2 >= 32 and items >= 148) or os.environ.get("IPDM_POOL_STRIDED_ALWAYS") is not None
+        s2d = pooled and big and (name + ".conv2.conv.s2d") in self.w and os.environ.get("IPDM_POOL_AFTER_CONV") is None
         a2 = self.f16(name + ".a2", N, H, W, Cmid)
         if s2d:     # the same values in space-to-depth order: (N, H/2, W/2, 4*Cmid) in the same buffer
             self.norm_elu_s2d(name + ".normalize2", h32, st_h, a2, N, H, W, Cmid)
@@ -326,7 +330,7 @@ class _Plan:
                 x16 = self.f16(name + ".x16", N, H, W, Cin)
                 self.to_f16(x32, x16, elu=False)
             sc = self.f32(name + ".sc", N, Ho, Wo, Cout)
-            if pooled and Cin % 8 == 0 and self.w[name + ".shortcut.conv"][0].shape[1] == 1 and os.environ.get("IPDM_POOL_AFTER_SHORTCUT") is None:
+            if pooled and big and Cin % 8 == 0 and self.w[name + ".shortcut.conv"][0].shape[1] == 1 and os.environ.get("IPDM_POOL_AFTER_SHORTCUT") is None:
                 # mean-pool and the 1x1 shortcut convolution commute (the bias too): pool the operand, convolve a quarter of the pixels
                 xp = self.f16(name + ".xp16", N, Ho, Wo, Cin)
                 _lib.check(self.L.ipdm_meanpool2_f16(x16.data_ptr(), xp.data_ptr(), N, H, W, Cin, _lib.stream()), "meanpool2_f16")

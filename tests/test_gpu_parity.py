@@ -726,6 +726,28 @@ def test_single_ald_step_ngf128():
         assert rel_l2(got, ref) < 1e-4, float(levels[0])
 
 
+def test_pooled_convs_strided_forms_tensor_core(monkeypatch):
+    """ConvMeanPool as a 4x4 stride-2 convolution on space-to-depth operands with the tap mask (16 of 36 weight blocks), and the
+    pooled 1x1 shortcuts on pooled operands, on the tensor-core kernels: forced on a 64x64 problem (the size heuristic would keep
+    the reference's order there), against the fp32 oracle and against the pool-after-conv order."""
+    y = torch.tensor([0, 9], device=DEV)
+    x = rrand(77, 2, 1, 64, 64) * 2 - 0.5
+    monkeypatch.setenv("IPDM_POOL_STRIDED_ALWAYS", "1")
+    net, Pd, cfg = _full_width_net(C.NCSNv2Deepest, "NCSNv2Deepest", 64, 21)
+    out = net(x.to(DEV), y).cpu()
+    plan = next(iter(net._plans.values()))
+    assert any(k.endswith(".xp16") for k in plan.bufs) and any(k.endswith(".conv2.conv.s2d") and v[2] for k, v in plan.w.items())
+    monkeypatch.delenv("IPDM_POOL_STRIDED_ALWAYS")
+    net2, _, _ = _full_width_net(C.NCSNv2Deepest, "NCSNv2Deepest", 64, 21)
+    ref_order = net2(x.to(DEV), y).cpu()
+    assert not any(k.endswith(".xp16") for k in next(iter(net2._plans.values())).bufs)
+    with torch.no_grad():
+        ref = SN.score_forward("NCSNv2Deepest", Pd, x, y.cpu())
+    e_new, e_old, e_pair = rel_l2(out, ref), rel_l2(ref_order, ref), rel_l2(out, ref_order)
+    print(f"strided forms: {e_new:.2e} vs fp32 oracle (pool-after-conv: {e_old:.2e}); the two orders differ by {e_pair:.2e}")
+    assert e_new < C.TOL_SCORE and e_old < C.TOL_SCORE and e_pair < C.TOL_SCORE_EMU
+
+
 def test_sampler_range_check_sees_the_real_state():
     """The captured-graph fast path primes its step graph on dummy zeros, so the sampler first runs one eager score forward on the
     REAL initial state: with a measurement 3e5 times too large the plan must have moved to an operand shift before the graph

@@ -44,10 +44,15 @@ def test_pooled_convs_in_their_strided_forms(emu, monkeypatch):
     conv-then-pool order (IPDM_POOL_AFTER_CONV / IPDM_POOL_AFTER_SHORTCUT) up to operand rounding."""
     cfg = C.make_config("ACDC", 8, 32, 12, 30.0)
     x, y = (C.rrand(1301, 2, 1, 32, 32) * 3 - 1), torch.tensor([0, 7])
+    net0, _ = C.build_net(C.NCSNv2Deepest, "NCSNv2Deepest_ngf8", 1, cfg, "cpu")
+    net0(x, y)                      # a problem this small keeps the pool-after-conv order (less than one wave of work items)
+    assert not any(k.endswith(".xp16") for k in next(iter(net0._plans.values())).bufs)
+    monkeypatch.setenv("IPDM_POOL_STRIDED_ALWAYS", "1")
     net, _ = C.build_net(C.NCSNv2Deepest, "NCSNv2Deepest_ngf8", 1, cfg, "cpu")
     out = net(x, y)
     plan = next(iter(net._plans.values()))
     assert any(k.endswith(".conv2.conv.s2d") for k in plan.w) and any(k.endswith(".xp16") for k in plan.bufs)
+    monkeypatch.delenv("IPDM_POOL_STRIDED_ALWAYS")
     monkeypatch.setenv("IPDM_POOL_AFTER_CONV", "1")
     monkeypatch.setenv("IPDM_POOL_AFTER_SHORTCUT", "1")
     net2, _ = C.build_net(C.NCSNv2Deepest, "NCSNv2Deepest_ngf8", 1, cfg, "cpu")

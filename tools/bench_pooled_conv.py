@@ -19,7 +19,10 @@ def timeit(d, reps=10):
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 
-for (N, H, Cin, Cout) in [(28, 256, 128, 256), (28, 128, 256, 256), (28, 64, 256, 256)]:
+shapes = [(28, 256, 128, 256), (28, 128, 256, 256), (28, 64, 256, 256)]
+if len(sys.argv) > 1 and sys.argv[1] == "small":     # one chain at 256^2 (cfg2-B1), 48 frames at 128^2 (cfg 4), 16 images at 28^2 (cfg 1)
+    shapes = [(2, 256, 128, 256), (2, 128, 256, 256), (2, 64, 256, 256), (48, 128, 128, 256), (48, 64, 256, 256), (48, 32, 256, 256), (16, 28, 128, 256)]
+for (N, H, Cin, Cout) in shapes:
     Ho = H // 2
     x = torch.randn(N, H, H, Cin, device=dev).half()
     xs = torch.randn(N, Ho, Ho, 4 * Cin, device=dev).half()

@@ -13,7 +13,7 @@ done
 python bench.py --impl reference --config cfg5-sweep --steps 3 --warmup 1 > $O/r2_bench_cfg5-sweep_reference.json 2>&1
 python tools/bench_sense.py > $O/r2_sense_sweep.jsonl 2>&1; echo "sweep rc=$?"
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-library-baseline"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/r2_launches_one_step.csv $CMD > $O/r2_ncu_launches.log 2>&1; echo "launches rc=$?"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1600 --csv --log-file $O/r2_launches_one_step.csv $CMD > $O/r2_ncu_launches.log 2>&1; echo "launches rc=$?"
 python tools/prof_one.py t16 > $O/prof_one_t16.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:k_conv_halo -s 2 -c 1 -f -o $O/r2_conv_t16 python tools/prof_one.py t16 > $O/ncu_t16.log 2>&1; echo "ncu t16 rc=$?"
 # summaries are made HERE (the reports themselves are too big to travel back: 64 MiB limit on gpurun_out)

@@ -4,7 +4,8 @@ path = sys.argv[1] if len(sys.argv) > 1 else 'gpurun_out/launches.csv'
 lines=[l for l in open(path) if not l.startswith('==')]
 rows=list(csv.DictReader(lines))
 idx=[i for i,r in enumerate(rows) if 'k_conv_first' in r['Kernel Name']]
-seg=rows[idx[0]:idx[1]] if len(idx) > 1 else rows[idx[0]:]
+# the LAST complete step of the run: the first forwards carry one-off work (buffer fills, the range audit, graph priming)
+seg=rows[idx[-2]:idx[-1]] if len(idx) > 1 else rows[idx[0]:]
 agg=collections.defaultdict(lambda:[0,0.0])
 for row in seg:
     name=re.sub(r'\(.*','',row['Kernel Name']).replace('ipdm::','').replace('void ','')
